@@ -1,0 +1,101 @@
+/* libwbk -- C-ABI of the B200-native WaveBreaking detection path.
+ *
+ * The reference (skaderli/WaveBreaking v0.3.8) is pure Python and defines no FFI of
+ * its own; its boundary is the Python API re-exported in wavebreaking/__init__.py:19-34.
+ * This header is the C boundary that the Python host layer (wavebreaking_b200/) binds
+ * with ctypes; every entry point names the reference code whose arithmetic it replaces.
+ *
+ * Conventions
+ *  - plain C types only; pointers named d_* are device pointers (in the emulator build
+ *    used by the CPU-only tests they are host pointers), h_* are host pointers;
+ *  - every function returns WBK_OK (0) or a negative error code; the message of the
+ *    last error of the calling thread is returned by wbk_last_error();
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *  - variable-length results live in capacity-bounded device arenas owned by a context;
+ *    an overflow yields WBK_ERR_CAPACITY and wbk_caps_needed() tells the sizes that
+ *    would have sufficed, so the caller can re-create the context and retry;
+ *  - lattice points are packed as x | (y << 16) in a uint32 (x = column on the
+ *    periodically extended grid, y = row).
+ */
+#ifndef WBK_H
+#define WBK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WBK_OK 0
+#define WBK_ERR_INVALID (-1)
+#define WBK_ERR_CUDA (-2)
+#define WBK_ERR_CAPACITY (-3)
+#define WBK_ERR_NODEVICE (-4)
+
+#define WBK_F32 0
+#define WBK_F64 1
+
+/* rounding of the smoothing passes (scipy keeps the input dtype, the division by
+ * np.sum(weights) promotes float32 to float64 under NumPy >= 2) */
+#define WBK_ROUND_NONE 0      /* float64 data: all passes in float64 */
+#define WBK_ROUND_FIRST 1     /* float32 data, NumPy >= 2: pass 1 rounds its sum to float32, then float64 */
+#define WBK_ROUND_ALL 2       /* float32 data, NumPy 1.x: every pass rounds to float32 */
+
+/* per-job status bits (job = one (time step, contour level)) */
+#define WBK_ST_SEG_OVERFLOW 1       /* more marching-squares segments than seg_cap */
+#define WBK_ST_CONTOUR_OVERFLOW 2   /* more contours than contour_cap */
+#define WBK_ST_LATTICE_VERTEX 4     /* a contour vertex fell exactly on a grid vertex (value == level):
+                                       skimage joins such points by float equality; result flagged */
+#define WBK_ST_PAIR_OVERFLOW 8      /* more streamer candidate pairs than pair_cap */
+#define WBK_ST_EVENT_OVERFLOW 16    /* more events than event_cap */
+#define WBK_ST_SEL_OVERFLOW 32      /* more full-width contours than sel_cap */
+#define WBK_ST_WIDTH_OVERFLOW 64    /* extended grid wider than the shared-memory column tables */
+
+const char* wbk_last_error(void);
+int wbk_version(void);
+/* number of CUDA devices visible; WBK_ERR_NODEVICE if none (the library has no CPU path) */
+int wbk_device_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * wavebreaking/processing/spatial.py:60-128  calculate_smoothed_field
+ *   `passes` x [scipy.ndimage.convolve(weights=[[0,1,0],[1,2,1],[0,1,0]], mode="wrap") / np.sum(weights) = 6]
+ *   then rows {0,1,nlat-2,nlat-1} := NaN (spatial.py:100-107).  All passes are fused in one
+ *   launch per WBK_SMOOTH_MAX_FUSED passes.  d_in [ntime,nlat,nlon] (in_dtype), d_out same shape
+ *   (out_dtype: F64 for ROUND_NONE / ROUND_FIRST, F32 for ROUND_ALL; passes == 0 needs
+ *   out_dtype == in_dtype).  d_tmp (same size as d_out) is needed only if
+ *   passes > WBK_SMOOTH_MAX_FUSED, else may be NULL.
+ */
+#define WBK_SMOOTH_MAX_FUSED 8
+int wbk_smooth(const void* d_in, int in_dtype, void* d_out, int out_dtype, void* d_tmp, int ntime, int nlat,
+               int nlon, int passes, int round_mode, void* stream);
+
+/* spatial.py:103 with user-supplied weights / mode: ONE pass of
+ * scipy.ndimage.convolve(in, weights, mode, cval=0) (output dtype = dtype, accumulation in
+ * double in scipy's tap order), followed by the division by `divisor` (np.sum(weights)) when
+ * divide != 0.  mode: 0 wrap ("wrap"/"grid-wrap"), 1 reflect, 2 mirror, 3 nearest, 4 constant.
+ * h_weights is the kh x kw kernel as given to scipy (row-major, host memory).
+ */
+int wbk_convolve2d(const void* d_in, int in_dtype, void* d_out, int out_dtype, int ntime, int nlat, int nlon,
+                   const double* h_weights, int kh, int kw, int mode, int divide, double divisor, void* stream);
+
+/* set rows {0..border-1} and {nlat-border..nlat-1} to NaN (spatial.py:106-107) */
+int wbk_nan_border(void* d_field, int dtype, int ntime, int nlat, int nlon, int border, void* stream);
+
+/* spatial.py:27-57 calculate_momentum_flux: (u - nanmean_lon(u)) * (v - nanmean_lon(v)) */
+int wbk_mflux(const void* d_u, const void* d_v, void* d_out, int dtype, int ntime, int nlat, int nlon, void* stream);
+
+/* utils/data_utils.py:196-213 correct_dimension_orientation: out[t, y, x] = in[t, flip_lat ? nlat-1-y : y,
+ * flip_lon ? nlon-1-x : x] */
+int wbk_flip(const void* d_in, void* d_out, int dtype, int ntime, int nlat, int nlon, int flip_lat, int flip_lon,
+             void* stream);
+
+/* synthetic Rossby-wave PV (host mirror: wavebreaking_b200/synthetic.py).
+ * h_blobs: [2][n_blob][3] doubles (lat0, lon0, radius); hours: first hour and step. */
+int wbk_synth_pv(void* d_out, int dtype, int ntime, int nlat, int nlon, double hour0, double hour_step,
+                 const double* h_blobs, int n_blob, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WBK_H */

@@ -1,0 +1,134 @@
+"""ctypes binding of libwbk.so (the C-ABI declared in include/wbk.h).
+
+There is no CPU implementation behind this module: ``get()`` raises if the nvcc-built
+library is missing or no CUDA device is visible.  (The CPU-only test-suite exercises the
+kernels' integer logic through ``tests/emu`` -- the same sources compiled against a SIMT
+emulation shim -- by calling :func:`use_library` explicitly; nothing in the package does.)
+"""
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_int, c_int64, c_size_t, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_PATH = os.path.join(HERE, "libwbk.so")
+
+OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_NODEVICE = 0, -1, -2, -3, -4
+F32, F64 = 0, 1
+ROUND_NONE, ROUND_FIRST, ROUND_ALL = 0, 1, 2
+SMOOTH_MAX_FUSED = 8
+
+ST_SEG_OVERFLOW = 1
+ST_CONTOUR_OVERFLOW = 2
+ST_LATTICE_VERTEX = 4
+ST_PAIR_OVERFLOW = 8
+ST_EVENT_OVERFLOW = 16
+ST_SEL_OVERFLOW = 32
+ST_WIDTH_OVERFLOW = 64
+
+
+class WbkError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libwbk error {}: {}".format(code, msg))
+        self.code = code
+
+
+class CapacityError(WbkError):
+    pass
+
+
+_SIGNATURES = {
+    "wbk_last_error": (c_char_p, []),
+    "wbk_version": (c_int, []),
+    "wbk_device_count": (c_int, []),
+    "wbk_smooth": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "wbk_convolve2d": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, POINTER(c_double), c_int,
+                               c_int, c_int, c_int, c_double, c_void_p]),
+    "wbk_nan_border": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "wbk_mflux": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "wbk_flip": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "wbk_synth_pv": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_double, c_double, POINTER(c_double), c_int,
+                             c_void_p]),
+}
+
+
+class Library:
+    """A loaded libwbk plus the torch device its buffers live on."""
+
+    def __init__(self, path, device):
+        import torch
+
+        self.path = path
+        self.cdll = ctypes.CDLL(path)
+        self.device = torch.device(device)
+        self.is_cuda = self.device.type == "cuda"
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(self.cdll, name)
+            fn.restype = res
+            fn.argtypes = args
+
+    def stream(self):
+        if not self.is_cuda:
+            return None
+        import torch
+
+        return c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def last_error(self):
+        msg = self.cdll.wbk_last_error()
+        return msg.decode() if msg else ""
+
+    def check(self, rc):
+        if rc == OK:
+            return
+        cls = CapacityError if rc == ERR_CAPACITY else WbkError
+        raise cls(rc, self.last_error())
+
+    def call(self, name, *args):
+        self.check(getattr(self.cdll, name)(*args))
+
+
+_LIB = None
+
+
+def get():
+    """The process-wide library; loads wavebreaking_b200/libwbk.so on first use."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(DEFAULT_PATH):
+            raise RuntimeError(
+                "libwbk.so is not built (run `python -m wavebreaking_b200._build`); "
+                "wavebreaking_b200 has no CPU fallback"
+            )
+        import torch
+
+        if not torch.cuda.is_available():
+            raise RuntimeError("no CUDA device visible; wavebreaking_b200 runs on sm_100a GPUs only (no CPU fallback)")
+        lib = Library(DEFAULT_PATH, "cuda:{}".format(torch.cuda.current_device()))
+        n = lib.cdll.wbk_device_count()
+        if n <= 0:
+            raise RuntimeError(lib.last_error())
+        _LIB = lib
+    return _LIB
+
+
+def use_library(path, device):
+    """TESTS ONLY: install an explicitly given library build (tests/emu) as the process-wide one."""
+    global _LIB
+    _LIB = Library(path, device) if path is not None else None
+    return _LIB
+
+
+def ptr(t):
+    """Raw pointer of a torch tensor (or None)."""
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def dtype_code(torch_dtype):
+    import torch
+
+    if torch_dtype == torch.float32:
+        return F32
+    if torch_dtype == torch.float64:
+        return F64
+    raise TypeError("only float32 / float64 fields are supported, got {}".format(torch_dtype))

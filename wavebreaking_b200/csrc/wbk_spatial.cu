@@ -1,0 +1,432 @@
+// Spatial pre-processing kernels: fused multi-pass smoothing stencil, generic convolution,
+// momentum flux, orientation flip, synthetic PV generator.
+// Reference: wavebreaking/processing/spatial.py:27-128, utils/data_utils.py:196-213.
+#include "wbk_common.cuh"
+
+// ------------------------------------------------------------------------------------------
+// K1: fused `passes` x (5-point stencil / 6), periodic in longitude AND latitude
+// (scipy mode="wrap" wraps both axes), accumulation in double in scipy's tap order
+//   ((((N + W) + 2C) + E) + S)      [SURVEY.md A.7, probed against scipy 1.18]
+// One CTA owns a TH x TW output tile and keeps the tile plus a `passes`-wide halo in shared
+// memory (ping-pong), so the field is read once and written once whatever `passes` is.
+// ------------------------------------------------------------------------------------------
+#define SM_TW 64
+#define SM_TH 32
+#define SM_THREADS 256
+
+__device__ __forceinline__ int wrap_idx(int i, int n) {
+  i %= n;
+  return i < 0 ? i + n : i;
+}
+
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(SM_THREADS)
+smooth_fused_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, int nlat, int nlon, int passes,
+                    int round_first, int round_all, int nan_border) {
+  WBK_DYN_SMEM(double, smem);
+  const int p = passes;
+  const int H = SM_TH + 2 * p;
+  const int Wd = SM_TW + 2 * p;
+  const int pitch = Wd | 1;  // odd pitch: no bank conflicts between rows
+  double* buf0 = smem;
+  double* buf1 = smem + (size_t)H * pitch;
+
+  const int x0 = blockIdx.x * SM_TW, y0 = blockIdx.y * SM_TH;
+  const size_t plane = (size_t)nlat * nlon;
+  const TIn* src = in + plane * blockIdx.z;
+  TOut* dst = out + plane * blockIdx.z;
+
+  // load tile + halo (wrapping both axes)
+  for (int idx = threadIdx.x; idx < H * Wd; idx += SM_THREADS) {
+    int r = idx / Wd, c = idx - r * Wd;
+    int gy = wrap_idx(y0 - p + r, nlat);
+    int gx = wrap_idx(x0 - p + c, nlon);
+    buf0[r * pitch + c] = (double)src[(size_t)gy * nlon + gx];
+  }
+  __syncthreads();
+
+  double* a = buf0;
+  double* b = buf1;
+  for (int k = 1; k <= p; ++k) {
+    const int rh = H - 2 * k, rw = Wd - 2 * k;
+    const bool rnd = round_all || (round_first && k == 1);
+    for (int idx = threadIdx.x; idx < rh * rw; idx += SM_THREADS) {
+      int r = idx / rw, c = idx - r * rw;
+      r += k;
+      c += k;
+      const double* q = a + r * pitch + c;
+      double acc = __dadd_rn(q[-pitch], q[-1]);
+      acc = __dadd_rn(acc, __dmul_rn(2.0, q[0]));
+      acc = __dadd_rn(acc, q[1]);
+      acc = __dadd_rn(acc, q[pitch]);
+      if (rnd) acc = (double)__double2float_rn(acc);
+      // np.sum(weights) == 6: a true division (float32 / float32 under NumPy 1.x promotion)
+      b[r * pitch + c] = round_all ? (double)(__double2float_rn(acc) / 6.0f) : __ddiv_rn(acc, 6.0);
+    }
+    __syncthreads();
+    double* t = a;
+    a = b;
+    b = t;
+  }
+
+  // write the inner tile
+  for (int idx = threadIdx.x; idx < SM_TH * SM_TW; idx += SM_THREADS) {
+    int r = idx / SM_TW, c = idx - r * SM_TW;
+    int gy = y0 + r, gx = x0 + c;
+    if (gy < nlat && gx < nlon) {
+      double v = a[(r + p) * pitch + (c + p)];
+      if (nan_border > 0 && (gy < nan_border || gy >= nlat - nan_border)) v = __longlong_as_double(0x7ff8000000000000LL);
+      dst[(size_t)gy * nlon + gx] = (TOut)v;
+    }
+  }
+}
+
+static size_t smooth_smem_bytes(int passes) {
+  int H = SM_TH + 2 * passes, Wd = SM_TW + 2 * passes;
+  int pitch = Wd | 1;
+  return (size_t)2 * H * pitch * sizeof(double);
+}
+
+template <typename TIn, typename TOut>
+static int launch_smooth(const void* in, void* out, int ntime, int nlat, int nlon, int passes, int round_first,
+                         int round_all, int nan_border, cudaStream_t st) {
+  size_t smem = smooth_smem_bytes(passes);
+  WBK_CUDA_CHECK(cudaFuncSetAttribute(smooth_fused_kernel<TIn, TOut>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+  dim3 grid((nlon + SM_TW - 1) / SM_TW, (nlat + SM_TH - 1) / SM_TH, ntime);
+  WBK_LAUNCH((smooth_fused_kernel<TIn, TOut>), grid, dim3(SM_THREADS), smem, st, (const TIn*)in, (TOut*)out, nlat,
+             nlon, passes, round_first, round_all, nan_border);
+  WBK_LAUNCH_CHECK();
+  return WBK_OK;
+}
+
+extern "C" int wbk_smooth(const void* d_in, int in_dtype, void* d_out, int out_dtype, void* d_tmp, int ntime,
+                          int nlat, int nlon, int passes, int round_mode, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!d_in || !d_out || ntime < 0 || nlat < 4 || nlon < 1 || passes < 0) {
+    wbk_set_error("wbk_smooth: invalid argument");
+    return WBK_ERR_INVALID;
+  }
+  if (ntime == 0) return WBK_OK;
+  const int border = 2;  // int(3 / 2 + 0.5), spatial.py:106
+  if (passes == 0) {
+    if (in_dtype != out_dtype) {
+      wbk_set_error("wbk_smooth: passes == 0 keeps the dtype");
+      return WBK_ERR_INVALID;
+    }
+    size_t bytes = (size_t)ntime * nlat * nlon * (in_dtype == WBK_F32 ? 4 : 8);
+    if (d_in != d_out) WBK_CUDA_CHECK(cudaMemcpyAsync(d_out, d_in, bytes, cudaMemcpyDeviceToDevice, st));
+    return wbk_nan_border(d_out, out_dtype, ntime, nlat, nlon, border, stream);
+  }
+  const bool f32_in = in_dtype == WBK_F32;
+  if ((round_mode == WBK_ROUND_NONE && (f32_in || out_dtype != WBK_F64)) ||
+      (round_mode == WBK_ROUND_FIRST && (!f32_in || out_dtype != WBK_F64)) ||
+      (round_mode == WBK_ROUND_ALL && (!f32_in || out_dtype != WBK_F32))) {
+    wbk_set_error("wbk_smooth: dtype / round_mode combination not supported");
+    return WBK_ERR_INVALID;
+  }
+  if (passes > WBK_SMOOTH_MAX_FUSED && !d_tmp) {
+    wbk_set_error("wbk_smooth: d_tmp required for passes > %d", WBK_SMOOTH_MAX_FUSED);
+    return WBK_ERR_INVALID;
+  }
+  const int round_all = round_mode == WBK_ROUND_ALL;
+  // chunk the passes; intermediates are stored in the output dtype (exact: f64, or f32 values under ROUND_ALL)
+  int nchunks = (passes + WBK_SMOOTH_MAX_FUSED - 1) / WBK_SMOOTH_MAX_FUSED;
+  const void* src = d_in;
+  int done = 0;
+  for (int ch = 0; ch < nchunks; ++ch) {
+    int n = passes - done < WBK_SMOOTH_MAX_FUSED ? passes - done : WBK_SMOOTH_MAX_FUSED;
+    bool last = ch == nchunks - 1;
+    // ping-pong so that the last chunk lands in d_out
+    void* dstp = ((nchunks - 1 - ch) % 2 == 0) ? d_out : d_tmp;
+    int rf = (round_mode == WBK_ROUND_FIRST && ch == 0) ? 1 : 0;
+    int nb = last ? border : 0;
+    int rc;
+    if (ch == 0) {
+      if (f32_in && out_dtype == WBK_F64) rc = launch_smooth<float, double>(src, dstp, ntime, nlat, nlon, n, rf, round_all, nb, st);
+      else if (f32_in) rc = launch_smooth<float, float>(src, dstp, ntime, nlat, nlon, n, rf, round_all, nb, st);
+      else rc = launch_smooth<double, double>(src, dstp, ntime, nlat, nlon, n, rf, round_all, nb, st);
+    } else {
+      if (out_dtype == WBK_F64) rc = launch_smooth<double, double>(src, dstp, ntime, nlat, nlon, n, 0, round_all, nb, st);
+      else rc = launch_smooth<float, float>(src, dstp, ntime, nlat, nlon, n, 0, round_all, nb, st);
+    }
+    if (rc != WBK_OK) return rc;
+    src = dstp;
+    done += n;
+  }
+  return WBK_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// generic single-pass scipy.ndimage.convolve (any 2-D weights, five boundary modes)
+// ------------------------------------------------------------------------------------------
+#define CV_MAX_TAPS 225
+struct ConvTaps {
+  int n;
+  int dy[CV_MAX_TAPS];
+  int dx[CV_MAX_TAPS];
+  double w[CV_MAX_TAPS];
+};
+
+__device__ __forceinline__ int extend_index(int i, int n, int mode, bool* outside) {
+  *outside = false;
+  if (i >= 0 && i < n) return i;
+  switch (mode) {
+    case 0:  // wrap
+      return wrap_idx(i, n);
+    case 1: {  // reflect: d c b a | a b c d | d c b a
+      int period = 2 * n;
+      int m = wrap_idx(i, period);
+      return m < n ? m : period - 1 - m;
+    }
+    case 2: {  // mirror: d c b | a b c d | c b a
+      if (n == 1) return 0;
+      int period = 2 * n - 2;
+      int m = wrap_idx(i, period);
+      return m < n ? m : period - m;
+    }
+    case 3:  // nearest
+      return i < 0 ? 0 : n - 1;
+    default:  // constant
+      *outside = true;
+      return 0;
+  }
+}
+
+template <typename TIn, typename TMid, typename TOut>
+__global__ void convolve2d_cast_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, int nlat, int nlon,
+                                       ConvTaps taps, int mode, int divide, double divisor) {
+  const size_t plane = (size_t)nlat * nlon;
+  const TIn* src = in + plane * blockIdx.z;
+  TOut* dst = out + plane * blockIdx.z;
+  int gx = blockIdx.x * blockDim.x + threadIdx.x;
+  int gy = blockIdx.y;
+  if (gx >= nlon) return;
+  double acc = 0.0;
+  for (int t = 0; t < taps.n; ++t) {
+    bool oy, ox;
+    int yy = extend_index(gy + taps.dy[t], nlat, mode, &oy);
+    int xx = extend_index(gx + taps.dx[t], nlon, mode, &ox);
+    double v = (oy || ox) ? 0.0 : (double)src[(size_t)yy * nlon + xx];
+    acc = __dadd_rn(acc, __dmul_rn(v, taps.w[t]));
+  }
+  TMid r = (TMid)acc;
+  double rr = (double)r;
+  if (divide) rr = __ddiv_rn(rr, divisor);
+  dst[(size_t)gy * nlon + gx] = (TOut)rr;
+}
+
+extern "C" int wbk_convolve2d(const void* d_in, int in_dtype, void* d_out, int out_dtype, int ntime, int nlat,
+                              int nlon, const double* h_weights, int kh, int kw, int mode, int divide, double divisor,
+                              void* stream) {
+  if (!d_in || !d_out || !h_weights || kh < 1 || kw < 1 || mode < 0 || mode > 4 || nlat < 1 || nlon < 1) {
+    wbk_set_error("wbk_convolve2d: invalid argument");
+    return WBK_ERR_INVALID;
+  }
+  if (ntime == 0) return WBK_OK;
+  ConvTaps taps;
+  taps.n = 0;
+  // convolve(input, w) == correlate(input, flipped w) with origin shifted by -1 on even sizes
+  const int cy = kh / 2 - ((kh % 2 == 0) ? 1 : 0);
+  const int cx = kw / 2 - ((kw % 2 == 0) ? 1 : 0);
+  for (int a = 0; a < kh; ++a)
+    for (int b = 0; b < kw; ++b) {
+      double w = h_weights[(kh - 1 - a) * kw + (kw - 1 - b)];
+      if (w != 0.0) {
+        if (taps.n >= CV_MAX_TAPS) {
+          wbk_set_error("wbk_convolve2d: more than %d non-zero weights", CV_MAX_TAPS);
+          return WBK_ERR_INVALID;
+        }
+        taps.dy[taps.n] = a - cy;
+        taps.dx[taps.n] = b - cx;
+        taps.w[taps.n] = w;
+        ++taps.n;
+      }
+    }
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 block(128);
+  dim3 grid((nlon + 127) / 128, nlat, ntime);
+  if (in_dtype == WBK_F32 && out_dtype == WBK_F32) {
+    WBK_LAUNCH((convolve2d_cast_kernel<float, float, float>), grid, block, 0, st, (const float*)d_in, (float*)d_out, nlat, nlon, taps, mode, divide, divisor);
+  } else if (in_dtype == WBK_F32 && out_dtype == WBK_F64) {
+    WBK_LAUNCH((convolve2d_cast_kernel<float, float, double>), grid, block, 0, st, (const float*)d_in, (double*)d_out, nlat, nlon, taps, mode, divide, divisor);
+  } else if (in_dtype == WBK_F64 && out_dtype == WBK_F64) {
+    WBK_LAUNCH((convolve2d_cast_kernel<double, double, double>), grid, block, 0, st, (const double*)d_in, (double*)d_out, nlat, nlon, taps, mode, divide, divisor);
+  } else {
+    wbk_set_error("wbk_convolve2d: unsupported dtype combination");
+    return WBK_ERR_INVALID;
+  }
+  WBK_LAUNCH_CHECK();
+  return WBK_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void nan_border_kernel(T* f, int nlat, int nlon, int border) {
+  int gx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gx >= nlon) return;
+  int k = blockIdx.y;  // 0 .. 2*border-1
+  int gy = k < border ? k : nlat - 2 * border + k;
+  if (gy < 0 || gy >= nlat) return;
+  f[(size_t)blockIdx.z * nlat * nlon + (size_t)gy * nlon + gx] = (T)__longlong_as_double(0x7ff8000000000000LL);
+}
+
+extern "C" int wbk_nan_border(void* d_field, int dtype, int ntime, int nlat, int nlon, int border, void* stream) {
+  if (!d_field || border < 0 || nlat < 1 || nlon < 1) {
+    wbk_set_error("wbk_nan_border: invalid argument");
+    return WBK_ERR_INVALID;
+  }
+  if (ntime == 0 || border == 0) return WBK_OK;
+  dim3 grid((nlon + 255) / 256, 2 * border, ntime);
+  if (dtype == WBK_F32) WBK_LAUNCH(nan_border_kernel<float>, grid, dim3(256), 0, (cudaStream_t)stream, (float*)d_field, nlat, nlon, border);
+  else WBK_LAUNCH(nan_border_kernel<double>, grid, dim3(256), 0, (cudaStream_t)stream, (double*)d_field, nlat, nlon, border);
+  WBK_LAUNCH_CHECK();
+  return WBK_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: momentum flux.  One CTA per (time, lat) row: NaN-skipping zonal means of u and v in double,
+// then (u - ubar) * (v - vbar) in the data dtype (xarray arithmetic keeps float32).
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void mflux_kernel(const T* __restrict__ u, const T* __restrict__ v, T* __restrict__ out, int nlon) {
+  __shared__ double red[34];
+  __shared__ double means[2];
+  const size_t row = ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * nlon;
+  double su = 0, sv = 0, cu = 0, cv = 0;
+  for (int x = threadIdx.x; x < nlon; x += blockDim.x) {
+    double a = (double)u[row + x], b = (double)v[row + x];
+    if (!isnan(a)) { su += a; cu += 1; }
+    if (!isnan(b)) { sv += b; cv += 1; }
+  }
+  su = wbk_block_sum_f64(su, red);
+  cu = wbk_block_sum_f64(cu, red);
+  sv = wbk_block_sum_f64(sv, red);
+  cv = wbk_block_sum_f64(cv, red);
+  if (threadIdx.x == 0) {
+    means[0] = (double)(T)(su / cu);  // nanmean returns the data dtype
+    means[1] = (double)(T)(sv / cv);
+  }
+  __syncthreads();
+  const T mu = (T)means[0], mv = (T)means[1];
+  for (int x = threadIdx.x; x < nlon; x += blockDim.x) {
+    T up = u[row + x] - mu;
+    T vp = v[row + x] - mv;
+    out[row + x] = up * vp;
+  }
+}
+
+extern "C" int wbk_mflux(const void* d_u, const void* d_v, void* d_out, int dtype, int ntime, int nlat, int nlon,
+                         void* stream) {
+  if (!d_u || !d_v || !d_out || nlat < 1 || nlon < 1) {
+    wbk_set_error("wbk_mflux: invalid argument");
+    return WBK_ERR_INVALID;
+  }
+  if (ntime == 0) return WBK_OK;
+  dim3 grid(nlat, ntime);
+  if (dtype == WBK_F32) WBK_LAUNCH(mflux_kernel<float>, grid, dim3(256), 0, (cudaStream_t)stream, (const float*)d_u, (const float*)d_v, (float*)d_out, nlon);
+  else WBK_LAUNCH(mflux_kernel<double>, grid, dim3(256), 0, (cudaStream_t)stream, (const double*)d_u, (const double*)d_v, (double*)d_out, nlon);
+  WBK_LAUNCH_CHECK();
+  return WBK_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void flip_kernel(const T* __restrict__ in, T* __restrict__ out, int nlat, int nlon, int flip_lat, int flip_lon) {
+  int gx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gx >= nlon) return;
+  int gy = blockIdx.y;
+  size_t base = (size_t)blockIdx.z * nlat * nlon;
+  int sy = flip_lat ? nlat - 1 - gy : gy;
+  int sx = flip_lon ? nlon - 1 - gx : gx;
+  out[base + (size_t)gy * nlon + gx] = in[base + (size_t)sy * nlon + sx];
+}
+
+extern "C" int wbk_flip(const void* d_in, void* d_out, int dtype, int ntime, int nlat, int nlon, int flip_lat,
+                        int flip_lon, void* stream) {
+  if (!d_in || !d_out || d_in == d_out || nlat < 1 || nlon < 1) {
+    wbk_set_error("wbk_flip: invalid argument (in-place is not supported)");
+    return WBK_ERR_INVALID;
+  }
+  if (ntime == 0) return WBK_OK;
+  dim3 grid((nlon + 255) / 256, nlat, ntime);
+  if (dtype == WBK_F32) WBK_LAUNCH(flip_kernel<float>, grid, dim3(256), 0, (cudaStream_t)stream, (const float*)d_in, (float*)d_out, nlat, nlon, flip_lat, flip_lon);
+  else WBK_LAUNCH(flip_kernel<double>, grid, dim3(256), 0, (cudaStream_t)stream, (const double*)d_in, (double*)d_out, nlat, nlon, flip_lat, flip_lon);
+  WBK_LAUNCH_CHECK();
+  return WBK_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// synthetic PV (mirror of wavebreaking_b200/synthetic.py)
+// ------------------------------------------------------------------------------------------
+#define SYN_MAX_BLOB 32
+struct SynthParams {
+  double A, k, tilt, c, env0, env1, env_speed, blob_amp, sh_shift;
+  int n_blob;
+  double lat0[2][SYN_MAX_BLOB], lon0[2][SYN_MAX_BLOB], rad[2][SYN_MAX_BLOB];
+};
+
+__device__ __forceinline__ double synth_background(double alat, double lam_deg, double hours, const SynthParams& p) {
+  const double d2r = 0.017453292519943295;
+  double lam = lam_deg * d2r;
+  double env = p.env0 + p.env1 * cos(lam - p.env_speed * hours * d2r);
+  double phase = p.k * (lam - p.c * hours * d2r) + p.tilt * (alat - 45.0) / 10.0 + 0.7 * sin(2.0 * lam);
+  double phi = alat - p.A * env * sin(phase);
+  double s = sin(phi * d2r) / sin(45.0 * d2r);
+  double a = fabs(s);
+  double r = 2.0 * a * a * a;
+  return s < 0 ? -r : r;
+}
+
+template <typename T>
+__global__ void synth_pv_kernel(T* out, int nlat, int nlon, double hour0, double hour_step, SynthParams p) {
+  int gx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gx >= nlon) return;
+  int gy = blockIdx.y;
+  int t = blockIdx.z;
+  const double d2r = 0.017453292519943295;
+  double hours = hour0 + hour_step * t;
+  double lat = -90.0 + 180.0 * gy / (double)(nlat - 1);
+  double lon = gx * (360.0 / nlon);
+  bool south = lat < 0;
+  double alat = fabs(lat);
+  int hemi = south ? 1 : 0;
+  double pv = synth_background(alat, south ? lon + p.sh_shift : lon, hours, p);
+  for (int b = 0; b < p.n_blob; ++b) {
+    double lonc = fmod(p.lon0[hemi][b] + p.c * hours, 360.0);
+    double bg = synth_background(p.lat0[hemi][b], lonc + (hemi ? p.sh_shift : 0.0), hours, p);
+    double sign = bg > 2.0 ? -1.0 : 1.0;
+    double dl = fmod(lon - lonc + 180.0, 360.0);
+    if (dl < 0) dl += 360.0;
+    dl -= 180.0;
+    double dy = alat - p.lat0[hemi][b];
+    double dxs = dl * cos(p.lat0[hemi][b] * d2r);
+    double d2 = dy * dy + dxs * dxs;
+    double rad = p.rad[hemi][b];
+    pv += sign * p.blob_amp * exp(-d2 / (2.0 * rad * rad));
+  }
+  out[((size_t)t * nlat + gy) * nlon + gx] = (T)(south ? -pv : pv);
+}
+
+extern "C" int wbk_synth_pv(void* d_out, int dtype, int ntime, int nlat, int nlon, double hour0, double hour_step,
+                            const double* h_blobs, int n_blob, void* stream) {
+  if (!d_out || nlat < 2 || nlon < 1 || n_blob < 0 || n_blob > SYN_MAX_BLOB || (n_blob > 0 && !h_blobs)) {
+    wbk_set_error("wbk_synth_pv: invalid argument");
+    return WBK_ERR_INVALID;
+  }
+  if (ntime == 0) return WBK_OK;
+  SynthParams p;
+  p.A = 11.0; p.k = 6.0; p.tilt = 1.6; p.c = 0.5; p.env0 = 0.6; p.env1 = 0.4; p.env_speed = 1.5;
+  p.blob_amp = 3.0; p.sh_shift = 37.0; p.n_blob = n_blob;
+  for (int h = 0; h < 2; ++h)
+    for (int b = 0; b < n_blob; ++b) {
+      p.lat0[h][b] = h_blobs[(h * n_blob + b) * 3 + 0];
+      p.lon0[h][b] = h_blobs[(h * n_blob + b) * 3 + 1];
+      p.rad[h][b] = h_blobs[(h * n_blob + b) * 3 + 2];
+    }
+  dim3 grid((nlon + 127) / 128, nlat, ntime);
+  if (dtype == WBK_F32) WBK_LAUNCH(synth_pv_kernel<float>, grid, dim3(128), 0, (cudaStream_t)stream, (float*)d_out, nlat, nlon, hour0, hour_step, p);
+  else WBK_LAUNCH(synth_pv_kernel<double>, grid, dim3(128), 0, (cudaStream_t)stream, (double*)d_out, nlat, nlon, hour0, hour_step, p);
+  WBK_LAUNCH_CHECK();
+  return WBK_OK;
+}
