@@ -95,6 +95,51 @@ int wbk_flip(const void* d_in, void* d_out, int dtype, int ntime, int nlat, int 
 int wbk_synth_pv(void* d_out, int dtype, int ntime, int nlat, int nlon, double hour0, double hour_step,
                  const double* h_blobs, int n_blob, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Detection context: owns the capacity-bounded device arenas of one batch of jobs
+ * (job = time step x contour level, job = t * nlevels + l: time-outer, level-inner, the row
+ * order of utils/index_utils.py:217-258).
+ */
+typedef struct wbk_caps {
+  int max_jobs;    /* time steps x levels per batch */
+  int seg_cap;     /* marching-squares segments per job */
+  int contour_cap; /* contours per job (before the length / duplicate filters) */
+  int sel_cap;     /* full-width contours (exp_lon == max) per job */
+  int pair_cap;    /* streamer candidate pairs per full-width contour */
+  int event_cap;   /* events per job and index */
+} wbk_caps;
+
+typedef struct wbk_ctx wbk_ctx;
+
+/* bytes of device workspace wbk_create() needs for these capacities */
+size_t wbk_workspace_bytes(const wbk_caps* caps, int nlat, int nlon, int add);
+/* d_workspace: caller-owned device buffer of >= wbk_workspace_bytes() bytes (256-byte aligned) */
+int wbk_create(wbk_ctx** out, const wbk_caps* caps, int nlat, int nlon, int add, void* d_workspace,
+               size_t workspace_bytes);
+int wbk_destroy(wbk_ctx* ctx);
+
+/* wavebreaking/indices/contour_index.py:86-194 calculate_contours (original_coordinates=False)
+ * for every (time step, level) of a batch: marching squares on the periodically extended grid
+ * (columns [0, nlon+add), extension = re-read of columns [0, add)), skimage's contour assembly
+ * order, np.round + keep-first dedupe, the >= 4 points filter, the periodic duplicate filter
+ * (:119-147) and the per-contour closed / exp_lon / mean_lat ingredients.  Results stay in the
+ * context until the next call.  d_field: [ntime, nlat, nlon], latitude and longitude ascending.
+ */
+int wbk_contours(wbk_ctx* ctx, const void* d_field, int dtype, int ntime, const double* h_levels, int nlevels,
+                 void* stream);
+/* per-job results of the last wbk_contours (synchronises the stream): number of contours, number
+ * of contour points, status bits (WBK_ST_*), and the batch-wide maximum number of distinct
+ * columns of a contour (exp_lon.max() / dlon).  Arrays have ntime*nlevels entries. */
+int wbk_contours_counts(wbk_ctx* ctx, int* h_ncontours, int* h_npoints, int* h_status, int* h_max_nx, void* stream);
+/* pack the batch's contours into caller-owned device arrays (sizes from wbk_contours_counts):
+ *   d_job_off [njobs+1]  first contour of every job
+ *   d_pt_off  [C+1]      first point of every contour
+ *   d_meta    [C*4]      closed, nx (distinct columns), sum of rows y, job
+ *   d_pts     [P]        packed points x | y << 16 in contour order
+ * h_job_off_in / h_pt_job_off_in: exclusive prefix sums of the per-job counts (host, njobs+1). */
+int wbk_contours_pack(wbk_ctx* ctx, const int* h_ncontours, const int* h_npoints, int* d_job_off, int* d_pt_off,
+                      int* d_meta, uint32_t* d_pts, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

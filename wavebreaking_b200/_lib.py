@@ -37,7 +37,21 @@ class CapacityError(WbkError):
     pass
 
 
+class Caps(ctypes.Structure):
+    """wbk_caps (include/wbk.h)."""
+
+    _fields_ = [("max_jobs", c_int), ("seg_cap", c_int), ("contour_cap", c_int), ("sel_cap", c_int),
+                ("pair_cap", c_int), ("event_cap", c_int)]
+
+
 _SIGNATURES = {
+    "wbk_workspace_bytes": (c_size_t, [POINTER(Caps), c_int, c_int, c_int]),
+    "wbk_create": (c_int, [POINTER(c_void_p), POINTER(Caps), c_int, c_int, c_int, c_void_p, c_size_t]),
+    "wbk_destroy": (c_int, [c_void_p]),
+    "wbk_contours": (c_int, [c_void_p, c_void_p, c_int, c_int, POINTER(c_double), c_int, c_void_p]),
+    "wbk_contours_counts": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int), c_void_p]),
+    "wbk_contours_pack": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p]),
     "wbk_last_error": (c_char_p, []),
     "wbk_version": (c_int, []),
     "wbk_device_count": (c_int, []),

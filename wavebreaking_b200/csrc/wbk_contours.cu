@@ -1,0 +1,674 @@
+// Contour extraction: marching squares on the periodically extended grid, contour assembly in
+// skimage's order, rounding + keep-first dedupe, length and periodic-duplicate filters.
+// Reference: wavebreaking/indices/contour_index.py:86-194 (skimage.measure.find_contours inside).
+#include "wbk_ctx.cuh"
+
+// ------------------------------------------------------------------------------------------ context
+namespace {
+struct Bump {
+  unsigned char* base;
+  size_t off;
+  template <typename T>
+  T* take(size_t n) {
+    off = (off + 255) & ~(size_t)255;
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+size_t layout(WbkDev& d, const wbk_caps& c, int nlat, int nlon, int add, unsigned char* base) {
+  Bump b{base, 0};
+  d.nlat = nlat; d.nlon = nlon; d.add = add; d.W = nlon + add;
+  d.S = c.seg_cap; d.CC = c.contour_cap; d.R = c.seg_cap + c.contour_cap;
+  d.HC = (int)wbk_pow2_ceil((u32)(2 * d.R));
+  d.CCp2 = (int)wbk_pow2_ceil((u32)c.contour_cap);
+  d.sel_cap = c.sel_cap; d.pair_cap = c.pair_cap; d.event_cap = c.event_cap; d.max_jobs = c.max_jobs;
+  const size_t J = c.max_jobs, S = d.S, CC = d.CC, R = d.R, HC = d.HC;
+  d.rid = b.take<u32>(J * S); d.fpid = b.take<u32>(J * S); d.tpid = b.take<u32>(J * S);
+  d.fxy = b.take<u32>(J * S); d.txy = b.take<u32>(J * S);
+  d.seg_count = b.take<int>(J); d.status = b.take<int>(J);
+  d.nxt = b.take<u32>(J * S); d.prv = b.take<u32>(J * S); d.w64 = b.take<u64>(J * S);
+  d.cminrid = b.take<u32>(J * S); d.cnseg = b.take<u32>(J * S); d.cidx = b.take<u32>(J * S); d.cflag = b.take<u32>(J * S);
+  d.hkeys = b.take<u64>(J * HC); d.hvals = b.take<u32>(J * HC);
+  d.raw = b.take<u32>(J * R); d.rawc = b.take<u32>(J * R); d.slot = b.take<u32>(J * R); d.scan = b.take<int>(J * R);
+  d.sortkeys = b.take<u64>(J * d.CCp2);
+  d.craw_off = b.take<int>(J * (CC + 1)); d.craw_n = b.take<int>(J * CC); d.cclosed = b.take<int>(J * CC);
+  d.cnuniq = b.take<int>(J * CC); d.cdrop = b.take<int>(J * CC); d.cymin = b.take<int>(J * CC);
+  d.cymax = b.take<int>(J * CC); d.cout = b.take<int>(J * CC); d.cand = b.take<int>(J * CC * 2);
+  d.out_pts = b.take<u32>(J * R); d.out_tab = b.take<int>(J * CC * 4); d.out_sumy = b.take<int>(J * CC);
+  d.out_nc = b.take<int>(J); d.out_np = b.take<int>(J); d.max_nx = b.take<int>(64);
+  return (b.off + 255) & ~(size_t)255;
+}
+
+bool caps_ok(const wbk_caps* c, int nlat, int nlon, int add) {
+  return c && c->max_jobs >= 1 && c->seg_cap >= 16 && c->contour_cap >= 4 && c->sel_cap >= 1 && c->pair_cap >= 16 &&
+         c->event_cap >= 1 && nlat >= 2 && nlon >= 2 && add >= 0 && nlon + add < 65536 && nlat < 65536;
+}
+}  // namespace
+
+size_t wbk_index_layout(struct wbk_ctx* ctx, unsigned char* base, size_t off);  // wbk_indices.cu
+
+extern "C" size_t wbk_workspace_bytes(const wbk_caps* caps, int nlat, int nlon, int add) {
+  if (!caps_ok(caps, nlat, nlon, add)) return 0;
+  wbk_ctx tmp;
+  tmp.caps = *caps;
+  size_t n = layout(tmp.d, *caps, nlat, nlon, add, nullptr);
+  return wbk_index_layout(&tmp, nullptr, n);
+}
+
+extern "C" int wbk_create(wbk_ctx** out, const wbk_caps* caps, int nlat, int nlon, int add, void* d_workspace,
+                          size_t workspace_bytes) {
+  if (!out || !caps_ok(caps, nlat, nlon, add)) {
+    wbk_set_error("wbk_create: invalid capacities or grid");
+    return WBK_ERR_INVALID;
+  }
+  size_t need = wbk_workspace_bytes(caps, nlat, nlon, add);
+  wbk_ctx* ctx = new wbk_ctx();
+  ctx->caps = *caps;
+  ctx->owned = nullptr;
+  ctx->njobs = 0;
+  ctx->nlevels = 0;
+  if (!d_workspace) {
+    if (cudaMalloc(&ctx->owned, need) != cudaSuccess) {
+      delete ctx;
+      wbk_set_error("wbk_create: cudaMalloc of %zu bytes failed", need);
+      return WBK_ERR_CUDA;
+    }
+    d_workspace = ctx->owned;
+  } else if (workspace_bytes < need || ((uintptr_t)d_workspace & 255)) {
+    delete ctx;
+    wbk_set_error("wbk_create: workspace too small (%zu < %zu) or not 256-byte aligned", workspace_bytes, need);
+    return WBK_ERR_INVALID;
+  }
+  size_t n = layout(ctx->d, *caps, nlat, nlon, add, (unsigned char*)d_workspace);
+  wbk_index_layout(ctx, (unsigned char*)d_workspace, n);
+  *out = ctx;
+  return WBK_OK;
+}
+
+extern "C" int wbk_destroy(wbk_ctx* ctx) {
+  if (!ctx) return WBK_OK;
+  if (ctx->owned) cudaFree(ctx->owned);
+  delete ctx;
+  return WBK_OK;
+}
+
+// ------------------------------------------------------------------------------------------ K3
+// One thread per base column, marching down a strip of rows.  Every grid value is loaded once per
+// strip (the right neighbour comes from a warp shuffle); squares of the periodic extension
+// (columns >= nlon) are emitted by the thread that owns the matching base column, so the extension
+// costs no extra reads.  Segments are appended to the job's arena with warp-aggregated atomics.
+struct LevelPack {
+  double v[WBK_MAX_LEVELS];
+};
+
+#define MS_THREADS 256
+#define MS_ROWS 16
+
+__device__ __forceinline__ double ms_fraction(double from_value, double to_value, double level) {
+  if (to_value == from_value) return 0.0;
+  return __ddiv_rn(__dsub_rn(level, from_value), __dsub_rn(to_value, from_value));
+}
+
+// edges: 0 top, 1 bottom, 2 left, 3 right;  code = from | to << 2 (first segment) | second << 4 | n << 8
+__device__ __forceinline__ int ms_case_code(int c) {
+  // (from, to) per case, fully_connected = 'low'
+  switch (c) {
+    case 1: return (0 | 2 << 2) | (1 << 8);
+    case 2: return (3 | 0 << 2) | (1 << 8);
+    case 3: return (3 | 2 << 2) | (1 << 8);
+    case 4: return (2 | 1 << 2) | (1 << 8);
+    case 5: return (0 | 1 << 2) | (1 << 8);
+    case 6: return (3 | 0 << 2) | ((2 | 1 << 2) << 4) | (2 << 8);
+    case 7: return (3 | 1 << 2) | (1 << 8);
+    case 8: return (1 | 3 << 2) | (1 << 8);
+    case 9: return (0 | 2 << 2) | ((1 | 3 << 2) << 4) | (2 << 8);
+    case 10: return (1 | 0 << 2) | (1 << 8);
+    case 11: return (1 | 2 << 2) | (1 << 8);
+    case 12: return (2 | 3 << 2) | (1 << 8);
+    case 13: return (0 | 3 << 2) | (1 << 8);
+    case 14: return (2 | 0 << 2) | (1 << 8);
+    default: return 0;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(MS_THREADS)
+ms_segments_kernel(const T* __restrict__ field, WbkDev d, LevelPack levels, int nlevels) {
+  const int nlat = d.nlat, nlon = d.nlon, add = d.add, W = d.W;
+  const int c0 = blockIdx.x * MS_THREADS + threadIdx.x;
+  const bool valid = c0 < nlon;
+  const int r_begin = blockIdx.y * MS_ROWS;
+  const int r_end = min(r_begin + MS_ROWS, nlat - 1);  // squares r0 in [r_begin, r_end)
+  const int t = blockIdx.z;
+  const T* src = field + (size_t)t * nlat * nlon;
+  const int lane = wbk_lane();
+  const int cw = (c0 + 1 == nlon) ? 0 : c0 + 1;  // right neighbour, periodic
+
+  // which squares does this thread own?  base square (r0, c0) exists if c0 <= W-2;
+  // extension square (r0, c0 + nlon) exists if c0 + nlon <= W-2
+  const bool own_base = valid && (c0 <= W - 2);
+  const bool own_ext = valid && (c0 + nlon <= W - 2);
+
+  double ul = 0, ur = 0;
+  {
+    double v = valid ? (double)src[(size_t)r_begin * nlon + c0] : 0.0;
+    double rn = __shfl_down_sync(WBK_FULL, v, 1);
+    if (lane == 31 && valid) rn = (double)src[(size_t)r_begin * nlon + cw];
+    if (valid && cw == 0) rn = (double)src[(size_t)r_begin * nlon];
+    ul = v;
+    ur = rn;
+  }
+  for (int r0 = r_begin; r0 < r_end; ++r0) {
+    double ll, lr;
+    {
+      double v = valid ? (double)src[(size_t)(r0 + 1) * nlon + c0] : 0.0;
+      double rn = __shfl_down_sync(WBK_FULL, v, 1);
+      if (lane == 31 && valid) rn = (double)src[(size_t)(r0 + 1) * nlon + cw];
+      if (valid && cw == 0) rn = (double)src[(size_t)(r0 + 1) * nlon];
+      ll = v;
+      lr = rn;
+    }
+    const bool has_nan = isnan(ul) || isnan(ur) || isnan(ll) || isnan(lr);
+    for (int l = 0; l < nlevels; ++l) {
+      const double level = levels.v[l];
+      int sq = 0;
+      if (!has_nan && own_base) {
+        sq = (ul > level ? 1 : 0) | (ur > level ? 2 : 0) | (ll > level ? 4 : 0) | (lr > level ? 8 : 0);
+        if (sq == 15) sq = 0;
+      }
+      const int code = ms_case_code(sq);
+      const int nseg = code >> 8;
+      const int ncopy = own_ext ? 2 : 1;
+      const int nemit = nseg * ncopy;
+      if (!__any_sync(WBK_FULL, nemit > 0)) continue;
+      // warp-aggregated slot allocation
+      const int job = t * nlevels + l;
+      int incl = wbk_warp_incl_scan(nemit);
+      int total = __shfl_sync(WBK_FULL, incl, 31);
+      int base = 0;
+      if (lane == 31) base = atomicAdd(&d.seg_count[job], total);
+      base = __shfl_sync(WBK_FULL, base, 31);
+      if (nemit == 0) continue;
+      int slot = base + incl - nemit;
+      // edge fractions (computed once; identical expression from both squares sharing an edge)
+      const double ft = ms_fraction(ul, ur, level), fb = ms_fraction(ll, lr, level);
+      const double fl = ms_fraction(ul, ll, level), fr = ms_fraction(ur, lr, level);
+      bool lattice = false;
+      for (int copy = 0; copy < ncopy; ++copy) {
+        const int cc = c0 + copy * nlon;  // column of the square on the extended grid
+        // float coordinates exactly as skimage builds them, then np.round (half to even)
+        const double xt = __dadd_rn((double)cc, ft), xb = __dadd_rn((double)cc, fb);
+        const double yl = __dadd_rn((double)r0, fl), yr = __dadd_rn((double)r0, fr);
+        u32 pid[4], pxy[4];
+        pid[0] = 2u * (u32)(r0 * W + cc);             // top: horizontal edge (r0, cc)
+        pid[1] = 2u * (u32)((r0 + 1) * W + cc);       // bottom: horizontal edge (r0+1, cc)
+        pid[2] = 2u * (u32)(r0 * W + cc) + 1u;        // left: vertical edge (r0, cc)
+        pid[3] = 2u * (u32)(r0 * W + cc + 1) + 1u;    // right: vertical edge (r0, cc+1)
+        pxy[0] = wbk_pack_xy((int)rint(xt), r0);
+        pxy[1] = wbk_pack_xy((int)rint(xb), r0 + 1);
+        pxy[2] = wbk_pack_xy(cc, (int)rint(yl));
+        pxy[3] = wbk_pack_xy(cc + 1, (int)rint(yr));
+        const bool vt = xt == rint(xt), vb = xb == rint(xb), vl = yl == rint(yl), vr = yr == rint(yr);
+        for (int s = 0; s < nseg; ++s) {
+          const int fe = (code >> (4 * s)) & 3, te = (code >> (4 * s + 2)) & 3;
+          const bool lf = fe == 0 ? vt : fe == 1 ? vb : fe == 2 ? vl : vr;
+          const bool lt = te == 0 ? vt : te == 1 ? vb : te == 2 ? vl : vr;
+          lattice = lattice || lf || lt;
+          if (slot < d.S) {
+            const size_t o = (size_t)job * d.S + slot;
+            d.rid[o] = 2u * (u32)(r0 * (W - 1) + cc) + (u32)s;
+            d.fpid[o] = pid[fe];
+            d.tpid[o] = pid[te];
+            d.fxy[o] = pxy[fe];
+            d.txy[o] = pxy[te];
+          }
+          ++slot;
+        }
+      }
+      if (lattice) atomicOr(&d.status[job], (int)WBK_ST_LATTICE_VERTEX);
+    }
+    ul = ll;
+    ur = lr;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ K4
+// One CTA per job: link segments by edge identity, find the skimage contour order (R1: by the
+// smallest raster id), start points (R2: open chains start where nothing comes in; R3: rings start
+// at the `to` point of their largest raster id), emit rounded points, keep-first dedupe, >= 4 filter,
+// periodic duplicate filter, per-contour nx / sum(y).
+__global__ void __launch_bounds__(WBK_CONTOUR_THREADS) contour_link_kernel(WbkDev d, int njobs) {
+  const int job = blockIdx.x;
+  if (job >= njobs) return;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  __shared__ int sscan[40];
+  __shared__ int s_nheads, s_ncand, s_bad;
+
+  const int S = d.S, CC = d.CC, R = d.R;
+  const u32* rid = d.rid + (size_t)job * S;
+  const u32* fpid = d.fpid + (size_t)job * S;
+  const u32* tpid = d.tpid + (size_t)job * S;
+  const u32* fxy = d.fxy + (size_t)job * S;
+  const u32* txy = d.txy + (size_t)job * S;
+  u32* nxt = d.nxt + (size_t)job * S;
+  u32* prv = d.prv + (size_t)job * S;
+  u64* w64 = d.w64 + (size_t)job * S;
+  u32* cminrid = d.cminrid + (size_t)job * S;
+  u32* cnseg = d.cnseg + (size_t)job * S;
+  u32* cidx = d.cidx + (size_t)job * S;
+  u32* cflag = d.cflag + (size_t)job * S;
+  u64* hkeys = d.hkeys + (size_t)job * d.HC;
+  u32* hvals = d.hvals + (size_t)job * d.HC;
+  u32* raw = d.raw + (size_t)job * R;
+  u32* rawc = d.rawc + (size_t)job * R;
+  u32* slot = d.slot + (size_t)job * R;
+  int* scan = d.scan + (size_t)job * R;
+  u64* sortkeys = d.sortkeys + (size_t)job * d.CCp2;
+  int* craw_off = d.craw_off + (size_t)job * (CC + 1);
+  int* craw_n = d.craw_n + (size_t)job * CC;
+  int* cclosed = d.cclosed + (size_t)job * CC;
+  int* cnuniq = d.cnuniq + (size_t)job * CC;
+  int* cdrop = d.cdrop + (size_t)job * CC;
+  int* cymin = d.cymin + (size_t)job * CC;
+  int* cymax = d.cymax + (size_t)job * CC;
+  int* cout = d.cout + (size_t)job * CC;
+  int* cand = d.cand + (size_t)job * CC * 2;
+  u32* out_pts = d.out_pts + (size_t)job * R;
+  int* out_tab = d.out_tab + (size_t)job * CC * 4;
+  int* out_sumy = d.out_sumy + (size_t)job * CC;
+
+  int n = d.seg_count[job];
+  if (tid == 0) {
+    s_nheads = 0;
+    s_ncand = 0;
+    s_bad = 0;
+    d.out_nc[job] = 0;
+    d.out_np[job] = 0;
+  }
+  __syncthreads();
+  if (n > S) {
+    if (tid == 0) atomicOr(&d.status[job], (int)WBK_ST_SEG_OVERFLOW);
+    return;
+  }
+  if (n == 0) return;
+
+  // ---- P1: hash  from-edge -> segment
+  u32* k32 = reinterpret_cast<u32*>(hkeys);
+  const u32 hcap = wbk_pow2_ceil((u32)(2 * n) < 64u ? 64u : (u32)(2 * n));
+  u32* v32 = k32 + hcap;  // hkeys region holds 2*HC u32 >= 2*hcap
+  for (u32 i = tid; i < hcap; i += nt) k32[i] = WBK_NONE;
+  for (int s = tid; s < n; s += nt) {
+    prv[s] = WBK_NONE;
+    cminrid[s] = WBK_NONE;
+    cnseg[s] = 0;
+    cflag[s] = 0;
+  }
+  __syncthreads();
+  for (int s = tid; s < n; s += nt) wbk_hash_insert32(k32, v32, hcap, fpid[s], (u32)s);
+  __syncthreads();
+  // ---- P2: links
+  for (int s = tid; s < n; s += nt) {
+    u32 nx = wbk_hash_find32(k32, v32, hcap, tpid[s]);
+    nxt[s] = nx;
+    if (nx != WBK_NONE) prv[nx] = (u32)s;
+  }
+  __syncthreads();
+  // ---- P3: pointer doubling with max(rid): detects rings and their largest raster id
+  for (int s = tid; s < n; s += nt) w64[s] = ((u64)rid[s] << 32) | (u64)nxt[s];
+  __syncthreads();
+  const int rounds = wbk_log2_ceil((u32)n) + 1;
+  for (int it = 0; it < rounds; ++it) {
+    for (int s = tid; s < n; s += nt) {
+      u64 w = w64[s];
+      u32 p = (u32)w;
+      if (p != WBK_NONE) {
+        u64 w2 = w64[p];
+        u32 v = (u32)(w >> 32), v2 = (u32)(w2 >> 32);
+        w64[s] = ((u64)(v > v2 ? v : v2) << 32) | (u64)(u32)w2;
+      }
+    }
+    __syncthreads();
+  }
+  // ---- P4: cut every ring after its largest-id segment
+  for (int s = tid; s < n; s += nt) {
+    u64 w = w64[s];
+    if ((u32)w != WBK_NONE && (u32)(w >> 32) == rid[s]) {
+      u32 h = nxt[s];
+      cflag[h] = 1;  // ring: closed contour starting at h
+      prv[h] = WBK_NONE;
+      // nxt[s] stays (not used below)
+    }
+  }
+  __syncthreads();
+  // ---- P5: rank from the head by pointer jumping along prv
+  for (int s = tid; s < n; s += nt) {
+    u32 p = prv[s];
+    w64[s] = (p == WBK_NONE) ? (u64)(u32)s : (((u64)1 << 32) | (u64)p);
+  }
+  __syncthreads();
+  while (true) {
+    int changed = 0;
+    for (int s = tid; s < n; s += nt) {
+      u64 w = w64[s];
+      u32 p = (u32)w;
+      if (p != (u32)s) {
+        u64 w2 = w64[p];
+        u32 p2 = (u32)w2;
+        if (p2 != p) {
+          w64[s] = ((((w >> 32) + (w2 >> 32)) << 32) | (u64)p2);
+          changed = 1;
+        }
+      }
+    }
+    if (!__syncthreads_or(changed)) break;
+  }
+  // ---- P6: per-contour statistics keyed by the head segment
+  for (int s = tid; s < n; s += nt) {
+    u32 h = (u32)w64[s];
+    atomicMin(&cminrid[h], rid[s]);
+    atomicAdd(&cnseg[h], 1u);
+    if (h == (u32)s) {
+      int k = atomicAdd(&s_nheads, 1);
+      if (k < CC) sortkeys[k] = (u64)s;  // temporarily the head id
+    }
+  }
+  __syncthreads();
+  const int nh = s_nheads;
+  if (nh > CC) {
+    if (tid == 0) atomicOr(&d.status[job], (int)WBK_ST_CONTOUR_OVERFLOW);
+    return;
+  }
+  // ---- P7: contour order = ascending smallest raster id
+  const u32 np2 = wbk_pow2_ceil((u32)nh);
+  for (u32 i = tid; i < np2; i += nt) {
+    if ((int)i < nh) {
+      u32 h = (u32)sortkeys[i];
+      sortkeys[i] = ((u64)cminrid[h] << 32) | (u64)h;
+    } else {
+      sortkeys[i] = ~0ull;
+    }
+  }
+  __syncthreads();
+  wbk_block_bitonic_sort(sortkeys, np2);
+  for (int k = tid; k < nh; k += nt) {
+    u32 h = (u32)sortkeys[k];
+    cidx[h] = (u32)k;
+    craw_n[k] = (int)cnseg[h] + 1;
+    craw_off[k] = (int)cnseg[h] + 1;
+    cclosed[k] = (int)cflag[h];
+    cnuniq[k] = 0;
+    cdrop[k] = 0;
+    cymin[k] = 0x7fffffff;
+    cymax[k] = -1;
+  }
+  __syncthreads();
+  const int nraw = wbk_block_excl_scan(craw_off, nh, sscan);  // == n + nh
+  if (tid == 0) craw_off[nh] = nraw;
+  // ---- P8: raw (rounded) points in contour order
+  for (int s = tid; s < n; s += nt) {
+    u64 w = w64[s];
+    u32 h = (u32)w;
+    int k = (int)cidx[h];
+    int pos = craw_off[k] + (int)(w >> 32) + 1;
+    raw[pos] = txy[s];
+    rawc[pos] = (u32)k;
+    if (h == (u32)s) {
+      raw[craw_off[k]] = fxy[s];
+      rawc[craw_off[k]] = (u32)k;
+    }
+  }
+  // ---- P9: keep-first dedupe of the rounded points inside every contour
+  const u32 dcap = wbk_pow2_ceil((u32)(2 * nraw) < 64u ? 64u : (u32)(2 * nraw));
+  for (u32 i = tid; i < dcap; i += nt) {
+    hkeys[i] = ~0ull;
+    hvals[i] = WBK_NONE;
+  }
+  __syncthreads();
+  for (int i = tid; i < nraw; i += nt) {
+    u64 key = ((u64)rawc[i] << 32) | (u64)raw[i];
+    u32 sl = wbk_hash_slot64(hkeys, dcap, key, nullptr);
+    slot[i] = sl;
+    atomicMin(&hvals[sl], (u32)i);
+  }
+  __syncthreads();
+  for (int i = tid; i < nraw; i += nt) {
+    int keep = hvals[slot[i]] == (u32)i ? 1 : 0;
+    scan[i] = keep;
+    if (keep) {
+      int k = (int)rawc[i];
+      atomicAdd(&cnuniq[k], 1);
+      int y = wbk_py(raw[i]);
+      atomicMin(&cymin[k], y);
+      atomicMax(&cymax[k], y);
+    }
+  }
+  __syncthreads();
+  // ---- P11: periodic duplicates (contour_index.py:119-140) among contours with >= 4 points:
+  //      e1 (folded with x % nlon) subset of e2  ->  drop the shorter one (equal length: the later one)
+  for (u32 i = tid; i < dcap; i += nt) hkeys[i] = ~0ull;
+  __syncthreads();
+  const int nlon = d.nlon;
+  for (int i = tid; i < nraw; i += nt) {
+    int k = (int)rawc[i];
+    if (scan[i] && cnuniq[k] >= 4) {
+      u32 p = raw[i];
+      u64 key = ((u64)(u32)k << 32) | (u64)wbk_pack_xy(wbk_px(p) % nlon, wbk_py(p));
+      wbk_hash_slot64(hkeys, dcap, key, nullptr);
+    }
+  }
+  __syncthreads();
+  for (long long q = tid; q < (long long)nh * nh; q += nt) {
+    int k1 = (int)(q / nh), k2 = (int)(q % nh);
+    if (k1 == k2 || cnuniq[k1] < 4 || cnuniq[k2] < 4) continue;
+    if (cymin[k1] < cymin[k2] || cymax[k1] > cymax[k2]) continue;
+    u32 p = raw[craw_off[k1]];  // first point of k1 (always kept)
+    u64 key = ((u64)(u32)k2 << 32) | (u64)wbk_pack_xy(wbk_px(p) % nlon, wbk_py(p));
+    if (wbk_hash_lookup64(hkeys, dcap, key) == WBK_NONE) continue;
+    int c = atomicAdd(&s_ncand, 1);
+    if (c < CC) {
+      cand[2 * c] = k1;
+      cand[2 * c + 1] = k2;
+    }
+  }
+  __syncthreads();
+  int ncand = s_ncand;
+  if (ncand > CC) {
+    if (tid == 0) atomicOr(&d.status[job], (int)WBK_ST_CONTOUR_OVERFLOW);
+    return;
+  }
+  {
+    const int lane = wbk_lane(), warp = wbk_warp(), nwarps = nt >> 5;
+    for (int c = warp; c < ncand; c += nwarps) {
+      const int k1 = cand[2 * c], k2 = cand[2 * c + 1];
+      const int b = craw_off[k1], e = b + craw_n[k1];
+      int ok = 1;
+      for (int i0 = b; i0 < e; i0 += 32) {
+        int i = i0 + lane;
+        int good = 1;
+        if (i < e && scan[i]) {
+          u32 p = raw[i];
+          u64 key = ((u64)(u32)k2 << 32) | (u64)wbk_pack_xy(wbk_px(p) % nlon, wbk_py(p));
+          good = wbk_hash_lookup64(hkeys, dcap, key) != WBK_NONE;
+        }
+        if (!__all_sync(WBK_FULL, good)) {
+          ok = 0;
+          break;
+        }
+      }
+      if (ok && lane == 0) {
+        int l1 = cnuniq[k1], l2 = cnuniq[k2];
+        int drop = (l1 == l2) ? (k1 > k2 ? k1 : k2) : (l1 < l2 ? k1 : k2);
+        cdrop[drop] = 1;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- P12: compaction of contours and points
+  for (int k = tid; k < nh; k += nt) cout[k] = (cnuniq[k] >= 4 && !cdrop[k]) ? 1 : 0;
+  __syncthreads();
+  for (int i = tid; i < nraw; i += nt) scan[i] = (scan[i] && cout[rawc[i]]) ? 1 : 0;
+  __syncthreads();
+  // remember the flags in `slot` (scan is overwritten by the prefix sum)
+  for (int i = tid; i < nraw; i += nt) slot[i] = (u32)scan[i];
+  __syncthreads();
+  const int nout_pts = wbk_block_excl_scan(scan, nraw, sscan);
+  // contour output index
+  for (int k = tid; k < nh; k += nt) cymin[k] = cout[k];  // reuse cymin as scan buffer
+  __syncthreads();
+  const int nout_c = wbk_block_excl_scan(cymin, nh, sscan);
+  for (int k = tid; k < nh; k += nt) {
+    if (cout[k]) {
+      int o = cymin[k];
+      out_tab[4 * o + 0] = scan[craw_off[k]];
+      out_tab[4 * o + 1] = cnuniq[k];
+      out_tab[4 * o + 2] = cclosed[k];
+      out_tab[4 * o + 3] = 0;
+      out_sumy[o] = 0;
+    }
+  }
+  // reset the hash for the distinct-column count
+  for (u32 i = tid; i < dcap; i += nt) hkeys[i] = ~0ull;
+  __syncthreads();
+  for (int i = tid; i < nraw; i += nt) {
+    if (slot[i]) {
+      u32 p = raw[i];
+      out_pts[scan[i]] = p;
+      int o = cymin[rawc[i]];
+      atomicAdd(&out_sumy[o], wbk_py(p));
+      bool is_new;
+      wbk_hash_slot64(hkeys, dcap, ((u64)(u32)o << 32) | (u64)(u32)wbk_px(p), &is_new);
+      if (is_new) atomicAdd(&out_tab[4 * o + 3], 1);
+    }
+  }
+  __syncthreads();
+  int mx = 0;
+  for (int o = tid; o < nout_c; o += nt) mx = max(mx, out_tab[4 * o + 3]);
+  mx = wbk_warp_max(mx);
+  if (wbk_lane() == 0 && mx > 0) atomicMax(d.max_nx, mx);
+  if (tid == 0) {
+    d.out_nc[job] = nout_c;
+    d.out_np[job] = nout_pts;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host API
+extern "C" int wbk_contours(wbk_ctx* ctx, const void* d_field, int dtype, int ntime, const double* h_levels,
+                            int nlevels, void* stream) {
+  if (!ctx || !d_field || !h_levels || ntime < 0 || nlevels < 1 || nlevels > WBK_MAX_LEVELS) {
+    wbk_set_error("wbk_contours: invalid argument (1..%d levels)", WBK_MAX_LEVELS);
+    return WBK_ERR_INVALID;
+  }
+  const int njobs = ntime * nlevels;
+  if (njobs > ctx->caps.max_jobs) {
+    wbk_set_error("wbk_contours: %d jobs exceed max_jobs=%d", njobs, ctx->caps.max_jobs);
+    return WBK_ERR_CAPACITY;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  ctx->njobs = njobs;
+  ctx->nlevels = nlevels;
+  if (njobs == 0) return WBK_OK;
+  WbkDev& d = ctx->d;
+  WBK_CUDA_CHECK(cudaMemsetAsync(d.seg_count, 0, sizeof(int) * njobs, st));
+  WBK_CUDA_CHECK(cudaMemsetAsync(d.status, 0, sizeof(int) * njobs, st));
+  WBK_CUDA_CHECK(cudaMemsetAsync(d.max_nx, 0, sizeof(int), st));
+  LevelPack lv;
+  for (int i = 0; i < WBK_MAX_LEVELS; ++i) lv.v[i] = i < nlevels ? h_levels[i] : 0.0;
+  dim3 grid((d.nlon + MS_THREADS - 1) / MS_THREADS, (d.nlat - 1 + MS_ROWS - 1) / MS_ROWS, ntime);
+  if (dtype == WBK_F32) {
+    WBK_LAUNCH(ms_segments_kernel<float>, grid, dim3(MS_THREADS), 0, st, (const float*)d_field, d, lv, nlevels);
+  } else if (dtype == WBK_F64) {
+    WBK_LAUNCH(ms_segments_kernel<double>, grid, dim3(MS_THREADS), 0, st, (const double*)d_field, d, lv, nlevels);
+  } else {
+    wbk_set_error("wbk_contours: unsupported dtype");
+    return WBK_ERR_INVALID;
+  }
+  WBK_LAUNCH_CHECK();
+  WBK_LAUNCH(contour_link_kernel, dim3(njobs), dim3(WBK_CONTOUR_THREADS), 0, st, d, njobs);
+  WBK_LAUNCH_CHECK();
+  return WBK_OK;
+}
+
+extern "C" int wbk_contours_counts(wbk_ctx* ctx, int* h_ncontours, int* h_npoints, int* h_status, int* h_max_nx,
+                                   void* stream) {
+  if (!ctx || !h_ncontours || !h_npoints || !h_status || !h_max_nx) {
+    wbk_set_error("wbk_contours_counts: invalid argument");
+    return WBK_ERR_INVALID;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int J = ctx->njobs;
+  *h_max_nx = 0;
+  if (J == 0) return WBK_OK;
+  WBK_CUDA_CHECK(cudaMemcpyAsync(h_ncontours, ctx->d.out_nc, sizeof(int) * J, cudaMemcpyDeviceToHost, st));
+  WBK_CUDA_CHECK(cudaMemcpyAsync(h_npoints, ctx->d.out_np, sizeof(int) * J, cudaMemcpyDeviceToHost, st));
+  WBK_CUDA_CHECK(cudaMemcpyAsync(h_status, ctx->d.status, sizeof(int) * J, cudaMemcpyDeviceToHost, st));
+  WBK_CUDA_CHECK(cudaMemcpyAsync(h_max_nx, ctx->d.max_nx, sizeof(int), cudaMemcpyDeviceToHost, st));
+  WBK_CUDA_CHECK(cudaStreamSynchronize(st));
+  for (int j = 0; j < J; ++j) {
+    if (h_status[j] & (WBK_ST_SEG_OVERFLOW | WBK_ST_CONTOUR_OVERFLOW)) {
+      wbk_set_error("wbk_contours: job %d overflowed its arena (status %d); raise seg_cap / contour_cap", j, h_status[j]);
+      return WBK_ERR_CAPACITY;
+    }
+  }
+  return WBK_OK;
+}
+
+__global__ void contours_pack_kernel(WbkDev d, int njobs, const int* __restrict__ job_off, const int* __restrict__ pt_job_off,
+                                     int* __restrict__ pt_off, int* __restrict__ meta, u32* __restrict__ pts) {
+  const int job = blockIdx.x;
+  if (job >= njobs) return;
+  const int nc = d.out_nc[job], np = d.out_np[job];
+  const int c0 = job_off[job], p0 = pt_job_off[job];
+  const int* tab = d.out_tab + (size_t)job * d.CC * 4;
+  const int* sumy = d.out_sumy + (size_t)job * d.CC;
+  const u32* src = d.out_pts + (size_t)job * d.R;
+  for (int c = threadIdx.x; c < nc; c += blockDim.x) {
+    pt_off[c0 + c] = p0 + tab[4 * c + 0];
+    meta[4 * (c0 + c) + 0] = tab[4 * c + 2];
+    meta[4 * (c0 + c) + 1] = tab[4 * c + 3];
+    meta[4 * (c0 + c) + 2] = sumy[c];
+    meta[4 * (c0 + c) + 3] = job;
+  }
+  for (int i = threadIdx.x; i < np; i += blockDim.x) pts[p0 + i] = src[i];
+  if (job == njobs - 1 && threadIdx.x == 0) pt_off[c0 + nc] = p0 + np;
+}
+
+extern "C" int wbk_contours_pack(wbk_ctx* ctx, const int* h_ncontours, const int* h_npoints, int* d_job_off,
+                                 int* d_pt_off, int* d_meta, uint32_t* d_pts, void* stream) {
+  if (!ctx || !h_ncontours || !h_npoints || !d_job_off || !d_pt_off || !d_meta || !d_pts) {
+    wbk_set_error("wbk_contours_pack: invalid argument");
+    return WBK_ERR_INVALID;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int J = ctx->njobs;
+  // exclusive prefix sums on the host (J is small), staged through the scan arena
+  int* h = new int[2 * (J + 1)];
+  int c = 0, p = 0;
+  for (int j = 0; j < J; ++j) {
+    h[j] = c;
+    h[J + 1 + j] = p;
+    c += h_ncontours[j];
+    p += h_npoints[j];
+  }
+  h[J] = c;
+  h[2 * J + 1] = p;
+  int* d_pt_job_off = ctx->d.scan;  // scratch, free after wbk_contours
+  cudaError_t e1 = cudaMemcpyAsync(d_job_off, h, sizeof(int) * (J + 1), cudaMemcpyHostToDevice, st);
+  cudaError_t e2 = cudaMemcpyAsync(d_pt_job_off, h + J + 1, sizeof(int) * (J + 1), cudaMemcpyHostToDevice, st);
+  cudaError_t e3 = cudaStreamSynchronize(st);  // h is pageable: make sure it was consumed
+  delete[] h;
+  WBK_CUDA_CHECK(e1);
+  WBK_CUDA_CHECK(e2);
+  WBK_CUDA_CHECK(e3);
+  if (J == 0) return WBK_OK;
+  if (c == 0) {
+    int zero = 0;
+    WBK_CUDA_CHECK(cudaMemcpyAsync(d_pt_off, &zero, sizeof(int), cudaMemcpyHostToDevice, st));
+    WBK_CUDA_CHECK(cudaStreamSynchronize(st));
+    return WBK_OK;
+  }
+  WBK_LAUNCH(contours_pack_kernel, dim3(J), dim3(256), 0, st, ctx->d, J, (const int*)d_job_off, (const int*)d_pt_job_off, d_pt_off, d_meta, (u32*)d_pts);
+  WBK_LAUNCH_CHECK();
+  return WBK_OK;
+}

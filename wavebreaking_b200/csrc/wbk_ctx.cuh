@@ -1,0 +1,46 @@
+// Detection context: device arenas of one batch of jobs (job = time step x contour level).
+#pragma once
+#include "wbk_common.cuh"
+
+#define WBK_MAX_LEVELS 16
+#define WBK_CONTOUR_THREADS 1024
+
+// Device-side view of the arenas (passed to kernels by value).  Per-job arrays have a fixed
+// stride; `S` = seg_cap, `CC` = contour_cap, `R` = S + CC (raw contour points per job),
+// `HC` = hash capacity per job (power of two >= 2 * R).
+struct WbkDev {
+  int nlat, nlon, add, W;  // W = nlon + add (extended width)
+  int S, CC, R, HC;
+  int sel_cap, pair_cap, event_cap, max_jobs;
+
+  // marching-squares segments (written by ms_segments_kernel)
+  u32 *rid, *fpid, *tpid, *fxy, *txy;  // [J][S]
+  int* seg_count;                      // [J]
+  int* status;                         // [J]
+  // linking scratch
+  u32 *nxt, *prv;           // [J][S]
+  u64* w64;                 // [J][S]
+  u32 *cminrid, *cnseg, *cidx, *cflag;  // [J][S]   (indexed by head segment)
+  u64* hkeys;               // [J][HC]
+  u32* hvals;               // [J][HC]
+  u32 *raw, *rawc, *slot;   // [J][R]
+  int* scan;                // [J][R]
+  // per-contour (assembly order) scratch [J][CC]
+  u64* sortkeys;            // [J][CCp2]
+  int *craw_off, *craw_n, *cclosed, *cnuniq, *cdrop, *cymin, *cymax, *cout, *cand;
+  int CCp2;
+  // results of the contour stage
+  u32* out_pts;             // [J][R]
+  int* out_tab;             // [J][CC][4]: pt_off, npts, closed, nx
+  int* out_sumy;            // [J][CC]
+  int *out_nc, *out_np;     // [J]
+  int* max_nx;              // [1]
+};
+
+struct wbk_ctx {
+  wbk_caps caps;
+  WbkDev d;
+  int njobs;      // jobs of the last wbk_contours call
+  int nlevels;
+  void* owned;    // workspace allocated by the library (NULL if caller-owned)
+};
