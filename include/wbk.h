@@ -140,6 +140,68 @@ int wbk_contours_counts(wbk_ctx* ctx, int* h_ncontours, int* h_npoints, int* h_s
 int wbk_contours_pack(wbk_ctx* ctx, const int* h_ncontours, const int* h_npoints, int* d_job_off, int* d_pt_off,
                       int* d_meta, uint32_t* d_pts, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Index stage on a packed contour set (wbk_contours_pack layout; may also be uploaded by the
+ * caller, e.g. contours passed by the user).
+ */
+typedef struct wbk_index_params {
+  int do_streamers;    /* indices/streamer_index.py:100-275 */
+  int do_overturnings; /* indices/overturning_index.py:99-215 */
+  int do_cutoffs;      /* indices/cutoff_index.py:83-98 */
+  int gmax_nx;         /* exp_lon.max() / dlon over ALL contours of the call (streamer_index.py:106) */
+  double dlon, dlat;
+  double geo_dis, cont_dis;        /* streamers: km */
+  double range_group, ot_min_exp;  /* overturnings: degrees */
+  double co_min_exp;               /* cutoffs: degrees */
+} wbk_index_params;
+
+/* event kinds */
+#define WBK_EV_STREAMER 0
+#define WBK_EV_OVERTURNING 1
+#define WBK_EV_CUTOFF 2
+/* ints per event record: contour (index into the packed set), i1, i2 (streamer base points; cutoff:
+ * 0, npts-1), x0, y0, x1, y1 (overturning box min_lon, min_lat, max_lon, max_lat; else bounding box),
+ * orientation (overturning: 0 cyclonic, 1 anticyclonic), split (1 if a vertex has x >= nlon and one has
+ * x <= nlon-1: needs the meridian split of utils/index_utils.py:148-173), near (streamers: the decision
+ * that kept this pair had a distance within 1e-9 relative of geo_dis / cont_dis) */
+#define WBK_EV_INTS 10
+/* doubles per event record: sum(area), sum(area*data), sum(area*intensity), sum(area*x), sum(area*y),
+ * number of member cells  (utils/index_utils.py:66-102) */
+#define WBK_EV_F64 6
+
+/* d_coords: device doubles  [lat_deg(nlat) | lat_rad(nlat) | cos(lat_rad)(nlat) | cell_area(nlat) | lon_rad(nlon)]
+ * (host-built with the libm calls of the reference so that the trig inputs are identical).
+ * d_work: device scratch of 2*npoints doubles (along-contour distances and their prefix sums). */
+int wbk_index_run(wbk_ctx* ctx, int njobs, int nlevels, const int* d_job_off, const int* d_pt_off, const int* d_meta,
+                  const uint32_t* d_pts, int ncontours, int npoints, const double* d_coords, double* d_work,
+                  const wbk_index_params* params, void* stream);
+
+/* utils/index_utils.py:35-126 calculate_properties sums and processing/events.py:66-106 to_xarray flags for
+ * the events of the last wbk_index_run.  d_data / d_intensity: [ntime, nlat, nlon] (intensity may be NULL).
+ * d_flags: NULL or int8 [3][ntime][nlat][nlon] (kind-major), zeroed here and set to 1 where an event of that
+ * kind is present; events that need the meridian split are NOT rasterised here (split = 1 in their record;
+ * the caller clips them and uses wbk_rasterize_rings). */
+int wbk_events_raster(wbk_ctx* ctx, const int* d_job_off, const int* d_pt_off, const uint32_t* d_pts,
+                      const double* d_coords, const void* d_data, int dtype, const void* d_intensity, int ntime,
+                      int8_t* d_flags, const wbk_index_params* params, void* stream);
+
+/* per-kind, per-job event counts of the last wbk_index_run (synchronises): h_counts [3][njobs] */
+int wbk_events_counts(wbk_ctx* ctx, int* h_counts, int* h_status, void* stream);
+/* events of one kind, job-major in reference row order: h_ints [n][WBK_EV_INTS], h_f64 [n][WBK_EV_F64], h_job [n] */
+int wbk_events_fetch(wbk_ctx* ctx, int kind, int n, int* h_ints, double* h_f64, int* h_job, void* stream);
+
+/* generic lattice-polygon rasteriser (to_xarray for arbitrary event tables, and the split pieces):
+ * rings in index coordinates of the REAL grid (no folding), ring r = vertices
+ * [d_ring_off[r], d_ring_off[r+1]) of d_xy (int32 x,y pairs), written at time index d_ring_t[r].
+ * Cells inside (non-zero winding), on the boundary or closer than sqrt(r2) cells to an edge are selected
+ * (processing/events.py:75-79).  d_out_i8 != NULL: int8 [ntime][nlat][nlon], selected cells := 1.
+ * d_out_f64 != NULL: double [ntime][nlat][nlon], selected cells := d_ring_val[r] where r is the LAST ring
+ * (highest index) selecting the cell (events.py:96-102); needs d_owner, int32 [ntime][nlat][nlon] scratch.
+ * Outputs are NOT zeroed here. */
+int wbk_rasterize_rings(const int* d_xy, const int* d_ring_off, const int* d_ring_t, const double* d_ring_val,
+                        int nrings, int nlat, int nlon, int ntime, double r2, int8_t* d_out_i8, double* d_out_f64,
+                        int* d_owner, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

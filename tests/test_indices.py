@@ -1,0 +1,144 @@
+"""Streamers / overturnings / cutoffs + properties + flags: CUDA kernels vs the oracle."""
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import geom as G
+from oracle import pipeline as P
+from wavebreaking_b200 import detect, geometry, spatial, synthetic
+from test_contours import make_case
+
+
+def run_case(grid, sm, levels, periodic_add=120, intensity=None, **kw):
+    add = int(periodic_add / grid.dlon)
+    field = spatial.to_device(sm)
+    cs = detect.contours(field, levels, add)
+    coords = detect.coord_tables(grid.lat, grid.lon, grid.dlon, grid.dlat)
+    inten = spatial.to_device(intensity) if intensity is not None else None
+    tables, flags = detect.run_indices(cs, field, coords, grid.dlon, grid.dlat, intensity=inten, want_flags=True, **kw)
+    return cs, tables, flags
+
+
+def oracle_case(grid, sm, levels, periodic_add=120, intensity=None):
+    c = P.calculate_contours(sm, levels, grid, periodic_add, original_coordinates=False)
+    return c, dict(
+        streamers=P.calculate_streamers(sm, grid, c, intensity=intensity, periodic_add=periodic_add),
+        overturnings=P.calculate_overturnings(sm, grid, c, intensity=intensity, periodic_add=periodic_add),
+        cutoffs=P.calculate_cutoffs(sm, grid, c, intensity=intensity, periodic_add=periodic_add),
+    )
+
+
+def compare_events(cs, tables, flags, want, grid, levels, sm):
+    nlev = len(levels)
+    for kind in detect.KINDS:
+        tab, w = tables[kind], want[kind]
+        assert len(tab) == len(w), (kind, len(tab), len(w))
+        if len(w) == 0:
+            continue
+        rings = detect.event_rings(cs, tab)
+        props = detect.finish_properties(tab, grid.lon, grid.lat, grid.nlon)
+        for e, row in enumerate(w.itertuples()):
+            t, l = divmod(int(tab.job[e]), nlev)
+            assert grid.time[t] == row.date and levels[l] == row.level
+            want_ring = np.asarray(w.attrs["_index_rings"][e])
+            if kind == "overturnings":
+                assert set(map(tuple, rings[e])) == set(map(tuple, want_ring))
+                assert ("anticyclonic" if tab.orientation[e] else "cyclonic") == row.orientation
+            else:
+                assert np.array_equal(rings[e], want_ring), (kind, e)
+            # membership count and area-weighted sums
+            sums = w.attrs["_sums"].iloc[e]
+            assert tab.sums[e, 5] == len(w.attrs["_members"][e]), (kind, e)
+            np.testing.assert_allclose(tab.sums[e, 0], sums.areas, rtol=1e-12)
+            np.testing.assert_allclose(tab.sums[e, 1], sums.mean_var, rtol=1e-9)
+            np.testing.assert_allclose(tab.sums[e, 3], sums.x_com, rtol=1e-12)
+            np.testing.assert_allclose(tab.sums[e, 4], sums.y_com, rtol=1e-12)
+            assert props["com"][e] == row.com
+            assert props["mean_var"][e] == row.mean_var
+            assert props["event_area"][e] == row.event_area
+            # transformed pieces (fold / meridian split)
+            pieces = geometry.transform_ring(rings[e], grid.nlon)
+            want_pieces = w.attrs["_index_pieces"][e]
+            assert len(pieces) == len(want_pieces)
+            for a, b in zip(pieces, want_pieces):
+                assert np.array_equal(a, b)
+        # flag grid: device flags + split events through the generic rasteriser == oracle to_xarray
+        fl = flags[detect.KINDS.index(kind)]
+        split = np.nonzero(tab.split == 1)[0]
+        if len(split):
+            prs, pt = [], []
+            for e in split:
+                for piece in geometry.transform_ring(rings[e], grid.nlon):
+                    prs.append(piece)
+                    pt.append(int(tab.job[e]) // nlev)
+            detect.rasterize_rings(prs, pt, grid.nlat, grid.nlon, grid.ntime, 0.5, out_i8=fl)
+        want_flags = P.to_xarray(np.zeros_like(sm), w, grid)
+        assert np.array_equal(fl.cpu().numpy(), want_flags), kind
+
+
+def test_indices_emu_small(emu):
+    grid, pv, sm = make_case(46, 90, 2)
+    # coarse grid (4 degrees): scale the thresholds so that events exist
+    levels = [2, -2]
+    cs, tables, flags = run_case(grid, sm, levels)
+    c, want = oracle_case(grid, sm, levels)
+    compare_events(cs, tables, flags, want, grid, levels, sm)
+
+
+def test_indices_emu_one_degree(emu):
+    grid, pv, sm = make_case(181, 360, 1)
+    levels = [2]
+    rng = np.random.default_rng(0)
+    inten = rng.standard_normal(sm.shape)
+    cs, tables, flags = run_case(grid, sm, levels, intensity=inten)
+    c, want = oracle_case(grid, sm, levels, intensity=inten)
+    assert len(want["streamers"]) > 0 and len(want["overturnings"]) > 0 and len(want["cutoffs"]) > 0
+    compare_events(cs, tables, flags, want, grid, levels, sm)
+    props = detect.finish_properties(tables["streamers"], grid.lon, grid.lat, grid.nlon)
+    assert np.array_equal(props["intensity"], want["streamers"].intensity.values)
+
+
+def test_rasterize_rings_kat_emu(emu):
+    """tests/test_wavebreaking.py:116-128: square (0,0)-(10,10) flags lon 5 / lat 5."""
+    lat = np.arange(-89.0, 90.0)
+    lon = np.arange(-180.0, 180.0)
+    ring = np.array([[0, 0], [10, 0], [10, 10], [0, 10]])
+    idx = np.c_[ring[:, 0] - lon[0], ring[:, 1] - lat[0]].astype(np.int32)
+    out = detect.rasterize_rings([idx], [0], len(lat), len(lon), 1, 0.5).cpu().numpy()
+    assert out[0, list(lat).index(5.0), list(lon).index(5.0)] == 1
+    assert out.sum() == 11 * 11
+    want = G.buffered_contains([ring], 0.5, *map(np.ravel, np.meshgrid(lon, lat)))
+    assert np.array_equal(out[0].ravel().astype(bool), want)
+
+
+def test_split_ring_matches_oracle():
+    rng = np.random.default_rng(1)
+    nlon = 40
+    for _ in range(200):
+        # random star-shaped lattice polygon straddling the seam
+        cx, cy = nlon + rng.integers(-3, 4), 20
+        ang = np.sort(rng.uniform(0, 2 * np.pi, rng.integers(4, 12)))
+        rad = rng.uniform(2, 9, len(ang))
+        ring = np.unique(np.c_[np.rint(cx + rad * np.cos(ang)), np.rint(cy + rad * np.sin(ang))].astype(int), axis=0)
+        order = np.argsort(np.arctan2(ring[:, 1] - cy, ring[:, 0] - cx))
+        ring = ring[order]
+        if len(ring) < 3:
+            continue
+        got = geometry.transform_ring(ring, nlon)
+        if (ring[:, 0] >= nlon).any() and not (ring[:, 0] >= nlon).all():
+            want = G.split_ring_at_meridian(ring, nlon)
+            assert len(got) == len(want)
+            for a, b in zip(got, want):
+                assert np.array_equal(a, b)
+
+
+# ------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,levels,nt", [((181, 360), [2, -2], 3), ((721, 1440), [2], 1)])
+def test_indices_gpu(gpu, shape, levels, nt):
+    grid, pv, sm = make_case(shape[0], shape[1], nt)
+    cs, tables, flags = run_case(grid, sm, levels)
+    c, want = oracle_case(grid, sm, levels)
+    assert sum(len(v) for v in want.values()) > 0
+    compare_events(cs, tables, flags, want, grid, levels, sm)

@@ -44,7 +44,26 @@ class Caps(ctypes.Structure):
                 ("pair_cap", c_int), ("event_cap", c_int)]
 
 
+class IndexParams(ctypes.Structure):
+    """wbk_index_params (include/wbk.h)."""
+
+    _fields_ = [("do_streamers", c_int), ("do_overturnings", c_int), ("do_cutoffs", c_int), ("gmax_nx", c_int),
+                ("dlon", c_double), ("dlat", c_double), ("geo_dis", c_double), ("cont_dis", c_double),
+                ("range_group", c_double), ("ot_min_exp", c_double), ("co_min_exp", c_double)]
+
+
+EV_STREAMER, EV_OVERTURNING, EV_CUTOFF = 0, 1, 2
+EV_INTS, EV_F64 = 10, 6
+
 _SIGNATURES = {
+    "wbk_index_run": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
+                              c_void_p, POINTER(IndexParams), c_void_p]),
+    "wbk_events_raster": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int,
+                                  c_void_p, POINTER(IndexParams), c_void_p]),
+    "wbk_events_counts": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), c_void_p]),
+    "wbk_events_fetch": (c_int, [c_void_p, c_int, c_int, POINTER(c_int), POINTER(c_double), POINTER(c_int), c_void_p]),
+    "wbk_rasterize_rings": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double,
+                                    c_void_p, c_void_p, c_void_p, c_void_p]),
     "wbk_workspace_bytes": (c_size_t, [POINTER(Caps), c_int, c_int, c_int]),
     "wbk_create": (c_int, [POINTER(c_void_p), POINTER(Caps), c_int, c_int, c_int, c_void_p, c_size_t]),
     "wbk_destroy": (c_int, [c_void_p]),

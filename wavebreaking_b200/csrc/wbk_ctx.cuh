@@ -37,9 +37,29 @@ struct WbkDev {
   int* max_nx;              // [1]
 };
 
+// Index-stage arenas.  PC = pair_cap rounded up to a power of two, EC = event_cap.
+struct WbkIdx {
+  int PC, EC, SC;            // SC = sel_cap
+  int* sel;                  // [J][SC] packed-set contour index of the full-width contours
+  int* nsel;                 // [J]
+  u64* pairs;                // [J][SC][PC]  candidate pairs (i << 32 | j)
+  int* pair_count;           // [J][SC]
+  int* tile_off;             // [J*SC + 1]
+  u64* pairs_b;              // [J][PC]
+  int *flag, *scanb, *label; // [J][PC]
+  u64* hk;                   // [J][2*PC]
+  u32 *hv1, *hv2;            // [J][2*PC]
+  int* ev_int;               // [3][J][EC][WBK_EV_INTS]
+  double* ev_f64;            // [3][J][EC][WBK_EV_F64]
+  int* ev_count;             // [3][J]
+  int* ev_off;               // [3*J + 1]
+  int* total;                // [4] scratch totals
+};
+
 struct wbk_ctx {
   wbk_caps caps;
   WbkDev d;
+  WbkIdx x;
   int njobs;      // jobs of the last wbk_contours call
   int nlevels;
   void* owned;    // workspace allocated by the library (NULL if caller-owned)

@@ -1,7 +1,831 @@
-// Streamer / overturning / cutoff indices on the device-resident contour tables.
+// Streamer / overturning / cutoff indices on a packed, device-resident contour set.
+// Reference: wavebreaking/indices/streamer_index.py:100-275, overturning_index.py:99-215,
+// cutoff_index.py:83-98.
 #include "wbk_ctx.cuh"
 
+// ------------------------------------------------------------------------------------------ arenas
 size_t wbk_index_layout(struct wbk_ctx* ctx, unsigned char* base, size_t off) {
-  (void)ctx; (void)base;
-  return off;
+  WbkIdx& x = ctx->x;
+  const wbk_caps& c = ctx->caps;
+  x.PC = (int)wbk_pow2_ceil((u32)c.pair_cap);
+  x.EC = c.event_cap;
+  x.SC = c.sel_cap;
+  const size_t J = c.max_jobs, PC = x.PC, EC = x.EC, SC = x.SC;
+  size_t o = off;
+  auto take = [&](size_t bytes) -> unsigned char* {
+    o = (o + 255) & ~(size_t)255;
+    unsigned char* p = base ? base + o : nullptr;
+    o += bytes;
+    return p;
+  };
+  x.sel = (int*)take(J * SC * 4);
+  x.nsel = (int*)take(J * 4);
+  x.pairs = (u64*)take(J * SC * PC * 8);
+  x.pair_count = (int*)take(J * SC * 4);
+  x.tile_off = (int*)take((J * SC + 1) * 4);
+  x.pairs_b = (u64*)take(J * PC * 8);
+  x.flag = (int*)take(J * PC * 4);
+  x.scanb = (int*)take(J * PC * 4);
+  x.label = (int*)take(J * PC * 4);
+  x.hk = (u64*)take(J * 2 * PC * 8);
+  x.hv1 = (u32*)take(J * 2 * PC * 4);
+  x.hv2 = (u32*)take(J * 2 * PC * 4);
+  x.ev_int = (int*)take(3 * J * EC * WBK_EV_INTS * 4);
+  x.ev_f64 = (double*)take(3 * J * EC * WBK_EV_F64 * 8);
+  x.ev_count = (int*)take(3 * J * 4);
+  x.ev_off = (int*)take((3 * J + 1) * 4);
+  x.total = (int*)take(64);
+  return (o + 255) & ~(size_t)255;
+}
+
+struct PackedSet {
+  const int* job_off;
+  const int* pt_off;
+  const int* meta;
+  const u32* pts;
+  int njobs, nlevels, ncontours, npoints;
+};
+
+struct CoordTabs {
+  const double *lat_deg, *lat_rad, *cos_lat, *area, *lon_rad;
+};
+
+__host__ __device__ inline CoordTabs make_coords(const double* c, int nlat) {
+  CoordTabs t;
+  t.lat_deg = c;
+  t.lat_rad = c + nlat;
+  t.cos_lat = c + 2 * nlat;
+  t.area = c + 3 * nlat;
+  t.lon_rad = c + 4 * nlat;
+  return t;
+}
+
+__device__ __forceinline__ int* ev_int_ptr(const WbkIdx& x, int J, int kind, int job, int e) {
+  return x.ev_int + (((size_t)kind * J + job) * x.EC + e) * WBK_EV_INTS;
+}
+
+// ------------------------------------------------------------------------------------------ selection + cutoffs
+// One warp per job: ordered compaction of the full-width contours (exp_lon == max) and of the cutoffs
+// (closed, exp_lon < max, exp_lon >= min_exp: cutoff_index.py:89-93).
+__global__ void select_kernel(WbkDev d, WbkIdx x, PackedSet ps, wbk_index_params prm, int J) {
+  const int job = blockIdx.x * (blockDim.x >> 5) + wbk_warp();
+  if (job >= ps.njobs) return;
+  const int lane = wbk_lane();
+  const int c0 = ps.job_off[job], c1 = ps.job_off[job + 1];
+  int nsel = 0, ncut = 0;
+  for (int cb = c0; cb < c1; cb += 32) {
+    const int c = cb + lane;
+    int is_sel = 0, is_cut = 0, npts = 0;
+    if (c < c1) {
+      const int closed = ps.meta[4 * c + 0], nx = ps.meta[4 * c + 1];
+      npts = ps.pt_off[c + 1] - ps.pt_off[c];
+      is_sel = nx == prm.gmax_nx;
+      is_cut = prm.do_cutoffs && closed && nx < prm.gmax_nx && ((double)nx * prm.dlon >= prm.co_min_exp);
+    }
+    const u32 bs = __ballot_sync(WBK_FULL, is_sel), bc = __ballot_sync(WBK_FULL, is_cut);
+    const u32 below = (1u << lane) - 1u;
+    if (is_sel) {
+      int k = nsel + __popc(bs & below);
+      if (k < x.SC) x.sel[(size_t)job * x.SC + k] = c;
+    }
+    if (is_cut) {
+      int k = ncut + __popc(bc & below);
+      if (k < x.EC) {
+        int* ev = ev_int_ptr(x, J, WBK_EV_CUTOFF, job, k);
+        ev[0] = c; ev[1] = 0; ev[2] = npts - 1;
+        for (int q = 3; q < WBK_EV_INTS; ++q) ev[q] = 0;
+      }
+    }
+    nsel += __popc(bs);
+    ncut += __popc(bc);
+  }
+  if (lane == 0) {
+    if (nsel > x.SC) {
+      atomicOr(&d.status[job], (int)WBK_ST_SEL_OVERFLOW);
+      nsel = x.SC;
+    }
+    if (ncut > x.EC) {
+      atomicOr(&d.status[job], (int)WBK_ST_EVENT_OVERFLOW);
+      ncut = x.EC;
+    }
+    x.nsel[job] = nsel;
+    x.ev_count[WBK_EV_CUTOFF * J + job] = ncut;
+    x.ev_count[WBK_EV_STREAMER * J + job] = 0;
+    x.ev_count[WBK_EV_OVERTURNING * J + job] = 0;
+    for (int s = 0; s < x.SC; ++s) x.pair_count[(size_t)job * x.SC + s] = 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ overturnings
+#define OT_THREADS 256
+#define OT_GMAX 512
+
+__device__ __forceinline__ bool arc_subset(int min_i, int max_i, int min_j, int max_j, int nlon) {
+  // set(range(min_i, max_i + 1) % nlon) subset of set(range(min_j, max_j + 1) % nlon)
+  const int li = max_i - min_i + 1, lj = max_j - min_j + 1;
+  if (lj >= nlon) return true;
+  if (li >= nlon) return false;
+  int a = min_i % nlon, b = min_j % nlon;
+  int off = a - b;
+  if (off < 0) off += nlon;
+  return off + li <= lj;
+}
+
+__global__ void __launch_bounds__(OT_THREADS) overturning_kernel(WbkDev d, WbkIdx x, PackedSet ps, CoordTabs ct,
+                                                                 wbk_index_params prm, int J) {
+  const int job = blockIdx.x;
+  if (job >= ps.njobs) return;
+  WBK_DYN_SMEM(int, sm);
+  const int W = d.W, tid = threadIdx.x, nt = blockDim.x;
+  int* cnt = sm;            // [W] crossings per column
+  int* ymin = sm + W;       // [W]
+  int* ymax = sm + 2 * W;   // [W]
+  int* first = sm + 3 * W;  // [W] first contour position with this column
+  int* last = sm + 4 * W;   // [W] last contour position with this column
+  int* tmp = sm + 5 * W;    // [W] scan buffer
+  __shared__ int sscan[40];
+  __shared__ int g_min[OT_GMAX], g_max[OT_GMAX], g_keep[OT_GMAX], g_pos[OT_GMAX];
+  __shared__ int s_ng, s_nev;
+  if (tid == 0) s_nev = 0;
+  __syncthreads();
+  const double rg = prm.range_group / prm.dlon, mexp = prm.ot_min_exp / prm.dlon;
+
+  const int nsel = x.nsel[job];
+  for (int si = 0; si < nsel; ++si) {
+    const int c = x.sel[(size_t)job * x.SC + si];
+    const int base = ps.pt_off[c], n = ps.pt_off[c + 1] - base;
+    for (int i = tid; i < W; i += nt) {
+      cnt[i] = 0;
+      ymin[i] = 0x7fffffff;
+      ymax[i] = -1;
+      first[i] = 0x7fffffff;
+      last[i] = -1;
+    }
+    __syncthreads();
+    for (int k = tid; k < n; k += nt) {
+      const u32 p = ps.pts[base + k];
+      const int px = wbk_px(p), py = wbk_py(p);
+      atomicAdd(&cnt[px], 1);
+      atomicMin(&ymin[px], py);
+      atomicMax(&ymax[px], py);
+      atomicMin(&first[px], k);
+      atomicMax(&last[px], k);
+    }
+    __syncthreads();
+    // previous overturning longitude of every column (running max of "column if count >= 3")
+    for (int i = tid; i < W; i += nt) tmp[i] = cnt[i] >= 3 ? i : -1;
+    __syncthreads();
+    wbk_block_incl_max_scan(tmp, W, sscan);
+    // group starts (overturning_index.py:129): first ot longitude, or gap > range_group / dlon
+    if (tid == 0) s_ng = 0;
+    __syncthreads();
+    // start flags into `first`-independent buffer: reuse tmp after reading prev values -> two passes
+    // the start flag is kept in bit 30 of cnt
+    for (int i = tid; i < W; i += nt) {
+      if (cnt[i] >= 3) {
+        const int prev = i > 0 ? tmp[i - 1] : -1;
+        const bool start = prev < 0 || ((double)(i - prev) > rg);
+        if (start) cnt[i] |= (1 << 30);
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < W; i += nt) tmp[i] = (cnt[i] >> 30) & 1;
+    __syncthreads();
+    const int ng = wbk_block_excl_scan(tmp, W, sscan);  // tmp[i] = number of starts before column i
+    if (ng > OT_GMAX) {
+      if (tid == 0) atomicOr(&d.status[job], (int)WBK_ST_EVENT_OVERFLOW);
+      __syncthreads();
+      continue;
+    }
+    for (int g = tid; g < ng; g += nt) g_max[g] = -1;
+    __syncthreads();
+    for (int i = tid; i < W; i += nt) {
+      const int cv = cnt[i];
+      if ((cv & 0x3fffffff) >= 3) {
+        const bool start = (cv >> 30) & 1;
+        const int g = tmp[i] + (start ? 1 : 0) - 1;  // group id of this column
+        if (start) g_min[g] = i;
+        atomicMax(&g_max[g], i);
+      }
+    }
+    __syncthreads();
+    // check_duplicates (overturning_index.py:136-162)
+    for (int g = tid; g < ng; g += nt) g_keep[g] = 1;
+    __syncthreads();
+    for (int q = tid; q < ng * ng; q += nt) {
+      const int a = q / ng, b = q % ng;
+      if (a == b) continue;
+      if (arc_subset(g_min[a], g_max[a], g_min[b], g_max[b], d.nlon)) {
+        const int la = g_max[a] - g_min[a] + 1, lb = g_max[b] - g_min[b] + 1;
+        const int drop = (la == lb) ? (a > b ? a : b) : (la < lb ? a : b);
+        g_keep[drop] = 0;
+      }
+    }
+    __syncthreads();
+    // check_expansion (:164-166) runs only if something is left (it is a filter, so order is irrelevant)
+    for (int g = tid; g < ng; g += nt)
+      if (g_keep[g] && !((double)(g_max[g] - g_min[g]) >= mexp)) g_keep[g] = 0;
+    __syncthreads();
+    // ordered compaction -> events
+    for (int g = tid; g < ng; g += nt) g_pos[g] = g_keep[g];
+    __syncthreads();
+    const int nkeep = wbk_block_excl_scan(g_pos, ng, sscan);
+    const int ev_base = s_nev;
+    __syncthreads();
+    for (int g = tid; g < ng; g += nt) {
+      if (!g_keep[g]) continue;
+      const int e = ev_base + g_pos[g];
+      if (e >= x.EC) continue;
+      int lo = 0x7fffffff, hi = -1;
+      for (int cx = g_min[g]; cx <= g_max[g]; ++cx) {
+        if ((cnt[cx] & 0x3fffffff) > 0) {
+          lo = min(lo, ymin[cx]);
+          hi = max(hi, ymax[cx]);
+        }
+      }
+      // orientation (:191-202): first point with x == min_lon vs last point with x == max_lon
+      const int yw = wbk_py(ps.pts[base + first[g_min[g]]]);
+      const int ye = wbk_py(ps.pts[base + last[g_max[g]]]);
+      const int anti = fabs(ct.lat_deg[yw]) <= fabs(ct.lat_deg[ye]) ? 0 : 1;
+      int* ev = ev_int_ptr(x, J, WBK_EV_OVERTURNING, job, e);
+      ev[0] = c; ev[1] = 0; ev[2] = 0;
+      ev[3] = g_min[g]; ev[4] = lo; ev[5] = g_max[g]; ev[6] = hi;
+      ev[7] = anti; ev[8] = 0; ev[9] = 0;
+    }
+    __syncthreads();
+    if (tid == 0) s_nev = ev_base + nkeep;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    int nev = s_nev;
+    if (nev > x.EC) {
+      atomicOr(&d.status[job], (int)WBK_ST_EVENT_OVERFLOW);
+      nev = x.EC;
+    }
+    x.ev_count[WBK_EV_OVERTURNING * J + job] = nev;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ streamers
+#define ST_THREADS 1024
+#define PT 128           // pair-scan tile edge
+#define PS_THREADS 256
+#define EARTH_R 6371.0
+
+// sklearn DistanceMetric("haversine") between X[a] and X[b] (radians), times 6371 (streamer_index.py:130)
+__device__ __forceinline__ double hav_km(double la1, double lo1, double c1, double la2, double lo2, double c2) {
+  const double s0 = sin(__dmul_rn(0.5, __dsub_rn(la1, la2)));
+  const double s1 = sin(__dmul_rn(0.5, __dsub_rn(lo1, lo2)));
+  const double t = __dmul_rn(__dmul_rn(__dmul_rn(c1, c2), s1), s1);
+  const double h = __dadd_rn(__dmul_rn(s0, s0), t);
+  return __dmul_rn(__dmul_rn(2.0, asin(sqrt(h))), EARTH_R);
+}
+
+// inclusive prefix sum of doubles over data[0..n), in place
+__device__ inline void block_incl_scan_f64(double* data, int n, double* scratch /* >= 34 */) {
+  const int tid = wbk_tid(), nt = wbk_nthreads(), lane = wbk_lane(), warp = wbk_warp(), nwarps = nt >> 5;
+  const int chunk = (n + nt - 1) / nt;
+  const int b = min(n, tid * chunk), e = min(n, b + chunk);
+  double s = 0.0;
+  for (int i = b; i < e; ++i) s += data[i];
+  double incl = s;
+#pragma unroll
+  for (int dd = 1; dd < 32; dd <<= 1) {
+    double t = __shfl_up_sync(WBK_FULL, incl, dd);
+    if (lane >= dd) incl += t;
+  }
+  if (lane == 31) scratch[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    double w = lane < nwarps ? scratch[lane] : 0.0;
+    double wi = w;
+#pragma unroll
+    for (int dd = 1; dd < 32; dd <<= 1) {
+      double t = __shfl_up_sync(WBK_FULL, wi, dd);
+      if (lane >= dd) wi += t;
+    }
+    if (lane < nwarps) scratch[lane] = wi - w;
+  }
+  __syncthreads();
+  double run = scratch[warp] + (incl - s);
+  for (int i = b; i < e; ++i) {
+    run += data[i];
+    data[i] = run;
+  }
+  __syncthreads();
+}
+
+// along-contour distances on[k] and their prefix sums for every full-width contour; tile counts
+__global__ void __launch_bounds__(ST_THREADS) streamer_prep_kernel(WbkDev d, WbkIdx x, PackedSet ps, CoordTabs ct,
+                                                                   double* on, double* pfx) {
+  const int job = blockIdx.x;
+  if (job >= ps.njobs) return;
+  __shared__ double sscan[40];
+  const int tid = threadIdx.x, nt = blockDim.x, nlon = d.nlon;
+  const int nsel = x.nsel[job];
+  for (int si = 0; si < x.SC; ++si) {
+    if (si >= nsel) {
+      if (tid == 0) x.tile_off[(size_t)job * x.SC + si] = 0;
+      continue;
+    }
+    const int c = x.sel[(size_t)job * x.SC + si];
+    const int base = ps.pt_off[c], n = ps.pt_off[c + 1] - base;
+    for (int k = tid; k < n; k += nt) {
+      double v = 0.0;
+      if (k > 0) {
+        const u32 p0 = ps.pts[base + k - 1], p1 = ps.pts[base + k];
+        const int y0 = wbk_py(p0), x0 = wbk_px(p0) % nlon, y1 = wbk_py(p1), x1 = wbk_px(p1) % nlon;
+        v = hav_km(ct.lat_rad[y0], ct.lon_rad[x0], ct.cos_lat[y0], ct.lat_rad[y1], ct.lon_rad[x1], ct.cos_lat[y1]);
+      }
+      on[base + k] = v;
+      pfx[base + k] = v;
+    }
+    __syncthreads();
+    block_incl_scan_f64(pfx + base, n, sscan);
+    if (tid == 0) {
+      const int T = (n + PT - 1) / PT;
+      x.tile_off[(size_t)job * x.SC + si] = T * (T + 1) / 2;
+    }
+  }
+}
+
+// exclusive scan of the tile counts over all (job, sel) slots (single CTA)
+__global__ void __launch_bounds__(1024) tile_scan_kernel(WbkIdx x, int nslots) {
+  __shared__ int sscan[40];
+  const int total = wbk_block_excl_scan(x.tile_off, nslots, sscan);
+  if (threadIdx.x == 0) {
+    x.tile_off[nslots] = total;
+    x.total[0] = total;
+  }
+}
+
+// tiled pair scan: geo < geo_dis and cont > cont_dis and |x1 - x2| <= 120 (streamer_index.py:130-157),
+// without materialising the N x N matrices.  Persistent CTAs stride over the (contour, tile) work list.
+__global__ void __launch_bounds__(PS_THREADS) pair_scan_kernel(WbkDev d, WbkIdx x, PackedSet ps, CoordTabs ct,
+                                                               const double* __restrict__ pfx, wbk_index_params prm,
+                                                               int nslots) {
+  __shared__ int sx[2][PT], sy[2][PT];
+  __shared__ double sla[2][PT], slo[2][PT], sco[2][PT], spf[2][PT];
+  const int tid = threadIdx.x, nlon = d.nlon;
+  const int total = x.tile_off[nslots];
+  for (int w = blockIdx.x; w < total; w += gridDim.x) {
+    // slot = last index with tile_off[slot] <= w
+    int lo = 0, hi = nslots - 1;
+    while (lo < hi) {
+      int mid = (lo + hi + 1) >> 1;
+      if (x.tile_off[mid] <= w) lo = mid; else hi = mid - 1;
+    }
+    const int slot = lo, job = slot / x.SC;
+    const int c = x.sel[slot];
+    const int base = ps.pt_off[c], n = ps.pt_off[c + 1] - base;
+    const int T = (n + PT - 1) / PT;
+    int t = w - x.tile_off[slot], bi = 0;
+    while (t >= T - bi) {
+      t -= T - bi;
+      ++bi;
+    }
+    const int bj = bi + t;
+    {
+      const int which = tid >> 7, k = tid & (PT - 1);
+      const int idx = (which ? bj : bi) * PT + k;
+      if (idx < n) {
+        const u32 p = ps.pts[base + idx];
+        const int py = wbk_py(p), pxx = wbk_px(p);
+        sx[which][k] = pxx;
+        sy[which][k] = py;
+        sla[which][k] = ct.lat_rad[py];
+        slo[which][k] = ct.lon_rad[pxx % nlon];
+        sco[which][k] = ct.cos_lat[py];
+        spf[which][k] = pfx[base + idx];
+      }
+    }
+    __syncthreads();
+    {
+      const int ii = tid & (PT - 1), half = tid >> 7;
+      const int i = bi * PT + ii;
+      if (i < n) {
+        const int xi = sx[0][ii];
+        const double lai = sla[0][ii], loi = slo[0][ii], ci = sco[0][ii], pfi = spf[0][ii];
+        for (int jj = half * (PT / 2); jj < (half + 1) * (PT / 2); ++jj) {
+          const int j = bj * PT + jj;
+          if (j >= n || j <= i) continue;
+          int dxi = xi - sx[1][jj];
+          if (dxi < 0) dxi = -dxi;
+          if (dxi > 120) continue;  // hard-coded index units (streamer_index.py:157)
+          const double cont = __dsub_rn(spf[1][jj], pfi);
+          if (!(cont > prm.cont_dis)) continue;
+          const double dlat = fabs(__dsub_rn(lai, sla[1][jj]));
+          if (dlat * EARTH_R > prm.geo_dis * 1.000001) continue;  // d >= R * |dlat|
+          const double dist = hav_km(lai, loi, ci, sla[1][jj], slo[1][jj], sco[1][jj]);
+          if (!(dist < prm.geo_dis)) continue;
+          const int near = (fabs(dist - prm.geo_dis) <= 1e-9 * prm.geo_dis) || (fabs(cont - prm.cont_dis) <= 1e-9 * prm.cont_dis);
+          const int k = atomicAdd(&x.pair_count[slot], 1);
+          if (k < x.PC) x.pairs[(size_t)slot * x.PC + k] = ((u64)(u32)i << 32) | ((u64)(u32)j << 1) | (u64)near;
+        }
+      }
+    }
+    __syncthreads();
+    (void)job;
+  }
+}
+
+__device__ __forceinline__ int orient_i(int ax, int ay, int bx, int by, int cx, int cy) {
+  return (bx - ax) * (cy - ay) - (by - ay) * (cx - ax);
+}
+
+// closed segments [p1,q1] and [p2,q2] share a point (shapely intersects on LineStrings)
+__device__ __forceinline__ bool seg_intersect(int p1x, int p1y, int q1x, int q1y, int p2x, int p2y, int q2x, int q2y) {
+  const int d1 = orient_i(p1x, p1y, q1x, q1y, p2x, p2y), d2 = orient_i(p1x, p1y, q1x, q1y, q2x, q2y);
+  const int d3 = orient_i(p2x, p2y, q2x, q2y, p1x, p1y), d4 = orient_i(p2x, p2y, q2x, q2y, q1x, q1y);
+  if (((d1 > 0 && d2 < 0) || (d1 < 0 && d2 > 0)) && ((d3 > 0 && d4 < 0) || (d3 < 0 && d4 > 0))) return true;
+  if (d1 == 0 && min(p1x, q1x) <= p2x && p2x <= max(p1x, q1x) && min(p1y, q1y) <= p2y && p2y <= max(p1y, q1y)) return true;
+  if (d2 == 0 && min(p1x, q1x) <= q2x && q2x <= max(p1x, q1x) && min(p1y, q1y) <= q2y && q2y <= max(p1y, q1y)) return true;
+  if (d3 == 0 && min(p2x, q2x) <= p1x && p1x <= max(p2x, q2x) && min(p2y, q2y) <= p1y && p1y <= max(p2y, q2y)) return true;
+  if (d4 == 0 && min(p2x, q2x) <= q1x && q1x <= max(p2x, q2x) && min(p2y, q2y) <= q1y && q1y <= max(p2y, q2y)) return true;
+  return false;
+}
+
+// does contour segment [a,b] put a point of the polyline's interior into the OPEN chord (p,q)?
+// (shapely LineString([p,q]).touches(contour) is false iff some segment does)
+__device__ __forceinline__ bool chord_violation(int px, int py, int qx, int qy, int ax, int ay, int bx, int by,
+                                                int e0x, int e0y, int e1x, int e1y) {
+  const int ux = qx - px, uy = qy - py;
+  const int l2 = ux * ux + uy * uy;
+  const int d1 = orient_i(px, py, qx, qy, ax, ay), d2 = orient_i(px, py, qx, qy, bx, by);
+  const int ta = (ax - px) * ux + (ay - py) * uy, tb = (bx - px) * ux + (by - py) * uy;
+  if (d1 == 0 && d2 == 0) {  // collinear: overlap of positive length
+    const int lo = max(min(ta, tb), 0), hi = min(max(ta, tb), l2);
+    if (lo < hi) return true;
+  }
+  if (d1 == 0 && ta > 0 && ta < l2 && !((ax == e0x && ay == e0y) || (ax == e1x && ay == e1y))) return true;
+  if (d2 == 0 && tb > 0 && tb < l2 && !((bx == e0x && by == e0y) || (bx == e1x && by == e1y))) return true;
+  if ((d1 > 0 && d2 < 0) || (d1 < 0 && d2 > 0)) {
+    const int d3 = orient_i(ax, ay, bx, by, px, py), d4 = orient_i(ax, ay, bx, by, qx, qy);
+    if ((d3 > 0 && d4 < 0) || (d3 < 0 && d4 > 0)) {
+      // proper crossing; exempt if the crossing point is the location of a polyline end point
+      const bool at_e0 = orient_i(px, py, qx, qy, e0x, e0y) == 0 && orient_i(ax, ay, bx, by, e0x, e0y) == 0;
+      const bool at_e1 = orient_i(px, py, qx, qy, e1x, e1y) == 0 && orient_i(ax, ay, bx, by, e1x, e1y) == 0;
+      if (!at_e0 && !at_e1) return true;
+    }
+  }
+  return false;
+}
+
+// ordered compaction of src[0..P) with flag[] into dst; returns the new count to every thread
+__device__ inline int compact_pairs(const u64* src, u64* dst, const int* flag, int* scanb, int P, int* sscan) {
+  const int tid = wbk_tid(), nt = wbk_nthreads();
+  for (int a = tid; a < P; a += nt) scanb[a] = flag[a];
+  __syncthreads();
+  const int total = wbk_block_excl_scan(scanb, P, sscan);
+  for (int a = tid; a < P; a += nt)
+    if (flag[a]) dst[scanb[a]] = src[a];
+  __syncthreads();
+  return total;
+}
+
+// filter cascade of streamer_index.py:160-264, one CTA per job (its full-width contours in turn)
+__global__ void __launch_bounds__(ST_THREADS) streamer_cascade_kernel(WbkDev d, WbkIdx x, PackedSet ps,
+                                                                      const double* __restrict__ on,
+                                                                      const double* __restrict__ pfx, int J) {
+  const int job = blockIdx.x;
+  if (job >= ps.njobs) return;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = wbk_lane(), warp = wbk_warp(), nwarps = nt >> 5;
+  const int nlon = d.nlon;
+  __shared__ int sscan[40];
+  __shared__ int s_nev;
+  if (tid == 0) s_nev = 0;
+  __syncthreads();
+  u64* B = x.pairs_b + (size_t)job * x.PC;
+  int* flag = x.flag + (size_t)job * x.PC;
+  int* scanb = x.scanb + (size_t)job * x.PC;
+  int* label = x.label + (size_t)job * x.PC;
+  u64* hk = x.hk + (size_t)job * 2 * x.PC;
+  u32* hv1 = x.hv1 + (size_t)job * 2 * x.PC;
+  u32* hv2 = x.hv2 + (size_t)job * 2 * x.PC;
+
+  const int nsel = x.nsel[job];
+  for (int si = 0; si < nsel; ++si) {
+    const int slot = job * x.SC + si;
+    const int c = x.sel[slot];
+    const int base = ps.pt_off[c], n = ps.pt_off[c + 1] - base;
+    const u32* pts = ps.pts + base;
+    int P = x.pair_count[slot];
+    if (P > x.PC) {
+      if (tid == 0) atomicOr(&d.status[job], (int)WBK_ST_PAIR_OVERFLOW);
+      continue;  // uniform
+    }
+    u64* A = x.pairs + (size_t)slot * x.PC;
+    // row-major order of np.nonzero: sort by (i, j)
+    const u32 p2 = wbk_pow2_ceil((u32)(P > 0 ? P : 1));
+    for (u32 a = P + tid; a < p2; a += nt) A[a] = ~0ull;
+    __syncthreads();
+    wbk_block_bitonic_sort(A, p2);
+    u64* cur = A;
+    u64* oth = B;
+
+    // (1) check_duplicates (:160-183): rows equal after x % nlon -> drop the second of each group
+    if (P > 1) {
+      const u32 dcap = wbk_pow2_ceil((u32)(2 * P));
+      for (u32 a = tid; a < dcap; a += nt) {
+        hk[a] = ~0ull;
+        hv1[a] = WBK_NONE;
+        hv2[a] = WBK_NONE;
+      }
+      __syncthreads();
+      for (int a = tid; a < P; a += nt) {
+        const u64 k = cur[a];
+        const u32 pi = pts[(u32)(k >> 32)], pj = pts[((u32)k) >> 1];
+        const u64 key = ((u64)wbk_pack_xy(wbk_px(pi) % nlon, wbk_py(pi)) << 32) | (u64)wbk_pack_xy(wbk_px(pj) % nlon, wbk_py(pj));
+        const u32 sl = wbk_hash_slot64(hk, dcap, key, nullptr);
+        label[a] = (int)sl;
+        atomicMin(&hv1[sl], (u32)a);
+      }
+      __syncthreads();
+      for (int a = tid; a < P; a += nt)
+        if (hv1[label[a]] != (u32)a) atomicMin(&hv2[label[a]], (u32)a);
+      __syncthreads();
+      for (int a = tid; a < P; a += nt) flag[a] = hv2[label[a]] == (u32)a ? 0 : 1;
+      __syncthreads();
+      P = compact_pairs(cur, oth, flag, scanb, P, sscan);
+      u64* t = cur; cur = oth; oth = t;
+    }
+    // (2) check_intersections (:185-200): keep chords that only touch the contour
+    if (P > 1) {
+      const u32 e0 = pts[0], e1 = pts[n - 1];
+      const int e0x = wbk_px(e0), e0y = wbk_py(e0), e1x = wbk_px(e1), e1y = wbk_py(e1);
+      for (int a = warp; a < P; a += nwarps) {
+        const u64 k = cur[a];
+        const u32 pi = pts[(u32)(k >> 32)], pj = pts[((u32)k) >> 1];
+        const int px = wbk_px(pi), py = wbk_py(pi), qx = wbk_px(pj), qy = wbk_py(pj);
+        const int bx0 = min(px, qx), bx1 = max(px, qx), by0 = min(py, qy), by1 = max(py, qy);
+        int bad = 0;
+        for (int s0 = 0; s0 < n - 1; s0 += 32) {
+          const int s = s0 + lane;
+          if (s < n - 1) {
+            const u32 pa = pts[s], pb = pts[s + 1];
+            const int ax = wbk_px(pa), ay = wbk_py(pa), bx = wbk_px(pb), by = wbk_py(pb);
+            if (!(max(ax, bx) < bx0 || min(ax, bx) > bx1 || max(ay, by) < by0 || min(ay, by) > by1))
+              bad |= chord_violation(px, py, qx, qy, ax, ay, bx, by, e0x, e0y, e1x, e1y) ? 1 : 0;
+          }
+          if (__any_sync(WBK_FULL, bad)) break;
+        }
+        bad = __any_sync(WBK_FULL, bad);
+        if (lane == 0) flag[a] = bad ? 0 : 1;
+      }
+      __syncthreads();
+      P = compact_pairs(cur, oth, flag, scanb, P, sscan);
+      u64* t = cur; cur = oth; oth = t;
+    }
+    // (3) check_overlapping (:202-222): drop [ind1, ind2] fully covered by another pair
+    if (P > 1) {
+      for (int a = tid; a < P; a += nt) {
+        const u64 k = cur[a];
+        scanb[a] = (int)(((u32)k) >> 1);  // ind2
+        const bool rs = a == 0 || (u32)(cur[a - 1] >> 32) != (u32)(k >> 32);
+        label[a] = rs ? a : 0;
+      }
+      __syncthreads();
+      wbk_block_incl_max_scan(scanb, P, sscan);  // prefix max of ind2
+      wbk_block_incl_max_scan(label, P, sscan);  // row start of every pair
+      for (int a = tid; a < P; a += nt) {
+        const u64 k = cur[a];
+        const int i2 = (int)(((u32)k) >> 1);
+        const int rs = label[a];
+        bool covered = rs > 0 && scanb[rs - 1] >= i2;
+        if (a + 1 < P && (u32)(cur[a + 1] >> 32) == (u32)(k >> 32)) covered = true;
+        flag[a] = covered ? 0 : 1;
+      }
+      __syncthreads();
+      P = compact_pairs(cur, oth, flag, scanb, P, sscan);
+      u64* t = cur; cur = oth; oth = t;
+    }
+    // (4) check_groups (:224-251): chords that intersect describe one streamer; keep the longest
+    int nout = P;
+    if (P > 1) {
+      for (int a = tid; a < P; a += nt) label[a] = a;
+      __syncthreads();
+      while (true) {
+        int changed = 0;
+        for (int a = tid; a < P; a += nt) {
+          const u64 ka = cur[a];
+          const u32 pa = pts[(u32)(ka >> 32)], qa = pts[((u32)ka) >> 1];
+          int m = label[a];
+          for (int b = 0; b < P; ++b) {
+            const int lb = label[b];
+            if (lb >= m) continue;
+            const u64 kb = cur[b];
+            const u32 pb = pts[(u32)(kb >> 32)], qb = pts[((u32)kb) >> 1];
+            if (seg_intersect(wbk_px(pa), wbk_py(pa), wbk_px(qa), wbk_py(qa), wbk_px(pb), wbk_py(pb), wbk_px(qb), wbk_py(qb)))
+              m = lb;
+          }
+          if (m < label[a]) {
+            atomicMin(&label[a], m);
+            changed = 1;
+          }
+        }
+        __syncthreads();
+        for (int a = tid; a < P; a += nt) {  // pointer jumping
+          const int l = label[a], ll = label[l];
+          if (ll < l) {
+            label[a] = ll;
+            changed = 1;
+          }
+        }
+        if (!__syncthreads_or(changed)) break;
+      }
+      // winner of every component: max of on[ind1 : ind2 + 1].sum(), first index on ties
+      for (int a = tid; a < P; a += nt) {
+        hk[a] = 0ull;
+        hv1[a] = WBK_NONE;
+      }
+      __syncthreads();
+      for (int a = tid; a < P; a += nt) {
+        const u64 k = cur[a];
+        const int i1 = (int)(k >> 32), i2 = (int)(((u32)k) >> 1);
+        const double len = (pfx[base + i2] - pfx[base + i1]) + on[base + i1];
+        atomicMax(&hk[label[a]], (u64)__double_as_longlong(len));
+      }
+      __syncthreads();
+      for (int a = tid; a < P; a += nt) {
+        const u64 k = cur[a];
+        const int i1 = (int)(k >> 32), i2 = (int)(((u32)k) >> 1);
+        const double len = (pfx[base + i2] - pfx[base + i1]) + on[base + i1];
+        if ((u64)__double_as_longlong(len) == hk[label[a]]) atomicMin(&hv1[label[a]], (u32)a);
+      }
+      __syncthreads();
+      // components in order of their smallest member (combine_shared output order)
+      for (int a = tid; a < P; a += nt) flag[a] = label[a] == a ? 1 : 0;
+      __syncthreads();
+      for (int a = tid; a < P; a += nt) scanb[a] = flag[a];
+      __syncthreads();
+      nout = wbk_block_excl_scan(scanb, P, sscan);
+      for (int a = tid; a < P; a += nt)
+        if (flag[a]) oth[scanb[a]] = cur[hv1[a]];
+      __syncthreads();
+      u64* t = cur; cur = oth; oth = t;
+    }
+    // events: polygon = contour points [ind1, ind2] (:269-272)
+    const int ev_base = s_nev;
+    __syncthreads();
+    for (int a = tid; a < nout; a += nt) {
+      const int e = ev_base + a;
+      if (e >= x.EC) continue;
+      const u64 k = cur[a];
+      int* ev = ev_int_ptr(x, J, WBK_EV_STREAMER, job, e);
+      ev[0] = c; ev[1] = (int)(k >> 32); ev[2] = (int)(((u32)k) >> 1);
+      for (int q = 3; q < WBK_EV_INTS - 1; ++q) ev[q] = 0;
+      ev[9] = (int)(k & 1ull);
+    }
+    if (tid == 0) s_nev = ev_base + nout;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    int nev = s_nev;
+    if (nev > x.EC) {
+      atomicOr(&d.status[job], (int)WBK_ST_EVENT_OVERFLOW);
+      nev = x.EC;
+    }
+    x.ev_count[WBK_EV_STREAMER * J + job] = nev;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host API
+extern "C" int wbk_index_run(wbk_ctx* ctx, int njobs, int nlevels, const int* d_job_off, const int* d_pt_off,
+                             const int* d_meta, const uint32_t* d_pts, int ncontours, int npoints,
+                             const double* d_coords, double* d_work, const wbk_index_params* prm, void* stream) {
+  if (!ctx || !prm || njobs < 0 || nlevels < 1 || !d_job_off || !d_pt_off || !d_coords) {
+    wbk_set_error("wbk_index_run: invalid argument");
+    return WBK_ERR_INVALID;
+  }
+  if (njobs > ctx->caps.max_jobs) {
+    wbk_set_error("wbk_index_run: %d jobs exceed max_jobs=%d", njobs, ctx->caps.max_jobs);
+    return WBK_ERR_CAPACITY;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  ctx->njobs = njobs;
+  ctx->nlevels = nlevels;
+  if (njobs == 0) return WBK_OK;
+  WbkDev& d = ctx->d;
+  WbkIdx& x = ctx->x;
+  const int J = ctx->caps.max_jobs;
+  PackedSet ps{d_job_off, d_pt_off, d_meta, (const u32*)d_pts, njobs, nlevels, ncontours, npoints};
+  CoordTabs ct = make_coords(d_coords, d.nlat);
+  WBK_CUDA_CHECK(cudaMemsetAsync(d.status, 0, sizeof(int) * njobs, st));
+  WBK_LAUNCH(select_kernel, dim3((njobs + 7) / 8), dim3(256), 0, st, d, x, ps, *prm, J);
+  WBK_LAUNCH_CHECK();
+  if (prm->do_overturnings) {
+    const size_t smem = (size_t)6 * d.W * sizeof(int);
+    if (smem > 200 * 1024) {
+      wbk_set_error("wbk_index_run: extended width %d too large for the overturning column tables", d.W);
+      return WBK_ERR_CAPACITY;
+    }
+    WBK_CUDA_CHECK(cudaFuncSetAttribute(overturning_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    WBK_LAUNCH(overturning_kernel, dim3(njobs), dim3(OT_THREADS), smem, st, d, x, ps, ct, *prm, J);
+    WBK_LAUNCH_CHECK();
+  }
+  if (prm->do_streamers) {
+    if (!d_work) {
+      wbk_set_error("wbk_index_run: d_work required for streamers");
+      return WBK_ERR_INVALID;
+    }
+    double* on = d_work;
+    double* pfx = d_work + npoints;
+    const int nslots = njobs * x.SC;
+    WBK_LAUNCH(streamer_prep_kernel, dim3(njobs), dim3(ST_THREADS), 0, st, d, x, ps, ct, on, pfx);
+    WBK_LAUNCH_CHECK();
+    WBK_LAUNCH(tile_scan_kernel, dim3(1), dim3(1024), 0, st, x, nslots);
+    WBK_LAUNCH_CHECK();
+    WBK_LAUNCH(pair_scan_kernel, dim3(148 * 8), dim3(PS_THREADS), 0, st, d, x, ps, ct, (const double*)pfx, *prm, nslots);
+    WBK_LAUNCH_CHECK();
+    WBK_LAUNCH(streamer_cascade_kernel, dim3(njobs), dim3(ST_THREADS), 0, st, d, x, ps, (const double*)on, (const double*)pfx, J);
+    WBK_LAUNCH_CHECK();
+  }
+  return WBK_OK;
+}
+
+extern "C" int wbk_events_counts(wbk_ctx* ctx, int* h_counts, int* h_status, void* stream) {
+  if (!ctx || !h_counts || !h_status) {
+    wbk_set_error("wbk_events_counts: invalid argument");
+    return WBK_ERR_INVALID;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = ctx->njobs, J = ctx->caps.max_jobs;
+  if (n == 0) return WBK_OK;
+  for (int k = 0; k < 3; ++k)
+    WBK_CUDA_CHECK(cudaMemcpyAsync(h_counts + (size_t)k * n, ctx->x.ev_count + (size_t)k * J, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+  WBK_CUDA_CHECK(cudaMemcpyAsync(h_status, ctx->d.status, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+  WBK_CUDA_CHECK(cudaStreamSynchronize(st));
+  for (int j = 0; j < n; ++j) {
+    if (h_status[j] & (WBK_ST_PAIR_OVERFLOW | WBK_ST_EVENT_OVERFLOW | WBK_ST_SEL_OVERFLOW)) {
+      wbk_set_error("wbk_index_run: job %d overflowed an arena (status %d); raise pair_cap / event_cap / sel_cap", j, h_status[j]);
+      return WBK_ERR_CAPACITY;
+    }
+  }
+  return WBK_OK;
+}
+
+__global__ void events_gather_kernel(WbkIdx x, int J, int njobs, int kind, const int* __restrict__ off, int* __restrict__ o_int,
+                                     double* __restrict__ o_f64, int* __restrict__ o_job) {
+  const int job = blockIdx.x;
+  if (job >= njobs) return;
+  const int n = x.ev_count[kind * J + job], o = off[job];
+  const int* si = x.ev_int + (((size_t)kind * J + job) * x.EC) * WBK_EV_INTS;
+  const double* sf = x.ev_f64 + (((size_t)kind * J + job) * x.EC) * WBK_EV_F64;
+  for (int i = threadIdx.x; i < n * WBK_EV_INTS; i += blockDim.x) o_int[(size_t)o * WBK_EV_INTS + i] = si[i];
+  for (int i = threadIdx.x; i < n * WBK_EV_F64; i += blockDim.x) o_f64[(size_t)o * WBK_EV_F64 + i] = sf[i];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) o_job[o + i] = job;
+}
+
+extern "C" int wbk_events_fetch(wbk_ctx* ctx, int kind, int n, int* h_ints, double* h_f64, int* h_job, void* stream) {
+  if (!ctx || kind < 0 || kind > 2 || n < 0 || (n > 0 && (!h_ints || !h_f64 || !h_job))) {
+    wbk_set_error("wbk_events_fetch: invalid argument");
+    return WBK_ERR_INVALID;
+  }
+  if (n == 0 || ctx->njobs == 0) return WBK_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nj = ctx->njobs, J = ctx->caps.max_jobs;
+  // job-major gather into the (now free) contour scratch, then one copy per table
+  int* hc = new int[nj + 1];
+  cudaError_t e = cudaMemcpyAsync(hc, ctx->x.ev_count + (size_t)kind * J, sizeof(int) * nj, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) {
+    delete[] hc;
+    WBK_CUDA_CHECK(e);
+  }
+  int tot = 0;
+  for (int j = 0; j < nj; ++j) {
+    int c = hc[j];
+    hc[j] = tot;
+    tot += c;
+  }
+  hc[nj] = tot;
+  if (tot != n) {
+    delete[] hc;
+    wbk_set_error("wbk_events_fetch: n=%d but the context holds %d events of kind %d", n, tot, kind);
+    return WBK_ERR_INVALID;
+  }
+  // staging buffers inside the linking scratch (sized [J][S] u32 / u64: ample for J*EC records)
+  WbkDev& d = ctx->d;
+  const size_t need_i = (size_t)n * WBK_EV_INTS * 4, need_f = (size_t)n * WBK_EV_F64 * 8;
+  const size_t have_i = (size_t)J * d.S * 4, have_f = (size_t)J * d.S * 8;
+  if (need_i > have_i || need_f > have_f || (size_t)(nj + 1) * 4 > have_i || (size_t)n * 4 > have_i) {
+    delete[] hc;
+    wbk_set_error("wbk_events_fetch: staging arena too small");
+    return WBK_ERR_CAPACITY;
+  }
+  int* s_off = (int*)d.nxt;
+  int* s_int = (int*)d.rid;
+  int* s_job = (int*)d.prv;
+  double* s_f64 = (double*)d.w64;
+  e = cudaMemcpyAsync(s_off, hc, sizeof(int) * (nj + 1), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  delete[] hc;
+  WBK_CUDA_CHECK(e);
+  WBK_LAUNCH(events_gather_kernel, dim3(nj), dim3(128), 0, st, ctx->x, J, nj, kind, (const int*)s_off, s_int, s_f64, s_job);
+  WBK_LAUNCH_CHECK();
+  WBK_CUDA_CHECK(cudaMemcpyAsync(h_ints, s_int, need_i, cudaMemcpyDeviceToHost, st));
+  WBK_CUDA_CHECK(cudaMemcpyAsync(h_f64, s_f64, need_f, cudaMemcpyDeviceToHost, st));
+  WBK_CUDA_CHECK(cudaMemcpyAsync(h_job, s_job, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  WBK_CUDA_CHECK(cudaStreamSynchronize(st));
+  return WBK_OK;
 }

@@ -180,3 +180,166 @@ def contours(field, levels, add, caps=None):
     return ContourSet(njobs=njobs, nlevels=nlevels, nlat=nlat, nlon=nlon, add=int(add), levels=levels,
                       job_off=job_off, pt_off=pt_off, meta=meta, pts=pts, status=status.copy(),
                       max_nx=int(max_nx.value), h_ncontours=nc.copy(), h_npoints=npnt.copy())
+
+
+# --------------------------------------------------------------------------------------------- index stage
+KINDS = ("streamers", "overturnings", "cutoffs")
+
+
+def cell_area_km2(dlon, dlat):
+    """Equatorial cell area used by calculate_properties (utils/index_utils.py:58-60)."""
+    return np.round(6371 * 2 * np.pi / (360 / ((dlon + dlat) / 2))) ** 2
+
+
+def coord_tables(lat, lon, dlon, dlat, lib=None):
+    """Device doubles [lat_deg | lat_rad | cos(lat_rad) | cell area | lon_rad] (wbk_index_run's d_coords).
+
+    Built on the host with the calls the reference makes (np.radians, np.cos for the areas) and
+    libm's cos for the haversine factor (what sklearn's C code evaluates).
+    """
+    import math
+
+    lib = lib or _lib.get()
+    lat = np.asarray(lat, dtype=np.float64)
+    lon = np.asarray(lon, dtype=np.float64)
+    lat_rad = np.radians(lat)
+    cos_lat = np.array([math.cos(v) for v in lat_rad])
+    area = np.cos(np.radians(lat)) * cell_area_km2(dlon, dlat)
+    tab = np.concatenate([lat, lat_rad, cos_lat, area, np.radians(lon)])
+    return torch.from_numpy(tab).to(lib.device)
+
+
+@dataclass
+class EventTable:
+    """Events of one index in reference row order (host arrays)."""
+
+    kind: str
+    job: np.ndarray        # [n]
+    contour: np.ndarray    # [n] index into the contour set
+    ind1: np.ndarray
+    ind2: np.ndarray
+    box: np.ndarray        # [n, 4]: x0, y0, x1, y1 (overturning box / bounding box)
+    orientation: np.ndarray  # 0 cyclonic, 1 anticyclonic (overturnings)
+    split: np.ndarray      # 0 on the real grid, 1 straddles the last meridian, 2 entirely in the extension
+    near: np.ndarray       # streamers: base-point decision within 1e-9 of a threshold
+    sums: np.ndarray       # [n, 6]: sum a, sum a*data, sum a*intensity, sum a*x, sum a*y, member count
+
+    def __len__(self):
+        return len(self.job)
+
+
+def run_indices(cs, data, coords, dlon, dlat, intensity=None, which=KINDS, gmax_nx=None, geo_dis=800.0,
+                cont_dis=1500.0, range_group=5.0, ot_min_exp=5.0, co_min_exp=5.0, want_flags=False, min_caps=None):
+    """Streamers / overturnings / cutoffs + properties (+ to_xarray flags) for a contour set.
+
+    ``data`` / ``intensity``: device tensors [ntime, nlat, nlon].  Returns ``(tables, flags)`` where
+    tables maps kind -> EventTable and flags is an int8 tensor [3, ntime, nlat, nlon] or None.
+    Events that straddle the last meridian (split == 1) are not yet in ``flags``.
+    """
+    lib = _lib.get()
+    ntime = int(data.shape[0])
+    nlevels = cs.nlevels
+    prm = _lib.IndexParams(
+        do_streamers=int("streamers" in which), do_overturnings=int("overturnings" in which),
+        do_cutoffs=int("cutoffs" in which), gmax_nx=int(cs.max_nx if gmax_nx is None else gmax_nx),
+        dlon=float(dlon), dlat=float(dlat), geo_dis=float(geo_dis), cont_dis=float(cont_dis),
+        range_group=float(range_group), ot_min_exp=float(ot_min_exp), co_min_exp=float(co_min_exp))
+    work = torch.empty(2 * max(cs.npoints, 1), dtype=torch.float64, device=lib.device)
+    flags = None
+    if want_flags:
+        flags = torch.empty((3, ntime, cs.nlat, cs.nlon), dtype=torch.int8, device=lib.device)
+    data = data.contiguous()
+    if intensity is not None:
+        intensity = intensity.contiguous().to(data.dtype)
+    grow = dict(min_caps or {})
+    counts = np.zeros((3, max(cs.njobs, 1)), dtype=np.int32)
+    status = np.zeros(max(cs.njobs, 1), dtype=np.int32)
+    for _attempt in range(8):
+        ctx = get_context(cs.nlat, cs.nlon, cs.add, max(cs.njobs, 1), grow)
+        lib.call("wbk_index_run", ctx.handle, cs.njobs, nlevels, _lib.ptr(cs.job_off), _lib.ptr(cs.pt_off),
+                 _lib.ptr(cs.meta), _lib.ptr(cs.pts), cs.ncontours, cs.npoints, _lib.ptr(coords), _lib.ptr(work),
+                 ctypes.byref(prm), lib.stream())
+        lib.call("wbk_events_raster", ctx.handle, _lib.ptr(cs.job_off), _lib.ptr(cs.pt_off), _lib.ptr(cs.pts),
+                 _lib.ptr(coords), _lib.ptr(data), _lib.dtype_code(data.dtype), _lib.ptr(intensity), ntime,
+                 _lib.ptr(flags), ctypes.byref(prm), lib.stream())
+        try:
+            lib.call("wbk_events_counts", ctx.handle, _iptr(counts), _iptr(status), lib.stream())
+            break
+        except _lib.CapacityError:
+            if np.any(status & _lib.ST_PAIR_OVERFLOW):
+                grow["pair_cap"] = ctx.caps["pair_cap"] * 4
+            if np.any(status & _lib.ST_EVENT_OVERFLOW):
+                grow["event_cap"] = ctx.caps["event_cap"] * 4
+            if np.any(status & _lib.ST_SEL_OVERFLOW):
+                grow["sel_cap"] = ctx.caps["sel_cap"] * 4
+    else:
+        raise _lib.WbkError(_lib.ERR_CAPACITY, "index arenas still overflow after 8 regrowths")
+    counts = counts.reshape(3, -1)[:, :cs.njobs] if cs.njobs else counts[:, :0]
+    tables = {}
+    for kind_id, kind in enumerate(KINDS):
+        n = int(counts[kind_id].sum()) if cs.njobs else 0
+        ints = np.zeros((n, _lib.EV_INTS), dtype=np.int32)
+        f64 = np.zeros((n, _lib.EV_F64), dtype=np.float64)
+        job = np.zeros(n, dtype=np.int32)
+        if n:
+            lib.call("wbk_events_fetch", ctx.handle, kind_id, n, _iptr(ints),
+                     f64.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), _iptr(job), lib.stream())
+        tables[kind] = EventTable(kind=kind, job=job, contour=ints[:, 0].copy(), ind1=ints[:, 1].copy(),
+                                  ind2=ints[:, 2].copy(), box=ints[:, 3:7].copy(), orientation=ints[:, 7].copy(),
+                                  split=ints[:, 8].copy(), near=ints[:, 9].copy(), sums=f64)
+    return tables, flags
+
+
+def event_rings(cs, table):
+    """Index-space ring (n, 2) of every event of a table (host)."""
+    h = cs.host()
+    rings = []
+    for e in range(len(table)):
+        if table.kind == "overturnings":
+            x0, y0, x1, y1 = (int(v) for v in table.box[e])
+            rings.append(np.array([[x1, y0], [x1, y1], [x0, y1], [x0, y0]], dtype=np.int64))
+        else:
+            a = h["pt_off"][table.contour[e]]
+            rings.append(np.c_[h["x"][a + table.ind1[e]: a + table.ind2[e] + 1],
+                               h["y"][a + table.ind1[e]: a + table.ind2[e] + 1]])
+    return rings
+
+
+def rasterize_rings(rings, ring_t, nlat, nlon, ntime, r_cells, out_i8=None, values=None):
+    """OR lattice rings into an int8 grid (or write ``values`` into a float64 grid, last ring wins)."""
+    lib = _lib.get()
+    dev = lib.device
+    n = len(rings)
+    if out_i8 is None and values is None:
+        out_i8 = torch.zeros((ntime, nlat, nlon), dtype=torch.int8, device=dev)
+    if n == 0:
+        return out_i8
+    off = np.zeros(n + 1, dtype=np.int32)
+    off[1:] = np.cumsum([len(r) for r in rings])
+    xy = np.ascontiguousarray(np.concatenate([np.asarray(r, dtype=np.int32).reshape(-1, 2) for r in rings]),
+                              dtype=np.int32)
+    d_xy = torch.from_numpy(xy).to(dev)
+    d_off = torch.from_numpy(off).to(dev)
+    d_t = torch.from_numpy(np.ascontiguousarray(ring_t, dtype=np.int32)).to(dev)
+    if values is None:
+        lib.call("wbk_rasterize_rings", _lib.ptr(d_xy), _lib.ptr(d_off), _lib.ptr(d_t), None, n, nlat, nlon, ntime,
+                 float(r_cells) ** 2, _lib.ptr(out_i8), None, None, lib.stream())
+        return out_i8
+    out, vals = values
+    d_val = torch.from_numpy(np.ascontiguousarray(vals, dtype=np.float64)).to(dev)
+    owner = torch.empty((ntime, nlat, nlon), dtype=torch.int32, device=dev)
+    lib.call("wbk_rasterize_rings", _lib.ptr(d_xy), _lib.ptr(d_off), _lib.ptr(d_t), _lib.ptr(d_val), n, nlat, nlon,
+             ntime, float(r_cells) ** 2, None, _lib.ptr(out), _lib.ptr(owner), lib.stream())
+    return out
+
+
+def finish_properties(table, lon, lat, nlon):
+    """com / mean_var / intensity / event_area columns from the device sums (index_utils.py:105-120)."""
+    s = table.sums
+    with np.errstate(divide="ignore", invalid="ignore"):
+        xi = (s[:, 3] / s[:, 0]).astype("int") % nlon if len(s) else np.zeros(0, dtype=int)
+        yi = (s[:, 4] / s[:, 0]).astype("int") if len(s) else np.zeros(0, dtype=int)
+        mean_var = np.round(s[:, 1] / s[:, 0], 2)
+        intensity = np.round(s[:, 2] / s[:, 0], 2)
+    com = list(map(tuple, np.c_[np.asarray(lon)[xi], np.asarray(lat)[yi]]))
+    return dict(com=com, mean_var=mean_var, intensity=intensity, event_area=np.round(s[:, 0], 2))
