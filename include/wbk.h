@@ -202,6 +202,19 @@ int wbk_rasterize_rings(const int* d_xy, const int* d_ring_off, const int* d_rin
                         int nrings, int nlat, int nlon, int ntime, double r2, int8_t* d_out_i8, double* d_out_f64,
                         int* d_owner, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Per-kernel device timing (CUDA events on the launching stream around every kernel launch of the
+ * library).  wbk_prof_enable(1) starts collecting, wbk_prof_read synchronises the device and returns, for
+ * kernel id k < WBK_PROF_NKERNELS, the number of launches and the summed duration in milliseconds since
+ * the last wbk_prof_reset().  Names: wbk_prof_name(k). */
+#define WBK_PROF_NKERNELS 24
+int wbk_prof_enable(int on);
+int wbk_prof_reset(void);
+int wbk_prof_read(int* h_launches, double* h_ms);
+const char* wbk_prof_name(int k);
+/* total number of kernel launches issued by the library in this process (always counted) */
+long long wbk_launch_count(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -585,3 +585,20 @@ def track_events(events, time_range=None, method="by_overlap", buffer=0, overlap
     _, dense = np.unique(label, return_inverse=True)
     events["label"] = dense
     return events.sort_values(by=["label", "date"], kind="stable")
+
+
+# --------------------------------------------------------------------------- whole path (bench / tests)
+def detect_steps(raw, grid, levels=(2,), passes=5, periodic_add=120, intensity=None):
+    """The benchmarked path on the CPU, call for call as a user of the reference would write it:
+    smoothing -> contours -> streamers / overturnings / cutoffs -> to_xarray of each."""
+    sm = smooth_field(raw, passes) if passes > 0 else raw
+    contours = calculate_contours(sm, list(levels), grid, periodic_add, original_coordinates=False)
+    events = dict(
+        streamers=calculate_streamers(sm, grid, contours, intensity=intensity, periodic_add=periodic_add),
+        overturnings=calculate_overturnings(sm, grid, contours, intensity=intensity, periodic_add=periodic_add),
+        cutoffs=calculate_cutoffs(sm, grid, contours, intensity=intensity, periodic_add=periodic_add),
+    )
+    flags = {}
+    for kind, ev in events.items():
+        flags[kind] = to_xarray(np.zeros_like(sm), ev, grid) if len(ev) else np.zeros(sm.shape, dtype="int8")
+    return dict(smoothed=sm, contours=contours, events=events, flags=flags)

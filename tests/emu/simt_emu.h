@@ -229,4 +229,3 @@ inline void launch(K kernel, dim3 grid, dim3 block, size_t smem, Args... args) {
 }
 }  // namespace simt
 
-#define WBK_LAUNCH(kernel, grid, block, smem, stream, ...) simt::launch(kernel, dim3(grid), dim3(block), (size_t)(smem), __VA_ARGS__)

@@ -1,0 +1,71 @@
+"""Whole detection path (Detector) vs the oracle's call-for-call CPU path."""
+
+import numpy as np
+import pytest
+
+from oracle import pipeline as P
+from wavebreaking_b200 import detect, pipeline, spatial, synthetic
+
+
+def _run(nlat, nlon, ntime, levels, step_hours=6.0):
+    lat, lon = synthetic.grid_coords(nlat, nlon)
+    raw = synthetic.pv_field(nlat, nlon, np.arange(ntime) * step_hours)
+    grid = P.Grid(lon, lat, synthetic.time_axis(ntime, step_hours))
+    det = pipeline.Detector(lat, lon, levels=levels)
+    res = det.run_batch(spatial.to_device(raw))
+    want = P.detect_steps(raw, grid, levels=levels)
+    return res, want
+
+
+def _compare(res, want):
+    for k, kind in enumerate(detect.KINDS):
+        assert len(res.tables[kind]) == len(want["events"][kind]), kind
+        assert np.array_equal(res.flags[k].cpu().numpy(), want["flags"][kind]), kind
+    assert res.contours.ncontours == len(want["contours"])
+
+
+def test_detector_emu(emu):
+    res, want = _run(91, 180, 2, [2.0, -2.0])
+    _compare(res, want)
+    assert sum(len(t) for t in res.tables.values()) > 0
+
+
+def test_detector_host_path_emu(emu):
+    import torch
+
+    lat, lon = synthetic.grid_coords(46, 90)
+    raw = synthetic.pv_field(46, 90, np.arange(2) * 6.0)
+    det = pipeline.Detector(lat, lon, levels=[2.0])
+    res = det.run_batch_host(torch.from_numpy(raw))
+    res2 = det.run_batch(spatial.to_device(raw))
+    assert np.array_equal(res.flags.numpy(), res2.flags.numpy())
+    assert pipeline.summarize(res) == pipeline.summarize(res2)
+
+
+@pytest.mark.gpu
+def test_detector_gpu_one_degree(gpu):
+    res, want = _run(181, 360, 4, [2.0, -2.0])
+    _compare(res, want)
+
+
+@pytest.mark.gpu
+def test_detector_gpu_quarter_degree(gpu):
+    res, want = _run(721, 1440, 1, [2.0], step_hours=1.0)
+    _compare(res, want)
+    assert len(res.tables["streamers"]) > 0
+
+
+@pytest.mark.gpu
+def test_detector_gpu_batch_invariance(gpu):
+    """Size-independent property at the benchmark shape: a batch of T steps == T batches of one step."""
+    lat, lon = synthetic.grid_coords(721, 1440)
+    raw = spatial.synth_pv(6, 721, 1440, hour0=0.0, hour_step=1.0)
+    det = pipeline.Detector(lat, lon, levels=[2.0])
+    whole = det.run_batch(raw)
+    for t in range(6):
+        one = det.run_batch(raw[t:t + 1])
+        assert np.array_equal(one.flags[:, 0].cpu().numpy(), whole.flags[:, t].cpu().numpy())
+        for kind in detect.KINDS:
+            sel = whole.tables[kind].job == t
+            assert int(sel.sum()) == len(one.tables[kind])
+            assert np.array_equal(whole.tables[kind].sums[sel], one.tables[kind].sums)

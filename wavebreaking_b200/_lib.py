@@ -71,6 +71,11 @@ _SIGNATURES = {
     "wbk_contours_counts": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int), c_void_p]),
     "wbk_contours_pack": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p]),
+    "wbk_prof_enable": (c_int, [c_int]),
+    "wbk_prof_reset": (c_int, []),
+    "wbk_prof_read": (c_int, [POINTER(c_int), POINTER(c_double)]),
+    "wbk_prof_name": (c_char_p, [c_int]),
+    "wbk_launch_count": (ctypes.c_longlong, []),
     "wbk_last_error": (c_char_p, []),
     "wbk_version": (c_int, []),
     "wbk_device_count": (c_int, []),
@@ -119,6 +124,21 @@ class Library:
 
     def call(self, name, *args):
         self.check(getattr(self.cdll, name)(*args))
+
+
+PROF_NKERNELS = 24
+
+
+def prof_read(lib):
+    """dict kernel name -> (launches, total ms) since the last reset."""
+    n = (c_int * PROF_NKERNELS)()
+    ms = (c_double * PROF_NKERNELS)()
+    lib.call("wbk_prof_read", n, ms)
+    out = {}
+    for k in range(PROF_NKERNELS):
+        if n[k]:
+            out[lib.cdll.wbk_prof_name(k).decode()] = (int(n[k]), float(ms[k]))
+    return out
 
 
 _LIB = None

@@ -7,13 +7,32 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
-#define WBK_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define WBK_LAUNCH_RAW(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define WBK_DYN_SMEM(type, name)                        \
   extern __shared__ __align__(16) unsigned char wbk_dyn_smem_raw[]; \
   type* name = reinterpret_cast<type*>(wbk_dyn_smem_raw)
 #endif
 
 #include "../../include/wbk.h"
+
+// kernel ids for the profiler (names in wbk_core.cu)
+enum WbkKernelId {
+  KID_SMOOTH = 0, KID_CONVOLVE, KID_NAN_BORDER, KID_MFLUX, KID_FLIP, KID_SYNTH, KID_MS_SEGMENTS, KID_CONTOUR_LINK,
+  KID_CONTOUR_PACK, KID_SELECT, KID_OVERTURNING, KID_STREAMER_PREP, KID_TILE_SCAN, KID_PAIR_SCAN, KID_CASCADE,
+  KID_EVENT_LIST, KID_EVENTS_RASTER, KID_RINGS_RASTER, KID_OWNER, KID_EVENTS_GATHER, KID_TRACK_OVERLAP, KID_MISC
+};
+void wbk_prof_begin(int kid, void* stream);
+void wbk_prof_end(int kid, void* stream);
+#ifdef WBK_EMU
+#define WBK_LAUNCH_RAW(kernel, grid, block, smem, stream, ...) simt::launch(kernel, dim3(grid), dim3(block), (size_t)(smem), __VA_ARGS__)
+#endif
+// launch with launch counting / optional event timing
+#define WBK_LAUNCH(kid, kernel, grid, block, smem, stream, ...)             \
+  do {                                                                      \
+    wbk_prof_begin((kid), (void*)(stream));                                 \
+    WBK_LAUNCH_RAW(kernel, grid, block, smem, stream, __VA_ARGS__);         \
+    wbk_prof_end((kid), (void*)(stream));                                   \
+  } while (0)
 
 #define WBK_FULL 0xffffffffu
 #define WBK_NONE 0xffffffffu

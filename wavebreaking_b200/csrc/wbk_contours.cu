@@ -577,15 +577,15 @@ extern "C" int wbk_contours(wbk_ctx* ctx, const void* d_field, int dtype, int nt
   for (int i = 0; i < WBK_MAX_LEVELS; ++i) lv.v[i] = i < nlevels ? h_levels[i] : 0.0;
   dim3 grid((d.nlon + MS_THREADS - 1) / MS_THREADS, (d.nlat - 1 + MS_ROWS - 1) / MS_ROWS, ntime);
   if (dtype == WBK_F32) {
-    WBK_LAUNCH(ms_segments_kernel<float>, grid, dim3(MS_THREADS), 0, st, (const float*)d_field, d, lv, nlevels);
+    WBK_LAUNCH(KID_MS_SEGMENTS, ms_segments_kernel<float>, grid, dim3(MS_THREADS), 0, st, (const float*)d_field, d, lv, nlevels);
   } else if (dtype == WBK_F64) {
-    WBK_LAUNCH(ms_segments_kernel<double>, grid, dim3(MS_THREADS), 0, st, (const double*)d_field, d, lv, nlevels);
+    WBK_LAUNCH(KID_MS_SEGMENTS, ms_segments_kernel<double>, grid, dim3(MS_THREADS), 0, st, (const double*)d_field, d, lv, nlevels);
   } else {
     wbk_set_error("wbk_contours: unsupported dtype");
     return WBK_ERR_INVALID;
   }
   WBK_LAUNCH_CHECK();
-  WBK_LAUNCH(contour_link_kernel, dim3(njobs), dim3(WBK_CONTOUR_THREADS), 0, st, d, njobs);
+  WBK_LAUNCH(KID_CONTOUR_LINK, contour_link_kernel, dim3(njobs), dim3(WBK_CONTOUR_THREADS), 0, st, d, njobs);
   WBK_LAUNCH_CHECK();
   return WBK_OK;
 }
@@ -668,7 +668,7 @@ extern "C" int wbk_contours_pack(wbk_ctx* ctx, const int* h_ncontours, const int
     WBK_CUDA_CHECK(cudaStreamSynchronize(st));
     return WBK_OK;
   }
-  WBK_LAUNCH(contours_pack_kernel, dim3(J), dim3(256), 0, st, ctx->d, J, (const int*)d_job_off, (const int*)d_pt_job_off, d_pt_off, d_meta, (u32*)d_pts);
+  WBK_LAUNCH(KID_CONTOUR_PACK, contours_pack_kernel, dim3(J), dim3(256), 0, st, ctx->d, J, (const int*)d_job_off, (const int*)d_pt_job_off, d_pt_off, d_meta, (u32*)d_pts);
   WBK_LAUNCH_CHECK();
   return WBK_OK;
 }

@@ -711,7 +711,7 @@ extern "C" int wbk_index_run(wbk_ctx* ctx, int njobs, int nlevels, const int* d_
   PackedSet ps{d_job_off, d_pt_off, d_meta, (const u32*)d_pts, njobs, nlevels, ncontours, npoints};
   CoordTabs ct = make_coords(d_coords, d.nlat);
   WBK_CUDA_CHECK(cudaMemsetAsync(d.status, 0, sizeof(int) * njobs, st));
-  WBK_LAUNCH(select_kernel, dim3((njobs + 7) / 8), dim3(256), 0, st, d, x, ps, *prm, J);
+  WBK_LAUNCH(KID_SELECT, select_kernel, dim3((njobs + 7) / 8), dim3(256), 0, st, d, x, ps, *prm, J);
   WBK_LAUNCH_CHECK();
   if (prm->do_overturnings) {
     const size_t smem = (size_t)6 * d.W * sizeof(int);
@@ -720,7 +720,7 @@ extern "C" int wbk_index_run(wbk_ctx* ctx, int njobs, int nlevels, const int* d_
       return WBK_ERR_CAPACITY;
     }
     WBK_CUDA_CHECK(cudaFuncSetAttribute(overturning_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    WBK_LAUNCH(overturning_kernel, dim3(njobs), dim3(OT_THREADS), smem, st, d, x, ps, ct, *prm, J);
+    WBK_LAUNCH(KID_OVERTURNING, overturning_kernel, dim3(njobs), dim3(OT_THREADS), smem, st, d, x, ps, ct, *prm, J);
     WBK_LAUNCH_CHECK();
   }
   if (prm->do_streamers) {
@@ -731,13 +731,13 @@ extern "C" int wbk_index_run(wbk_ctx* ctx, int njobs, int nlevels, const int* d_
     double* on = d_work;
     double* pfx = d_work + npoints;
     const int nslots = njobs * x.SC;
-    WBK_LAUNCH(streamer_prep_kernel, dim3(njobs), dim3(ST_THREADS), 0, st, d, x, ps, ct, on, pfx);
+    WBK_LAUNCH(KID_STREAMER_PREP, streamer_prep_kernel, dim3(njobs), dim3(ST_THREADS), 0, st, d, x, ps, ct, on, pfx);
     WBK_LAUNCH_CHECK();
-    WBK_LAUNCH(tile_scan_kernel, dim3(1), dim3(1024), 0, st, x, nslots);
+    WBK_LAUNCH(KID_TILE_SCAN, tile_scan_kernel, dim3(1), dim3(1024), 0, st, x, nslots);
     WBK_LAUNCH_CHECK();
-    WBK_LAUNCH(pair_scan_kernel, dim3(148 * 8), dim3(PS_THREADS), 0, st, d, x, ps, ct, (const double*)pfx, *prm, nslots);
+    WBK_LAUNCH(KID_PAIR_SCAN, pair_scan_kernel, dim3(148 * 8), dim3(PS_THREADS), 0, st, d, x, ps, ct, (const double*)pfx, *prm, nslots);
     WBK_LAUNCH_CHECK();
-    WBK_LAUNCH(streamer_cascade_kernel, dim3(njobs), dim3(ST_THREADS), 0, st, d, x, ps, (const double*)on, (const double*)pfx, J);
+    WBK_LAUNCH(KID_CASCADE, streamer_cascade_kernel, dim3(njobs), dim3(ST_THREADS), 0, st, d, x, ps, (const double*)on, (const double*)pfx, J);
     WBK_LAUNCH_CHECK();
   }
   return WBK_OK;
@@ -821,7 +821,7 @@ extern "C" int wbk_events_fetch(wbk_ctx* ctx, int kind, int n, int* h_ints, doub
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   delete[] hc;
   WBK_CUDA_CHECK(e);
-  WBK_LAUNCH(events_gather_kernel, dim3(nj), dim3(128), 0, st, ctx->x, J, nj, kind, (const int*)s_off, s_int, s_f64, s_job);
+  WBK_LAUNCH(KID_EVENTS_GATHER, events_gather_kernel, dim3(nj), dim3(128), 0, st, ctx->x, J, nj, kind, (const int*)s_off, s_int, s_f64, s_job);
   WBK_LAUNCH_CHECK();
   WBK_CUDA_CHECK(cudaMemcpyAsync(h_ints, s_int, need_i, cudaMemcpyDeviceToHost, st));
   WBK_CUDA_CHECK(cudaMemcpyAsync(h_f64, s_f64, need_f, cudaMemcpyDeviceToHost, st));

@@ -304,7 +304,7 @@ extern "C" int wbk_events_raster(wbk_ctx* ctx, const int* d_job_off, const int* 
     wbk_set_error("wbk_events_raster: to_xarray flags need dlon == dlat (buffer radius is isotropic in degrees)");
     return WBK_ERR_INVALID;
   }
-  WBK_LAUNCH(event_list_kernel, dim3(1), dim3(1024), 0, st, ctx->x, J, njobs);
+  WBK_LAUNCH(KID_EVENT_LIST, event_list_kernel, dim3(1), dim3(1024), 0, st, ctx->x, J, njobs);
   WBK_LAUNCH_CHECK();
   const double r_prop = (prm->dlon + prm->dlat) / 2.0 / 2.0;  // index units (index_utils.py:47-50)
   const double r_flag = d_flags ? ((prm->dlon + prm->dlat) / 2.0 / 2.0) / prm->dlon : r_prop;  // degrees -> cells
@@ -319,12 +319,12 @@ extern "C" int wbk_events_raster(wbk_ctx* ctx, const int* d_job_off, const int* 
   const int grid = 148 * 4;
   if (dtype == WBK_F32) {
     WBK_CUDA_CHECK(cudaFuncSetAttribute(events_raster_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    WBK_LAUNCH(events_raster_kernel<float>, dim3(grid), dim3(RS_THREADS), smem, st, d, ctx->x, d_job_off, d_pt_off,
+    WBK_LAUNCH(KID_EVENTS_RASTER, events_raster_kernel<float>, dim3(grid), dim3(RS_THREADS), smem, st, d, ctx->x, d_job_off, d_pt_off,
                (const u32*)d_pts, area, (const float*)d_data, (const float*)d_intensity, d_flags, ntime, ctx->nlevels, J,
                njobs, r_prop * r_prop, r_flag * r_flag, rowcap);
   } else if (dtype == WBK_F64) {
     WBK_CUDA_CHECK(cudaFuncSetAttribute(events_raster_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    WBK_LAUNCH(events_raster_kernel<double>, dim3(grid), dim3(RS_THREADS), smem, st, d, ctx->x, d_job_off, d_pt_off,
+    WBK_LAUNCH(KID_EVENTS_RASTER, events_raster_kernel<double>, dim3(grid), dim3(RS_THREADS), smem, st, d, ctx->x, d_job_off, d_pt_off,
                (const u32*)d_pts, area, (const double*)d_data, (const double*)d_intensity, d_flags, ntime, ctx->nlevels,
                J, njobs, r_prop * r_prop, r_flag * r_flag, rowcap);
   } else {
@@ -418,16 +418,16 @@ extern "C" int wbk_rasterize_rings(const int* d_xy, const int* d_ring_off, const
   }
   const size_t ncell = (size_t)ntime * nlat * nlon;
   if (d_out_f64) {
-    WBK_LAUNCH(owner_fill_kernel, dim3(592), dim3(256), 0, st, d_owner, ncell, -1);
+    WBK_LAUNCH(KID_OWNER, owner_fill_kernel, dim3(592), dim3(256), 0, st, d_owner, ncell, -1);
     WBK_LAUNCH_CHECK();
   }
   WBK_CUDA_CHECK(cudaFuncSetAttribute(rings_raster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = nrings < 148 * 4 ? nrings : 148 * 4;
-  WBK_LAUNCH(rings_raster_kernel, dim3(grid), dim3(RS_THREADS), smem, st, d_xy, d_ring_off, d_ring_t, nrings, nlat, nlon,
+  WBK_LAUNCH(KID_RINGS_RASTER, rings_raster_kernel, dim3(grid), dim3(RS_THREADS), smem, st, d_xy, d_ring_off, d_ring_t, nrings, nlat, nlon,
              ntime, r2, d_out_i8, d_out_f64 ? d_owner : (int*)nullptr, rowcap);
   WBK_LAUNCH_CHECK();
   if (d_out_f64) {
-    WBK_LAUNCH(owner_apply_kernel, dim3(592), dim3(256), 0, st, (const int*)d_owner, d_ring_val, d_out_f64, ncell);
+    WBK_LAUNCH(KID_OWNER, owner_apply_kernel, dim3(592), dim3(256), 0, st, (const int*)d_owner, d_ring_val, d_out_f64, ncell);
     WBK_LAUNCH_CHECK();
   }
   return WBK_OK;

@@ -94,7 +94,7 @@ static int launch_smooth(const void* in, void* out, int ntime, int nlat, int nlo
   WBK_CUDA_CHECK(cudaFuncSetAttribute(smooth_fused_kernel<TIn, TOut>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
   dim3 grid((nlon + SM_TW - 1) / SM_TW, (nlat + SM_TH - 1) / SM_TH, ntime);
-  WBK_LAUNCH((smooth_fused_kernel<TIn, TOut>), grid, dim3(SM_THREADS), smem, st, (const TIn*)in, (TOut*)out, nlat,
+  WBK_LAUNCH(KID_SMOOTH, (smooth_fused_kernel<TIn, TOut>), grid, dim3(SM_THREADS), smem, st, (const TIn*)in, (TOut*)out, nlat,
              nlon, passes, round_first, round_all, nan_border);
   WBK_LAUNCH_CHECK();
   return WBK_OK;
@@ -247,11 +247,11 @@ extern "C" int wbk_convolve2d(const void* d_in, int in_dtype, void* d_out, int o
   dim3 block(128);
   dim3 grid((nlon + 127) / 128, nlat, ntime);
   if (in_dtype == WBK_F32 && out_dtype == WBK_F32) {
-    WBK_LAUNCH((convolve2d_cast_kernel<float, float, float>), grid, block, 0, st, (const float*)d_in, (float*)d_out, nlat, nlon, taps, mode, divide, divisor);
+    WBK_LAUNCH(KID_CONVOLVE, (convolve2d_cast_kernel<float, float, float>), grid, block, 0, st, (const float*)d_in, (float*)d_out, nlat, nlon, taps, mode, divide, divisor);
   } else if (in_dtype == WBK_F32 && out_dtype == WBK_F64) {
-    WBK_LAUNCH((convolve2d_cast_kernel<float, float, double>), grid, block, 0, st, (const float*)d_in, (double*)d_out, nlat, nlon, taps, mode, divide, divisor);
+    WBK_LAUNCH(KID_CONVOLVE, (convolve2d_cast_kernel<float, float, double>), grid, block, 0, st, (const float*)d_in, (double*)d_out, nlat, nlon, taps, mode, divide, divisor);
   } else if (in_dtype == WBK_F64 && out_dtype == WBK_F64) {
-    WBK_LAUNCH((convolve2d_cast_kernel<double, double, double>), grid, block, 0, st, (const double*)d_in, (double*)d_out, nlat, nlon, taps, mode, divide, divisor);
+    WBK_LAUNCH(KID_CONVOLVE, (convolve2d_cast_kernel<double, double, double>), grid, block, 0, st, (const double*)d_in, (double*)d_out, nlat, nlon, taps, mode, divide, divisor);
   } else {
     wbk_set_error("wbk_convolve2d: unsupported dtype combination");
     return WBK_ERR_INVALID;
@@ -278,8 +278,8 @@ extern "C" int wbk_nan_border(void* d_field, int dtype, int ntime, int nlat, int
   }
   if (ntime == 0 || border == 0) return WBK_OK;
   dim3 grid((nlon + 255) / 256, 2 * border, ntime);
-  if (dtype == WBK_F32) WBK_LAUNCH(nan_border_kernel<float>, grid, dim3(256), 0, (cudaStream_t)stream, (float*)d_field, nlat, nlon, border);
-  else WBK_LAUNCH(nan_border_kernel<double>, grid, dim3(256), 0, (cudaStream_t)stream, (double*)d_field, nlat, nlon, border);
+  if (dtype == WBK_F32) WBK_LAUNCH(KID_NAN_BORDER, nan_border_kernel<float>, grid, dim3(256), 0, (cudaStream_t)stream, (float*)d_field, nlat, nlon, border);
+  else WBK_LAUNCH(KID_NAN_BORDER, nan_border_kernel<double>, grid, dim3(256), 0, (cudaStream_t)stream, (double*)d_field, nlat, nlon, border);
   WBK_LAUNCH_CHECK();
   return WBK_OK;
 }
@@ -324,8 +324,8 @@ extern "C" int wbk_mflux(const void* d_u, const void* d_v, void* d_out, int dtyp
   }
   if (ntime == 0) return WBK_OK;
   dim3 grid(nlat, ntime);
-  if (dtype == WBK_F32) WBK_LAUNCH(mflux_kernel<float>, grid, dim3(256), 0, (cudaStream_t)stream, (const float*)d_u, (const float*)d_v, (float*)d_out, nlon);
-  else WBK_LAUNCH(mflux_kernel<double>, grid, dim3(256), 0, (cudaStream_t)stream, (const double*)d_u, (const double*)d_v, (double*)d_out, nlon);
+  if (dtype == WBK_F32) WBK_LAUNCH(KID_MFLUX, mflux_kernel<float>, grid, dim3(256), 0, (cudaStream_t)stream, (const float*)d_u, (const float*)d_v, (float*)d_out, nlon);
+  else WBK_LAUNCH(KID_MFLUX, mflux_kernel<double>, grid, dim3(256), 0, (cudaStream_t)stream, (const double*)d_u, (const double*)d_v, (double*)d_out, nlon);
   WBK_LAUNCH_CHECK();
   return WBK_OK;
 }
@@ -350,8 +350,8 @@ extern "C" int wbk_flip(const void* d_in, void* d_out, int dtype, int ntime, int
   }
   if (ntime == 0) return WBK_OK;
   dim3 grid((nlon + 255) / 256, nlat, ntime);
-  if (dtype == WBK_F32) WBK_LAUNCH(flip_kernel<float>, grid, dim3(256), 0, (cudaStream_t)stream, (const float*)d_in, (float*)d_out, nlat, nlon, flip_lat, flip_lon);
-  else WBK_LAUNCH(flip_kernel<double>, grid, dim3(256), 0, (cudaStream_t)stream, (const double*)d_in, (double*)d_out, nlat, nlon, flip_lat, flip_lon);
+  if (dtype == WBK_F32) WBK_LAUNCH(KID_FLIP, flip_kernel<float>, grid, dim3(256), 0, (cudaStream_t)stream, (const float*)d_in, (float*)d_out, nlat, nlon, flip_lat, flip_lon);
+  else WBK_LAUNCH(KID_FLIP, flip_kernel<double>, grid, dim3(256), 0, (cudaStream_t)stream, (const double*)d_in, (double*)d_out, nlat, nlon, flip_lat, flip_lon);
   WBK_LAUNCH_CHECK();
   return WBK_OK;
 }
@@ -425,8 +425,8 @@ extern "C" int wbk_synth_pv(void* d_out, int dtype, int ntime, int nlat, int nlo
       p.rad[h][b] = h_blobs[(h * n_blob + b) * 3 + 2];
     }
   dim3 grid((nlon + 127) / 128, nlat, ntime);
-  if (dtype == WBK_F32) WBK_LAUNCH(synth_pv_kernel<float>, grid, dim3(128), 0, (cudaStream_t)stream, (float*)d_out, nlat, nlon, hour0, hour_step, p);
-  else WBK_LAUNCH(synth_pv_kernel<double>, grid, dim3(128), 0, (cudaStream_t)stream, (double*)d_out, nlat, nlon, hour0, hour_step, p);
+  if (dtype == WBK_F32) WBK_LAUNCH(KID_SYNTH, synth_pv_kernel<float>, grid, dim3(128), 0, (cudaStream_t)stream, (float*)d_out, nlat, nlon, hour0, hour_step, p);
+  else WBK_LAUNCH(KID_SYNTH, synth_pv_kernel<double>, grid, dim3(128), 0, (cudaStream_t)stream, (double*)d_out, nlat, nlon, hour0, hour_step, p);
   WBK_LAUNCH_CHECK();
   return WBK_OK;
 }
