@@ -179,8 +179,8 @@ int wbk_index_run(wbk_ctx* ctx, int njobs, int nlevels, const int* d_job_off, co
 /* utils/index_utils.py:35-126 calculate_properties sums and processing/events.py:66-106 to_xarray flags for
  * the events of the last wbk_index_run.  d_data / d_intensity: [ntime, nlat, nlon] (intensity may be NULL).
  * d_flags: NULL or int8 [3][ntime][nlat][nlon] (kind-major), zeroed here and set to 1 where an event of that
- * kind is present; events that need the meridian split are NOT rasterised here (split = 1 in their record;
- * the caller clips them and uses wbk_rasterize_rings). */
+ * kind is present; events that straddle the last meridian (split = 1 in their record) are clipped on the
+ * device (utils/index_utils.py:148-173) and their pieces rasterised too. */
 int wbk_events_raster(wbk_ctx* ctx, const int* d_job_off, const int* d_pt_off, const uint32_t* d_pts,
                       const double* d_coords, const void* d_data, int dtype, const void* d_intensity, int ntime,
                       int8_t* d_flags, const wbk_index_params* params, void* stream);

@@ -229,3 +229,11 @@ inline void launch(K kernel, dim3 grid, dim3 block, size_t smem, Args... args) {
 }
 }  // namespace simt
 
+
+struct double2 { double x, y; };
+struct float4 { float x, y, z, w; };
+struct float2 { float x, y; };
+struct int2 { int x, y; };
+struct int4 { int x, y, z, w; };
+struct uint4 { unsigned x, y, z, w; };
+inline float __sinf(float v) { return std::sin(v); }

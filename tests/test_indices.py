@@ -63,16 +63,8 @@ def compare_events(cs, tables, flags, want, grid, levels, sm):
             assert len(pieces) == len(want_pieces)
             for a, b in zip(pieces, want_pieces):
                 assert np.array_equal(a, b)
-        # flag grid: device flags + split events through the generic rasteriser == oracle to_xarray
+        # flag grid (split events are clipped + rasterised on the device): == oracle to_xarray
         fl = flags[detect.KINDS.index(kind)]
-        split = np.nonzero(tab.split == 1)[0]
-        if len(split):
-            prs, pt = [], []
-            for e in split:
-                for piece in geometry.transform_ring(rings[e], grid.nlon):
-                    prs.append(piece)
-                    pt.append(int(tab.job[e]) // nlev)
-            detect.rasterize_rings(prs, pt, grid.nlat, grid.nlon, grid.ntime, 0.5, out_i8=fl)
         want_flags = P.to_xarray(np.zeros_like(sm), w, grid)
         assert np.array_equal(fl.cpu().numpy(), want_flags), kind
 

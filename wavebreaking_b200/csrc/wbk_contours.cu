@@ -136,40 +136,39 @@ __device__ __forceinline__ int ms_case_code(int c) {
 template <typename T>
 __global__ void __launch_bounds__(MS_THREADS)
 ms_segments_kernel(const T* __restrict__ field, WbkDev d, LevelPack levels, int nlevels) {
-  const int nlat = d.nlat, nlon = d.nlon, add = d.add, W = d.W;
-  const int c0 = blockIdx.x * MS_THREADS + threadIdx.x;
-  const bool valid = c0 < nlon;
+  const int nlat = d.nlat, nlon = d.nlon, W = d.W;
+  // every warp covers 31 base columns; lane 31 only supplies the right neighbour of lane 30 (so no thread
+  // needs a second, uncoalesced load) -- column nlon wraps to column 0 (periodic extension)
+  const int lane = wbk_lane();
+  const int c0 = (blockIdx.x * (MS_THREADS / 32) + wbk_warp()) * 31 + lane;
+  const bool loads = c0 <= nlon;
+  const int csrc = c0 == nlon ? 0 : c0;
+  const bool valid = c0 < nlon && lane < 31;
   const int r_begin = blockIdx.y * MS_ROWS;
   const int r_end = min(r_begin + MS_ROWS, nlat - 1);  // squares r0 in [r_begin, r_end)
   const int t = blockIdx.z;
   const T* src = field + (size_t)t * nlat * nlon;
-  const int lane = wbk_lane();
-  const int cw = (c0 + 1 == nlon) ? 0 : c0 + 1;  // right neighbour, periodic
 
   // which squares does this thread own?  base square (r0, c0) exists if c0 <= W-2;
   // extension square (r0, c0 + nlon) exists if c0 + nlon <= W-2
   const bool own_base = valid && (c0 <= W - 2);
   const bool own_ext = valid && (c0 + nlon <= W - 2);
 
-  double ul = 0, ur = 0;
-  {
-    double v = valid ? (double)src[(size_t)r_begin * nlon + c0] : 0.0;
-    double rn = __shfl_down_sync(WBK_FULL, v, 1);
-    if (lane == 31 && valid) rn = (double)src[(size_t)r_begin * nlon + cw];
-    if (valid && cw == 0) rn = (double)src[(size_t)r_begin * nlon];
-    ul = v;
-    ur = rn;
+  // all rows of the strip are requested before any is used (MS_ROWS + 1 independent loads in flight)
+  T vals[MS_ROWS + 1];
+#pragma unroll
+  for (int i = 0; i <= MS_ROWS; ++i) {
+    const int r = r_begin + i;
+    vals[i] = (loads && r <= r_end) ? src[(size_t)r * nlon + csrc] : (T)0;
   }
-  for (int r0 = r_begin; r0 < r_end; ++r0) {
-    double ll, lr;
-    {
-      double v = valid ? (double)src[(size_t)(r0 + 1) * nlon + c0] : 0.0;
-      double rn = __shfl_down_sync(WBK_FULL, v, 1);
-      if (lane == 31 && valid) rn = (double)src[(size_t)(r0 + 1) * nlon + cw];
-      if (valid && cw == 0) rn = (double)src[(size_t)(r0 + 1) * nlon];
-      ll = v;
-      lr = rn;
-    }
+  double ul = (double)vals[0];
+  double ur = __shfl_down_sync(WBK_FULL, ul, 1);
+#pragma unroll
+  for (int i = 0; i < MS_ROWS; ++i) {
+    const int r0 = r_begin + i;
+    if (r0 >= r_end) break;
+    const double ll = (double)vals[i + 1];
+    const double lr = __shfl_down_sync(WBK_FULL, ll, 1);
     const bool has_nan = isnan(ul) || isnan(ur) || isnan(ll) || isnan(lr);
     for (int l = 0; l < nlevels; ++l) {
       const double level = levels.v[l];
@@ -575,7 +574,8 @@ extern "C" int wbk_contours(wbk_ctx* ctx, const void* d_field, int dtype, int nt
   WBK_CUDA_CHECK(cudaMemsetAsync(d.max_nx, 0, sizeof(int), st));
   LevelPack lv;
   for (int i = 0; i < WBK_MAX_LEVELS; ++i) lv.v[i] = i < nlevels ? h_levels[i] : 0.0;
-  dim3 grid((d.nlon + MS_THREADS - 1) / MS_THREADS, (d.nlat - 1 + MS_ROWS - 1) / MS_ROWS, ntime);
+  const int cols_per_block = (MS_THREADS / 32) * 31;
+  dim3 grid((d.nlon + cols_per_block - 1) / cols_per_block, (d.nlat - 1 + MS_ROWS - 1) / MS_ROWS, ntime);
   if (dtype == WBK_F32) {
     WBK_LAUNCH(KID_MS_SEGMENTS, ms_segments_kernel<float>, grid, dim3(MS_THREADS), 0, st, (const float*)d_field, d, lv, nlevels);
   } else if (dtype == WBK_F64) {

@@ -45,6 +45,8 @@ struct WbkIdx {
   u64* pairs;                // [J][SC][PC]  candidate pairs (i << 32 | j)
   int* pair_count;           // [J][SC]
   int* tile_off;             // [J*SC + 1]
+  int NB;                    // blocks of PT points per contour (capacity)
+  int* blk_x;                // [J*SC][NB][2] column range of every block of a full-width contour
   u64* pairs_b;              // [J][PC]
   int *flag, *scanb, *label; // [J][PC]
   u64* hk;                   // [J][2*PC]
@@ -54,6 +56,11 @@ struct WbkIdx {
   int* ev_count;             // [3][J]
   int* ev_off;               // [3*J + 1]
   int* total;                // [4] scratch totals
+  // meridian split (utils/index_utils.py:148-173) of the events that straddle the last meridian
+  int SPV, SPR;              // vertex pool / ring list capacities
+  int* split_xy;             // [SPV][2] vertex pool (chain scratch and final folded, truncated pieces)
+  int* split_ring;           // [SPR][4] start, len, time index, kind
+  int* split_count;          // [0] vertex cursor, [1] ring cursor, [2] overflow flag
 };
 
 struct wbk_ctx {

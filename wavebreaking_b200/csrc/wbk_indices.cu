@@ -4,6 +4,7 @@
 #include "wbk_ctx.cuh"
 
 // ------------------------------------------------------------------------------------------ arenas
+#define PT_HOST 128  // == PT, the pair-scan tile edge
 size_t wbk_index_layout(struct wbk_ctx* ctx, unsigned char* base, size_t off) {
   WbkIdx& x = ctx->x;
   const wbk_caps& c = ctx->caps;
@@ -35,6 +36,13 @@ size_t wbk_index_layout(struct wbk_ctx* ctx, unsigned char* base, size_t off) {
   x.ev_count = (int*)take(3 * J * 4);
   x.ev_off = (int*)take((3 * J + 1) * 4);
   x.total = (int*)take(64);
+  x.NB = (c.seg_cap + c.contour_cap + PT_HOST - 1) / PT_HOST;
+  x.blk_x = (int*)take(J * SC * (size_t)x.NB * 2 * 4);
+  x.SPV = (int)(J * 4096 < (size_t)1 << 26 ? J * 4096 : (size_t)1 << 26);
+  x.SPR = (int)(J * 32);
+  x.split_xy = (int*)take((size_t)x.SPV * 2 * 4);
+  x.split_ring = (int*)take((size_t)x.SPR * 4 * 4);
+  x.split_count = (int*)take(64);
   return (o + 255) & ~(size_t)255;
 }
 
@@ -269,6 +277,9 @@ __global__ void __launch_bounds__(OT_THREADS) overturning_kernel(WbkDev d, WbkId
 // ------------------------------------------------------------------------------------------ streamers
 #define ST_THREADS 1024
 #define PT 128           // pair-scan tile edge
+#define CS_PTS 16384     // contour points staged in shared memory by the cascade
+#define CS_SORT 8192     // candidate pairs sorted in shared memory
+#define CS_SMEM ((size_t)CS_PTS * 4 + (size_t)(CS_PTS / 32) * 16 + (size_t)CS_SORT * 8)
 #define PS_THREADS 256
 #define EARTH_R 6371.0
 
@@ -342,10 +353,24 @@ __global__ void __launch_bounds__(ST_THREADS) streamer_prep_kernel(WbkDev d, Wbk
     }
     __syncthreads();
     block_incl_scan_f64(pfx + base, n, sscan);
-    if (tid == 0) {
-      const int T = (n + PT - 1) / PT;
-      x.tile_off[(size_t)job * x.SC + si] = T * (T + 1) / 2;
+    const int T = (n + PT - 1) / PT;
+    // column range of every PT-point block (tile skipping in the pair scan)
+    for (int b = wbk_warp(); b < T; b += (nt >> 5)) {
+      int mn = 0x7fffffff, mx = -1;
+      for (int k = b * PT + wbk_lane(); k < min(n, (b + 1) * PT); k += 32) {
+        const int px = wbk_px(ps.pts[base + k]);
+        mn = min(mn, px);
+        mx = max(mx, px);
+      }
+      mn = wbk_warp_min(mn);
+      mx = wbk_warp_max(mx);
+      if (wbk_lane() == 0 && b < x.NB) {
+        int* bx = x.blk_x + ((size_t)job * x.SC + si) * x.NB * 2;
+        bx[2 * b] = mn;
+        bx[2 * b + 1] = mx;
+      }
     }
+    if (tid == 0) x.tile_off[(size_t)job * x.SC + si] = T * (T + 1) / 2;
   }
 }
 
@@ -360,14 +385,21 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(WbkIdx x, int nslots) {
 }
 
 // tiled pair scan: geo < geo_dis and cont > cont_dis and |x1 - x2| <= 120 (streamer_index.py:130-157),
-// without materialising the N x N matrices.  Persistent CTAs stride over the (contour, tile) work list.
+// without materialising the N x N matrices.  Persistent CTAs stride over the (contour, tile) work list; tiles
+// whose column ranges are more than 120 apart are skipped.  The haversine test is decided in fp32 on
+// h = sin^2(dlat/2) + cos cos sin^2(dlon/2) against sin^2(geo_dis / 2R) with a 1e-4 relative margin; only pairs
+// inside the margin evaluate the reference's fp64 expression (and carry the near-threshold flag).
 __global__ void __launch_bounds__(PS_THREADS) pair_scan_kernel(WbkDev d, WbkIdx x, PackedSet ps, CoordTabs ct,
                                                                const double* __restrict__ pfx, wbk_index_params prm,
                                                                int nslots) {
-  __shared__ int sx[2][PT], sy[2][PT];
+  __shared__ int sx[2][PT];
+  __shared__ float fla[2][PT], flo[2][PT], fco[2][PT];
   __shared__ double sla[2][PT], slo[2][PT], sco[2][PT], spf[2][PT];
   const int tid = threadIdx.x, nlon = d.nlon;
   const int total = x.tile_off[nslots];
+  const double sthr = sin(prm.geo_dis / (2.0 * EARTH_R));
+  const float hthr = (float)(sthr * sthr);
+  const float h_lo = hthr * 0.9999f, h_hi = hthr * 1.0001f;
   for (int w = blockIdx.x; w < total; w += gridDim.x) {
     // slot = last index with tile_off[slot] <= w
     int lo = 0, hi = nslots - 1;
@@ -375,7 +407,7 @@ __global__ void __launch_bounds__(PS_THREADS) pair_scan_kernel(WbkDev d, WbkIdx 
       int mid = (lo + hi + 1) >> 1;
       if (x.tile_off[mid] <= w) lo = mid; else hi = mid - 1;
     }
-    const int slot = lo, job = slot / x.SC;
+    const int slot = lo;
     const int c = x.sel[slot];
     const int base = ps.pt_off[c], n = ps.pt_off[c + 1] - base;
     const int T = (n + PT - 1) / PT;
@@ -386,16 +418,20 @@ __global__ void __launch_bounds__(PS_THREADS) pair_scan_kernel(WbkDev d, WbkIdx 
     }
     const int bj = bi + t;
     {
+      const int* bx = x.blk_x + (size_t)slot * x.NB * 2;
+      const int imin = bx[2 * bi], imax = bx[2 * bi + 1], jmin = bx[2 * bj], jmax = bx[2 * bj + 1];
+      if (jmin - imax > 120 || imin - jmax > 120) continue;  // uniform for the CTA
+    }
+    {
       const int which = tid >> 7, k = tid & (PT - 1);
       const int idx = (which ? bj : bi) * PT + k;
       if (idx < n) {
         const u32 p = ps.pts[base + idx];
         const int py = wbk_py(p), pxx = wbk_px(p);
+        const double la = ct.lat_rad[py], lo2 = ct.lon_rad[pxx % nlon], co = ct.cos_lat[py];
         sx[which][k] = pxx;
-        sy[which][k] = py;
-        sla[which][k] = ct.lat_rad[py];
-        slo[which][k] = ct.lon_rad[pxx % nlon];
-        sco[which][k] = ct.cos_lat[py];
+        sla[which][k] = la; slo[which][k] = lo2; sco[which][k] = co;
+        fla[which][k] = (float)la; flo[which][k] = (float)lo2; fco[which][k] = (float)co;
         spf[which][k] = pfx[base + idx];
       }
     }
@@ -405,7 +441,8 @@ __global__ void __launch_bounds__(PS_THREADS) pair_scan_kernel(WbkDev d, WbkIdx 
       const int i = bi * PT + ii;
       if (i < n) {
         const int xi = sx[0][ii];
-        const double lai = sla[0][ii], loi = slo[0][ii], ci = sco[0][ii], pfi = spf[0][ii];
+        const float lai = fla[0][ii], loi = flo[0][ii], ci = fco[0][ii];
+        const double pfi = spf[0][ii];
         for (int jj = half * (PT / 2); jj < (half + 1) * (PT / 2); ++jj) {
           const int j = bj * PT + jj;
           if (j >= n || j <= i) continue;
@@ -414,18 +451,21 @@ __global__ void __launch_bounds__(PS_THREADS) pair_scan_kernel(WbkDev d, WbkIdx 
           if (dxi > 120) continue;  // hard-coded index units (streamer_index.py:157)
           const double cont = __dsub_rn(spf[1][jj], pfi);
           if (!(cont > prm.cont_dis)) continue;
-          const double dlat = fabs(__dsub_rn(lai, sla[1][jj]));
-          if (dlat * EARTH_R > prm.geo_dis * 1.000001) continue;  // d >= R * |dlat|
-          const double dist = hav_km(lai, loi, ci, sla[1][jj], slo[1][jj], sco[1][jj]);
-          if (!(dist < prm.geo_dis)) continue;
-          const int near = (fabs(dist - prm.geo_dis) <= 1e-9 * prm.geo_dis) || (fabs(cont - prm.cont_dis) <= 1e-9 * prm.cont_dis);
+          const float s0 = __sinf(0.5f * (lai - fla[1][jj])), s1 = __sinf(0.5f * (loi - flo[1][jj]));
+          const float h = s0 * s0 + ci * fco[1][jj] * s1 * s1;
+          if (h > h_hi) continue;
+          int near = fabs(cont - prm.cont_dis) <= 1e-9 * prm.cont_dis;
+          if (h >= h_lo) {  // inside the margin: the reference's fp64 expression decides
+            const double dist = hav_km(sla[0][ii], slo[0][ii], sco[0][ii], sla[1][jj], slo[1][jj], sco[1][jj]);
+            if (!(dist < prm.geo_dis)) continue;
+            near |= fabs(dist - prm.geo_dis) <= 1e-9 * prm.geo_dis;
+          }
           const int k = atomicAdd(&x.pair_count[slot], 1);
           if (k < x.PC) x.pairs[(size_t)slot * x.PC + k] = ((u64)(u32)i << 32) | ((u64)(u32)j << 1) | (u64)near;
         }
       }
     }
     __syncthreads();
-    (void)job;
   }
 }
 
@@ -493,6 +533,10 @@ __global__ void __launch_bounds__(ST_THREADS) streamer_cascade_kernel(WbkDev d, 
   const int nlon = d.nlon;
   __shared__ int sscan[40];
   __shared__ int s_nev;
+  WBK_DYN_SMEM(unsigned char, dsm);
+  u32* spts = reinterpret_cast<u32*>(dsm);                                   // [CS_PTS] contour points
+  int* sbb = reinterpret_cast<int*>(dsm + (size_t)CS_PTS * 4);               // [CS_PTS / 32][4] block boxes
+  u64* ssort = reinterpret_cast<u64*>(dsm + (size_t)CS_PTS * 4 + (size_t)(CS_PTS / 32) * 16);  // [CS_SORT]
   if (tid == 0) s_nev = 0;
   __syncthreads();
   u64* B = x.pairs_b + (size_t)job * x.PC;
@@ -508,18 +552,54 @@ __global__ void __launch_bounds__(ST_THREADS) streamer_cascade_kernel(WbkDev d, 
     const int slot = job * x.SC + si;
     const int c = x.sel[slot];
     const int base = ps.pt_off[c], n = ps.pt_off[c + 1] - base;
-    const u32* pts = ps.pts + base;
     int P = x.pair_count[slot];
     if (P > x.PC) {
       if (tid == 0) atomicOr(&d.status[job], (int)WBK_ST_PAIR_OVERFLOW);
       continue;  // uniform
     }
+    // stage the contour in shared memory (L2 latency would dominate the chord x segment tests) together with
+    // the bounding box of every run of 32 segments
+    const bool staged = n <= CS_PTS;
+    const u32* pts = ps.pts + base;
+    __syncthreads();
+    if (staged && P > 1) {
+      for (int k = tid; k < n; k += nt) spts[k] = pts[k];
+      __syncthreads();
+      const int nb = (n - 1 + 31) >> 5;
+      for (int bb = warp; bb < nb; bb += nwarps) {
+        const int k = bb * 32 + lane;
+        int x0 = 0x7fffffff, y0 = 0x7fffffff, x1 = -1, y1 = -1;
+        if (k < n) {
+          const u32 pp = spts[k];
+          x0 = x1 = wbk_px(pp);
+          y0 = y1 = wbk_py(pp);
+        }
+        if (lane == 0 && k + 32 < n) {  // the run's last segment ends at point k + 32
+          const u32 pp = spts[k + 32];
+          x0 = min(x0, wbk_px(pp)); x1 = max(x1, wbk_px(pp)); y0 = min(y0, wbk_py(pp)); y1 = max(y1, wbk_py(pp));
+        }
+        x0 = wbk_warp_min(x0); y0 = wbk_warp_min(y0); x1 = wbk_warp_max(x1); y1 = wbk_warp_max(y1);
+        if (lane == 0) {
+          sbb[4 * bb] = x0; sbb[4 * bb + 1] = y0; sbb[4 * bb + 2] = x1; sbb[4 * bb + 3] = y1;
+        }
+      }
+      __syncthreads();
+      pts = spts;
+    }
     u64* A = x.pairs + (size_t)slot * x.PC;
     // row-major order of np.nonzero: sort by (i, j)
     const u32 p2 = wbk_pow2_ceil((u32)(P > 0 ? P : 1));
-    for (u32 a = P + tid; a < p2; a += nt) A[a] = ~0ull;
-    __syncthreads();
-    wbk_block_bitonic_sort(A, p2);
+    if (p2 <= CS_SORT) {
+      for (u32 a = tid; a < p2; a += nt) ssort[a] = (int)a < P ? A[a] : ~0ull;
+      __syncthreads();
+      wbk_block_bitonic_sort(ssort, p2);
+      for (int a = tid; a < P; a += nt) A[a] = ssort[a];
+      __syncthreads();
+    } else {
+      for (u32 a = P + tid; a < p2; a += nt) A[a] = ~0ull;
+      __syncthreads();
+      wbk_block_bitonic_sort(A, p2);
+    }
     u64* cur = A;
     u64* oth = B;
 
@@ -559,17 +639,42 @@ __global__ void __launch_bounds__(ST_THREADS) streamer_cascade_kernel(WbkDev d, 
         const int px = wbk_px(pi), py = wbk_py(pi), qx = wbk_px(pj), qy = wbk_py(pj);
         const int bx0 = min(px, qx), bx1 = max(px, qx), by0 = min(py, qy), by1 = max(py, qy);
         int bad = 0;
-        for (int s0 = 0; s0 < n - 1; s0 += 32) {
-          const int s = s0 + lane;
-          if (s < n - 1) {
-            const u32 pa = pts[s], pb = pts[s + 1];
-            const int ax = wbk_px(pa), ay = wbk_py(pa), bx = wbk_px(pb), by = wbk_py(pb);
-            if (!(max(ax, bx) < bx0 || min(ax, bx) > bx1 || max(ay, by) < by0 || min(ay, by) > by1))
-              bad |= chord_violation(px, py, qx, qy, ax, ay, bx, by, e0x, e0y, e1x, e1y) ? 1 : 0;
+        if (staged) {
+          const int nb = (n - 1 + 31) >> 5;
+          for (int b0 = 0; b0 < nb && !bad; b0 += 32) {
+            const int bb = b0 + lane;
+            const bool hit = bb < nb && !(sbb[4 * bb + 2] < bx0 || sbb[4 * bb] > bx1 || sbb[4 * bb + 3] < by0 || sbb[4 * bb + 1] > by1);
+            u32 mask = __ballot_sync(WBK_FULL, hit);
+            while (mask) {
+              const int hb = b0 + __ffs((int)mask) - 1;
+              mask &= mask - 1;
+              const int s = hb * 32 + lane;
+              int v = 0;
+              if (s < n - 1) {
+                const u32 pa = pts[s], pb = pts[s + 1];
+                const int ax = wbk_px(pa), ay = wbk_py(pa), bx = wbk_px(pb), by = wbk_py(pb);
+                if (!(max(ax, bx) < bx0 || min(ax, bx) > bx1 || max(ay, by) < by0 || min(ay, by) > by1))
+                  v = chord_violation(px, py, qx, qy, ax, ay, bx, by, e0x, e0y, e1x, e1y) ? 1 : 0;
+              }
+              if (__any_sync(WBK_FULL, v)) {
+                bad = 1;
+                break;
+              }
+            }
           }
-          if (__any_sync(WBK_FULL, bad)) break;
+        } else {
+          for (int s0 = 0; s0 < n - 1; s0 += 32) {
+            const int s = s0 + lane;
+            if (s < n - 1) {
+              const u32 pa = pts[s], pb = pts[s + 1];
+              const int ax = wbk_px(pa), ay = wbk_py(pa), bx = wbk_px(pb), by = wbk_py(pb);
+              if (!(max(ax, bx) < bx0 || min(ax, bx) > bx1 || max(ay, by) < by0 || min(ay, by) > by1))
+                bad |= chord_violation(px, py, qx, qy, ax, ay, bx, by, e0x, e0y, e1x, e1y) ? 1 : 0;
+            }
+            if (__any_sync(WBK_FULL, bad)) break;
+          }
+          bad = __any_sync(WBK_FULL, bad);
         }
-        bad = __any_sync(WBK_FULL, bad);
         if (lane == 0) flag[a] = bad ? 0 : 1;
       }
       __syncthreads();
@@ -737,7 +842,8 @@ extern "C" int wbk_index_run(wbk_ctx* ctx, int njobs, int nlevels, const int* d_
     WBK_LAUNCH_CHECK();
     WBK_LAUNCH(KID_PAIR_SCAN, pair_scan_kernel, dim3(148 * 8), dim3(PS_THREADS), 0, st, d, x, ps, ct, (const double*)pfx, *prm, nslots);
     WBK_LAUNCH_CHECK();
-    WBK_LAUNCH(KID_CASCADE, streamer_cascade_kernel, dim3(njobs), dim3(ST_THREADS), 0, st, d, x, ps, (const double*)on, (const double*)pfx, J);
+    WBK_CUDA_CHECK(cudaFuncSetAttribute(streamer_cascade_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CS_SMEM));
+    WBK_LAUNCH(KID_CASCADE, streamer_cascade_kernel, dim3(njobs), dim3(ST_THREADS), CS_SMEM, st, d, x, ps, (const double*)on, (const double*)pfx, J);
     WBK_LAUNCH_CHECK();
   }
   return WBK_OK;

@@ -285,6 +285,304 @@ events_raster_kernel(WbkDev d, WbkIdx x, const int* __restrict__ job_off, const 
   }
 }
 
+// ------------------------------------------------------------------------------------------ meridian split
+// utils/index_utils.py:148-173 for the events that have vertices on both sides of the last meridian: the faces
+// of the ring left of x = nlon-1 and right of x = nlon are kept as separate pieces (no bridge edges between
+// faces: crossings on the cut line are sorted and paired, every chain of kept vertices is linked from its exit
+// crossing to the paired entry crossing), cut vertices are truncated to ints and x is folded with % nlon.
+// One thread per event (the work is sequential and tiny); pieces go to a vertex pool + ring list that
+// split_raster_kernel then rasterises into the flag grids.
+#define SPLIT_MAX_CHAINS 24
+
+struct SplitChain {
+  int off, cnt;            // vertices in the pool (chain scratch)
+  long long yin_n, yin_d;  // entry / exit ordinates on the cut line as exact fractions (den > 0)
+  long long yout_n, yout_d;
+};
+
+__device__ __forceinline__ bool frac_less(long long an, long long ad, long long bn, long long bd) {
+  return an * bd < bn * ad;
+}
+__device__ __forceinline__ bool frac_eq(long long an, long long ad, long long bn, long long bd) {
+  return an * bd == bn * ad;
+}
+
+// clip one ring against x = c keeping x <= c (keep_le) or x >= c; appends pieces to the ring list
+__device__ void split_clip_side(const RingView& rv, int c, bool keep_le, int nlon, int t, int kind, WbkIdx& x) {
+  const int n = rv.n;
+  int nin = 0;
+  for (int k = 0; k < n; ++k) {
+    int vx, vy;
+    rv.get(k, vx, vy);
+    nin += (keep_le ? vx <= c : vx >= c) ? 1 : 0;
+  }
+  if (nin == 0) return;
+  SplitChain ch[SPLIT_MAX_CHAINS];
+  int nch = 0;
+  // scratch space for the chains: at most n + 2 * chains vertices
+  const int scratch_cap = n + 2 * SPLIT_MAX_CHAINS;
+  const int sbase = atomicAdd(&x.split_count[0], scratch_cap);
+  if (sbase + scratch_cap > x.SPV) {
+    atomicExch(&x.split_count[2], 1);
+    return;
+  }
+  int* sxy = x.split_xy + 2 * (size_t)sbase;
+  int sp = 0;
+  auto inside = [&](int k) {
+    int vx, vy;
+    rv.get(k, vx, vy);
+    return keep_le ? vx <= c : vx >= c;
+  };
+  if (nin == n) {
+    ch[0].off = 0;
+    ch[0].cnt = n;
+    for (int k = 0; k < n; ++k) {
+      int vx, vy;
+      rv.get(k, vx, vy);
+      sxy[2 * k] = vx;
+      sxy[2 * k + 1] = vy;
+    }
+    nch = -1;  // whole ring
+  } else {
+    int start = 0;
+    for (int k = 0; k < n; ++k)
+      if (inside(k) && !inside(k == 0 ? n - 1 : k - 1)) {
+        start = k;
+        break;
+      }
+    int k = start, visited = 0;
+    while (visited < n) {
+      const int prev = k == 0 ? n - 1 : k - 1;
+      if (inside(k) && !inside(prev)) {
+        if (nch >= SPLIT_MAX_CHAINS) {
+          atomicExch(&x.split_count[2], 1);
+          return;
+        }
+        SplitChain& cc = ch[nch];
+        cc.off = sp;
+        int kx, ky, px, py;
+        rv.get(k, kx, ky);
+        rv.get(prev, px, py);
+        if (kx != c) {  // entry crossing strictly inside the edge prev -> k
+          long long den = (long long)kx - px, num = (long long)py * den + (long long)(c - px) * (ky - py);
+          if (den < 0) { den = -den; num = -num; }
+          cc.yin_n = num; cc.yin_d = den;
+          sxy[2 * sp] = c;
+          sxy[2 * sp + 1] = (int)(num >= 0 ? num / den : -((-num) / den));  // astype(int): truncation
+          ++sp;
+        } else {
+          cc.yin_n = ky; cc.yin_d = 1;
+        }
+        int j = k;
+        while (inside(j)) {
+          int jx, jy;
+          rv.get(j, jx, jy);
+          sxy[2 * sp] = jx;
+          sxy[2 * sp + 1] = jy;
+          ++sp;
+          j = j + 1 == n ? 0 : j + 1;
+          ++visited;
+        }
+        const int last = j == 0 ? n - 1 : j - 1;
+        int lx, ly, jx, jy;
+        rv.get(last, lx, ly);
+        rv.get(j, jx, jy);
+        if (lx != c) {
+          long long den = (long long)jx - lx, num = (long long)ly * den + (long long)(c - lx) * (jy - ly);
+          if (den < 0) { den = -den; num = -num; }
+          cc.yout_n = num; cc.yout_d = den;
+          sxy[2 * sp] = c;
+          sxy[2 * sp + 1] = (int)(num >= 0 ? num / den : -((-num) / den));
+          ++sp;
+        } else {
+          cc.yout_n = ly; cc.yout_d = 1;
+        }
+        cc.cnt = sp - cc.off;
+        ++nch;
+        k = j;
+      } else {
+        k = k + 1 == n ? 0 : k + 1;
+        ++visited;
+      }
+    }
+  }
+  // pair the crossings along the cut line (sorted by ordinate; ties: chain id, entry before exit)
+  int partner[SPLIT_MAX_CHAINS];
+  const int nchains = nch < 0 ? 1 : nch;
+  if (nch < 0) {
+    partner[0] = 0;
+  } else {
+    int ord[2 * SPLIT_MAX_CHAINS];  // crossing id = 2 * chain + type (0 entry, 1 exit)
+    const int nc = 2 * nch;
+    for (int i = 0; i < nc; ++i) {
+      const int id = i;
+      const long long yn = (id & 1) ? ch[id >> 1].yout_n : ch[id >> 1].yin_n;
+      const long long yd = (id & 1) ? ch[id >> 1].yout_d : ch[id >> 1].yin_d;
+      int pos = i;
+      while (pos > 0) {
+        const int o = ord[pos - 1];
+        const long long on = (o & 1) ? ch[o >> 1].yout_n : ch[o >> 1].yin_n;
+        const long long od = (o & 1) ? ch[o >> 1].yout_d : ch[o >> 1].yin_d;
+        bool less = frac_less(yn, yd, on, od);
+        if (!less && frac_eq(yn, yd, on, od)) less = id < o;  // (chain, type) order == id order
+        if (!less) break;
+        ord[pos] = o;
+        --pos;
+      }
+      ord[pos] = id;
+    }
+    bool ok = true;
+    for (int i = 0; i < nch; ++i) partner[i] = i;
+    for (int i = 0; i + 1 < nc; i += 2) {
+      const int a0 = ord[i], a1 = ord[i + 1];
+      if ((a0 & 1) == 1 && (a1 & 1) == 0) partner[a0 >> 1] = a1 >> 1;
+      else if ((a0 & 1) == 0 && (a1 & 1) == 1) partner[a1 >> 1] = a0 >> 1;
+      else { ok = false; break; }
+    }
+    if (!ok)
+      for (int i = 0; i < nch; ++i) partner[i] = i;  // non-simple ring: close every chain on itself
+  }
+  // faces
+  bool used[SPLIT_MAX_CHAINS];
+  for (int i = 0; i < nchains; ++i) used[i] = false;
+  for (int f0 = 0; f0 < nchains; ++f0) {
+    if (used[f0]) continue;
+    // pass 1: vertex count and exact-enough doubled area (cut ordinates as double fractions)
+    int cnt = 0;
+    double area2 = 0.0, fx = 0, fy = 0, px = 0, py = 0;
+    bool first = true;
+    int cur = f0;
+    int guard = 0;
+    while (guard++ <= nchains) {
+      for (int i = 0; i < ch[cur].cnt; ++i) {
+        double vx = (double)sxy[2 * (ch[cur].off + i)], vy = (double)sxy[2 * (ch[cur].off + i) + 1];
+        if (nch >= 0) {
+          if (i == 0 && ch[cur].yin_d != 1) vy = (double)ch[cur].yin_n / (double)ch[cur].yin_d;
+          if (i == ch[cur].cnt - 1 && ch[cur].yout_d != 1) vy = (double)ch[cur].yout_n / (double)ch[cur].yout_d;
+        }
+        if (first) { fx = vx; fy = vy; first = false; } else area2 += px * vy - vx * py;
+        px = vx; py = vy;
+        ++cnt;
+      }
+      cur = partner[cur];
+      if (cur == f0) break;
+    }
+    area2 += px * fy - fx * py;
+    // mark used
+    cur = f0;
+    guard = 0;
+    while (guard++ <= nchains) {
+      used[cur] = true;
+      cur = partner[cur];
+      if (cur == f0) break;
+    }
+    if (cnt < 3 || fabs(area2) < 1e-9) continue;
+    // pass 2: emit (fold x, drop consecutive repeats and a closing repeat)
+    const int obase = atomicAdd(&x.split_count[0], cnt);
+    const int ridx = atomicAdd(&x.split_count[1], 1);
+    if (obase + cnt > x.SPV || ridx >= x.SPR) {
+      atomicExch(&x.split_count[2], 1);
+      return;
+    }
+    int* oxy = x.split_xy + 2 * (size_t)obase;
+    int m = 0;
+    cur = f0;
+    guard = 0;
+    while (guard++ <= nchains) {
+      for (int i = 0; i < ch[cur].cnt; ++i) {
+        const int vx = sxy[2 * (ch[cur].off + i)] % nlon, vy = sxy[2 * (ch[cur].off + i) + 1];
+        if (m > 0 && oxy[2 * (m - 1)] == vx && oxy[2 * (m - 1) + 1] == vy) continue;
+        oxy[2 * m] = vx;
+        oxy[2 * m + 1] = vy;
+        ++m;
+      }
+      cur = partner[cur];
+      if (cur == f0) break;
+    }
+    if (m > 1 && oxy[0] == oxy[2 * (m - 1)] && oxy[1] == oxy[2 * (m - 1) + 1]) --m;
+    int* rr = x.split_ring + 4 * (size_t)ridx;
+    rr[0] = obase; rr[1] = m; rr[2] = t; rr[3] = kind;
+  }
+}
+
+__global__ void split_events_kernel(WbkDev d, WbkIdx x, const int* __restrict__ pt_off, const u32* __restrict__ pts,
+                                    int nlevels, int J, int njobs) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nlist = 3 * njobs;
+  if (w >= x.ev_off[nlist]) return;
+  int lo = 0, hi = nlist - 1;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (x.ev_off[mid] <= w) lo = mid; else hi = mid - 1;
+  }
+  const int kind = lo / njobs, job = lo - kind * njobs, e = w - x.ev_off[lo];
+  const int* ev = x.ev_int + (((size_t)kind * J + job) * x.EC + e) * WBK_EV_INTS;
+  if (ev[8] != 1) return;
+  RingView rv;
+  rv.xy = nullptr;
+  if (kind == WBK_EV_OVERTURNING) {
+    rv.packed = nullptr;
+    rv.bx0 = ev[3]; rv.by0 = ev[4]; rv.bx1 = ev[5]; rv.by1 = ev[6];
+    rv.n = 4;
+  } else {
+    rv.packed = pts + pt_off[ev[0]] + ev[1];
+    rv.n = ev[2] - ev[1] + 1;
+    rv.bx0 = rv.by0 = rv.bx1 = rv.by1 = 0;
+  }
+  const int t = job / nlevels;
+  split_clip_side(rv, d.nlon - 1, true, d.nlon, t, kind, x);
+  split_clip_side(rv, d.nlon, false, d.nlon, t, kind, x);
+}
+
+// rasterise the split pieces (real grid, r = 1/2 cell: processing/events.py:75-79) into the flag grids
+__global__ void __launch_bounds__(RS_THREADS)
+split_raster_kernel(WbkIdx x, int nlat, int nlon, int ntime, int8_t* __restrict__ flags, int rowcap) {
+  WBK_DYN_SMEM(int, sm);
+  __shared__ int s_box[4];
+  const int tid = threadIdx.x, lane = wbk_lane(), warp = wbk_warp(), nwarps = blockDim.x >> 5;
+  int* acc = sm + (size_t)warp * 2 * rowcap;
+  u32* flg = reinterpret_cast<u32*>(acc + rowcap);
+  const int nrings = min(x.split_count[1], x.SPR);
+  for (int r = blockIdx.x; r < nrings; r += gridDim.x) {
+    const int* rr = x.split_ring + 4 * (size_t)r;
+    RingView rv;
+    rv.packed = nullptr;
+    rv.xy = x.split_xy + 2 * (size_t)rr[0];
+    rv.n = rr[1];
+    rv.bx0 = rv.by0 = rv.bx1 = rv.by1 = 0;
+    const int t = rr[2], kind = rr[3];
+    if (tid == 0) {
+      s_box[0] = 0x7fffffff; s_box[1] = 0x7fffffff; s_box[2] = -1; s_box[3] = -1;
+    }
+    __syncthreads();
+    {
+      int x0 = 0x7fffffff, y0 = 0x7fffffff, x1 = -1, y1 = -1;
+      for (int k = tid; k < rv.n; k += blockDim.x) {
+        int vx, vy;
+        rv.get(k, vx, vy);
+        x0 = min(x0, vx); x1 = max(x1, vx); y0 = min(y0, vy); y1 = max(y1, vy);
+      }
+      x0 = wbk_warp_min(x0); y0 = wbk_warp_min(y0); x1 = wbk_warp_max(x1); y1 = wbk_warp_max(y1);
+      if (lane == 0) {
+        atomicMin(&s_box[0], x0); atomicMin(&s_box[1], y0); atomicMax(&s_box[2], x1); atomicMax(&s_box[3], y1);
+      }
+    }
+    __syncthreads();
+    const int bx0 = max(s_box[0] - 1, 0), bx1 = min(s_box[2] + 1, nlon - 1);
+    const int by0 = max(s_box[1] - 1, 0), by1 = min(s_box[3] + 1, nlat - 1);
+    const int bw = bx1 - bx0 + 1;
+    if (rv.n > 0 && bw > 0) {
+      for (int y = by0 + warp; y <= by1; y += nwarps) {
+        raster_scan_row(rv, y, bx0, bw, acc, flg, 0.25, 0.25, 0.5, 0);
+        for (int i = lane; i < bw; i += 32)
+          if (acc[i] != 0 || (flg[i] & 1u)) flags[(((size_t)kind * ntime + t) * nlat + y) * nlon + (bx0 + i)] = 1;
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+  }
+}
+
 static int raster_rowcap(int W) { return (W + 2 + 31) & ~31; }
 
 extern "C" int wbk_events_raster(wbk_ctx* ctx, const int* d_job_off, const int* d_pt_off, const uint32_t* d_pts,
@@ -332,6 +630,20 @@ extern "C" int wbk_events_raster(wbk_ctx* ctx, const int* d_job_off, const int* 
     return WBK_ERR_INVALID;
   }
   WBK_LAUNCH_CHECK();
+  if (d_flags) {
+    // events straddling the last meridian: clip on the device, rasterise the pieces
+    WBK_CUDA_CHECK(cudaMemsetAsync(ctx->x.split_count, 0, 16, st));
+    const int max_events = 3 * njobs * ctx->x.EC;
+    WBK_LAUNCH(KID_SPLIT, split_events_kernel, dim3((max_events + 127) / 128), dim3(128), 0, st, d, ctx->x, d_pt_off,
+               (const u32*)d_pts, ctx->nlevels, J, njobs);
+    WBK_LAUNCH_CHECK();
+    const int rc2 = raster_rowcap(d.nlon);
+    const size_t smem2 = (size_t)(RS_THREADS / 32) * 2 * rc2 * sizeof(int);
+    WBK_CUDA_CHECK(cudaFuncSetAttribute(split_raster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    WBK_LAUNCH(KID_SPLIT_RASTER, split_raster_kernel, dim3(148 * 2), dim3(RS_THREADS), smem2, st, ctx->x, d.nlat, d.nlon,
+               ntime, d_flags, rc2);
+    WBK_LAUNCH_CHECK();
+  }
   return WBK_OK;
 }
 

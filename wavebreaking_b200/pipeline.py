@@ -5,8 +5,8 @@ reference produces with
 ``calculate_smoothed_field`` -> ``calculate_contours`` -> ``calculate_streamers`` /
 ``calculate_overturnings`` / ``calculate_cutoffs`` -> ``to_xarray`` (x3):
 columnar event tables (host) and the three int8 flag grids.  All arithmetic runs in libwbk's
-CUDA kernels; the host only sizes buffers (two small device->host count reads per batch), clips the
-few events that straddle the last meridian and assembles the tables.
+CUDA kernels (including the meridian split of the events that straddle the date line); the host only
+sizes buffers (two small device->host count reads per batch) and receives the tables.
 """
 
 from dataclasses import dataclass, field
@@ -14,7 +14,7 @@ from dataclasses import dataclass, field
 import numpy as np
 import torch
 
-from . import _lib, detect, geometry, spatial
+from . import _lib, detect, spatial
 
 
 @dataclass
@@ -55,36 +55,8 @@ class Detector:
         g = cs.max_nx if gmax_nx is None else max(int(gmax_nx), cs.max_nx)
         tables, flags = detect.run_indices(cs, sm, self.coords, self.dlon, self.dlat, which=self.which, gmax_nx=g,
                                            want_flags=self.want_flags, **self.params)
-        n_split = 0
-        if self.want_flags:
-            n_split = self._rasterize_split(cs, tables, flags)
+        n_split = int(sum(int((t.split == 1).sum()) for t in tables.values()))
         return BatchResult(ntime=int(sm.shape[0]), contours=cs, tables=tables, flags=flags, gmax_nx=g, n_split=n_split)
-
-    def _rasterize_split(self, cs, tables, flags):
-        """Flags of the events that straddle the last meridian (index_utils.py:148-173, events.py:75-79)."""
-        nlev = cs.nlevels
-        n_split = 0
-        for kind_id, kind in enumerate(detect.KINDS):
-            tab = tables[kind]
-            idx = np.nonzero(tab.split == 1)[0]
-            if len(idx) == 0:
-                continue
-            n_split += len(idx)
-            h = cs.host()
-            rings, ts = [], []
-            for e in idx:
-                if kind == "overturnings":
-                    x0, y0, x1, y1 = (int(v) for v in tab.box[e])
-                    ring = np.array([[x1, y0], [x1, y1], [x0, y1], [x0, y0]], dtype=np.int64)
-                else:
-                    a = h["pt_off"][tab.contour[e]]
-                    ring = np.c_[h["x"][a + tab.ind1[e]: a + tab.ind2[e] + 1],
-                                 h["y"][a + tab.ind1[e]: a + tab.ind2[e] + 1]]
-                for piece in geometry.split_ring(ring, self.nlon):
-                    rings.append(piece)
-                    ts.append(int(tab.job[e]) // nlev)
-            detect.rasterize_rings(rings, ts, self.nlat, self.nlon, int(flags.shape[1]), 0.5, out_i8=flags[kind_id])
-        return n_split
 
     # ------------------------------------------------------------------ host input (end to end)
     def run_batch_host(self, raw_host, flags_host=None):
