@@ -134,7 +134,7 @@ __device__ __forceinline__ int ms_case_code(int c) {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(MS_THREADS)
+__global__ void __launch_bounds__(MS_THREADS, 4)
 ms_segments_kernel(const T* __restrict__ field, WbkDev d, LevelPack levels, int nlevels) {
   const int nlat = d.nlat, nlon = d.nlon, W = d.W;
   // every warp covers 31 base columns; lane 31 only supplies the right neighbour of lane 30 (so no thread
@@ -162,21 +162,23 @@ ms_segments_kernel(const T* __restrict__ field, WbkDev d, LevelPack levels, int 
     vals[i] = (loads && r <= r_end) ? src[(size_t)r * nlon + csrc] : (T)0;
   }
   double ul = (double)vals[0];
-  double ur = __shfl_down_sync(WBK_FULL, ul, 1);
 #pragma unroll
   for (int i = 0; i < MS_ROWS; ++i) {
     const int r0 = r_begin + i;
     if (r0 >= r_end) break;
     const double ll = (double)vals[i + 1];
-    const double lr = __shfl_down_sync(WBK_FULL, ll, 1);
-    const bool has_nan = isnan(ul) || isnan(ur) || isnan(ll) || isnan(lr);
+    const int nan_own = (isnan(ul) || isnan(ll)) ? 4 : 0;
     for (int l = 0; l < nlevels; ++l) {
       const double level = levels.v[l];
-      int sq = 0;
-      if (!has_nan && own_base) {
-        sq = (ul > level ? 1 : 0) | (ur > level ? 2 : 0) | (ll > level ? 4 : 0) | (lr > level ? 8 : 0);
-        if (sq == 15) sq = 0;
-      }
+      // common path on packed comparison bits only: bit0 upper > level, bit1 lower > level, bit2 NaN
+      const int m = (ul > level ? 1 : 0) | (ll > level ? 2 : 0) | nan_own;
+      const int mr = __shfl_down_sync(WBK_FULL, m, 1);
+      int sq = (m & 1) | ((mr & 1) << 1) | ((m & 2) << 1) | ((mr & 2) << 2);
+      if (((m | mr) & 4) || !own_base || sq == 15) sq = 0;
+      if (!__any_sync(WBK_FULL, sq != 0)) continue;
+      // rare path: this warp emits segments; fetch the right neighbours' values
+      const double ur = __shfl_down_sync(WBK_FULL, ul, 1);
+      const double lr = __shfl_down_sync(WBK_FULL, ll, 1);
       const int code = ms_case_code(sq);
       const int nseg = code >> 8;
       const int ncopy = own_ext ? 2 : 1;
@@ -229,7 +231,6 @@ ms_segments_kernel(const T* __restrict__ field, WbkDev d, LevelPack levels, int 
       if (lattice) atomicOr(&d.status[job], (int)WBK_ST_LATTICE_VERTEX);
     }
     ul = ll;
-    ur = lr;
   }
 }
 

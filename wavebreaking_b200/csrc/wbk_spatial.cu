@@ -21,115 +21,136 @@ __device__ __forceinline__ int wrap_idx(int i, int n) {
 
 // x / 6 correctly rounded without the generic division sequence: q = RN(x * RN(1/6)), exact remainder by FMA,
 // one correction step (Markstein: with a correctly rounded reciprocal the corrected quotient is RN(x / 6)).
-// Checked against 1.5e9 random operands on the host; operands near the overflow / underflow range and
-// non-finite values take the plain division.
-__device__ __forceinline__ double div6(double x) {
-  const double ax = fabs(x);
-  if (ax < 1e290 && ax > 1e-290) {
-    const double R6 = 0.16666666666666666;  // RN(1/6) = 0x3FC5555555555555
-    const double q = __dmul_rn(x, R6);
-    const double r = __fma_rn(-6.0, q, x);
-    return __fma_rn(r, R6, q);
-  }
-  return __ddiv_rn(x, 6.0);
+// Checked against 1.5e9 random operands on the host.  Valid for finite operands whose quotient is a normal
+// number (or zero); a tile that holds anything else (NaN, Inf, |v| < 1e-150 or > 1e290) takes the plain division.
+__device__ __forceinline__ double div6_fast(double x) {
+  const double R6 = 0.16666666666666666;  // RN(1/6) = 0x3FC5555555555555
+  const double q = __dmul_rn(x, R6);
+  const double r = __fma_rn(-6.0, q, x);
+  return __fma_rn(r, R6, q);
 }
 
-// Thread layout: the (SM_TH + 2p) x (SM_TW + 2p) tile is split into column PAIRS x row BANDS; a thread walks
-// down its band with a sliding (north, centre, south) register window, so every cell update costs one
-// 128-bit and two 64-bit shared loads (instead of five) and one 128-bit store.
-template <typename TIn, typename TOut>
+// rounding of one pass: 0 none (float64), 1 sum rounded to float32 then float64 division (NumPy >= 2, first pass
+// of float32 data), 2 sum rounded to float32 and float32 division (NumPy 1.x, every pass)
+template <int RND, bool SAFE>
+__device__ __forceinline__ double smooth_finish(double v) {
+  if (RND == 2) return (double)(__double2float_rn(v) / 6.0f);
+  if (RND == 1) v = (double)__double2float_rn(v);
+  return SAFE ? div6_fast(v) : __ddiv_rn(v, 6.0);
+}
+
+// One pass over rows [K, H-K) of the shared tile: column pairs x row bands, sliding (north, centre, south)
+// register window -> one 128-bit + two 64-bit shared loads and one 128-bit store per pair of cell updates.
+template <int P, int K, int RND, bool SAFE>
+__device__ __forceinline__ void smooth_pass(const double* __restrict__ a, double* __restrict__ b) {
+  constexpr int H = SM_TH + 2 * P, Wd = SM_TW + 2 * P;
+  constexpr int NPAIRS = Wd / 2, NBANDS = SM_THREADS / NPAIRS;
+  constexpr int NROWS = H - 2 * K, PER = (NROWS + NBANDS - 1) / NBANDS;
+  const int pair = threadIdx.x % NPAIRS, band = threadIdx.x / NPAIRS;
+  const int c0 = 2 * pair;
+  const int cw = c0 > 0 ? c0 - 1 : 0;           // clamped: edge columns are never valid outputs
+  const int ce = c0 + 2 < Wd ? c0 + 2 : Wd - 1;
+  const int r_lo = K + band * PER;
+  if (band >= NBANDS || r_lo >= K + NROWS) return;
+  const int r_hi = r_lo + PER < K + NROWS ? r_lo + PER : K + NROWS;
+  const double* pc = a + r_lo * Wd + c0;
+  const double* pw = a + r_lo * Wd + cw;
+  const double* pe = a + r_lo * Wd + ce;
+  double* po = b + r_lo * Wd + c0;
+  double2 n2 = *reinterpret_cast<const double2*>(pc - Wd);
+  double2 c2 = *reinterpret_cast<const double2*>(pc);
+#pragma unroll 2
+  for (int r = r_lo; r < r_hi; ++r) {
+    const double2 s2 = *reinterpret_cast<const double2*>(pc + Wd);
+    const double wv = *pw, ev = *pe;
+    // scipy's tap order: ((((N + W) + 2C) + E) + S)
+    double v0 = __dadd_rn(n2.x, wv);
+    v0 = __dadd_rn(v0, __dadd_rn(c2.x, c2.x));
+    v0 = __dadd_rn(v0, c2.y);
+    v0 = __dadd_rn(v0, s2.x);
+    double v1 = __dadd_rn(n2.y, c2.x);
+    v1 = __dadd_rn(v1, __dadd_rn(c2.y, c2.y));
+    v1 = __dadd_rn(v1, ev);
+    v1 = __dadd_rn(v1, s2.y);
+    double2 o;
+    o.x = smooth_finish<RND, SAFE>(v0);
+    o.y = smooth_finish<RND, SAFE>(v1);
+    *reinterpret_cast<double2*>(po) = o;
+    n2 = c2;
+    c2 = s2;
+    pc += Wd; pw += Wd; pe += Wd; po += Wd;
+  }
+}
+
+template <int P, int RFIRST, int RREST, bool SAFE>
+__device__ __forceinline__ void smooth_all_passes(double*& a, double*& b) {
+  // unrolled at compile time (P <= WBK_SMOOTH_MAX_FUSED)
+#define WBK_PASS(K)                                                             \
+  if (P >= K) {                                                                 \
+    if (K == 1) smooth_pass<P, (K <= P ? K : 1), RFIRST, SAFE>(a, b);           \
+    else smooth_pass<P, (K <= P ? K : 1), RREST, SAFE>(a, b);                   \
+    __syncthreads();                                                            \
+    double* t_ = a; a = b; b = t_;                                              \
+  }
+  WBK_PASS(1) WBK_PASS(2) WBK_PASS(3) WBK_PASS(4) WBK_PASS(5) WBK_PASS(6) WBK_PASS(7) WBK_PASS(8)
+#undef WBK_PASS
+}
+
+// RMODE: WBK_ROUND_NONE / WBK_ROUND_FIRST (applies to the first pass of this launch) / WBK_ROUND_ALL
+template <int P, typename TIn, typename TOut, int RMODE>
 __global__ void __launch_bounds__(SM_THREADS)
-smooth_fused_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, int nlat, int nlon, int passes,
-                    int round_first, int round_all, int nan_border) {
+smooth_fused_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, int nlat, int nlon, int nan_border) {
   WBK_DYN_SMEM(double, smem);
-  const int p = passes;
-  const int H = SM_TH + 2 * p;
-  const int Wd = SM_TW + 2 * p;  // even
-  const int pitch = Wd;          // even: column pairs stay 16-byte aligned
+  constexpr int H = SM_TH + 2 * P, Wd = SM_TW + 2 * P;
   double* a = smem;
-  double* b = smem + (size_t)H * pitch;
+  double* b = smem + H * Wd;
 
   const int x0 = blockIdx.x * SM_TW, y0 = blockIdx.y * SM_TH;
   const size_t plane = (size_t)nlat * nlon;
   const TIn* src = in + plane * blockIdx.z;
   TOut* dst = out + plane * blockIdx.z;
-  const int lane = wbk_lane(), warp = wbk_warp(), nwarps = SM_THREADS / 32;
 
-  // load tile + halo (wrapping both axes): one warp per row, lanes along the row (coalesced)
-  for (int r = warp; r < H; r += nwarps) {
-    int gy = y0 - p + r;
+  // load tile + halo (wrapping both axes); all loads of a thread are issued before the first use
+  constexpr int NLOAD = (H * Wd + SM_THREADS - 1) / SM_THREADS;
+  TIn tmp[NLOAD];
+#pragma unroll
+  for (int i = 0; i < NLOAD; ++i) {
+    const int idx = threadIdx.x + i * SM_THREADS;
+    const int r = idx / Wd, c = idx - r * Wd;
+    int gy = y0 - P + r, gx = x0 - P + c;
     gy = gy < 0 ? gy + nlat : (gy >= nlat ? gy - nlat : gy);
-    if (gy < 0 || gy >= nlat) gy = wrap_idx(y0 - p + r, nlat);
-    const TIn* row = src + (size_t)gy * nlon;
-    for (int c = lane; c < Wd; c += 32) {
-      int gx = x0 - p + c;
-      gx = gx < 0 ? gx + nlon : (gx >= nlon ? gx - nlon : gx);
-      if (gx < 0 || gx >= nlon) gx = wrap_idx(x0 - p + c, nlon);
-      a[r * pitch + c] = (double)row[gx];
-    }
+    gx = gx < 0 ? gx + nlon : (gx >= nlon ? gx - nlon : gx);
+    if (gy < 0 || gy >= nlat) gy = wrap_idx(y0 - P + r, nlat);
+    if (gx < 0 || gx >= nlon) gx = wrap_idx(x0 - P + c, nlon);
+    tmp[i] = idx < H * Wd ? src[(size_t)gy * nlon + gx] : (TIn)0;
   }
-  __syncthreads();
-
-  const int npairs = Wd >> 1;
-  const int nbands = SM_THREADS / npairs;
-  const int pair = threadIdx.x % npairs, band = threadIdx.x / npairs;
-  const int c0 = 2 * pair;
-  const int cw = c0 > 0 ? c0 - 1 : 0;            // clamped west / east columns (edge columns are never valid)
-  const int ce = c0 + 2 < Wd ? c0 + 2 : Wd - 1;
-  for (int k = 1; k <= p; ++k) {
-    const bool rnd = round_all || (round_first && k == 1);
-    // rows [k, H - k) of this pass, split evenly over the bands
-    const int nrows = H - 2 * k;
-    const int per = (nrows + nbands - 1) / nbands;
-    const int r_lo = k + band * per, r_hi = min(k + nrows, r_lo + per);
-    if (band < nbands && r_lo < r_hi) {
-      double2 n2 = *reinterpret_cast<const double2*>(a + (r_lo - 1) * pitch + c0);
-      double2 c2 = *reinterpret_cast<const double2*>(a + r_lo * pitch + c0);
-      for (int r = r_lo; r < r_hi; ++r) {
-        const double* rowp = a + r * pitch;
-        const double2 s2 = *reinterpret_cast<const double2*>(rowp + pitch + c0);
-        const double wv = rowp[cw], ev = rowp[ce];
-        // scipy's tap order: ((((N + W) + 2C) + E) + S)
-        double v0 = __dadd_rn(n2.x, wv);
-        v0 = __dadd_rn(v0, __dadd_rn(c2.x, c2.x));
-        v0 = __dadd_rn(v0, c2.y);
-        v0 = __dadd_rn(v0, s2.x);
-        double v1 = __dadd_rn(n2.y, c2.x);
-        v1 = __dadd_rn(v1, __dadd_rn(c2.y, c2.y));
-        v1 = __dadd_rn(v1, ev);
-        v1 = __dadd_rn(v1, s2.y);
-        double2 o;
-        if (round_all) {
-          o.x = (double)(__double2float_rn(v0) / 6.0f);
-          o.y = (double)(__double2float_rn(v1) / 6.0f);
-        } else {
-          if (rnd) {
-            v0 = (double)__double2float_rn(v0);
-            v1 = (double)__double2float_rn(v1);
-          }
-          o.x = div6(v0);
-          o.y = div6(v1);
-        }
-        *reinterpret_cast<double2*>(b + r * pitch + c0) = o;
-        n2 = c2;
-        c2 = s2;
-      }
-    }
-    __syncthreads();
-    double* t = a;
-    a = b;
-    b = t;
+  int unsafe = 0;
+#pragma unroll
+  for (int i = 0; i < NLOAD; ++i) {
+    const int idx = threadIdx.x + i * SM_THREADS;
+    const double v = (double)tmp[i];
+    const double av = fabs(v);
+    unsafe |= !(av <= 1e290) || (av < 1e-150 && av != 0.0);
+    if (idx < H * Wd) a[idx] = v;
   }
+  const int slow = __syncthreads_or(unsafe);  // also the barrier after the tile load
 
-  // write the inner tile: one warp per row, two columns per lane
-  for (int r = warp; r < SM_TH; r += nwarps) {
+  constexpr int RFIRST = RMODE == WBK_ROUND_ALL ? 2 : (RMODE == WBK_ROUND_FIRST ? 1 : 0);
+  constexpr int RREST = RMODE == WBK_ROUND_ALL ? 2 : 0;
+  if (!slow) smooth_all_passes<P, RFIRST, RREST, true>(a, b);
+  else smooth_all_passes<P, RFIRST, RREST, false>(a, b);
+
+  // write the inner tile: one warp per row (coalesced)
+  const int lane = wbk_lane(), warp = wbk_warp();
+  for (int r = warp; r < SM_TH; r += SM_THREADS / 32) {
     const int gy = y0 + r;
     if (gy >= nlat) break;
     const bool nanrow = nan_border > 0 && (gy < nan_border || gy >= nlat - nan_border);
+#pragma unroll
     for (int c = lane; c < SM_TW; c += 32) {
       const int gx = x0 + c;
       if (gx < nlon) {
-        double v = a[(r + p) * pitch + (c + p)];
+        double v = a[(r + P) * Wd + (c + P)];
         if (nanrow) v = __longlong_as_double(0x7ff8000000000000LL);
         dst[(size_t)gy * nlon + gx] = (TOut)v;
       }
@@ -142,17 +163,41 @@ static size_t smooth_smem_bytes(int passes) {
   return (size_t)2 * H * Wd * sizeof(double);
 }
 
+template <int P, typename TIn, typename TOut, int RMODE>
+static int launch_smooth_p(const void* in, void* out, int ntime, int nlat, int nlon, int nan_border, cudaStream_t st) {
+  size_t smem = smooth_smem_bytes(P);
+  WBK_CUDA_CHECK(cudaFuncSetAttribute(smooth_fused_kernel<P, TIn, TOut, RMODE>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((nlon + SM_TW - 1) / SM_TW, (nlat + SM_TH - 1) / SM_TH, ntime);
+  WBK_LAUNCH(KID_SMOOTH, (smooth_fused_kernel<P, TIn, TOut, RMODE>), grid, dim3(SM_THREADS), smem, st, (const TIn*)in,
+             (TOut*)out, nlat, nlon, nan_border);
+  WBK_LAUNCH_CHECK();
+  return WBK_OK;
+}
+
+template <typename TIn, typename TOut, int RMODE>
+static int launch_smooth_mode(const void* in, void* out, int ntime, int nlat, int nlon, int passes, int nan_border,
+                              cudaStream_t st) {
+  switch (passes) {
+    case 1: return launch_smooth_p<1, TIn, TOut, RMODE>(in, out, ntime, nlat, nlon, nan_border, st);
+    case 2: return launch_smooth_p<2, TIn, TOut, RMODE>(in, out, ntime, nlat, nlon, nan_border, st);
+    case 3: return launch_smooth_p<3, TIn, TOut, RMODE>(in, out, ntime, nlat, nlon, nan_border, st);
+    case 4: return launch_smooth_p<4, TIn, TOut, RMODE>(in, out, ntime, nlat, nlon, nan_border, st);
+    case 5: return launch_smooth_p<5, TIn, TOut, RMODE>(in, out, ntime, nlat, nlon, nan_border, st);
+    case 6: return launch_smooth_p<6, TIn, TOut, RMODE>(in, out, ntime, nlat, nlon, nan_border, st);
+    case 7: return launch_smooth_p<7, TIn, TOut, RMODE>(in, out, ntime, nlat, nlon, nan_border, st);
+    case 8: return launch_smooth_p<8, TIn, TOut, RMODE>(in, out, ntime, nlat, nlon, nan_border, st);
+  }
+  wbk_set_error("wbk_smooth: internal pass count %d", passes);
+  return WBK_ERR_INVALID;
+}
+
 template <typename TIn, typename TOut>
 static int launch_smooth(const void* in, void* out, int ntime, int nlat, int nlon, int passes, int round_first,
                          int round_all, int nan_border, cudaStream_t st) {
-  size_t smem = smooth_smem_bytes(passes);
-  WBK_CUDA_CHECK(cudaFuncSetAttribute(smooth_fused_kernel<TIn, TOut>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem));
-  dim3 grid((nlon + SM_TW - 1) / SM_TW, (nlat + SM_TH - 1) / SM_TH, ntime);
-  WBK_LAUNCH(KID_SMOOTH, (smooth_fused_kernel<TIn, TOut>), grid, dim3(SM_THREADS), smem, st, (const TIn*)in, (TOut*)out, nlat,
-             nlon, passes, round_first, round_all, nan_border);
-  WBK_LAUNCH_CHECK();
-  return WBK_OK;
+  if (round_all) return launch_smooth_mode<TIn, TOut, WBK_ROUND_ALL>(in, out, ntime, nlat, nlon, passes, nan_border, st);
+  if (round_first) return launch_smooth_mode<TIn, TOut, WBK_ROUND_FIRST>(in, out, ntime, nlat, nlon, passes, nan_border, st);
+  return launch_smooth_mode<TIn, TOut, WBK_ROUND_NONE>(in, out, ntime, nlat, nlon, passes, nan_border, st);
 }
 
 extern "C" int wbk_smooth(const void* d_in, int in_dtype, void* d_out, int out_dtype, void* d_tmp, int ntime,
