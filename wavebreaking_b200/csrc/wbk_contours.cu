@@ -133,9 +133,66 @@ __device__ __forceinline__ int ms_case_code(int c) {
   }
 }
 
+// Rare path of the marching-squares kernel (a warp in which at least one lane found a contour square): builds
+// the segments exactly as skimage does and appends them to the job's arena.  Called warp-uniformly.
+__device__ __noinline__ void ms_emit(const WbkDev& d, int job, int r0, int c0, int sq, bool own_ext, double ul, double ur,
+                                     double ll, double lr, double level) {
+  const int lane = wbk_lane();
+  const int W = d.W, nlon = d.nlon;
+  const int code = ms_case_code(sq);
+  const int nseg = code >> 8;
+  const int ncopy = own_ext ? 2 : 1;
+  const int nemit = nseg * ncopy;
+  // warp-aggregated slot allocation
+  int incl = wbk_warp_incl_scan(nemit);
+  int total = __shfl_sync(WBK_FULL, incl, 31);
+  int base = 0;
+  if (lane == 31) base = atomicAdd(&d.seg_count[job], total);
+  base = __shfl_sync(WBK_FULL, base, 31);
+  if (nemit == 0) return;
+  int slot = base + incl - nemit;
+  // edge fractions (identical expression from both squares sharing an edge)
+  const double ft = ms_fraction(ul, ur, level), fb = ms_fraction(ll, lr, level);
+  const double fl = ms_fraction(ul, ll, level), fr = ms_fraction(ur, lr, level);
+  bool lattice = false;
+  for (int copy = 0; copy < ncopy; ++copy) {
+    const int cc = c0 + copy * nlon;  // column of the square on the extended grid
+    // float coordinates exactly as skimage builds them, then np.round (half to even)
+    const double xt = __dadd_rn((double)cc, ft), xb = __dadd_rn((double)cc, fb);
+    const double yl = __dadd_rn((double)r0, fl), yr = __dadd_rn((double)r0, fr);
+    u32 pid[4], pxy[4];
+    pid[0] = 2u * (u32)(r0 * W + cc);             // top: horizontal edge (r0, cc)
+    pid[1] = 2u * (u32)((r0 + 1) * W + cc);       // bottom: horizontal edge (r0+1, cc)
+    pid[2] = 2u * (u32)(r0 * W + cc) + 1u;        // left: vertical edge (r0, cc)
+    pid[3] = 2u * (u32)(r0 * W + cc + 1) + 1u;    // right: vertical edge (r0, cc+1)
+    pxy[0] = wbk_pack_xy((int)rint(xt), r0);
+    pxy[1] = wbk_pack_xy((int)rint(xb), r0 + 1);
+    pxy[2] = wbk_pack_xy(cc, (int)rint(yl));
+    pxy[3] = wbk_pack_xy(cc + 1, (int)rint(yr));
+    const bool vt = xt == rint(xt), vb = xb == rint(xb), vl = yl == rint(yl), vr = yr == rint(yr);
+    for (int s = 0; s < nseg; ++s) {
+      const int fe = (code >> (4 * s)) & 3, te = (code >> (4 * s + 2)) & 3;
+      const bool lf = fe == 0 ? vt : fe == 1 ? vb : fe == 2 ? vl : vr;
+      const bool lt = te == 0 ? vt : te == 1 ? vb : te == 2 ? vl : vr;
+      lattice = lattice || lf || lt;
+      if (slot < d.S) {
+        const size_t o = (size_t)job * d.S + slot;
+        d.rid[o] = 2u * (u32)(r0 * (W - 1) + cc) + (u32)s;
+        d.fpid[o] = pid[fe];
+        d.tpid[o] = pid[te];
+        d.fxy[o] = pxy[fe];
+        d.txy[o] = pxy[te];
+      }
+      ++slot;
+    }
+  }
+  if (lattice) atomicOr(&d.status[job], (int)WBK_ST_LATTICE_VERTEX);
+}
+
 template <typename T>
-__global__ void __launch_bounds__(MS_THREADS, 4)
-ms_segments_kernel(const T* __restrict__ field, WbkDev d, LevelPack levels, int nlevels) {
+__global__ void __launch_bounds__(MS_THREADS, 3)
+ms_segments_kernel(const T* __restrict__ field, const __grid_constant__ WbkDev d, const __grid_constant__ LevelPack levels,
+                   int nlevels) {
   const int nlat = d.nlat, nlon = d.nlon, W = d.W;
   // every warp covers 31 base columns; lane 31 only supplies the right neighbour of lane 30 (so no thread
   // needs a second, uncoalesced load) -- column nlon wraps to column 0 (periodic extension)
@@ -161,76 +218,34 @@ ms_segments_kernel(const T* __restrict__ field, WbkDev d, LevelPack levels, int 
     const int r = r_begin + i;
     vals[i] = (loads && r <= r_end) ? src[(size_t)r * nlon + csrc] : (T)0;
   }
-  double ul = (double)vals[0];
+  for (int l = 0; l < nlevels; ++l) {
+    const double level = levels.v[l];
+    const T tl = (T)level;
+    const bool exact_level = (double)tl == level;  // compare in T when the level is representable (always for f64)
+    const int job = t * nlevels + l;
+    // packed comparison bits of the own column: bit0 value > level, bit2 NaN
+    int mu = 0;
+    {
+      const T v = vals[0];
+      mu = ((exact_level ? v > tl : (double)v > level) ? 1 : 0) | (v != v ? 4 : 0);
+    }
 #pragma unroll
-  for (int i = 0; i < MS_ROWS; ++i) {
-    const int r0 = r_begin + i;
-    if (r0 >= r_end) break;
-    const double ll = (double)vals[i + 1];
-    const int nan_own = (isnan(ul) || isnan(ll)) ? 4 : 0;
-    for (int l = 0; l < nlevels; ++l) {
-      const double level = levels.v[l];
-      // common path on packed comparison bits only: bit0 upper > level, bit1 lower > level, bit2 NaN
-      const int m = (ul > level ? 1 : 0) | (ll > level ? 2 : 0) | nan_own;
+    for (int i = 0; i < MS_ROWS; ++i) {
+      const int r0 = r_begin + i;
+      const T v = vals[i + 1];
+      const int ml = ((exact_level ? v > tl : (double)v > level) ? 1 : 0) | (v != v ? 4 : 0);
+      const int m = mu | (ml << 1);  // bit0 upper, bit1 lower, bits 2/3 NaN
       const int mr = __shfl_down_sync(WBK_FULL, m, 1);
       int sq = (m & 1) | ((mr & 1) << 1) | ((m & 2) << 1) | ((mr & 2) << 2);
-      if (((m | mr) & 4) || !own_base || sq == 15) sq = 0;
-      if (!__any_sync(WBK_FULL, sq != 0)) continue;
-      // rare path: this warp emits segments; fetch the right neighbours' values
-      const double ur = __shfl_down_sync(WBK_FULL, ul, 1);
-      const double lr = __shfl_down_sync(WBK_FULL, ll, 1);
-      const int code = ms_case_code(sq);
-      const int nseg = code >> 8;
-      const int ncopy = own_ext ? 2 : 1;
-      const int nemit = nseg * ncopy;
-      if (!__any_sync(WBK_FULL, nemit > 0)) continue;
-      // warp-aggregated slot allocation
-      const int job = t * nlevels + l;
-      int incl = wbk_warp_incl_scan(nemit);
-      int total = __shfl_sync(WBK_FULL, incl, 31);
-      int base = 0;
-      if (lane == 31) base = atomicAdd(&d.seg_count[job], total);
-      base = __shfl_sync(WBK_FULL, base, 31);
-      if (nemit == 0) continue;
-      int slot = base + incl - nemit;
-      // edge fractions (computed once; identical expression from both squares sharing an edge)
-      const double ft = ms_fraction(ul, ur, level), fb = ms_fraction(ll, lr, level);
-      const double fl = ms_fraction(ul, ll, level), fr = ms_fraction(ur, lr, level);
-      bool lattice = false;
-      for (int copy = 0; copy < ncopy; ++copy) {
-        const int cc = c0 + copy * nlon;  // column of the square on the extended grid
-        // float coordinates exactly as skimage builds them, then np.round (half to even)
-        const double xt = __dadd_rn((double)cc, ft), xb = __dadd_rn((double)cc, fb);
-        const double yl = __dadd_rn((double)r0, fl), yr = __dadd_rn((double)r0, fr);
-        u32 pid[4], pxy[4];
-        pid[0] = 2u * (u32)(r0 * W + cc);             // top: horizontal edge (r0, cc)
-        pid[1] = 2u * (u32)((r0 + 1) * W + cc);       // bottom: horizontal edge (r0+1, cc)
-        pid[2] = 2u * (u32)(r0 * W + cc) + 1u;        // left: vertical edge (r0, cc)
-        pid[3] = 2u * (u32)(r0 * W + cc + 1) + 1u;    // right: vertical edge (r0, cc+1)
-        pxy[0] = wbk_pack_xy((int)rint(xt), r0);
-        pxy[1] = wbk_pack_xy((int)rint(xb), r0 + 1);
-        pxy[2] = wbk_pack_xy(cc, (int)rint(yl));
-        pxy[3] = wbk_pack_xy(cc + 1, (int)rint(yr));
-        const bool vt = xt == rint(xt), vb = xb == rint(xb), vl = yl == rint(yl), vr = yr == rint(yr);
-        for (int s = 0; s < nseg; ++s) {
-          const int fe = (code >> (4 * s)) & 3, te = (code >> (4 * s + 2)) & 3;
-          const bool lf = fe == 0 ? vt : fe == 1 ? vb : fe == 2 ? vl : vr;
-          const bool lt = te == 0 ? vt : te == 1 ? vb : te == 2 ? vl : vr;
-          lattice = lattice || lf || lt;
-          if (slot < d.S) {
-            const size_t o = (size_t)job * d.S + slot;
-            d.rid[o] = 2u * (u32)(r0 * (W - 1) + cc) + (u32)s;
-            d.fpid[o] = pid[fe];
-            d.tpid[o] = pid[te];
-            d.fxy[o] = pxy[fe];
-            d.txy[o] = pxy[te];
-          }
-          ++slot;
-        }
+      if (((m | mr) & 12) || !own_base || sq == 15 || r0 >= r_end) sq = 0;
+      if (__any_sync(WBK_FULL, sq != 0)) {
+        const double ul = (double)vals[i], ll = (double)v;
+        const double ur = __shfl_down_sync(WBK_FULL, ul, 1);
+        const double lr = __shfl_down_sync(WBK_FULL, ll, 1);
+        ms_emit(d, job, r0, c0, sq, own_ext, ul, ur, ll, lr, level);
       }
-      if (lattice) atomicOr(&d.status[job], (int)WBK_ST_LATTICE_VERTEX);
+      mu = ml;
     }
-    ul = ll;
   }
 }
 

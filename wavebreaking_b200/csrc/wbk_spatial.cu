@@ -59,26 +59,28 @@ __device__ __forceinline__ void smooth_pass(const double* __restrict__ a, double
   double* po = b + r_lo * Wd + c0;
   double2 n2 = *reinterpret_cast<const double2*>(pc - Wd);
   double2 c2 = *reinterpret_cast<const double2*>(pc);
-#pragma unroll 2
-  for (int r = r_lo; r < r_hi; ++r) {
-    const double2 s2 = *reinterpret_cast<const double2*>(pc + Wd);
-    const double wv = *pw, ev = *pe;
-    // scipy's tap order: ((((N + W) + 2C) + E) + S)
-    double v0 = __dadd_rn(n2.x, wv);
-    v0 = __dadd_rn(v0, __dadd_rn(c2.x, c2.x));
-    v0 = __dadd_rn(v0, c2.y);
-    v0 = __dadd_rn(v0, s2.x);
-    double v1 = __dadd_rn(n2.y, c2.x);
-    v1 = __dadd_rn(v1, __dadd_rn(c2.y, c2.y));
-    v1 = __dadd_rn(v1, ev);
-    v1 = __dadd_rn(v1, s2.y);
-    double2 o;
-    o.x = smooth_finish<RND, SAFE>(v0);
-    o.y = smooth_finish<RND, SAFE>(v1);
-    *reinterpret_cast<double2*>(po) = o;
-    n2 = c2;
-    c2 = s2;
-    pc += Wd; pw += Wd; pe += Wd; po += Wd;
+  // fully unrolled (PER is a compile-time constant): constant address offsets, no register shuffling
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    if (r_lo + i < r_hi) {
+      const double2 s2 = *reinterpret_cast<const double2*>(pc + (i + 1) * Wd);
+      const double wv = pw[i * Wd], ev = pe[i * Wd];
+      // scipy's tap order: ((((N + W) + 2C) + E) + S)
+      double v0 = __dadd_rn(n2.x, wv);
+      v0 = __dadd_rn(v0, __dadd_rn(c2.x, c2.x));
+      v0 = __dadd_rn(v0, c2.y);
+      v0 = __dadd_rn(v0, s2.x);
+      double v1 = __dadd_rn(n2.y, c2.x);
+      v1 = __dadd_rn(v1, __dadd_rn(c2.y, c2.y));
+      v1 = __dadd_rn(v1, ev);
+      v1 = __dadd_rn(v1, s2.y);
+      double2 o;
+      o.x = smooth_finish<RND, SAFE>(v0);
+      o.y = smooth_finish<RND, SAFE>(v1);
+      *reinterpret_cast<double2*>(po + i * Wd) = o;
+      n2 = c2;
+      c2 = s2;
+    }
   }
 }
 
