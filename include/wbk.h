@@ -215,6 +215,13 @@ const char* wbk_prof_name(int k);
 /* total number of kernel launches issued by the library in this process (always counted) */
 long long wbk_launch_count(void);
 
+/* wavebreaking/processing/events.py:205-214 track_events(method="by_overlap"): areas of event pairs.
+ * Polygons are given as rings of double (x, y) vertices: polygon p = rings [d_poly_off[p], d_poly_off[p+1]),
+ * ring r = vertices [d_ring_off[r], d_ring_off[r+1]) of d_xy (open rings).  For pair k = (d_pairs[2k],
+ * d_pairs[2k+1]) writes d_out[3k..3k+2] = area(A), area(B), area(A n B). */
+int wbk_track_overlap(const double* d_xy, const int* d_ring_off, const int* d_poly_off, const int* d_pairs, int npairs,
+                      double* d_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

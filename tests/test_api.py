@@ -1,0 +1,230 @@
+"""Drop-in API: the reference's own fixture-free tests (tests/test_wavebreaking.py) re-expressed, plus
+parity of the API results with the oracle on a demo-shaped synthetic field (179 x 360, lon -180..179)."""
+
+import numpy as np
+import pandas as pd
+import pytest
+
+import wavebreaking_b200 as wb
+from oracle import pipeline as P
+from wavebreaking_b200 import api, compat, synthetic
+
+
+def demo_like(ntime=3, dtype=np.float32, lat_descending=False):
+    """Shape / coordinates of the reference's demo file (tests/test_wavebreaking.py:54,68-77)."""
+    lat = np.arange(-89.0, 90.0)
+    lon = np.arange(-180.0, 180.0)
+    raw = synthetic.pv_field(181, 360, np.arange(ntime) * 6.0, dtype=np.float64)[:, 1:-1, :]
+    raw = np.roll(raw, 180, axis=2).astype(dtype)  # lon 0..359 -> -180..179
+    time = np.datetime64("1959-06-03T12", "ns") + np.arange(ntime) * np.timedelta64(6, "h")
+    if lat_descending:
+        return compat.Field(raw[:, ::-1, :].copy(), ("time", "lat", "lon"), {"time": time, "lat": lat[::-1].copy(), "lon": lon},
+                            name="PV"), P.Grid(lon, lat, time), raw
+    return compat.Field(raw, ("time", "lat", "lon"), {"time": time, "lat": lat, "lon": lon}, name="PV"), \
+        P.Grid(lon, lat, time), raw
+
+
+# ------------------------------------------------------------------ decorator runtime (no device needed)
+def test_check_argument_types():
+    @api.check_argument_types(["data"], ["field"])
+    def to_be_decorated(data, *args, **kwargs):
+        return None
+
+    with pytest.raises(TypeError, match="data has to be a xarray.core.dataarray.DataArray!"):
+        to_be_decorated("")
+
+
+def test_get_dimension_attributes():
+    data, _, _ = demo_like()
+
+    @api.get_dimension_attributes("data")
+    def to_be_decorated(data, *args, **kwargs):
+        assert kwargs["time_name"] == "time" and kwargs["lon_name"] == "lon" and kwargs["lat_name"] == "lat"
+        assert kwargs["ntime"] == 3 and kwargs["nlon"] == 360 and kwargs["nlat"] == 179
+        assert kwargs["dlon"] == 1 and kwargs["dlat"] == 1
+
+    to_be_decorated(data)
+    with pytest.raises(ValueError, match="No regular grid"):
+        bad = compat.Field(np.zeros((1, 3, 4)), ("time", "lat", "lon"),
+                           {"time": [0], "lat": [0.0, 1.0, 3.0], "lon": [0.0, 1.0, 2.0, 3.0]})
+        to_be_decorated(bad)
+
+
+def test_combine_shared():
+    assert wb.combine_shared([[1, 2, 3], [2, 3, 4], [5, 6]]) == [[1, 2, 3, 4], [5, 6]]
+    assert wb.combine_shared([[7, 8], [1, 2], [8, 1], [9]]) == P.combine_shared([[7, 8], [1, 2], [8, 1], [9]]) \
+        or [sorted(g) for g in P.combine_shared([[7, 8], [1, 2], [8, 1], [9]])] == wb.combine_shared([[7, 8], [1, 2], [8, 1], [9]])
+
+
+def test_empty_events_rejected(emu):
+    data, _, _ = demo_like(1)
+    with pytest.raises(ValueError, match="geopandas.GeoDataFrame is empty!"):
+        wb.to_xarray(data, pd.DataFrame())
+
+
+# ------------------------------------------------------------------ known-answer tests of the reference
+def _square_events(dates):
+    sq = [(0, 0), (10, 0), (10, 10), (0, 10)]
+    return compat.make_frame({"date": list(dates)}, [compat.Polygon(sq) for _ in dates])
+
+
+def test_to_xarray_kat(emu):
+    data, grid, _ = demo_like()
+    date = np.datetime64("1959-06-03T12")
+    flag = wb.to_xarray(data=data, events=_square_events([date]), name="test_flag")
+    assert flag.name == "test_flag" and flag.values.dtype == np.int8
+    ti = 0
+    assert flag.values[ti, list(grid.lat).index(5.0), list(grid.lon).index(5.0)] == 1
+    assert flag.values.sum() == 121
+    assert flag.attrs["long_name"] == "flag wave breaking"
+
+
+def test_to_xarray_flag_column_last_writer(emu):
+    data, grid, _ = demo_like(1)
+    date = grid.time[0]
+    ev = compat.make_frame({"date": [date, date], "val": [3.0, 7.0]},
+                           [compat.Polygon([(0, 0), (10, 0), (10, 10), (0, 10)]),
+                            compat.Polygon([(5, 5), (15, 5), (15, 15), (5, 15)])])
+    out = wb.to_xarray(data, ev, flag="val").values
+    li, lo = list(grid.lat).index, list(grid.lon).index
+    assert out[0, li(2.0), lo(2.0)] == 3.0 and out[0, li(7.0), lo(7.0)] == 7.0 and out[0, li(12.0), lo(12.0)] == 7.0
+    with pytest.raises(KeyError):
+        wb.to_xarray(data, ev, flag="nope")
+
+
+def test_track_events_kat(emu):
+    d1, d2 = np.datetime64("1959-06-03T12"), np.datetime64("1959-06-03T18")
+    tracked = wb.track_events(events=_square_events([d1, d2]), method="by_overlap")
+    assert tracked.iloc[0].label == 0 and tracked.iloc[1].label == 0
+
+
+def test_track_events_matches_oracle(emu):
+    rng = np.random.default_rng(4)
+    t0 = np.datetime64("2000-01-01T00", "ns")
+    dates, geoms, rings = [], [], []
+    for k in range(24):
+        cx, cy = rng.integers(0, 40), rng.integers(0, 20)
+        ang = np.sort(rng.uniform(0, 2 * np.pi, rng.integers(4, 9)))
+        rad = rng.uniform(2, 8, len(ang))
+        ring = np.unique(np.c_[np.rint(cx + rad * np.cos(ang)), np.rint(cy + rad * np.sin(ang))], axis=0)
+        ring = ring[np.argsort(np.arctan2(ring[:, 1] - ring[:, 1].mean(), ring[:, 0] - ring[:, 0].mean()))]
+        if len(ring) < 3:
+            continue
+        dates.append(t0 + (k // 6) * np.timedelta64(6, "h"))
+        geoms.append(compat.Polygon(ring))
+        rings.append([ring])
+    ev = compat.make_frame({"date": dates, "com": [(float(r[0][:, 0].mean()), float(r[0][:, 1].mean())) for r in rings]}, geoms)
+    ev_o = pd.DataFrame({"date": pd.to_datetime(dates), "geometry": rings, "com": ev["com"]})
+    for overlap in (0, 0.2):
+        got = wb.track_events(ev, method="by_overlap", overlap=overlap)
+        want = P.track_events(ev_o, method="by_overlap", overlap=overlap)
+        assert list(got.index) == list(want.index) and list(got.label) == list(want.label)
+    got = wb.track_events(ev, method="by_distance", distance=900)
+    want = P.track_events(ev_o, method="by_distance", distance=900)
+    assert list(got.index) == list(want.index) and list(got.label) == list(want.label)
+    with pytest.raises(ValueError):
+        wb.track_events(ev, method="nope")
+
+
+# ------------------------------------------------------------------ API results vs the oracle
+CONTOUR_COLS = ["date", "level", "closed", "exp_lon", "mean_lat", "geometry"]
+EVENT_COLS = ["date", "level", "com", "mean_var", "intensity", "event_area", "geometry"]
+
+
+def _check_contours(data, grid, raw):
+    sm = wb.calculate_smoothed_field(data, 5)
+    assert sm.name == "smooth_PV" and sm.attrs["smooth_passes"] == 5
+    want_sm = P.smooth_field(raw, 5)
+    assert np.array_equal(np.nan_to_num(sm.values), np.nan_to_num(want_sm))
+    coords = wb.calculate_contours(data=sm, contour_levels=2, periodic_add=120, original_coordinates=True)
+    index = wb.calculate_contours(data=sm, contour_levels=2, periodic_add=120, original_coordinates=False)
+    assert coords.columns.to_list() == CONTOUR_COLS and index.columns.to_list() == CONTOUR_COLS
+    full_c = coords[coords.exp_lon == 360]
+    full_i = index[index.exp_lon == 480]
+    assert min(np.asarray(full_c.iloc[0].geometry.coords.xy).T[:, 0]) == -180
+    assert min(np.asarray(full_i.iloc[0].geometry.coords.xy).T[:, 0]) == 0
+    for oc, frame in ((True, coords), (False, index)):
+        want = P.calculate_contours(want_sm, 2, grid, 120, original_coordinates=oc)
+        assert len(want) == len(frame)
+        for a, b in zip(frame.itertuples(), want.itertuples()):
+            assert a.date == b.date and a.level == b.level and a.closed == b.closed
+            assert a.exp_lon == b.exp_lon and a.mean_lat == b.mean_lat
+            assert np.array_equal(compat.line_coords(a.geometry), np.asarray(b.geometry, dtype=float))
+    return sm, want_sm, index
+
+
+def _rings_equal(geom, want_rings):
+    got = compat.geometry_rings(geom)
+    assert len(got) == len(want_rings)
+    for a, b in zip(got, want_rings):
+        assert np.array_equal(a, np.asarray(b, dtype=float))
+
+
+def _check_indices(sm, want_sm, grid, index):
+    c_o = P.calculate_contours(want_sm, 2, grid, 120, original_coordinates=False)
+    inten = compat.Field(np.asarray(sm.values) * 0.5, sm.dims, {d: sm[d].values for d in sm.dims}, name="I")
+    st = wb.calculate_streamers(data=sm, contour_levels=2, geo_dis=800, cont_dis=1500, intensity=inten, periodic_add=120)
+    ot = wb.calculate_overturnings(data=sm, contour_levels=2, range_group=5, min_exp=5, intensity=inten, periodic_add=120)
+    co = wb.calculate_cutoffs(data=sm, contour_levels=2, min_exp=5, intensity=inten, contours=index)
+    assert st.columns.to_list() == EVENT_COLS and co.columns.to_list() == EVENT_COLS
+    assert ot.columns.to_list() == EVENT_COLS[:-1] + ["orientation", "geometry"]
+    w_st = P.calculate_streamers(want_sm, grid, c_o, intensity=want_sm * 0.5)
+    w_ot = P.calculate_overturnings(want_sm, grid, c_o, intensity=want_sm * 0.5)
+    w_co = P.calculate_cutoffs(want_sm, grid, c_o, intensity=want_sm * 0.5)
+    for got, want in ((st, w_st), (ot, w_ot), (co, w_co)):
+        assert len(got) == len(want) and len(want) > 0
+        for a, b in zip(got.itertuples(), want.itertuples()):
+            assert a.date == b.date and a.level == b.level and tuple(a.com) == tuple(b.com)
+            assert a.mean_var == b.mean_var and a.event_area == b.event_area and a.intensity == b.intensity
+            _rings_equal(a.geometry, b.geometry)
+    assert list(ot.orientation) == list(w_ot.orientation)
+    fl = wb.to_xarray(sm, st)
+    assert np.array_equal(fl.values, P.to_xarray(np.zeros_like(want_sm), w_st, grid))
+    return st
+
+
+def test_api_pipeline_emu(emu):
+    data, grid, raw = demo_like(2)
+    sm, want_sm, index = _check_contours(data, grid, raw)
+    _check_indices(sm, want_sm, grid, index)
+
+
+def test_api_descending_latitude_emu(emu):
+    data_d, grid, raw = demo_like(1, lat_descending=True)
+    data_a, _, _ = demo_like(1)
+    sm_a = wb.calculate_smoothed_field(data_a, 5)
+    sm_d = compat.Field(sm_a.values[:, ::-1, :].copy(), sm_a.dims,
+                        {"time": sm_a["time"].values, "lat": sm_a["lat"].values[::-1].copy(), "lon": sm_a["lon"].values},
+                        name="smooth_PV")
+    a = wb.calculate_overturnings(sm_a, 2)
+    d = wb.calculate_overturnings(sm_d, 2)
+    assert len(a) == len(d) > 0
+    assert list(a.com) == list(d.com) and list(a.event_area) == list(d.event_area)
+    fa, fd = wb.to_xarray(sm_a, a), wb.to_xarray(sm_d, d)
+    assert np.array_equal(fa.values, fd.values[:, ::-1, :])
+
+
+def test_api_wrong_contours_rejected(emu):
+    data, grid, raw = demo_like(1)
+    sm = wb.calculate_smoothed_field(data, 5)
+    coords = wb.calculate_contours(sm, 2, original_coordinates=True)
+    with pytest.raises(ValueError, match="Original coordinates not supported"):
+        wb.calculate_streamers(sm, 2, contours=coords)
+    with pytest.raises(TypeError, match="contours has to be"):
+        wb.calculate_streamers(sm, 2, contours="x")
+
+
+def test_momentum_flux_api_emu(emu):
+    data, grid, raw = demo_like(1)
+    mf = wb.calculate_momentum_flux(data, data)
+    assert mf.name == "mflux" and mf.values.shape == raw.shape
+    np.testing.assert_allclose(mf.values, P.momentum_flux(raw, raw), rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.gpu
+def test_api_pipeline_gpu(gpu):
+    data, grid, raw = demo_like(3)
+    sm, want_sm, index = _check_contours(data, grid, raw)
+    st = _check_indices(sm, want_sm, grid, index)
+    tracked = wb.track_events(st, method="by_overlap")
+    assert "label" in tracked.columns and tracked.label.min() == 0

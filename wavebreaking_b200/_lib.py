@@ -71,6 +71,7 @@ _SIGNATURES = {
     "wbk_contours_counts": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int), c_void_p]),
     "wbk_contours_pack": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p]),
+    "wbk_track_overlap": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "wbk_prof_enable": (c_int, [c_int]),
     "wbk_prof_reset": (c_int, []),
     "wbk_prof_read": (c_int, [POINTER(c_int), POINTER(c_double)]),

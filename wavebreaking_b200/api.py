@@ -1,0 +1,512 @@
+"""Drop-in API of the detection path (same names, arguments and error behaviour as the reference).
+
+Mirrors ``wavebreaking/__init__.py:19-34``: ``calculate_smoothed_field``, ``calculate_momentum_flux``,
+``calculate_contours``, ``calculate_streamers``, ``calculate_overturnings``, ``calculate_cutoffs``,
+``to_xarray`` and ``track_events`` (alias ``event_tracking``), plus the decorator "runtime" of
+``wavebreaking/utils/data_utils.py`` (argument type checks, dimension discovery with ``key=value``
+overrides) and ``utils/index_utils.py`` (``combine_shared``).  Inputs are ``xarray.DataArray`` (or the
+:class:`wavebreaking_b200.compat.Field` stand-in when xarray is not installed); outputs are
+``geopandas.GeoDataFrame`` / ``xarray.DataArray`` when those packages are importable and pandas
+DataFrames with lightweight geometry objects / ``Field`` otherwise.  All arithmetic runs in libwbk.
+"""
+
+import functools
+import logging
+
+import numpy as np
+import pandas as pd
+import torch
+
+from . import _lib, compat, detect, geometry, spatial, tracking
+
+logger = logging.getLogger(__name__)
+
+__all__ = [
+    "calculate_smoothed_field", "calculate_momentum_flux", "calculate_contours", "calculate_streamers",
+    "calculate_overturnings", "calculate_cutoffs", "to_xarray", "track_events", "event_tracking", "combine_shared",
+    "check_argument_types", "get_dimension_attributes", "check_empty_dataframes",
+]
+
+_FIELD = "field"
+_FRAME = "frame"
+_PANDAS = "pandas"
+
+
+# ------------------------------------------------------------------------------------------- data_utils.py
+def _type_ok(value, kind):
+    if kind == _FIELD:
+        return compat.is_field(value)
+    if kind in (_FRAME, _PANDAS):
+        return compat.is_frame(value)
+    return isinstance(value, kind)
+
+
+def _type_name(kind):
+    if kind == _FIELD:
+        return compat.field_type_name()
+    if kind == _FRAME:
+        return compat.frame_type_name()
+    if kind == _PANDAS:
+        return "pandas.core.frame.DataFrame"
+    return str(kind)[8:-2]
+
+
+def check_argument_types(arguments, types):
+    """decorator to check the type of function arguments (utils/data_utils.py:28-50)"""
+
+    def decorator(func):
+        @functools.wraps(func)
+        def wrapper(*args, **kwargs):
+            for (arg_index, arg_name), arg_type in zip(enumerate(arguments), types):
+                value = kwargs[arg_name] if arg_name in kwargs else args[arg_index]
+                if not _type_ok(value, arg_type):
+                    raise TypeError(arg_name + " has to be a " + _type_name(arg_type) + "!")
+            return func(*args, **kwargs)
+
+        return wrapper
+
+    return decorator
+
+
+def check_empty_dataframes(func):
+    """decorator to check if there is an empty DataFrame (utils/data_utils.py:53-73)"""
+
+    @functools.wraps(func)
+    def wrapper(*args, **kwargs):
+        for item in args:
+            if compat.is_frame(item) and item.empty:
+                raise ValueError("geopandas.GeoDataFrame is empty!")
+        for key, item in kwargs.items():
+            if compat.is_frame(item) and item.empty:
+                raise ValueError(key + " geopandas.GeoDataFrame is empty!")
+        return func(*args, **kwargs)
+
+    return wrapper
+
+
+def get_time_name(data):
+    """utils/data_utils.py:76-93"""
+    for dim in data.dims:
+        values, attrs, encoding = compat.coord_info(data, dim)
+        if (
+            ("units" in attrs and "since" in attrs["units"])
+            or ("units" in encoding and "since" in encoding["units"])
+            or (values.dtype == np.dtype("datetime64[ns]"))
+            or (dim in ["time"])
+        ):
+            return dim
+    raise ValueError("'time' dimension (dtype='datetime64[ns]') not found."
+                     " Add time dimension with xarray.DataArray.expand_dims('time').")
+
+
+def get_lon_name(data):
+    """utils/data_utils.py:96-109"""
+    for dim in data.dims:
+        _, attrs, _ = compat.coord_info(data, dim)
+        if ("units" in attrs and attrs["units"] in ["degree_east", "degrees_east"]) or dim in ["lon", "longitude", "x"]:
+            return dim
+    raise ValueError("'longitude' dimension (units='degrees_east') not found.")
+
+
+def get_lat_name(data):
+    """utils/data_utils.py:112-126"""
+    for dim in data.dims:
+        _, attrs, _ = compat.coord_info(data, dim)
+        if ("units" in attrs and attrs["units"] in ["degree_north", "degrees_north"]) or dim in ["lat", "latitude", "y"]:
+            return dim
+    raise ValueError("latitude' dimension (units='degrees_north') not found.")
+
+
+def get_spatial_resolution(data, dim):
+    """utils/data_utils.py:129-144"""
+    values = compat.coord_info(data, dim)[0]
+    delta = abs(np.unique((values[1:] - values[:-1])))
+    if len(delta) > 1:
+        raise ValueError("No regular grid found for dimension {}.".format(dim))
+    elif delta[0] == 0:
+        raise ValueError("Two equivalent coordinates found for dimension {}.".format(dim))
+    return delta[0]
+
+
+def get_dimension_attributes(arg_name):
+    """decorator to get the dimension, size and resolution of the input data (utils/data_utils.py:147-193)"""
+
+    def decorator(func):
+        @functools.wraps(func)
+        def wrapper(*args, **kwargs):
+            data = kwargs[arg_name] if arg_name in kwargs else args[0]
+            names = ["time_name", "lon_name", "lat_name"]
+            sizes = ["ntime", "nlon", "nlat"]
+            resolutions = ["dlon", "dlat"]
+            get_dims = [get_time_name, get_lon_name, get_lat_name]
+            for name, get_dim in zip(names, get_dims):
+                if name not in kwargs:
+                    kwargs[name] = get_dim(data)
+            for size, name in zip(sizes, names):
+                if size not in kwargs:
+                    kwargs[size] = len(data[kwargs[name]])
+            for res, name in zip(resolutions, names[1:]):
+                if res not in kwargs:
+                    kwargs[res] = get_spatial_resolution(data, kwargs[name])
+            if len(data.dims) > 3:
+                err_dims = [dim for dim in data.dims if dim not in [kwargs[name] for name in names]]
+                raise ValueError("Unexpected dimension(s): {}. Select dimensions first.".format(err_dims))
+            return func(*args, **kwargs)
+
+        return wrapper
+
+    return decorator
+
+
+def combine_shared(lst):
+    """utils/index_utils.py:187-214 (connected components of index lists, first-appearance order)."""
+    return tracking.combine_shared(lst)
+
+
+# ------------------------------------------------------------------------------------------- helpers
+class _Canon:
+    """``data`` as a device tensor [time, lat, lon] with ascending lat / lon (data_utils.py:196-213)."""
+
+    def __init__(self, data, kwargs, need_values=True, orient=True):
+        self.time_name, self.lon_name, self.lat_name = kwargs["time_name"], kwargs["lon_name"], kwargs["lat_name"]
+        self.time = compat.coord_info(data, self.time_name)[0]
+        lon = compat.coord_info(data, self.lon_name)[0]
+        lat = compat.coord_info(data, self.lat_name)[0]
+        self.flip_lat = bool(np.average(np.diff(lat)) < 0) if (orient and len(lat) > 1) else False
+        self.flip_lon = bool(np.average(np.diff(lon)) < 0) if (orient and len(lon) > 1) else False
+        self.lat = lat[::-1].copy() if self.flip_lat else lat
+        self.lon = lon[::-1].copy() if self.flip_lon else lon
+        self.nlon, self.nlat, self.ntime = kwargs["nlon"], kwargs["nlat"], kwargs["ntime"]
+        self.dlon, self.dlat = kwargs["dlon"], kwargs["dlat"]
+        self.order = [data.dims.index(self.time_name), data.dims.index(self.lat_name), data.dims.index(self.lon_name)]
+        self.dims = tuple(data.dims)
+        self.tensor = None
+        if need_values:
+            values = np.asarray(data.values)
+            if values.dtype not in (np.float32, np.float64):
+                values = values.astype(np.float64)
+            values = np.ascontiguousarray(np.transpose(values, self.order))
+            t = spatial.to_device(values)
+            self.tensor = spatial.flip(t, self.flip_lat, self.flip_lon)
+
+    def to_input_layout(self, arr):
+        """[time, lat, lon] (ascending) numpy array -> the input's dim order and orientation."""
+        if self.flip_lat:
+            arr = arr[:, ::-1, :]
+        if self.flip_lon:
+            arr = arr[:, :, ::-1]
+        inv = np.argsort(self.order)
+        return np.transpose(arr, inv)
+
+
+def _as_levels(contour_levels):
+    try:
+        iter(contour_levels)
+    except Exception:
+        contour_levels = [contour_levels]
+    return list(contour_levels)
+
+
+# ------------------------------------------------------------------------------------------- spatial.py
+@check_argument_types(["u", "v"], [_FIELD, _FIELD])
+@get_dimension_attributes("u")
+def calculate_momentum_flux(u, v, *args, **kwargs):
+    """Momentum flux u'v' from the deviations of both wind components from the zonal mean
+    (processing/spatial.py:27-57)."""
+    cu = _Canon(u, kwargs)
+    vk = dict(kwargs)
+    cv = _Canon(v, vk)
+    out = spatial.momentum_flux(cu.tensor, cv.tensor).cpu().numpy()
+    return compat.like(u, cu.to_input_layout(out), u.dims, name="mflux")
+
+
+@check_argument_types(["data"], [_FIELD])
+@get_dimension_attributes("data")
+def calculate_smoothed_field(data, passes, weights=np.array([[0, 1, 0], [1, 2, 1], [0, 1, 0]]), mode="wrap", *args,
+                             **kwargs):
+    """``passes`` x 5-point smoothing (scipy.ndimage.convolve semantics), latitude border rows NaN
+    (processing/spatial.py:60-128).  The result has dims (time, lat, lon) like the reference's."""
+    c = _Canon(data, kwargs, orient=False)  # the reference convolves the (lat, lon) slices as they are stored
+    out = spatial.smooth(c.tensor, passes, np.asarray(weights), mode).cpu().numpy()
+    dims = (c.time_name, c.lat_name, c.lon_name)
+    attrs = dict(getattr(data, "attrs", {}) or {})
+    attrs["smooth_passes"] = passes
+    return compat.like(data, out, dims, name="smooth_" + str(data.name), attrs=attrs)
+
+
+# ------------------------------------------------------------------------------------------- contours
+class _DeviceContours:
+    """Device-resident contours attached to the frame returned by ``calculate_contours(original_coordinates=False)``."""
+
+    def __init__(self, batches, canon, levels, periodic_add):
+        self.batches = batches  # list of (t0, ContourSet)
+        self.key = (tuple(canon.time.tolist()), canon.nlat, canon.nlon, tuple(levels), periodic_add)
+
+
+def _batch_size(nlat, nlon, nlevels):
+    """Time steps per launch: fill the GPU (>= 2 jobs per SM) without excessive arena memory."""
+    per_job = max(nlat * nlon, 1)
+    return int(max(1, min(296 // max(nlevels, 1) + 1, (1 << 28) // per_job)))
+
+
+def _contour_batches(c, levels, periodic_add):
+    add = int(periodic_add / c.dlon)
+    tb = _batch_size(c.nlat, c.nlon, len(levels))
+    out = []
+    for t0 in range(0, c.ntime, tb):
+        cs = detect.contours(c.tensor[t0:t0 + tb], levels, add)
+        if np.any(cs.status & _lib.ST_LATTICE_VERTEX):
+            logger.warning("a contour vertex fell exactly on a grid vertex (field value == level) in %d job(s); "
+                           "skimage joins such points by float equality and the result may differ there",
+                           int(np.count_nonzero(cs.status & _lib.ST_LATTICE_VERTEX)))
+        out.append((t0, cs))
+    return out
+
+
+def _contour_frame(c, batches, levels, original_coordinates):
+    rows = dict(date=[], level=[], closed=[], exp_lon=[], mean_lat=[])
+    geoms = []
+    nlev = len(levels)
+    for t0, cs in batches:
+        h = cs.host()
+        for k in range(cs.ncontours):
+            a, b = h["pt_off"][k], h["pt_off"][k + 1]
+            x, y = h["x"][a:b], h["y"][a:b]
+            t, l = divmod(int(h["job"][k]), nlev)
+            rows["date"].append(c.time[t0 + t])
+            rows["level"].append(levels[l])
+            rows["closed"].append(bool(h["closed"][k]))
+            if original_coordinates:
+                # contour_index.py:179-191: map to coordinates, drop repeated points (keep first)
+                xy = np.c_[c.lon[x % c.nlon], c.lat[y]]
+                _, first = np.unique(xy, axis=0, return_index=True)
+                xy = xy[np.sort(first)]
+                rows["exp_lon"].append(len(set(xy[:, 0].tolist())) * c.dlon)
+                rows["mean_lat"].append(np.round(xy[:, 1].mean(), 2))
+                geoms.append(compat.LineString(xy))
+            else:
+                rows["exp_lon"].append(int(h["nx"][k]) * c.dlon)
+                rows["mean_lat"].append(np.round(y.mean(), 2))
+                geoms.append(compat.LineString(np.c_[x, y]))
+    return compat.make_frame(rows, geoms)
+
+
+@check_argument_types(["data"], [_FIELD])
+@get_dimension_attributes("data")
+def calculate_contours(data, contour_levels, periodic_add=120, original_coordinates=True, *args, **kwargs):
+    """Contour lines for a set of levels on the periodically extended grid
+    (indices/contour_index.py:45-194; time / level loops of utils/index_utils.py:217-258 batched)."""
+    c = _Canon(data, kwargs)
+    levels = _as_levels(contour_levels)
+    batches = _contour_batches(c, levels, periodic_add)
+    frame = _contour_frame(c, batches, levels, original_coordinates)
+    if not original_coordinates:
+        frame.attrs["_wbk_device"] = _DeviceContours(batches, c, levels, periodic_add)
+    return frame
+
+
+def _contours_from_frame(contours, c, levels, periodic_add):
+    """Upload user-supplied contours (index coordinates) as packed contour sets, one per batch."""
+    dev = contours.attrs.get("_wbk_device") if hasattr(contours, "attrs") else None
+    key = (tuple(c.time.tolist()), c.nlat, c.nlon, tuple(levels), periodic_add)
+    if dev is not None and dev.key == key and sum(cs.ncontours for _, cs in dev.batches) == len(contours):
+        return dev.batches
+    lib = _lib.get()
+    time_index = {t: i for i, t in enumerate(c.time.tolist())}
+    level_index = {float(l): i for i, l in enumerate(levels)}
+    nlev = len(levels)
+    jobs, closed, nx, sumy, offs, xs, ys = [], [], [], [], [0], [], []
+    for row in contours.itertuples():
+        lv = float(row.level)
+        if lv not in level_index:
+            continue
+        date = pd.Timestamp(row.date).to_datetime64().astype(c.time.dtype).item() \
+            if np.issubdtype(c.time.dtype, np.datetime64) else row.date
+        if date not in time_index:
+            continue
+        xy = compat.line_coords(row.geometry).astype(np.int64)
+        jobs.append(time_index[date] * nlev + level_index[lv])
+        closed.append(int(bool(row.closed)))
+        nx.append(len(set(xy[:, 0].tolist())))
+        sumy.append(int(xy[:, 1].sum()))
+        xs.append(xy[:, 0])
+        ys.append(xy[:, 1])
+        offs.append(offs[-1] + len(xy))
+    order = np.argsort(np.asarray(jobs, dtype=np.int64), kind="stable")
+    njobs = c.ntime * nlev
+    job_arr = np.asarray(jobs, dtype=np.int64)[order]
+    job_off = np.searchsorted(job_arr, np.arange(njobs + 1)).astype(np.int32)
+    pts = [(xs[i] | (ys[i] << 16)).astype(np.uint32) for i in order]
+    lens = np.array([len(p) for p in pts], dtype=np.int64)
+    pt_off = np.zeros(len(pts) + 1, dtype=np.int32)
+    pt_off[1:] = np.cumsum(lens)
+    meta = np.c_[np.asarray(closed)[order], np.asarray(nx)[order], np.asarray(sumy)[order], job_arr].astype(np.int32)
+    allp = np.concatenate(pts).astype(np.uint32) if pts else np.zeros(0, dtype=np.uint32)
+    dev_t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(lib.device)
+    cs = detect.ContourSet(
+        njobs=njobs, nlevels=nlev, nlat=c.nlat, nlon=c.nlon, add=int(periodic_add / c.dlon),
+        levels=np.asarray(levels, dtype=np.float64), job_off=dev_t(job_off), pt_off=dev_t(pt_off),
+        meta=dev_t(meta.reshape(-1, 4)), pts=dev_t(allp.view(np.int32)), status=np.zeros(njobs, dtype=np.int32),
+        max_nx=int(max(nx)) if nx else 0, h_ncontours=np.diff(job_off), h_npoints=None)
+    return [(0, cs)]
+
+
+def decorator_contour_calculation(func):
+    """wrap the contour calculation around the index functions (indices/contour_index.py:197-249)"""
+
+    @functools.wraps(func)
+    def wrapper(data, contour_levels, periodic_add=120, *args, **kwargs):
+        if "contours" not in kwargs:
+            kwargs["contours"] = calculate_contours(data, contour_levels, periodic_add, original_coordinates=False)
+        else:
+            if not compat.is_frame(kwargs["contours"]):
+                raise TypeError("contours has to be a geopandas.GeoDataFrame!")
+            if kwargs["contours"].empty:
+                raise ValueError("contours geopandas.GeoDataFrame is empty!")
+            levels = _as_levels(contour_levels)
+            check_levels = [i for i in levels if i not in set(kwargs["contours"].level)]
+            if len(check_levels) > 0:
+                logger.warning("\n The contour levels {} are not present in 'contours'".format(check_levels))
+            coords = compat.line_coords(kwargs["contours"].iloc[0].geometry)
+            check_int = (coords.astype("int") == coords).all()
+            check_zero = (coords[:, 0] >= 0).all()
+            if not (check_int and check_zero):
+                raise ValueError("Original coordinates not supported for the index calculation. "
+                                 "Use original_coordinates=False in the contour calculation.")
+        return func(data, contour_levels, periodic_add=periodic_add, *args, **kwargs)
+
+    return wrapper
+
+
+# ------------------------------------------------------------------------------------------- indices
+_EVENT_COLUMNS = ["date", "level", "com", "mean_var", "intensity", "event_area"]
+
+
+def _run_index(kind, data, contour_levels, contours, intensity, periodic_add, kwargs, **params):
+    c = _Canon(data, kwargs)
+    levels = _as_levels(contour_levels)
+    inten = None
+    if intensity is not None:
+        if not compat.is_field(intensity):
+            raise TypeError("intensity has to be a " + compat.field_type_name() + "!")
+        inten = _Canon(intensity, dict(kwargs)).tensor
+    batches = _contours_from_frame(contours, c, levels, periodic_add)
+    # exp_lon.max() is global over all dates and levels (streamer_index.py:106)
+    gmax = max([cs.max_nx for _, cs in batches] + [0])
+    if len(contours):
+        gmax = max(gmax, int(round(float(np.max(contours.exp_lon)) / c.dlon)))
+    coords = detect.coord_tables(c.lat, c.lon, c.dlon, c.dlat)
+    cols = {k: [] for k in _EVENT_COLUMNS}
+    orient, geoms = [], []
+    nlev = len(levels)
+    for t0, cs in batches:
+        nt = cs.njobs // nlev
+        field = c.tensor[t0:t0 + nt]
+        tables, _ = detect.run_indices(cs, field, coords, c.dlon, c.dlat,
+                                       intensity=None if inten is None else inten[t0:t0 + nt], which=(kind,),
+                                       gmax_nx=gmax, want_flags=False, **params)
+        tab = tables[kind]
+        props = detect.finish_properties(tab, c.lon, c.lat, c.nlon)
+        rings = detect.event_rings(cs, tab)
+        for e in range(len(tab)):
+            t, l = divmod(int(tab.job[e]), nlev)
+            cols["date"].append(c.time[t0 + t])
+            cols["level"].append(levels[l])
+            pieces = geometry.transform_ring(rings[e], c.nlon)
+            polys = [compat.Polygon(np.c_[c.lon[p[:, 0]], c.lat[p[:, 1]]]) for p in pieces]
+            geoms.append(compat.Polygon() if not polys else polys[0] if len(polys) == 1 else compat.MultiPolygon(polys))
+            orient.append("anticyclonic" if tab.orientation[e] else "cyclonic")
+        for k in ("com", "mean_var", "intensity", "event_area"):
+            cols[k].extend(list(props[k]))
+    if len(geoms) == 0:
+        return compat.empty_frame()
+    if kind == "overturnings":
+        cols["orientation"] = orient
+    return compat.make_frame(cols, geoms)
+
+
+@check_argument_types(["data"], [_FIELD])
+@get_dimension_attributes("data")
+@decorator_contour_calculation
+def calculate_streamers(data, contour_level, contours=None, geo_dis=800, cont_dis=1500, intensity=None,
+                        periodic_add=120, *args, **kwargs):
+    """Streamer index of Wernli and Sprenger (2007) (indices/streamer_index.py:44-289)."""
+    if contours is None:
+        contours = kwargs["contours"]
+    return _run_index("streamers", data, contour_level, contours, intensity, periodic_add, kwargs,
+                      geo_dis=geo_dis, cont_dis=cont_dis)
+
+
+@check_argument_types(["data"], [_FIELD])
+@get_dimension_attributes("data")
+@decorator_contour_calculation
+def calculate_overturnings(data, contour_levels, contours=None, range_group=5, min_exp=5, intensity=None,
+                           periodic_add=120, *args, **kwargs):
+    """Overturning index of Barnes and Hartmann (2012) (indices/overturning_index.py:40-232)."""
+    if contours is None:
+        contours = kwargs["contours"]
+    return _run_index("overturnings", data, contour_levels, contours, intensity, periodic_add, kwargs,
+                      range_group=range_group, ot_min_exp=min_exp)
+
+
+@check_argument_types(["data"], [_FIELD])
+@get_dimension_attributes("data")
+@decorator_contour_calculation
+def calculate_cutoffs(data, contour_level, contours=None, min_exp=5, intensity=None, periodic_add=120, *args,
+                      **kwargs):
+    """Cutoff index: closed contours shorter than the full longitudinal extent (indices/cutoff_index.py:33-104)."""
+    if contours is None:
+        contours = kwargs["contours"]
+    return _run_index("cutoffs", data, contour_level, contours, intensity, periodic_add, kwargs, co_min_exp=min_exp)
+
+
+# ------------------------------------------------------------------------------------------- events.py
+@check_argument_types(["data", "events"], [_FIELD, _FRAME])
+@check_empty_dataframes
+@get_dimension_attributes("data")
+def to_xarray(data, events, flag="ones", name="flag", *args, **kwargs):
+    """Flag the grid cells covered by events (processing/events.py:37-110)."""
+    c = _Canon(data, kwargs, need_values=False)
+    if c.dlon != c.dlat:
+        raise ValueError("to_xarray needs dlon == dlat (the buffer radius of events.py:75-78 is isotropic in degrees)")
+    if flag != "ones":
+        try:
+            set_val = np.asarray(events[flag].values, dtype=np.float64)
+        except KeyError:
+            raise KeyError("{} is not a column of the events geopandas.GeoDataFrame.".format(flag))
+    time_index = {t: i for i, t in enumerate(c.time.tolist())}
+    rings, ring_t, ring_v = [], [], []
+    lon0, lat0 = c.lon[0], c.lat[0]
+    for k, (date, geom) in enumerate(zip(events["date"], events["geometry"])):
+        key = pd.Timestamp(date).to_datetime64().astype(c.time.dtype).item() \
+            if np.issubdtype(c.time.dtype, np.datetime64) else date
+        if key not in time_index:
+            raise KeyError(date)
+        for ring in compat.geometry_rings(geom):
+            idx = np.c_[(ring[:, 0] - lon0) / c.dlon, (ring[:, 1] - lat0) / c.dlat]
+            snapped = np.rint(idx)
+            if not np.allclose(idx, snapped, atol=1e-6):
+                raise ValueError("to_xarray: event vertices must lie on grid points of `data`")
+            rings.append(snapped.astype(np.int32))
+            ring_t.append(time_index[key])
+            ring_v.append(1.0 if flag == "ones" else set_val[k])
+    lib = _lib.get()
+    if flag == "ones":
+        out = detect.rasterize_rings(rings, ring_t, c.nlat, c.nlon, c.ntime, 0.5).cpu().numpy()
+    else:
+        grid = torch.zeros((c.ntime, c.nlat, c.nlon), dtype=torch.float64, device=lib.device)
+        out = detect.rasterize_rings(rings, ring_t, c.nlat, c.nlon, c.ntime, 0.5, values=(grid, ring_v)).cpu().numpy()
+        out = out.astype(np.asarray(data.values).dtype, copy=False)
+    res = compat.like(data, c.to_input_layout(out), data.dims, name=name, attrs=dict(getattr(data, "attrs", {}) or {}))
+    res.attrs["long_name"] = "flag wave breaking"
+    return res
+
+
+@check_argument_types(["events"], [_PANDAS])
+@check_empty_dataframes
+def track_events(events, time_range=None, method="by_overlap", buffer=0, overlap=0, distance=1000):
+    """Temporal tracking of events (processing/events.py:113-241)."""
+    return tracking.track_events(events, time_range, method, buffer, overlap, distance)
+
+
+event_tracking = track_events

@@ -1,0 +1,288 @@
+"""Stand-ins for xarray / geopandas / shapely objects when those packages are not installed.
+
+The drop-in API (:mod:`wavebreaking_b200.api`) takes ``xarray.DataArray`` and returns
+``geopandas.GeoDataFrame`` / ``xarray.DataArray`` whenever those packages can be imported.  The build
+and test image of this repository has neither (no network), so the same API also accepts and returns
+the minimal containers below; they carry exactly what the detection path needs (values, dimension names,
+coordinates / coordinate rings) and convert to the real types on demand.
+"""
+
+import numpy as np
+
+try:  # pragma: no cover - not available in the build image
+    import xarray as _xr
+except Exception:  # noqa: BLE001
+    _xr = None
+try:  # pragma: no cover
+    import geopandas as _gpd
+    import shapely as _shapely
+except Exception:  # noqa: BLE001
+    _gpd = None
+    _shapely = None
+
+
+def have_xarray():
+    return _xr is not None
+
+
+def have_geopandas():
+    return _gpd is not None
+
+
+class _Coord:
+    """One coordinate axis (values + attrs), the part of xarray's IndexVariable the path reads."""
+
+    def __init__(self, values, attrs=None, encoding=None):
+        self.values = np.asarray(values)
+        self.data = self.values
+        self.attrs = dict(attrs or {})
+        self.encoding = dict(encoding or {})
+
+    @property
+    def dtype(self):
+        return self.values.dtype
+
+    def __len__(self):
+        return len(self.values)
+
+    def __iter__(self):
+        return iter(self.values)
+
+    def __getitem__(self, i):
+        return self.values[i]
+
+
+class Field:
+    """Minimal labelled array: ``values`` with named ``dims`` and 1-D ``coords`` (DataArray stand-in)."""
+
+    def __init__(self, values, dims, coords, name=None, attrs=None):
+        self.values = np.asarray(values)
+        self.dims = tuple(dims)
+        if len(self.dims) != self.values.ndim:
+            raise ValueError("dims do not match the array rank")
+        self.coords = {}
+        for d in self.dims:
+            c = coords[d]
+            self.coords[d] = c if isinstance(c, _Coord) else _Coord(c)
+            if len(self.coords[d]) != self.values.shape[self.dims.index(d)]:
+                raise ValueError("coordinate {} does not match the array shape".format(d))
+        for k, v in coords.items():  # scalar / extra coordinates (e.g. a level) are carried along
+            if k not in self.coords:
+                self.coords[k] = v if isinstance(v, _Coord) else _Coord(np.atleast_1d(v))
+        self.name = name
+        self.attrs = dict(attrs or {})
+
+    def __getitem__(self, dim):
+        return self.coords[dim]
+
+    @property
+    def shape(self):
+        return self.values.shape
+
+    @property
+    def dtype(self):
+        return self.values.dtype
+
+    def to_xarray(self):  # pragma: no cover
+        if _xr is None:
+            raise ImportError("xarray is not installed")
+        return _xr.DataArray(self.values, dims=self.dims, coords={d: self.coords[d].values for d in self.dims},
+                             name=self.name, attrs=self.attrs)
+
+
+def is_field(obj):
+    return isinstance(obj, Field) or (_xr is not None and isinstance(obj, _xr.DataArray))
+
+
+def field_type_name():
+    return "xarray.core.dataarray.DataArray"
+
+
+def coord_info(data, dim):
+    """(values, attrs, encoding) of a dimension coordinate of a Field or DataArray."""
+    c = data[dim]
+    values = np.asarray(c.values)
+    return values, dict(getattr(c, "attrs", {}) or {}), dict(getattr(c, "encoding", {}) or {})
+
+
+def like(data, values, dims, name=None, attrs=None):
+    """A new labelled array of the same flavour as ``data`` (DataArray in, DataArray out)."""
+    coords = {d: np.asarray(data[d].values) for d in dims}
+    if _xr is not None and isinstance(data, _xr.DataArray):  # pragma: no cover
+        return _xr.DataArray(values, dims=dims, coords=coords, name=name, attrs=attrs or {})
+    return Field(values, dims, coords, name=name, attrs=attrs)
+
+
+# --------------------------------------------------------------------------------------------- geometries
+class LineString:
+    """Ordered vertices (n, 2); ``.coords.xy`` / ``np.asarray(.coords)`` like shapely."""
+
+    geom_type = "LineString"
+
+    def __init__(self, coords):
+        self._xy = np.asarray(coords, dtype=np.float64).reshape(-1, 2)
+
+    class _Coords:
+        def __init__(self, xy):
+            self._xy = xy
+
+        @property
+        def xy(self):
+            return self._xy[:, 0].copy(), self._xy[:, 1].copy()
+
+        def __array__(self, dtype=None, copy=None):
+            return self._xy if dtype is None else self._xy.astype(dtype)
+
+        def __len__(self):
+            return len(self._xy)
+
+        def __iter__(self):
+            return iter(map(tuple, self._xy))
+
+    @property
+    def coords(self):
+        return LineString._Coords(self._xy)
+
+    @property
+    def bounds(self):
+        return (self._xy[:, 0].min(), self._xy[:, 1].min(), self._xy[:, 0].max(), self._xy[:, 1].max())
+
+    @property
+    def is_empty(self):
+        return len(self._xy) == 0
+
+    @property
+    def wkt(self):
+        return "LINESTRING ({})".format(", ".join("{:g} {:g}".format(x, y) for x, y in self._xy))
+
+    def __repr__(self):
+        return "<LineString n={}>".format(len(self._xy))
+
+    def to_shapely(self):  # pragma: no cover
+        return _shapely.LineString(self._xy)
+
+
+class Polygon:
+    """A single exterior ring (closed on output like shapely: first vertex repeated)."""
+
+    geom_type = "Polygon"
+
+    def __init__(self, shell=None):
+        xy = np.zeros((0, 2)) if shell is None else np.asarray(shell, dtype=np.float64).reshape(-1, 2)
+        if len(xy) and not np.array_equal(xy[0], xy[-1]):
+            xy = np.concatenate([xy, xy[:1]])
+        self._xy = xy
+
+    @property
+    def exterior(self):
+        return LineString(self._xy)
+
+    @property
+    def is_empty(self):
+        return len(self._xy) == 0
+
+    @property
+    def geoms(self):
+        return [self]
+
+    @property
+    def bounds(self):
+        return self.exterior.bounds
+
+    @property
+    def area(self):
+        x, y = self._xy[:, 0], self._xy[:, 1]
+        return 0.0 if len(x) < 4 else abs(float(np.sum(x[:-1] * y[1:] - x[1:] * y[:-1]))) / 2.0
+
+    @property
+    def wkt(self):
+        if self.is_empty:
+            return "POLYGON EMPTY"
+        return "POLYGON (({}))".format(", ".join("{:g} {:g}".format(x, y) for x, y in self._xy))
+
+    def __repr__(self):
+        return "<Polygon n={}>".format(max(len(self._xy) - 1, 0))
+
+    def rings(self):
+        """Open rings (n, 2) of this geometry."""
+        return [] if self.is_empty else [self._xy[:-1]]
+
+    def to_shapely(self):  # pragma: no cover
+        return _shapely.Polygon(self._xy) if len(self._xy) else _shapely.Polygon()
+
+
+class MultiPolygon:
+    geom_type = "MultiPolygon"
+
+    def __init__(self, polygons):
+        self.geoms = [p if isinstance(p, Polygon) else Polygon(p) for p in polygons]
+
+    @property
+    def is_empty(self):
+        return len(self.geoms) == 0
+
+    @property
+    def area(self):
+        return sum(p.area for p in self.geoms)
+
+    @property
+    def wkt(self):
+        return "MULTIPOLYGON ({})".format(", ".join(p.wkt[len("POLYGON "):] for p in self.geoms))
+
+    def __repr__(self):
+        return "<MultiPolygon parts={}>".format(len(self.geoms))
+
+    def rings(self):
+        return [r for p in self.geoms for r in p.rings()]
+
+    def to_shapely(self):  # pragma: no cover
+        return _shapely.MultiPolygon([p.to_shapely() for p in self.geoms])
+
+
+def geometry_rings(geom):
+    """Open exterior rings (list of (n, 2) arrays) of a compat or shapely (Multi)Polygon."""
+    if isinstance(geom, (Polygon, MultiPolygon)):
+        return geom.rings()
+    if geom is None or getattr(geom, "is_empty", False):
+        return []
+    parts = list(geom.geoms) if hasattr(geom, "geoms") else [geom]
+    out = []
+    for p in parts:
+        xy = np.asarray(p.exterior.coords)
+        out.append(xy[:-1] if len(xy) > 1 and np.array_equal(xy[0], xy[-1]) else xy)
+    return out
+
+
+def line_coords(geom):
+    """(n, 2) vertex array of a compat or shapely LineString."""
+    return np.asarray(geom.coords, dtype=np.float64).reshape(-1, 2)
+
+
+def make_frame(columns, geometry):
+    """GeoDataFrame when geopandas is importable, else a pandas DataFrame with a ``geometry`` column."""
+    import pandas as pd
+
+    if _gpd is not None:  # pragma: no cover
+        geoms = [g.to_shapely() if hasattr(g, "to_shapely") else g for g in geometry]
+        return _gpd.GeoDataFrame(pd.DataFrame(columns), geometry=geoms)
+    df = pd.DataFrame(columns)
+    df["geometry"] = pd.Series(list(geometry), index=df.index, dtype=object)
+    return df
+
+
+def empty_frame():
+    import pandas as pd
+
+    if _gpd is not None:  # pragma: no cover
+        return _gpd.GeoDataFrame()
+    return pd.DataFrame()
+
+
+def is_frame(obj):
+    import pandas as pd
+
+    return isinstance(obj, pd.DataFrame)
+
+
+def frame_type_name():
+    return "geopandas.geodataframe.GeoDataFrame"
