@@ -51,6 +51,8 @@ extern "C" {
 #define WBK_ST_EVENT_OVERFLOW 16    /* more events than event_cap */
 #define WBK_ST_SEL_OVERFLOW 32      /* more full-width contours than sel_cap */
 #define WBK_ST_WIDTH_OVERFLOW 64    /* extended grid wider than the shared-memory column tables */
+#define WBK_ST_PACK_OVERFLOW 128    /* (job 0 only) packed contour set larger than the caller's buffers */
+#define WBK_ST_FETCH_OVERFLOW 256   /* (job 0 only) more events / ring vertices than the caller's fetch buffers */
 
 const char* wbk_last_error(void);
 int wbk_version(void);
@@ -201,6 +203,25 @@ int wbk_events_fetch(wbk_ctx* ctx, int kind, int n, int* h_ints, double* h_f64, 
 int wbk_rasterize_rings(const int* d_xy, const int* d_ring_off, const int* d_ring_t, const double* d_ring_val,
                         int nrings, int nlat, int nlon, int ntime, double r2, int8_t* d_out_i8, double* d_out_f64,
                         int* d_owner, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Sync-free batch plumbing (what wavebreaking_b200/pipeline.py uses): nothing below waits for the device.
+ *
+ * wbk_contours_pack_auto: like wbk_contours_pack, but the prefix sums run on the device and the caller's
+ * buffers are capacity bounded (d_pt_off [cap_contours+1], d_meta [cap_contours*4], d_pts [cap_points]).
+ * wbk_index_run may then be called with gmax_nx < 0 (= use the batch maximum found by wbk_contours) and
+ * ncontours / npoints = the capacities.
+ *
+ * wbk_batch_fetch: after wbk_events_raster, gathers ALL events (kind-major, then job, then reference order)
+ * into d_out_int [cap_events][WBK_EV_INTS], d_out_f64 [cap_events][WBK_EV_F64], d_out_job [cap_events], the
+ * ring vertices of every streamer / cutoff event into d_ring_pts (event e = [d_ring_off[e], d_ring_off[e+1])),
+ * and writes the summary record d_summary[8] = contours, points, streamers, overturnings, cutoffs,
+ * OR of all status bits, max_nx, split pieces.  The caller copies these buffers to the host and synchronises once. */
+int wbk_contours_pack_auto(wbk_ctx* ctx, int* d_job_off, int* d_pt_off, int* d_meta, uint32_t* d_pts, int cap_contours,
+                           int cap_points, void* stream);
+int wbk_batch_fetch(wbk_ctx* ctx, const int* d_pt_off, const uint32_t* d_pts, int* d_out_int, double* d_out_f64,
+                    int* d_out_job, int* d_ring_off, uint32_t* d_ring_pts, int cap_events, int cap_ring, int* d_summary,
+                    void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Per-kernel device timing (CUDA events on the launching stream around every kernel launch of the

@@ -25,6 +25,8 @@ ST_PAIR_OVERFLOW = 8
 ST_EVENT_OVERFLOW = 16
 ST_SEL_OVERFLOW = 32
 ST_WIDTH_OVERFLOW = 64
+ST_PACK_OVERFLOW = 128
+ST_FETCH_OVERFLOW = 256
 
 
 class WbkError(RuntimeError):
@@ -71,6 +73,9 @@ _SIGNATURES = {
     "wbk_contours_counts": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int), c_void_p]),
     "wbk_contours_pack": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p]),
+    "wbk_contours_pack_auto": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "wbk_batch_fetch": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                c_int, c_void_p, c_void_p]),
     "wbk_track_overlap": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "wbk_prof_enable": (c_int, [c_int]),
     "wbk_prof_reset": (c_int, []),

@@ -80,6 +80,7 @@ __global__ void select_kernel(WbkDev d, WbkIdx x, PackedSet ps, wbk_index_params
   if (job >= ps.njobs) return;
   const int lane = wbk_lane();
   const int c0 = ps.job_off[job], c1 = ps.job_off[job + 1];
+  const int gmax = prm.gmax_nx >= 0 ? prm.gmax_nx : *d.max_nx;  // < 0: the batch maximum found by wbk_contours
   int nsel = 0, ncut = 0;
   for (int cb = c0; cb < c1; cb += 32) {
     const int c = cb + lane;
@@ -87,8 +88,8 @@ __global__ void select_kernel(WbkDev d, WbkIdx x, PackedSet ps, wbk_index_params
     if (c < c1) {
       const int closed = ps.meta[4 * c + 0], nx = ps.meta[4 * c + 1];
       npts = ps.pt_off[c + 1] - ps.pt_off[c];
-      is_sel = nx == prm.gmax_nx;
-      is_cut = prm.do_cutoffs && closed && nx < prm.gmax_nx && ((double)nx * prm.dlon >= prm.co_min_exp);
+      is_sel = nx == gmax;
+      is_cut = prm.do_cutoffs && closed && nx < gmax && ((double)nx * prm.dlon >= prm.co_min_exp);
     }
     const u32 bs = __ballot_sync(WBK_FULL, is_sel), bc = __ballot_sync(WBK_FULL, is_cut);
     const u32 below = (1u << lane) - 1u;
@@ -815,7 +816,7 @@ extern "C" int wbk_index_run(wbk_ctx* ctx, int njobs, int nlevels, const int* d_
   const int J = ctx->caps.max_jobs;
   PackedSet ps{d_job_off, d_pt_off, d_meta, (const u32*)d_pts, njobs, nlevels, ncontours, npoints};
   CoordTabs ct = make_coords(d_coords, d.nlat);
-  WBK_CUDA_CHECK(cudaMemsetAsync(d.status, 0, sizeof(int) * njobs, st));
+  if (prm->gmax_nx >= 0) WBK_CUDA_CHECK(cudaMemsetAsync(d.status, 0, sizeof(int) * njobs, st));
   WBK_LAUNCH(KID_SELECT, select_kernel, dim3((njobs + 7) / 8), dim3(256), 0, st, d, x, ps, *prm, J);
   WBK_LAUNCH_CHECK();
   if (prm->do_overturnings) {

@@ -223,6 +223,7 @@ class EventTable:
     split: np.ndarray      # 0 on the real grid, 1 straddles the last meridian, 2 entirely in the extension
     near: np.ndarray       # streamers: base-point decision within 1e-9 of a threshold
     sums: np.ndarray       # [n, 6]: sum a, sum a*data, sum a*intensity, sum a*x, sum a*y, member count
+    rings: list = None     # index-space ring (n, 2) of every streamer / cutoff event when fetched with the batch
 
     def __len__(self):
         return len(self.job)
@@ -292,8 +293,10 @@ def run_indices(cs, data, coords, dlon, dlat, intensity=None, which=KINDS, gmax_
 
 def event_rings(cs, table):
     """Index-space ring (n, 2) of every event of a table (host)."""
-    h = cs.host()
+    if table.kind != "overturnings" and table.rings is not None:
+        return list(table.rings)
     rings = []
+    h = cs.host() if table.kind != "overturnings" else None
     for e in range(len(table)):
         if table.kind == "overturnings":
             x0, y0, x1, y1 = (int(v) for v in table.box[e])

@@ -1,15 +1,20 @@
 """Batched per-time-step detection pipeline (the benchmarked hot path).
 
-One ``Detector.run_batch`` call takes ``T`` time steps of a raw field and produces what the
-reference produces with
+One batch = ``T`` time steps of a raw field through what the reference does with
 ``calculate_smoothed_field`` -> ``calculate_contours`` -> ``calculate_streamers`` /
 ``calculate_overturnings`` / ``calculate_cutoffs`` -> ``to_xarray`` (x3):
 columnar event tables (host) and the three int8 flag grids.  All arithmetic runs in libwbk's
-CUDA kernels (including the meridian split of the events that straddle the date line); the host only
-sizes buffers (two small device->host count reads per batch) and receives the tables.
+CUDA kernels (including the meridian split of the events that straddle the date line).
+
+A batch is *enqueued without any host synchronisation* (``submit``): smoothing, marching squares, linking,
+device-side packing, the three indices, rasterisation and one gather of all results, then the asynchronous
+device->host copies.  ``collect`` waits once and slices the tables.  Several slots (each with its own
+context, buffers and CUDA stream) keep the GPU busy while the host handles the previous batch and let
+host<->device copies overlap with kernels (``Detector.stream``).
 """
 
-from dataclasses import dataclass, field
+import ctypes
+from dataclasses import dataclass
 
 import numpy as np
 import torch
@@ -22,13 +27,73 @@ class BatchResult:
     ntime: int
     contours: detect.ContourSet
     tables: dict              # kind -> detect.EventTable
-    flags: torch.Tensor       # int8 [3, ntime, nlat, nlon] on the device (or pinned host if fetched)
+    flags: torch.Tensor       # int8 [3, ntime, nlat, nlon] (device, or pinned host in the end-to-end path)
     gmax_nx: int
     n_split: int = 0
 
 
+def _pinned(shape, dtype, lib):
+    return torch.empty(shape, dtype=dtype, pin_memory=lib.is_cuda)
+
+
+class _Slot:
+    """Context + device / pinned buffers + stream for one batch in flight."""
+
+    def __init__(self, det, T, caps=None):
+        lib = det.lib
+        self.det, self.T = det, int(T)
+        dev = lib.device
+        L = len(det.levels)
+        J = self.T * L
+        self.J = J
+        want = detect.default_caps(det.nlat, det.nlon, det.add, J)
+        if caps:
+            for k, v in caps.items():
+                want[k] = max(want[k], int(v))
+        self.ctx = detect.Context(det.nlat, det.nlon, det.add, want)
+        self.cap_c = int(max(64 * J, 1024))
+        self.cap_p = int(max(min(want["seg_cap"], 16384) * J, 1 << 16))
+        self.cap_e = int(max(48 * J, 1024))
+        self.cap_r = int(max(8192 * J, 1 << 16))
+        if caps:
+            self.cap_c = max(self.cap_c, int(caps.get("cap_c", 0)))
+            self.cap_p = max(self.cap_p, int(caps.get("cap_p", 0)))
+            self.cap_e = max(self.cap_e, int(caps.get("cap_e", 0)))
+            self.cap_r = max(self.cap_r, int(caps.get("cap_r", 0)))
+        shape = (self.T, det.nlat, det.nlon)
+        i32, f64 = torch.int32, torch.float64
+        self.sm = torch.empty(shape, dtype=f64, device=dev) if det.passes > 0 else None
+        self.sm_f32 = None
+        self.sm_tmp = torch.empty(shape, dtype=f64, device=dev) if det.passes > _lib.SMOOTH_MAX_FUSED else None
+        self.raw_dev = None  # allocated on first host submit
+        self.job_off = torch.empty(J + 1, dtype=i32, device=dev)
+        self.pt_off = torch.empty(self.cap_c + 1, dtype=i32, device=dev)
+        self.meta = torch.empty((self.cap_c, 4), dtype=i32, device=dev)
+        self.pts = torch.empty(self.cap_p, dtype=i32, device=dev)
+        self.work = torch.empty(2 * self.cap_p, dtype=f64, device=dev)
+        self.flags = None
+        self.ev_int = torch.empty((self.cap_e, _lib.EV_INTS), dtype=i32, device=dev)
+        self.ev_f64 = torch.empty((self.cap_e, _lib.EV_F64), dtype=f64, device=dev)
+        self.ev_job = torch.empty(self.cap_e, dtype=i32, device=dev)
+        self.ring_off = torch.empty(self.cap_e + 1, dtype=i32, device=dev)
+        self.ring_pts = torch.empty(self.cap_r, dtype=i32, device=dev)
+        self.summary = torch.zeros(8, dtype=i32, device=dev)
+        self.h_summary = _pinned(8, i32, lib)
+        self.h_ev_int = _pinned((self.cap_e, _lib.EV_INTS), i32, lib)
+        self.h_ev_f64 = _pinned((self.cap_e, _lib.EV_F64), f64, lib)
+        self.h_ev_job = _pinned(self.cap_e, i32, lib)
+        self.h_ring_off = _pinned(self.cap_e + 1, i32, lib)
+        self.h_ring_pts = _pinned(self.cap_r, i32, lib)
+        self.stream = torch.cuda.Stream(device=dev) if lib.is_cuda else None
+        self.done = torch.cuda.Event() if lib.is_cuda else None
+        self.pending = None   # (raw, ntime, flags_dev, flags_host, gmax)
+
+    def close(self):
+        self.ctx.close()
+
+
 class Detector:
-    """Holds the grid, thresholds and reusable device buffers of one detection configuration."""
+    """Holds the grid, thresholds and the reusable slots of one detection configuration."""
 
     def __init__(self, lat, lon, levels=(2.0,), periodic_add=120, passes=5, which=detect.KINDS, geo_dis=800.0,
                  cont_dis=1500.0, range_group=5.0, ot_min_exp=5.0, co_min_exp=5.0, want_flags=True):
@@ -39,38 +104,238 @@ class Detector:
         self.dlon = float(abs(self.lon[1] - self.lon[0]))
         self.dlat = float(abs(self.lat[1] - self.lat[0]))
         self.add = int(periodic_add / self.dlon)
-        self.levels = np.atleast_1d(np.asarray(levels, dtype=np.float64))
+        self.levels = np.ascontiguousarray(np.atleast_1d(np.asarray(levels, dtype=np.float64)))
         self.passes = int(passes)
         self.which = tuple(which)
         self.params = dict(geo_dis=geo_dis, cont_dis=cont_dis, range_group=range_group, ot_min_exp=ot_min_exp,
                            co_min_exp=co_min_exp)
         self.want_flags = want_flags
         self.coords = detect.coord_tables(self.lat, self.lon, self.dlon, self.dlat, self.lib)
+        self._slots = {}
+        self._grow = {}
 
-    # ------------------------------------------------------------------ device-resident input
+    # ------------------------------------------------------------------ slots
+    def _slot(self, T, index=0):
+        key = (int(T), int(index))
+        s = self._slots.get(key)
+        if s is None:
+            s = _Slot(self, T, self._grow)
+            self._slots[key] = s
+        return s
+
+    def close(self):
+        for s in self._slots.values():
+            s.close()
+        self._slots.clear()
+
+    def _prm(self, gmax):
+        p = self.params
+        return _lib.IndexParams(
+            do_streamers=int("streamers" in self.which), do_overturnings=int("overturnings" in self.which),
+            do_cutoffs=int("cutoffs" in self.which), gmax_nx=int(gmax), dlon=self.dlon, dlat=self.dlat,
+            geo_dis=float(p["geo_dis"]), cont_dis=float(p["cont_dis"]), range_group=float(p["range_group"]),
+            ot_min_exp=float(p["ot_min_exp"]), co_min_exp=float(p["co_min_exp"]))
+
+    # ------------------------------------------------------------------ enqueue / collect
+    def submit(self, slot, raw, flags_out=None, flags_host=None, gmax_nx=None, smoothed=None):
+        """Enqueue one batch on the slot's stream.  ``raw``: device tensor or (pinned) host tensor
+        [T' <= T, nlat, nlon].  No host synchronisation happens here."""
+        lib = self.lib
+        nt = int(raw.shape[0])
+        if nt > slot.T:
+            raise ValueError("batch of {} time steps exceeds the slot size {}".format(nt, slot.T))
+        ctx_mgr = torch.cuda.stream(slot.stream) if slot.stream is not None else _null()
+        with ctx_mgr:
+            if slot.stream is not None:
+                slot.stream.wait_stream(torch.cuda.default_stream(lib.device))
+            st = lib.stream()
+            if raw.device != lib.device:  # host input: H2D on this slot's stream
+                if slot.raw_dev is None or slot.raw_dev.dtype != raw.dtype:
+                    slot.raw_dev = torch.empty((slot.T, self.nlat, self.nlon), dtype=raw.dtype, device=lib.device)
+                slot.raw_dev[:nt].copy_(raw, non_blocking=True)
+                raw = slot.raw_dev[:nt]
+            raw = raw.contiguous()
+            if smoothed is not None:
+                sm = smoothed
+            elif self.passes > 0:
+                f32 = raw.dtype == torch.float32
+                if f32 and not spatial._numpy2():
+                    if slot.sm_f32 is None:
+                        slot.sm_f32 = torch.empty((slot.T, self.nlat, self.nlon), dtype=torch.float32, device=lib.device)
+                    sm, rmode = slot.sm_f32[:nt], _lib.ROUND_ALL
+                else:
+                    sm, rmode = slot.sm[:nt], (_lib.ROUND_FIRST if f32 else _lib.ROUND_NONE)
+                lib.call("wbk_smooth", _lib.ptr(raw), _lib.dtype_code(raw.dtype), _lib.ptr(sm), _lib.dtype_code(sm.dtype),
+                         _lib.ptr(slot.sm_tmp), nt, self.nlat, self.nlon, self.passes, rmode, st)
+            else:
+                sm = raw
+            h = slot.ctx.handle
+            L = len(self.levels)
+            lib.call("wbk_contours", h, _lib.ptr(sm), _lib.dtype_code(sm.dtype), nt,
+                     self.levels.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), L, st)
+            lib.call("wbk_contours_pack_auto", h, _lib.ptr(slot.job_off), _lib.ptr(slot.pt_off), _lib.ptr(slot.meta),
+                     _lib.ptr(slot.pts), slot.cap_c, slot.cap_p, st)
+            prm = self._prm(-1 if gmax_nx is None else gmax_nx)
+            lib.call("wbk_index_run", h, nt * L, L, _lib.ptr(slot.job_off), _lib.ptr(slot.pt_off), _lib.ptr(slot.meta),
+                     _lib.ptr(slot.pts), slot.cap_c, slot.cap_p, _lib.ptr(self.coords), _lib.ptr(slot.work),
+                     ctypes.byref(prm), st)
+            flags = None
+            if self.want_flags:
+                if flags_out is not None:
+                    flags = flags_out
+                else:
+                    if slot.flags is None:
+                        slot.flags = torch.empty((3, slot.T, self.nlat, self.nlon), dtype=torch.int8, device=lib.device)
+                    flags = slot.flags if nt == slot.T else torch.empty((3, nt, self.nlat, self.nlon), dtype=torch.int8,
+                                                                        device=lib.device)
+            lib.call("wbk_events_raster", h, _lib.ptr(slot.job_off), _lib.ptr(slot.pt_off), _lib.ptr(slot.pts),
+                     _lib.ptr(self.coords), _lib.ptr(sm), _lib.dtype_code(sm.dtype), None, nt, _lib.ptr(flags),
+                     ctypes.byref(prm), st)
+            lib.call("wbk_batch_fetch", h, _lib.ptr(slot.pt_off), _lib.ptr(slot.pts), _lib.ptr(slot.ev_int),
+                     _lib.ptr(slot.ev_f64), _lib.ptr(slot.ev_job), _lib.ptr(slot.ring_off), _lib.ptr(slot.ring_pts),
+                     slot.cap_e, slot.cap_r, _lib.ptr(slot.summary), st)
+            # asynchronous read-back of everything the host needs (tables are small; flags only on request)
+            slot.h_summary.copy_(slot.summary, non_blocking=True)
+            slot.h_ev_int.copy_(slot.ev_int, non_blocking=True)
+            slot.h_ev_f64.copy_(slot.ev_f64, non_blocking=True)
+            slot.h_ev_job.copy_(slot.ev_job, non_blocking=True)
+            slot.h_ring_off.copy_(slot.ring_off, non_blocking=True)
+            slot.h_ring_pts.copy_(slot.ring_pts, non_blocking=True)
+            if flags_host is not None and flags is not None:
+                flags_host[:, :nt].copy_(flags[:, :nt] if flags.shape[1] != nt else flags, non_blocking=True)
+            if slot.done is not None:
+                slot.done.record()
+        slot.pending = dict(raw=raw, nt=nt, flags=flags, flags_host=flags_host, gmax=gmax_nx, smoothed=smoothed, sm=sm)
+        return slot
+
+    def collect(self, slot):
+        """Wait for the slot's batch and return its BatchResult (re-runs it with larger arenas on overflow)."""
+        pend = slot.pending
+        if pend is None:
+            raise RuntimeError("nothing was submitted on this slot")
+        if slot.done is not None:
+            slot.done.synchronize()
+        s = slot.h_summary.numpy()
+        C, P, ns, no, nc, status, max_nx, n_split = (int(v) for v in s)
+        bad = status & (_lib.ST_SEG_OVERFLOW | _lib.ST_CONTOUR_OVERFLOW | _lib.ST_PAIR_OVERFLOW | _lib.ST_EVENT_OVERFLOW
+                        | _lib.ST_SEL_OVERFLOW | _lib.ST_PACK_OVERFLOW | _lib.ST_FETCH_OVERFLOW)
+        if bad:
+            return self._regrow_and_rerun(slot, status)
+        slot.pending = None
+        nt = pend["nt"]
+        L = len(self.levels)
+        counts = (ns, no, nc)
+        tables, o = {}, 0
+        ring_off = slot.h_ring_off.numpy()
+        ring_pts = slot.h_ring_pts.numpy().view(np.uint32)
+        for kind, n in zip(detect.KINDS, counts):
+            ints = slot.h_ev_int.numpy()[o:o + n].copy()
+            f64 = slot.h_ev_f64.numpy()[o:o + n].copy()
+            job = slot.h_ev_job.numpy()[o:o + n].copy()
+            rings = None
+            if kind != "overturnings":
+                rings = []
+                for e in range(o, o + n):
+                    p = ring_pts[ring_off[e]:ring_off[e + 1]]
+                    rings.append(np.c_[(p & 0xFFFF).astype(np.int64), (p >> 16).astype(np.int64)])
+            tab = detect.EventTable(kind=kind, job=job, contour=ints[:, 0].copy(), ind1=ints[:, 1].copy(),
+                                    ind2=ints[:, 2].copy(), box=ints[:, 3:7].copy(), orientation=ints[:, 7].copy(),
+                                    split=ints[:, 8].copy(), near=ints[:, 9].copy(), sums=f64)
+            tab.rings = rings
+            tables[kind] = tab
+            o += n
+        cs = detect.ContourSet(
+            njobs=nt * L, nlevels=L, nlat=self.nlat, nlon=self.nlon, add=self.add, levels=self.levels,
+            job_off=slot.job_off[:nt * L + 1], pt_off=slot.pt_off[:C + 1], meta=slot.meta[:C], pts=slot.pts[:P],
+            status=np.full(nt * L, status, dtype=np.int32), max_nx=max_nx, h_ncontours=None, h_npoints=None)
+        flags = pend["flags_host"] if pend["flags_host"] is not None else pend["flags"]
+        n_sp = int(sum(int((t.split == 1).sum()) for t in tables.values()))
+        return BatchResult(ntime=nt, contours=cs, tables=tables, flags=flags,
+                           gmax_nx=max_nx if pend["gmax"] is None else int(pend["gmax"]), n_split=n_sp)
+
+    def _regrow_and_rerun(self, slot, status):
+        pend = slot.pending
+        caps = dict(slot.ctx.caps)
+        grow = dict(self._grow)
+        if status & _lib.ST_SEG_OVERFLOW:
+            grow["seg_cap"] = caps["seg_cap"] * 2
+        if status & _lib.ST_CONTOUR_OVERFLOW:
+            grow["contour_cap"] = caps["contour_cap"] * 2
+        if status & _lib.ST_PAIR_OVERFLOW:
+            grow["pair_cap"] = caps["pair_cap"] * 4
+        if status & _lib.ST_EVENT_OVERFLOW:
+            grow["event_cap"] = caps["event_cap"] * 4
+        if status & _lib.ST_SEL_OVERFLOW:
+            grow["sel_cap"] = caps["sel_cap"] * 4
+        if status & _lib.ST_PACK_OVERFLOW:
+            grow["cap_c"], grow["cap_p"] = slot.cap_c * 2, slot.cap_p * 2
+        if status & _lib.ST_FETCH_OVERFLOW:
+            grow["cap_e"], grow["cap_r"] = slot.cap_e * 2, slot.cap_r * 2
+        self._grow = grow
+        if len(grow) and max(grow.values()) > (1 << 28):
+            raise _lib.WbkError(_lib.ERR_CAPACITY, "arenas still overflow after repeated regrowth (status {})".format(status))
+        key = next(k for k, v in self._slots.items() if v is slot)
+        if self.lib.is_cuda:
+            torch.cuda.synchronize()
+        slot.close()
+        new = _Slot(self, slot.T, grow)
+        self._slots[key] = new
+        self.submit(new, pend["raw"], flags_out=pend["flags"], flags_host=pend["flags_host"], gmax_nx=pend["gmax"],
+                    smoothed=pend["smoothed"])
+        return self.collect(new)
+
+    # ------------------------------------------------------------------ convenience
     def run_batch(self, raw, gmax_nx=None, smoothed=None):
-        """raw: device tensor [T, nlat, nlon] (float32 / float64).  Returns a BatchResult."""
-        sm = smoothed if smoothed is not None else (spatial.smooth(raw, self.passes) if self.passes > 0 else raw)
-        cs = detect.contours(sm, self.levels, self.add)
-        g = cs.max_nx if gmax_nx is None else max(int(gmax_nx), cs.max_nx)
-        tables, flags = detect.run_indices(cs, sm, self.coords, self.dlon, self.dlat, which=self.which, gmax_nx=g,
-                                           want_flags=self.want_flags, **self.params)
-        n_split = int(sum(int((t.split == 1).sum()) for t in tables.values()))
-        return BatchResult(ntime=int(sm.shape[0]), contours=cs, tables=tables, flags=flags, gmax_nx=g, n_split=n_split)
-
-    # ------------------------------------------------------------------ host input (end to end)
-    def run_batch_host(self, raw_host, flags_host=None):
-        """raw_host: pinned host tensor [T, nlat, nlon]; copies in, runs, copies the flag grids out."""
-        raw = raw_host.to(self.lib.device, non_blocking=True)
-        res = self.run_batch(raw)
+        """Synchronous: raw device tensor [T, nlat, nlon] -> BatchResult (flags and contour set are private
+        copies, valid after further calls)."""
+        nt = int(raw.shape[0])
+        slot = self._slot(nt)
+        flags = None
         if self.want_flags:
-            if flags_host is None:
-                flags_host = torch.empty(res.flags.shape, dtype=torch.int8, pin_memory=self.lib.is_cuda)
-            flags_host.copy_(res.flags, non_blocking=True)
-            if self.lib.is_cuda:
-                torch.cuda.current_stream().synchronize()
-            res.flags = flags_host
+            flags = torch.empty((3, nt, self.nlat, self.nlon), dtype=torch.int8, device=self.lib.device)
+        self.submit(slot, raw, flags_out=flags, gmax_nx=gmax_nx, smoothed=smoothed)
+        res = self.collect(slot)
+        cs = res.contours
+        cs.job_off, cs.pt_off, cs.meta, cs.pts = cs.job_off.clone(), cs.pt_off.clone(), cs.meta.clone(), cs.pts.clone()
         return res
+
+    def run_batch_host(self, raw_host, flags_host=None):
+        """Synchronous end-to-end: (pinned) host input -> tables + flag grids in (pinned) host memory."""
+        nt = int(raw_host.shape[0])
+        slot = self._slot(nt)
+        if self.want_flags and flags_host is None:
+            flags_host = _pinned((3, nt, self.nlat, self.nlon), torch.int8, self.lib)
+        self.submit(slot, raw_host, flags_host=flags_host)
+        return self.collect(slot)
+
+    def stream(self, batches, depth=3, flags_host=None):
+        """Pipelined execution: yields one BatchResult per input batch, in order.
+
+        ``batches``: iterable of device or pinned-host tensors of (at most) equal length.  ``depth`` batches are
+        in flight at once, each on its own CUDA stream, so uploads, kernels, downloads and the host-side table
+        handling overlap.  ``flags_host``: optional list of pinned int8 buffers, one per slot.
+        The flag grids / contour set of a result are only valid until its slot is reused (``depth`` batches later).
+        """
+        inflight = []
+        i = 0
+        for raw in batches:
+            idx = i % depth
+            if len(inflight) == depth:
+                yield self.collect(inflight.pop(0))
+            slot = self._slot(int(raw.shape[0]), idx)
+            fh = flags_host[idx] if flags_host is not None else None
+            inflight.append(self.submit(slot, raw, flags_host=fh))
+            i += 1
+        while inflight:
+            yield self.collect(inflight.pop(0))
+
+
+class _null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
 
 
 def summarize(res):
