@@ -259,7 +259,7 @@ def run_b200(a):
     # ---- device-resident leg (value)
     stats = {"segments": 0, "points": 0, "pairs": 0}
     depth = 3
-    for res in det.stream((slabs[s % nslab] for s in range(W)), depth=depth):
+    for res in det.stream((slabs[s % nslab] for s in range(W)), depth=depth, shared_stream=True):
         pass
     barrier()
     launches0 = lib.cdll.wbk_launch_count()
@@ -270,7 +270,7 @@ def run_b200(a):
     ev0.record()
     t_wall0 = time.perf_counter()
     counts = []
-    for res in det.stream((slabs[(W + s) % nslab] for s in range(K)), depth=depth):
+    for res in det.stream((slabs[(W + s) % nslab] for s in range(K)), depth=depth, shared_stream=True):
         counts.append(pipeline.summarize(res))
     torch.cuda.synchronize()
     wall_ms = (time.perf_counter() - t_wall0) * 1000.0
@@ -324,7 +324,7 @@ def run_b200(a):
         d2h = 0
         for r in det.stream((host_in[s % depth] for s in range(K)), depth=depth, flags_host=flags_host):
             d2h = flags_host[0].numel() + sum(t.sums.nbytes + 11 * 4 * len(t) for t in r.tables.values()) \
-                + 4 * sum(len(x) * 2 for t in r.tables.values() if t.rings for x in t.rings)
+                + sum(t.rings.nbytes for t in r.tables.values() if t.rings is not None)
         torch.cuda.synchronize()
         e1.record()
         barrier()

@@ -239,3 +239,4 @@ struct int2 { int x, y; };
 struct int4 { int x, y, z, w; };
 struct uint4 { unsigned x, y, z, w; };
 inline float __sinf(float v) { return std::sin(v); }
+inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }

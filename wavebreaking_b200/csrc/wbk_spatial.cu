@@ -39,139 +39,127 @@ __device__ __forceinline__ double smooth_finish(double v) {
   return SAFE ? div6_fast(v) : __ddiv_rn(v, 6.0);
 }
 
-// One pass over rows [K, H-K) of the shared tile: column pairs x row bands, sliding (north, centre, south)
-// register window -> one 128-bit + two 64-bit shared loads and one 128-bit store per pair of cell updates.
-template <int P, int K, int RND, bool SAFE>
-__device__ __forceinline__ void smooth_pass(const double* __restrict__ a, double* __restrict__ b) {
-  constexpr int H = SM_TH + 2 * P, Wd = SM_TW + 2 * P;
-  constexpr int NPAIRS = Wd / 2, NBANDS = SM_THREADS / NPAIRS;
-  constexpr int NROWS = H - 2 * K, PER = (NROWS + NBANDS - 1) / NBANDS;
-  const int pair = threadIdx.x % NPAIRS, band = threadIdx.x / NPAIRS;
-  const int c0 = 2 * pair;
-  const int cw = c0 > 0 ? c0 - 1 : 0;           // clamped: edge columns are never valid outputs
-  const int ce = c0 + 2 < Wd ? c0 + 2 : Wd - 1;
-  const int r_lo = K + band * PER;
-  if (band >= NBANDS || r_lo >= K + NROWS) return;
-  const int r_hi = r_lo + PER < K + NROWS ? r_lo + PER : K + NROWS;
-  const double* pc = a + r_lo * Wd + c0;
-  const double* pw = a + r_lo * Wd + cw;
-  const double* pe = a + r_lo * Wd + ce;
-  double* po = b + r_lo * Wd + c0;
-  double2 n2 = *reinterpret_cast<const double2*>(pc - Wd);
-  double2 c2 = *reinterpret_cast<const double2*>(pc);
-  // fully unrolled (PER is a compile-time constant): constant address offsets, no register shuffling
-#pragma unroll
-  for (int i = 0; i < PER; ++i) {
-    if (r_lo + i < r_hi) {
-      const double2 s2 = *reinterpret_cast<const double2*>(pc + (i + 1) * Wd);
-      const double wv = pw[i * Wd], ev = pe[i * Wd];
-      // scipy's tap order: ((((N + W) + 2C) + E) + S)
-      double v0 = __dadd_rn(n2.x, wv);
-      v0 = __dadd_rn(v0, __dadd_rn(c2.x, c2.x));
-      v0 = __dadd_rn(v0, c2.y);
-      v0 = __dadd_rn(v0, s2.x);
-      double v1 = __dadd_rn(n2.y, c2.x);
-      v1 = __dadd_rn(v1, __dadd_rn(c2.y, c2.y));
-      v1 = __dadd_rn(v1, ev);
-      v1 = __dadd_rn(v1, s2.y);
-      double2 o;
-      o.x = smooth_finish<RND, SAFE>(v0);
-      o.y = smooth_finish<RND, SAFE>(v1);
-      *reinterpret_cast<double2*>(po + i * Wd) = o;
-      n2 = c2;
-      c2 = s2;
-    }
-  }
-}
+// ------------------------------------------------------------------------------------------
+// Register-resident fused smoothing.  A warp owns a strip of 64 columns (lane l: columns 2l, 2l+1) and a band of
+// SM_PER rows that stay in registers for all P passes; 8 warps stack their bands into a 64 x 64 tile of which
+// the inner (64-2P) x (64-2P) cells are valid outputs.  Per pass the only traffic is two 64-bit shuffles per row
+// (west / east neighbours) and one row of halo per band edge through shared memory; the arithmetic
+// (4 DP adds/FMA + the 3-op exact division per cell) is what remains, so the kernel runs on the FP64 pipe.
+// ------------------------------------------------------------------------------------------
+#define SM_PER 8                       // rows per warp band
+#define SM_TILE 64                     // tile edge = 8 bands x SM_PER rows = 32 lanes x 2 columns
 
 template <int P, int RFIRST, int RREST, bool SAFE>
-__device__ __forceinline__ void smooth_all_passes(double*& a, double*& b) {
-  // unrolled at compile time (P <= WBK_SMOOTH_MAX_FUSED)
-#define WBK_PASS(K)                                                             \
-  if (P >= K) {                                                                 \
-    if (K == 1) smooth_pass<P, (K <= P ? K : 1), RFIRST, SAFE>(a, b);           \
-    else smooth_pass<P, (K <= P ? K : 1), RREST, SAFE>(a, b);                   \
-    __syncthreads();                                                            \
-    double* t_ = a; a = b; b = t_;                                              \
+__device__ __forceinline__ void smooth_strip_passes(double (&vx)[SM_PER], double (&vy)[SM_PER],
+                                                    double (*halo)[8][2][SM_TILE], int lane, int band, int r_base) {
+#pragma unroll
+  for (int k = 1; k <= P; ++k) {
+    const int par = k & 1;
+    // publish the band's edge rows (old values), fetch the neighbours' after the barrier
+    *reinterpret_cast<double2*>(&halo[par][band][0][2 * lane]) = make_double2(vx[0], vy[0]);
+    *reinterpret_cast<double2*>(&halo[par][band][1][2 * lane]) = make_double2(vx[SM_PER - 1], vy[SM_PER - 1]);
+    __syncthreads();
+    const double2 north = band > 0 ? *reinterpret_cast<const double2*>(&halo[par][band - 1][1][2 * lane]) : make_double2(0.0, 0.0);
+    const double2 south = band < 7 ? *reinterpret_cast<const double2*>(&halo[par][band + 1][0][2 * lane]) : make_double2(0.0, 0.0);
+    double nx = north.x, ny = north.y;
+#pragma unroll
+    for (int i = 0; i < SM_PER; ++i) {
+      const int r = r_base + i;
+      const double cx = vx[i], cy = vy[i];
+      if (r >= k && r < SM_TILE - k) {  // warp-uniform: rows outside are no longer needed
+        const double sx = i + 1 < SM_PER ? vx[i + 1] : south.x;
+        const double sy = i + 1 < SM_PER ? vy[i + 1] : south.y;
+        const double wv = __shfl_up_sync(WBK_FULL, cy, 1);    // column 2l-1 (lane 0: unused halo garbage)
+        const double ev = __shfl_down_sync(WBK_FULL, cx, 1);  // column 2l+2
+        // scipy's tap order ((((N + W) + 2C) + E) + S); (N+W) + 2C in one FMA is the same single rounding
+        double a0 = __dadd_rn(nx, wv);
+        a0 = __fma_rn(2.0, cx, a0);
+        a0 = __dadd_rn(a0, cy);
+        a0 = __dadd_rn(a0, sx);
+        double a1 = __dadd_rn(ny, cx);
+        a1 = __fma_rn(2.0, cy, a1);
+        a1 = __dadd_rn(a1, ev);
+        a1 = __dadd_rn(a1, sy);
+        if (k == 1) {
+          vx[i] = smooth_finish<RFIRST, SAFE>(a0);
+          vy[i] = smooth_finish<RFIRST, SAFE>(a1);
+        } else {
+          vx[i] = smooth_finish<RREST, SAFE>(a0);
+          vy[i] = smooth_finish<RREST, SAFE>(a1);
+        }
+      }
+      nx = cx;
+      ny = cy;
+    }
   }
-  WBK_PASS(1) WBK_PASS(2) WBK_PASS(3) WBK_PASS(4) WBK_PASS(5) WBK_PASS(6) WBK_PASS(7) WBK_PASS(8)
-#undef WBK_PASS
+
 }
 
-// RMODE: WBK_ROUND_NONE / WBK_ROUND_FIRST (applies to the first pass of this launch) / WBK_ROUND_ALL
 template <int P, typename TIn, typename TOut, int RMODE>
 __global__ void __launch_bounds__(SM_THREADS)
 smooth_fused_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, int nlat, int nlon, int nan_border) {
-  WBK_DYN_SMEM(double, smem);
-  constexpr int H = SM_TH + 2 * P, Wd = SM_TW + 2 * P;
-  double* a = smem;
-  double* b = smem + H * Wd;
-
-  const int x0 = blockIdx.x * SM_TW, y0 = blockIdx.y * SM_TH;
+  constexpr int OUTW = SM_TILE - 2 * P;  // valid outputs per tile edge
+  __shared__ double halo[2][8][2][SM_TILE];  // [parity][band][top/bottom][column]
+  const int lane = wbk_lane(), band = wbk_warp();
+  const int x0 = blockIdx.x * OUTW - P, y0 = blockIdx.y * OUTW - P;  // tile origin (may be negative: wraps)
   const size_t plane = (size_t)nlat * nlon;
   const TIn* src = in + plane * blockIdx.z;
   TOut* dst = out + plane * blockIdx.z;
 
-  // load tile + halo (wrapping both axes); all loads of a thread are issued before the first use
-  constexpr int NLOAD = (H * Wd + SM_THREADS - 1) / SM_THREADS;
-  TIn tmp[NLOAD];
-#pragma unroll
-  for (int i = 0; i < NLOAD; ++i) {
-    const int idx = threadIdx.x + i * SM_THREADS;
-    const int r = idx / Wd, c = idx - r * Wd;
-    int gy = y0 - P + r, gx = x0 - P + c;
-    gy = gy < 0 ? gy + nlat : (gy >= nlat ? gy - nlat : gy);
-    gx = gx < 0 ? gx + nlon : (gx >= nlon ? gx - nlon : gx);
-    if (gy < 0 || gy >= nlat) gy = wrap_idx(y0 - P + r, nlat);
-    if (gx < 0 || gx >= nlon) gx = wrap_idx(x0 - P + c, nlon);
-    tmp[i] = idx < H * Wd ? src[(size_t)gy * nlon + gx] : (TIn)0;
-  }
+  // this lane's two columns (periodic)
+  int gx0 = x0 + 2 * lane, gx1 = gx0 + 1;
+  gx0 = wrap_idx(gx0, nlon);
+  gx1 = wrap_idx(gx1, nlon);
+  const int r_base = band * SM_PER;
+
+  double vx[SM_PER], vy[SM_PER];
   int unsafe = 0;
+  {
+    TIn tx[SM_PER], ty[SM_PER];
 #pragma unroll
-  for (int i = 0; i < NLOAD; ++i) {
-    const int idx = threadIdx.x + i * SM_THREADS;
-    const double v = (double)tmp[i];
-    const double av = fabs(v);
-    unsafe |= !(av <= 1e290) || (av < 1e-150 && av != 0.0);
-    if (idx < H * Wd) a[idx] = v;
+    for (int i = 0; i < SM_PER; ++i) {
+      const int gy = wrap_idx(y0 + r_base + i, nlat);
+      tx[i] = src[(size_t)gy * nlon + gx0];
+      ty[i] = src[(size_t)gy * nlon + gx1];
+    }
+#pragma unroll
+    for (int i = 0; i < SM_PER; ++i) {
+      vx[i] = (double)tx[i];
+      vy[i] = (double)ty[i];
+      const double ax = fabs(vx[i]), ay = fabs(vy[i]);
+      unsafe |= !(ax <= 1e290) || (ax < 1e-150 && ax != 0.0) || !(ay <= 1e290) || (ay < 1e-150 && ay != 0.0);
+    }
   }
-  const int slow = __syncthreads_or(unsafe);  // also the barrier after the tile load
+  const int slow = __syncthreads_or(unsafe);
 
   constexpr int RFIRST = RMODE == WBK_ROUND_ALL ? 2 : (RMODE == WBK_ROUND_FIRST ? 1 : 0);
   constexpr int RREST = RMODE == WBK_ROUND_ALL ? 2 : 0;
-  if (!slow) smooth_all_passes<P, RFIRST, RREST, true>(a, b);
-  else smooth_all_passes<P, RFIRST, RREST, false>(a, b);
 
-  // write the inner tile: one warp per row (coalesced)
-  const int lane = wbk_lane(), warp = wbk_warp();
-  for (int r = warp; r < SM_TH; r += SM_THREADS / 32) {
-    const int gy = y0 + r;
-    if (gy >= nlat) break;
-    const bool nanrow = nan_border > 0 && (gy < nan_border || gy >= nlat - nan_border);
+  if (!slow) smooth_strip_passes<P, RFIRST, RREST, true>(vx, vy, halo, lane, band, r_base);
+  else smooth_strip_passes<P, RFIRST, RREST, false>(vx, vy, halo, lane, band, r_base);
+
+  // write the valid interior: tile rows / columns [P, 64 - P)
+  const int c_lo = 2 * lane;
 #pragma unroll
-    for (int c = lane; c < SM_TW; c += 32) {
-      const int gx = x0 + c;
-      if (gx < nlon) {
-        double v = a[(r + P) * Wd + (c + P)];
-        if (nanrow) v = __longlong_as_double(0x7ff8000000000000LL);
-        dst[(size_t)gy * nlon + gx] = (TOut)v;
-      }
-    }
+  for (int i = 0; i < SM_PER; ++i) {
+    const int r = r_base + i;
+    const int gy = y0 + r;
+    if (r < P || r >= SM_TILE - P || gy >= nlat) continue;
+    const bool nanrow = nan_border > 0 && (gy < nan_border || gy >= nlat - nan_border);
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    const int ox0 = x0 + c_lo, ox1 = ox0 + 1;
+    if (c_lo >= P && c_lo < SM_TILE - P && ox0 < nlon) dst[(size_t)gy * nlon + ox0] = (TOut)(nanrow ? qnan : vx[i]);
+    if (c_lo + 1 >= P && c_lo + 1 < SM_TILE - P && ox1 < nlon) dst[(size_t)gy * nlon + ox1] = (TOut)(nanrow ? qnan : vy[i]);
   }
 }
 
-static size_t smooth_smem_bytes(int passes) {
-  int H = SM_TH + 2 * passes, Wd = SM_TW + 2 * passes;
-  return (size_t)2 * H * Wd * sizeof(double);
-}
+
 
 template <int P, typename TIn, typename TOut, int RMODE>
 static int launch_smooth_p(const void* in, void* out, int ntime, int nlat, int nlon, int nan_border, cudaStream_t st) {
-  size_t smem = smooth_smem_bytes(P);
-  WBK_CUDA_CHECK(cudaFuncSetAttribute(smooth_fused_kernel<P, TIn, TOut, RMODE>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((nlon + SM_TW - 1) / SM_TW, (nlat + SM_TH - 1) / SM_TH, ntime);
-  WBK_LAUNCH(KID_SMOOTH, (smooth_fused_kernel<P, TIn, TOut, RMODE>), grid, dim3(SM_THREADS), smem, st, (const TIn*)in,
+  constexpr int OUTW = SM_TILE - 2 * P;
+  dim3 grid((nlon + OUTW - 1) / OUTW, (nlat + OUTW - 1) / OUTW, ntime);
+  WBK_LAUNCH(KID_SMOOTH, (smooth_fused_kernel<P, TIn, TOut, RMODE>), grid, dim3(SM_THREADS), 0, st, (const TIn*)in,
              (TOut*)out, nlat, nlon, nan_border);
   WBK_LAUNCH_CHECK();
   return WBK_OK;

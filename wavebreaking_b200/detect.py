@@ -209,6 +209,32 @@ def coord_tables(lat, lon, dlon, dlat, lib=None):
     return torch.from_numpy(tab).to(lib.device)
 
 
+class LazyRings:
+    """Ragged ring vertices of the events of one table; ring e is built on access as an (n, 2) int array."""
+
+    def __init__(self, off, packed):
+        self.off = np.asarray(off, dtype=np.int64)
+        self.packed = np.asarray(packed).view(np.uint32)
+
+    def __len__(self):
+        return len(self.off) - 1
+
+    def __getitem__(self, e):
+        if isinstance(e, slice):
+            return [self[i] for i in range(*e.indices(len(self)))]
+        if e < 0:
+            e += len(self)
+        p = self.packed[self.off[e] - self.off[0]: self.off[e + 1] - self.off[0]]
+        return np.c_[(p & 0xFFFF).astype(np.int64), (p >> 16).astype(np.int64)]
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+    @property
+    def nbytes(self):
+        return self.packed.nbytes + self.off.nbytes
+
+
 @dataclass
 class EventTable:
     """Events of one index in reference row order (host arrays)."""
@@ -223,7 +249,7 @@ class EventTable:
     split: np.ndarray      # 0 on the real grid, 1 straddles the last meridian, 2 entirely in the extension
     near: np.ndarray       # streamers: base-point decision within 1e-9 of a threshold
     sums: np.ndarray       # [n, 6]: sum a, sum a*data, sum a*intensity, sum a*x, sum a*y, member count
-    rings: list = None     # index-space ring (n, 2) of every streamer / cutoff event when fetched with the batch
+    rings: object = None   # LazyRings: index-space ring of every streamer / cutoff event (fetched with the batch)
 
     def __len__(self):
         return len(self.job)

@@ -137,17 +137,18 @@ class Detector:
             ot_min_exp=float(p["ot_min_exp"]), co_min_exp=float(p["co_min_exp"]))
 
     # ------------------------------------------------------------------ enqueue / collect
-    def submit(self, slot, raw, flags_out=None, flags_host=None, gmax_nx=None, smoothed=None):
-        """Enqueue one batch on the slot's stream.  ``raw``: device tensor or (pinned) host tensor
-        [T' <= T, nlat, nlon].  No host synchronisation happens here."""
+    def submit(self, slot, raw, flags_out=None, flags_host=None, gmax_nx=None, smoothed=None, stream=None):
+        """Enqueue one batch on the slot's stream (or ``stream``).  ``raw``: device tensor or (pinned) host
+        tensor [T' <= T, nlat, nlon].  No host synchronisation happens here."""
         lib = self.lib
         nt = int(raw.shape[0])
         if nt > slot.T:
             raise ValueError("batch of {} time steps exceeds the slot size {}".format(nt, slot.T))
-        ctx_mgr = torch.cuda.stream(slot.stream) if slot.stream is not None else _null()
+        use_stream = stream if stream is not None else slot.stream
+        ctx_mgr = torch.cuda.stream(use_stream) if use_stream is not None else _null()
         with ctx_mgr:
-            if slot.stream is not None:
-                slot.stream.wait_stream(torch.cuda.default_stream(lib.device))
+            if use_stream is not None:
+                use_stream.wait_stream(torch.cuda.default_stream(lib.device))
             st = lib.stream()
             if raw.device != lib.device:  # host input: H2D on this slot's stream
                 if slot.raw_dev is None or slot.raw_dev.dtype != raw.dtype:
@@ -234,10 +235,8 @@ class Detector:
             job = slot.h_ev_job.numpy()[o:o + n].copy()
             rings = None
             if kind != "overturnings":
-                rings = []
-                for e in range(o, o + n):
-                    p = ring_pts[ring_off[e]:ring_off[e + 1]]
-                    rings.append(np.c_[(p & 0xFFFF).astype(np.int64), (p >> 16).astype(np.int64)])
+                ro = ring_off[o:o + n + 1].copy()
+                rings = detect.LazyRings(ro, ring_pts[ro[0]:ro[-1]].copy())
             tab = detect.EventTable(kind=kind, job=job, contour=ints[:, 0].copy(), ind1=ints[:, 1].copy(),
                                     ind2=ints[:, 2].copy(), box=ints[:, 3:7].copy(), orientation=ints[:, 7].copy(),
                                     split=ints[:, 8].copy(), near=ints[:, 9].copy(), sums=f64)
@@ -308,14 +307,21 @@ class Detector:
         self.submit(slot, raw_host, flags_host=flags_host)
         return self.collect(slot)
 
-    def stream(self, batches, depth=3, flags_host=None):
+    def stream(self, batches, depth=3, flags_host=None, shared_stream=False):
         """Pipelined execution: yields one BatchResult per input batch, in order.
 
         ``batches``: iterable of device or pinned-host tensors of (at most) equal length.  ``depth`` batches are
         in flight at once, each on its own CUDA stream, so uploads, kernels, downloads and the host-side table
-        handling overlap.  ``flags_host``: optional list of pinned int8 buffers, one per slot.
+        handling overlap.  With ``shared_stream`` all slots enqueue on ONE side stream: kernels of different
+        batches do not overlap each other, the host merely runs ahead (device-resident inputs).
+        ``flags_host``: optional list of pinned int8 buffers, one per slot.
         The flag grids / contour set of a result are only valid until its slot is reused (``depth`` batches later).
         """
+        common = None
+        if shared_stream and self.lib.is_cuda:
+            if getattr(self, "_shared", None) is None:
+                self._shared = torch.cuda.Stream(device=self.lib.device)
+            common = self._shared
         inflight = []
         i = 0
         for raw in batches:
@@ -324,7 +330,7 @@ class Detector:
                 yield self.collect(inflight.pop(0))
             slot = self._slot(int(raw.shape[0]), idx)
             fh = flags_host[idx] if flags_host is not None else None
-            inflight.append(self.submit(slot, raw, flags_host=fh))
+            inflight.append(self.submit(slot, raw, flags_host=fh, stream=common))
             i += 1
         while inflight:
             yield self.collect(inflight.pop(0))
