@@ -19,6 +19,13 @@ __device__ __forceinline__ int wrap_idx(int i, int n) {
   return i < 0 ? i + n : i;
 }
 
+// periodic index for values that are at most one period outside (falls back to the modulo otherwise)
+__device__ __forceinline__ int wrap_near(int i, int n) {
+  i = i < 0 ? i + n : (i >= n ? i - n : i);
+  if (i < 0 || i >= n) i = wrap_idx(i, n);
+  return i;
+}
+
 // x / 6 correctly rounded without the generic division sequence: q = RN(x * RN(1/6)), exact remainder by FMA,
 // one correction step (Markstein: with a correctly rounded reciprocal the corrected quotient is RN(x / 6)).
 // Checked against 1.5e9 random operands on the host.  Valid for finite operands whose quotient is a normal
@@ -64,9 +71,8 @@ __device__ __forceinline__ void smooth_strip_passes(double (&vx)[SM_PER], double
     double nx = north.x, ny = north.y;
 #pragma unroll
     for (int i = 0; i < SM_PER; ++i) {
-      const int r = r_base + i;
       const double cx = vx[i], cy = vy[i];
-      if (r >= k && r < SM_TILE - k) {  // warp-uniform: rows outside are no longer needed
+      {  // rows outside [k, 64-k) are computed too (no longer needed, but branch-free)
         const double sx = i + 1 < SM_PER ? vx[i + 1] : south.x;
         const double sy = i + 1 < SM_PER ? vy[i + 1] : south.y;
         const double wv = __shfl_up_sync(WBK_FULL, cy, 1);    // column 2l-1 (lane 0: unused halo garbage)
@@ -95,33 +101,47 @@ __device__ __forceinline__ void smooth_strip_passes(double (&vx)[SM_PER], double
 
 }
 
+// Persistent CTAs stride over the (time, tile row, tile column) list; the raw values of the NEXT tile are
+// requested before the current tile is computed, so the DRAM latency hides behind the FP64 work.
 template <int P, typename TIn, typename TOut, int RMODE>
-__global__ void __launch_bounds__(SM_THREADS)
-smooth_fused_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, int nlat, int nlon, int nan_border) {
+__global__ void __launch_bounds__(SM_THREADS, 2)
+smooth_fused_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, int nlat, int nlon, int nan_border, int tiles_x,
+                    int tiles_y, int ntime) {
   constexpr int OUTW = SM_TILE - 2 * P;  // valid outputs per tile edge
   __shared__ double halo[2][8][2][SM_TILE];  // [parity][band][top/bottom][column]
   const int lane = wbk_lane(), band = wbk_warp();
-  const int x0 = blockIdx.x * OUTW - P, y0 = blockIdx.y * OUTW - P;  // tile origin (may be negative: wraps)
-  const size_t plane = (size_t)nlat * nlon;
-  const TIn* src = in + plane * blockIdx.z;
-  TOut* dst = out + plane * blockIdx.z;
-
-  // this lane's two columns (periodic)
-  int gx0 = x0 + 2 * lane, gx1 = gx0 + 1;
-  gx0 = wrap_idx(gx0, nlon);
-  gx1 = wrap_idx(gx1, nlon);
   const int r_base = band * SM_PER;
+  const size_t plane = (size_t)nlat * nlon;
+  const long long ntiles = (long long)tiles_x * tiles_y * ntime;
 
-  double vx[SM_PER], vy[SM_PER];
-  int unsafe = 0;
-  {
-    TIn tx[SM_PER], ty[SM_PER];
+  auto load_tile = [&](long long w, TIn (&tx)[SM_PER], TIn (&ty)[SM_PER]) {
+    const int bx = (int)(w % tiles_x);
+    const long long q = w / tiles_x;
+    const int by = (int)(q % tiles_y), bt = (int)(q / tiles_y);
+    const int x0 = bx * OUTW - P, y0 = by * OUTW - P;
+    const TIn* src = in + plane * bt;
+    const int gx0 = wrap_near(x0 + 2 * lane, nlon), gx1 = wrap_near(x0 + 2 * lane + 1, nlon);
+    int gy = wrap_near(y0 + r_base, nlat);
+    const TIn* row = src + (size_t)gy * nlon;
 #pragma unroll
     for (int i = 0; i < SM_PER; ++i) {
-      const int gy = wrap_idx(y0 + r_base + i, nlat);
-      tx[i] = src[(size_t)gy * nlon + gx0];
-      ty[i] = src[(size_t)gy * nlon + gx1];
+      tx[i] = row[gx0];
+      ty[i] = row[gx1];
+      ++gy;
+      row += nlon;
+      if (gy == nlat) {  // periodic in latitude too (scipy mode="wrap")
+        gy = 0;
+        row = src;
+      }
     }
+  };
+
+  TIn tx[SM_PER], ty[SM_PER];
+  long long w = blockIdx.x;
+  if (w < ntiles) load_tile(w, tx, ty);
+  for (; w < ntiles; w += gridDim.x) {
+    double vx[SM_PER], vy[SM_PER];
+    int unsafe = 0;
 #pragma unroll
     for (int i = 0; i < SM_PER; ++i) {
       vx[i] = (double)tx[i];
@@ -129,38 +149,45 @@ smooth_fused_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, int nlat
       const double ax = fabs(vx[i]), ay = fabs(vy[i]);
       unsafe |= !(ax <= 1e290) || (ax < 1e-150 && ax != 0.0) || !(ay <= 1e290) || (ay < 1e-150 && ay != 0.0);
     }
-  }
-  const int slow = __syncthreads_or(unsafe);
+    // prefetch the next tile of this CTA
+    if (w + gridDim.x < ntiles) load_tile(w + gridDim.x, tx, ty);
+    const int slow = __syncthreads_or(unsafe);
 
-  constexpr int RFIRST = RMODE == WBK_ROUND_ALL ? 2 : (RMODE == WBK_ROUND_FIRST ? 1 : 0);
-  constexpr int RREST = RMODE == WBK_ROUND_ALL ? 2 : 0;
+    constexpr int RFIRST = RMODE == WBK_ROUND_ALL ? 2 : (RMODE == WBK_ROUND_FIRST ? 1 : 0);
+    constexpr int RREST = RMODE == WBK_ROUND_ALL ? 2 : 0;
+    if (!slow) smooth_strip_passes<P, RFIRST, RREST, true>(vx, vy, halo, lane, band, r_base);
+    else smooth_strip_passes<P, RFIRST, RREST, false>(vx, vy, halo, lane, band, r_base);
 
-  if (!slow) smooth_strip_passes<P, RFIRST, RREST, true>(vx, vy, halo, lane, band, r_base);
-  else smooth_strip_passes<P, RFIRST, RREST, false>(vx, vy, halo, lane, band, r_base);
-
-  // write the valid interior: tile rows / columns [P, 64 - P)
-  const int c_lo = 2 * lane;
-#pragma unroll
-  for (int i = 0; i < SM_PER; ++i) {
-    const int r = r_base + i;
-    const int gy = y0 + r;
-    if (r < P || r >= SM_TILE - P || gy >= nlat) continue;
-    const bool nanrow = nan_border > 0 && (gy < nan_border || gy >= nlat - nan_border);
+    // write the valid interior: tile rows / columns [P, 64 - P)
+    const int bx = (int)(w % tiles_x);
+    const long long q = w / tiles_x;
+    const int by = (int)(q % tiles_y), bt = (int)(q / tiles_y);
+    const int x0 = bx * OUTW - P, y0 = by * OUTW - P;
+    TOut* dst = out + plane * bt;
+    const int c_lo = 2 * lane;
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
-    const int ox0 = x0 + c_lo, ox1 = ox0 + 1;
-    if (c_lo >= P && c_lo < SM_TILE - P && ox0 < nlon) dst[(size_t)gy * nlon + ox0] = (TOut)(nanrow ? qnan : vx[i]);
-    if (c_lo + 1 >= P && c_lo + 1 < SM_TILE - P && ox1 < nlon) dst[(size_t)gy * nlon + ox1] = (TOut)(nanrow ? qnan : vy[i]);
+#pragma unroll
+    for (int i = 0; i < SM_PER; ++i) {
+      const int r = r_base + i;
+      const int gy = y0 + r;
+      if (r < P || r >= SM_TILE - P || gy >= nlat) continue;
+      const bool nanrow = nan_border > 0 && (gy < nan_border || gy >= nlat - nan_border);
+      const int ox0 = x0 + c_lo, ox1 = ox0 + 1;
+      if (c_lo >= P && c_lo < SM_TILE - P && ox0 < nlon) dst[(size_t)gy * nlon + ox0] = (TOut)(nanrow ? qnan : vx[i]);
+      if (c_lo + 1 >= P && c_lo + 1 < SM_TILE - P && ox1 < nlon) dst[(size_t)gy * nlon + ox1] = (TOut)(nanrow ? qnan : vy[i]);
+    }
+    __syncthreads();  // the halo buffers are reused by the next tile
   }
 }
-
-
 
 template <int P, typename TIn, typename TOut, int RMODE>
 static int launch_smooth_p(const void* in, void* out, int ntime, int nlat, int nlon, int nan_border, cudaStream_t st) {
   constexpr int OUTW = SM_TILE - 2 * P;
-  dim3 grid((nlon + OUTW - 1) / OUTW, (nlat + OUTW - 1) / OUTW, ntime);
-  WBK_LAUNCH(KID_SMOOTH, (smooth_fused_kernel<P, TIn, TOut, RMODE>), grid, dim3(SM_THREADS), 0, st, (const TIn*)in,
-             (TOut*)out, nlat, nlon, nan_border);
+  const int tiles_x = (nlon + OUTW - 1) / OUTW, tiles_y = (nlat + OUTW - 1) / OUTW;
+  const long long ntiles = (long long)tiles_x * tiles_y * ntime;
+  const int grid = (int)(ntiles < 148 * 2 ? ntiles : 148 * 2);  // persistent: 2 CTAs per SM
+  WBK_LAUNCH(KID_SMOOTH, (smooth_fused_kernel<P, TIn, TOut, RMODE>), dim3(grid), dim3(SM_THREADS), 0, st, (const TIn*)in,
+             (TOut*)out, nlat, nlon, nan_border, tiles_x, tiles_y, ntime);
   WBK_LAUNCH_CHECK();
   return WBK_OK;
 }
