@@ -53,12 +53,14 @@ __device__ __forceinline__ double smooth_finish(double v) {
 // (west / east neighbours) and one row of halo per band edge through shared memory; the arithmetic
 // (4 DP adds/FMA + the 3-op exact division per cell) is what remains, so the kernel runs on the FP64 pipe.
 // ------------------------------------------------------------------------------------------
-#define SM_PER 8                       // rows per warp band
-#define SM_TILE 64                     // tile edge = 8 bands x SM_PER rows = 32 lanes x 2 columns
+#define SM_PER 4                       // rows per warp band
+#define SM_TILE 64                     // tile edge = SM_NB bands x SM_PER rows = 32 lanes x 2 columns
+#define SM_NB (SM_TILE / SM_PER)       // bands (= warps) per CTA
+#define SM_STRIP_THREADS (32 * SM_NB)
 
 template <int P, int RFIRST, int RREST, bool SAFE>
 __device__ __forceinline__ void smooth_strip_passes(double (&vx)[SM_PER], double (&vy)[SM_PER],
-                                                    double (*halo)[8][2][SM_TILE], int lane, int band, int r_base) {
+                                                    double (*halo)[SM_NB][2][SM_TILE], int lane, int band, int r_base) {
 #pragma unroll
   for (int k = 1; k <= P; ++k) {
     const int par = k & 1;
@@ -67,7 +69,7 @@ __device__ __forceinline__ void smooth_strip_passes(double (&vx)[SM_PER], double
     *reinterpret_cast<double2*>(&halo[par][band][1][2 * lane]) = make_double2(vx[SM_PER - 1], vy[SM_PER - 1]);
     __syncthreads();
     const double2 north = band > 0 ? *reinterpret_cast<const double2*>(&halo[par][band - 1][1][2 * lane]) : make_double2(0.0, 0.0);
-    const double2 south = band < 7 ? *reinterpret_cast<const double2*>(&halo[par][band + 1][0][2 * lane]) : make_double2(0.0, 0.0);
+    const double2 south = band < SM_NB - 1 ? *reinterpret_cast<const double2*>(&halo[par][band + 1][0][2 * lane]) : make_double2(0.0, 0.0);
     double nx = north.x, ny = north.y;
 #pragma unroll
     for (int i = 0; i < SM_PER; ++i) {
@@ -104,11 +106,11 @@ __device__ __forceinline__ void smooth_strip_passes(double (&vx)[SM_PER], double
 // Persistent CTAs stride over the (time, tile row, tile column) list; the raw values of the NEXT tile are
 // requested before the current tile is computed, so the DRAM latency hides behind the FP64 work.
 template <int P, typename TIn, typename TOut, int RMODE>
-__global__ void __launch_bounds__(SM_THREADS, 2)
+__global__ void __launch_bounds__(SM_STRIP_THREADS, 2)
 smooth_fused_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, int nlat, int nlon, int nan_border, int tiles_x,
                     int tiles_y, int ntime) {
   constexpr int OUTW = SM_TILE - 2 * P;  // valid outputs per tile edge
-  __shared__ double halo[2][8][2][SM_TILE];  // [parity][band][top/bottom][column]
+  __shared__ double halo[2][SM_NB][2][SM_TILE];  // [parity][band][top/bottom][column]
   const int lane = wbk_lane(), band = wbk_warp();
   const int r_base = band * SM_PER;
   const size_t plane = (size_t)nlat * nlon;
@@ -186,7 +188,7 @@ static int launch_smooth_p(const void* in, void* out, int ntime, int nlat, int n
   const int tiles_x = (nlon + OUTW - 1) / OUTW, tiles_y = (nlat + OUTW - 1) / OUTW;
   const long long ntiles = (long long)tiles_x * tiles_y * ntime;
   const int grid = (int)(ntiles < 148 * 2 ? ntiles : 148 * 2);  // persistent: 2 CTAs per SM
-  WBK_LAUNCH(KID_SMOOTH, (smooth_fused_kernel<P, TIn, TOut, RMODE>), dim3(grid), dim3(SM_THREADS), 0, st, (const TIn*)in,
+  WBK_LAUNCH(KID_SMOOTH, (smooth_fused_kernel<P, TIn, TOut, RMODE>), dim3(grid), dim3(SM_STRIP_THREADS), 0, st, (const TIn*)in,
              (TOut*)out, nlat, nlon, nan_border, tiles_x, tiles_y, ntime);
   WBK_LAUNCH_CHECK();
   return WBK_OK;

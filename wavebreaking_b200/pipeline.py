@@ -137,7 +137,8 @@ class Detector:
             ot_min_exp=float(p["ot_min_exp"]), co_min_exp=float(p["co_min_exp"]))
 
     # ------------------------------------------------------------------ enqueue / collect
-    def submit(self, slot, raw, flags_out=None, flags_host=None, gmax_nx=None, smoothed=None, stream=None):
+    def submit(self, slot, raw, flags_out=None, flags_host=None, gmax_nx=None, smoothed=None, stream=None,
+               intensity=None):
         """Enqueue one batch on the slot's stream (or ``stream``).  ``raw``: device tensor or (pinned) host
         tensor [T' <= T, nlat, nlon].  No host synchronisation happens here."""
         lib = self.lib
@@ -156,6 +157,8 @@ class Detector:
                 slot.raw_dev[:nt].copy_(raw, non_blocking=True)
                 raw = slot.raw_dev[:nt]
             raw = raw.contiguous()
+            if intensity is not None:
+                intensity = intensity.to(lib.device).contiguous()
             if smoothed is not None:
                 sm = smoothed
             elif self.passes > 0:
@@ -176,6 +179,8 @@ class Detector:
                      self.levels.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), L, st)
             lib.call("wbk_contours_pack_auto", h, _lib.ptr(slot.job_off), _lib.ptr(slot.pt_off), _lib.ptr(slot.meta),
                      _lib.ptr(slot.pts), slot.cap_c, slot.cap_p, st)
+            if intensity is not None and intensity.dtype != sm.dtype:
+                intensity = intensity.to(sm.dtype)
             prm = self._prm(-1 if gmax_nx is None else gmax_nx)
             lib.call("wbk_index_run", h, nt * L, L, _lib.ptr(slot.job_off), _lib.ptr(slot.pt_off), _lib.ptr(slot.meta),
                      _lib.ptr(slot.pts), slot.cap_c, slot.cap_p, _lib.ptr(self.coords), _lib.ptr(slot.work),
@@ -190,8 +195,8 @@ class Detector:
                     flags = slot.flags if nt == slot.T else torch.empty((3, nt, self.nlat, self.nlon), dtype=torch.int8,
                                                                         device=lib.device)
             lib.call("wbk_events_raster", h, _lib.ptr(slot.job_off), _lib.ptr(slot.pt_off), _lib.ptr(slot.pts),
-                     _lib.ptr(self.coords), _lib.ptr(sm), _lib.dtype_code(sm.dtype), None, nt, _lib.ptr(flags),
-                     ctypes.byref(prm), st)
+                     _lib.ptr(self.coords), _lib.ptr(sm), _lib.dtype_code(sm.dtype),
+                     None if intensity is None else _lib.ptr(intensity), nt, _lib.ptr(flags), ctypes.byref(prm), st)
             lib.call("wbk_batch_fetch", h, _lib.ptr(slot.pt_off), _lib.ptr(slot.pts), _lib.ptr(slot.ev_int),
                      _lib.ptr(slot.ev_f64), _lib.ptr(slot.ev_job), _lib.ptr(slot.ring_off), _lib.ptr(slot.ring_pts),
                      slot.cap_e, slot.cap_r, _lib.ptr(slot.summary), st)
@@ -206,7 +211,8 @@ class Detector:
                 flags_host[:, :nt].copy_(flags[:, :nt] if flags.shape[1] != nt else flags, non_blocking=True)
             if slot.done is not None:
                 slot.done.record()
-        slot.pending = dict(raw=raw, nt=nt, flags=flags, flags_host=flags_host, gmax=gmax_nx, smoothed=smoothed, sm=sm)
+        slot.pending = dict(raw=raw, nt=nt, flags=flags, flags_host=flags_host, gmax=gmax_nx, smoothed=smoothed, sm=sm,
+                            intensity=intensity)
         return slot
 
     def collect(self, slot):
@@ -280,11 +286,11 @@ class Detector:
         new = _Slot(self, slot.T, grow)
         self._slots[key] = new
         self.submit(new, pend["raw"], flags_out=pend["flags"], flags_host=pend["flags_host"], gmax_nx=pend["gmax"],
-                    smoothed=pend["smoothed"])
+                    smoothed=pend["smoothed"], intensity=pend["intensity"])
         return self.collect(new)
 
     # ------------------------------------------------------------------ convenience
-    def run_batch(self, raw, gmax_nx=None, smoothed=None):
+    def run_batch(self, raw, gmax_nx=None, smoothed=None, intensity=None):
         """Synchronous: raw device tensor [T, nlat, nlon] -> BatchResult (flags and contour set are private
         copies, valid after further calls)."""
         nt = int(raw.shape[0])
@@ -292,7 +298,7 @@ class Detector:
         flags = None
         if self.want_flags:
             flags = torch.empty((3, nt, self.nlat, self.nlon), dtype=torch.int8, device=self.lib.device)
-        self.submit(slot, raw, flags_out=flags, gmax_nx=gmax_nx, smoothed=smoothed)
+        self.submit(slot, raw, flags_out=flags, gmax_nx=gmax_nx, smoothed=smoothed, intensity=intensity)
         res = self.collect(slot)
         cs = res.contours
         cs.job_off, cs.pt_off, cs.meta, cs.pts = cs.job_off.clone(), cs.pt_off.clone(), cs.meta.clone(), cs.pts.clone()
