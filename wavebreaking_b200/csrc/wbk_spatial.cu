@@ -53,7 +53,7 @@ __device__ __forceinline__ double smooth_finish(double v) {
 // (west / east neighbours) and one row of halo per band edge through shared memory; the arithmetic
 // (4 DP adds/FMA + the 3-op exact division per cell) is what remains, so the kernel runs on the FP64 pipe.
 // ------------------------------------------------------------------------------------------
-#define SM_PER 4                       // rows per warp band
+#define SM_PER 8                       // rows per warp band
 #define SM_TILE 64                     // tile edge = SM_NB bands x SM_PER rows = 32 lanes x 2 columns
 #define SM_NB (SM_TILE / SM_PER)       // bands (= warps) per CTA
 #define SM_STRIP_THREADS (32 * SM_NB)
