@@ -133,71 +133,109 @@ __device__ __forceinline__ int ms_case_code(int c) {
   }
 }
 
-// Rare path of the marching-squares kernel (a warp in which at least one lane found a contour square): builds
-// the segments exactly as skimage does and appends them to the job's arena.  Called warp-uniformly.
-__device__ __noinline__ void ms_emit(const WbkDev& d, int job, int r0, int c0, int sq, bool own_ext, double ul, double ur,
-                                     double ll, double lr, double level) {
+// Emission of the marching-squares kernel: the hits (squares crossed by a contour) of one warp strip are
+// compacted first, then every lane builds the segments of ONE hit exactly as skimage does (float coordinates,
+// np.round) and appends them to the job's arena with a warp-aggregated atomic.  The four corner values are
+// re-read from global memory (L1 / L2 hits: the strip has just been loaded).
+template <typename T>
+__device__ __noinline__ void ms_emit_hits(const WbkDev& d, const T* __restrict__ src, const u32* __restrict__ masks,
+                                          int nrows, int job, int r_begin, int col_base, double level) {
   const int lane = wbk_lane();
   const int W = d.W, nlon = d.nlon;
-  const int code = ms_case_code(sq);
-  const int nseg = code >> 8;
-  const int ncopy = own_ext ? 2 : 1;
-  const int nemit = nseg * ncopy;
-  // warp-aggregated slot allocation
-  int incl = wbk_warp_incl_scan(nemit);
-  int total = __shfl_sync(WBK_FULL, incl, 31);
-  int base = 0;
-  if (lane == 31) base = atomicAdd(&d.seg_count[job], total);
-  base = __shfl_sync(WBK_FULL, base, 31);
-  if (nemit == 0) return;
-  int slot = base + incl - nemit;
-  // edge fractions (identical expression from both squares sharing an edge)
-  const double ft = ms_fraction(ul, ur, level), fb = ms_fraction(ll, lr, level);
-  const double fl = ms_fraction(ul, ll, level), fr = ms_fraction(ur, lr, level);
-  bool lattice = false;
-  for (int copy = 0; copy < ncopy; ++copy) {
-    const int cc = c0 + copy * nlon;  // column of the square on the extended grid
-    // float coordinates exactly as skimage builds them, then np.round (half to even)
-    const double xt = __dadd_rn((double)cc, ft), xb = __dadd_rn((double)cc, fb);
-    const double yl = __dadd_rn((double)r0, fl), yr = __dadd_rn((double)r0, fr);
-    u32 pid[4], pxy[4];
-    pid[0] = 2u * (u32)(r0 * W + cc);             // top: horizontal edge (r0, cc)
-    pid[1] = 2u * (u32)((r0 + 1) * W + cc);       // bottom: horizontal edge (r0+1, cc)
-    pid[2] = 2u * (u32)(r0 * W + cc) + 1u;        // left: vertical edge (r0, cc)
-    pid[3] = 2u * (u32)(r0 * W + cc + 1) + 1u;    // right: vertical edge (r0, cc+1)
-    pxy[0] = wbk_pack_xy((int)rint(xt), r0);
-    pxy[1] = wbk_pack_xy((int)rint(xb), r0 + 1);
-    pxy[2] = wbk_pack_xy(cc, (int)rint(yl));
-    pxy[3] = wbk_pack_xy(cc + 1, (int)rint(yr));
-    const bool vt = xt == rint(xt), vb = xb == rint(xb), vl = yl == rint(yl), vr = yr == rint(yr);
-    for (int s = 0; s < nseg; ++s) {
-      const int fe = (code >> (4 * s)) & 3, te = (code >> (4 * s + 2)) & 3;
-      const bool lf = fe == 0 ? vt : fe == 1 ? vb : fe == 2 ? vl : vr;
-      const bool lt = te == 0 ? vt : te == 1 ? vb : te == 2 ? vl : vr;
-      lattice = lattice || lf || lt;
-      if (slot < d.S) {
-        const size_t o = (size_t)job * d.S + slot;
-        d.rid[o] = 2u * (u32)(r0 * (W - 1) + cc) + (u32)s;
-        d.fpid[o] = pid[fe];
-        d.tpid[o] = pid[te];
-        d.fxy[o] = pxy[fe];
-        d.txy[o] = pxy[te];
+  int total = 0;
+  for (int i = 0; i < nrows; ++i) total += __popc(masks[i]);
+  for (int h0 = 0; h0 < total; h0 += 32) {
+    const int h = h0 + lane;
+    int nemit = 0, code = 0, r0 = 0, c0 = 0, ncopy = 1;
+    double ul = 0, ur = 0, ll = 0, lr = 0;
+    if (h < total) {
+      // locate hit h: row i, then the k-th set bit of its mask
+      int cum = 0, i = 0;
+      for (; i < nrows; ++i) {
+        const int c = __popc(masks[i]);
+        if (h < cum + c) break;
+        cum += c;
       }
-      ++slot;
+      u32 m = masks[i];
+      for (int k = h - cum; k > 0; --k) m &= m - 1;
+      const int src_lane = __ffs((int)m) - 1;
+      r0 = r_begin + i;
+      c0 = col_base + src_lane;
+      const int cr = c0 + 1 == nlon ? 0 : c0 + 1;
+      ul = (double)src[(size_t)r0 * nlon + c0];
+      ur = (double)src[(size_t)r0 * nlon + cr];
+      ll = (double)src[(size_t)(r0 + 1) * nlon + c0];
+      lr = (double)src[(size_t)(r0 + 1) * nlon + cr];
+      const int sq = (ul > level ? 1 : 0) | (ur > level ? 2 : 0) | (ll > level ? 4 : 0) | (lr > level ? 8 : 0);
+      code = ms_case_code(sq);
+      ncopy = (c0 + nlon <= W - 2) ? 2 : 1;
+      nemit = (code >> 8) * ncopy;
     }
+    // warp-aggregated slot allocation
+    const int incl = wbk_warp_incl_scan(nemit);
+    const int tot = __shfl_sync(WBK_FULL, incl, 31);
+    int base = 0;
+    if (lane == 31) base = atomicAdd(&d.seg_count[job], tot);
+    base = __shfl_sync(WBK_FULL, base, 31);
+    if (nemit == 0) continue;
+    int slot = base + incl - nemit;
+    const int nseg = code >> 8;
+    bool lattice = false;
+    // only the edges this square uses are interpolated (identical expression from both adjacent squares)
+    double frac[4];
+    bool need[4] = {false, false, false, false};
+    for (int s2 = 0; s2 < nseg; ++s2) {
+      need[(code >> (4 * s2)) & 3] = true;
+      need[(code >> (4 * s2 + 2)) & 3] = true;
+    }
+    frac[0] = need[0] ? ms_fraction(ul, ur, level) : 0.0;
+    frac[1] = need[1] ? ms_fraction(ll, lr, level) : 0.0;
+    frac[2] = need[2] ? ms_fraction(ul, ll, level) : 0.0;
+    frac[3] = need[3] ? ms_fraction(ur, lr, level) : 0.0;
+    for (int copy = 0; copy < ncopy; ++copy) {
+      const int cc = c0 + copy * nlon;  // column of the square on the extended grid
+      // float coordinates exactly as skimage builds them, then np.round (half to even)
+      const double xt = __dadd_rn((double)cc, frac[0]), xb = __dadd_rn((double)cc, frac[1]);
+      const double yl = __dadd_rn((double)r0, frac[2]), yr = __dadd_rn((double)r0, frac[3]);
+      u32 pid[4], pxy[4];
+      pid[0] = 2u * (u32)(r0 * W + cc);             // top: horizontal edge (r0, cc)
+      pid[1] = 2u * (u32)((r0 + 1) * W + cc);       // bottom: horizontal edge (r0+1, cc)
+      pid[2] = 2u * (u32)(r0 * W + cc) + 1u;        // left: vertical edge (r0, cc)
+      pid[3] = 2u * (u32)(r0 * W + cc + 1) + 1u;    // right: vertical edge (r0, cc+1)
+      pxy[0] = wbk_pack_xy((int)rint(xt), r0);
+      pxy[1] = wbk_pack_xy((int)rint(xb), r0 + 1);
+      pxy[2] = wbk_pack_xy(cc, (int)rint(yl));
+      pxy[3] = wbk_pack_xy(cc + 1, (int)rint(yr));
+      const bool von[4] = {xt == rint(xt), xb == rint(xb), yl == rint(yl), yr == rint(yr)};
+      for (int s2 = 0; s2 < nseg; ++s2) {
+        const int fe = (code >> (4 * s2)) & 3, te = (code >> (4 * s2 + 2)) & 3;
+        lattice = lattice || von[fe] || von[te];
+        if (slot < d.S) {
+          const size_t o = (size_t)job * d.S + slot;
+          d.rid[o] = 2u * (u32)(r0 * (W - 1) + cc) + (u32)s2;
+          d.fpid[o] = pid[fe];
+          d.tpid[o] = pid[te];
+          d.fxy[o] = pxy[fe];
+          d.txy[o] = pxy[te];
+        }
+        ++slot;
+      }
+    }
+    if (lattice) atomicOr(&d.status[job], (int)WBK_ST_LATTICE_VERTEX);
   }
-  if (lattice) atomicOr(&d.status[job], (int)WBK_ST_LATTICE_VERTEX);
 }
 
 template <typename T>
 __global__ void __launch_bounds__(MS_THREADS, 3)
 ms_segments_kernel(const T* __restrict__ field, const __grid_constant__ WbkDev d, const __grid_constant__ LevelPack levels,
                    int nlevels) {
+  __shared__ u32 smask[MS_THREADS / 32][MS_ROWS];
   const int nlat = d.nlat, nlon = d.nlon, W = d.W;
   // every warp covers 31 base columns; lane 31 only supplies the right neighbour of lane 30 (so no thread
   // needs a second, uncoalesced load) -- column nlon wraps to column 0 (periodic extension)
-  const int lane = wbk_lane();
-  const int c0 = (blockIdx.x * (MS_THREADS / 32) + wbk_warp()) * 31 + lane;
+  const int lane = wbk_lane(), warp = wbk_warp();
+  const int col_base = (blockIdx.x * (MS_THREADS / 32) + warp) * 31;
+  const int c0 = col_base + lane;
   const bool loads = c0 <= nlon;
   const int csrc = c0 == nlon ? 0 : c0;
   const bool valid = c0 < nlon && lane < 31;
@@ -205,11 +243,7 @@ ms_segments_kernel(const T* __restrict__ field, const __grid_constant__ WbkDev d
   const int r_end = min(r_begin + MS_ROWS, nlat - 1);  // squares r0 in [r_begin, r_end)
   const int t = blockIdx.z;
   const T* src = field + (size_t)t * nlat * nlon;
-
-  // which squares does this thread own?  base square (r0, c0) exists if c0 <= W-2;
-  // extension square (r0, c0 + nlon) exists if c0 + nlon <= W-2
-  const bool own_base = valid && (c0 <= W - 2);
-  const bool own_ext = valid && (c0 + nlon <= W - 2);
+  const bool own_base = valid && (c0 <= W - 2);  // base square (r0, c0) exists
 
   // all rows of the strip are requested before any is used (MS_ROWS + 1 independent loads in flight)
   T vals[MS_ROWS + 1];
@@ -222,13 +256,13 @@ ms_segments_kernel(const T* __restrict__ field, const __grid_constant__ WbkDev d
     const double level = levels.v[l];
     const T tl = (T)level;
     const bool exact_level = (double)tl == level;  // compare in T when the level is representable (always for f64)
-    const int job = t * nlevels + l;
     // packed comparison bits of the own column: bit0 value > level, bit2 NaN
     int mu = 0;
     {
       const T v = vals[0];
       mu = ((exact_level ? v > tl : (double)v > level) ? 1 : 0) | (v != v ? 4 : 0);
     }
+    u32 any_hits = 0;
 #pragma unroll
     for (int i = 0; i < MS_ROWS; ++i) {
       const int r0 = r_begin + i;
@@ -238,13 +272,15 @@ ms_segments_kernel(const T* __restrict__ field, const __grid_constant__ WbkDev d
       const int mr = __shfl_down_sync(WBK_FULL, m, 1);
       int sq = (m & 1) | ((mr & 1) << 1) | ((m & 2) << 1) | ((mr & 2) << 2);
       if (((m | mr) & 12) || !own_base || sq == 15 || r0 >= r_end) sq = 0;
-      if (__any_sync(WBK_FULL, sq != 0)) {
-        const double ul = (double)vals[i], ll = (double)v;
-        const double ur = __shfl_down_sync(WBK_FULL, ul, 1);
-        const double lr = __shfl_down_sync(WBK_FULL, ll, 1);
-        ms_emit(d, job, r0, c0, sq, own_ext, ul, ur, ll, lr, level);
-      }
+      const u32 hits = __ballot_sync(WBK_FULL, sq != 0);
+      if (lane == 0) smask[warp][i] = hits;
+      any_hits |= hits;
       mu = ml;
+    }
+    if (any_hits) {  // warp-uniform
+      __syncwarp();
+      ms_emit_hits<T>(d, src, smask[warp], MS_ROWS, t * nlevels + l, r_begin, col_base, level);
+      __syncwarp();
     }
   }
 }

@@ -249,13 +249,15 @@ events_raster_kernel(WbkDev d, WbkIdx x, const int* __restrict__ job_off, const 
     const int bw = bx1 - bx0 + 1;
     DD s_a = {0, 0}, s_v = {0, 0}, s_i = {0, 0}, s_x = {0, 0}, s_y = {0, 0}, s_n = {0, 0};
     for (int y = by0 + warp; y <= by1; y += nwarps) {
-      raster_scan_row(rv, y, bx0, bw, acc, flg, r2_prop, r2_flag, rmax, R);
+     for (int cx0 = bx0; cx0 <= bx1; cx0 += rowcap) {  // wide events: the row is scanned in column chunks
+      const int cw = min(rowcap, bx1 - cx0 + 1);
+      raster_scan_row(rv, y, cx0, cw, acc, flg, r2_prop, r2_flag, rmax, R);
       const double a = area[y];
       const size_t rowbase = ((size_t)t * nlat + y) * nlon;
-      for (int i = lane; i < bw; i += 32) {
+      for (int i = lane; i < cw; i += 32) {
         const bool in = acc[i] != 0;
         const u32 f = flg[i];
-        const int px = bx0 + i;
+        const int px = cx0 + i;
         if (in || (f & 1u)) {
           const int xf = px % nlon;
           dd_add(s_a, a);
@@ -271,6 +273,7 @@ events_raster_kernel(WbkDev d, WbkIdx x, const int* __restrict__ job_off, const 
         }
       }
       __syncwarp();
+     }
     }
     const double t_a = dd_block_sum(s_a, red), t_v = dd_block_sum(s_v, red), t_i = dd_block_sum(s_i, red);
     const double t_x = dd_block_sum(s_x, red), t_y = dd_block_sum(s_y, red), t_n = dd_block_sum(s_n, red);
@@ -584,6 +587,7 @@ split_raster_kernel(WbkIdx x, int nlat, int nlon, int ntime, int8_t* __restrict_
 }
 
 static int raster_rowcap(int W) { return (W + 2 + 31) & ~31; }
+#define RS_EVENT_ROWCAP 512  // row-buffer columns of the event rasteriser (wider events are scanned in chunks)
 
 extern "C" int wbk_events_raster(wbk_ctx* ctx, const int* d_job_off, const int* d_pt_off, const uint32_t* d_pts,
                                  const double* d_coords, const void* d_data, int dtype, const void* d_intensity,
@@ -606,15 +610,11 @@ extern "C" int wbk_events_raster(wbk_ctx* ctx, const int* d_job_off, const int* 
   WBK_LAUNCH_CHECK();
   const double r_prop = (prm->dlon + prm->dlat) / 2.0 / 2.0;  // index units (index_utils.py:47-50)
   const double r_flag = d_flags ? ((prm->dlon + prm->dlat) / 2.0 / 2.0) / prm->dlon : r_prop;  // degrees -> cells
-  const int rowcap = raster_rowcap(d.W);
+  const int rowcap = raster_rowcap(d.W) < RS_EVENT_ROWCAP ? raster_rowcap(d.W) : RS_EVENT_ROWCAP;
   int nwarps = RS_THREADS / 32;
   const size_t smem = (size_t)nwarps * 2 * rowcap * sizeof(int);
-  if (smem > 200 * 1024) {
-    wbk_set_error("wbk_events_raster: extended width %d too large for the row buffers", d.W);
-    return WBK_ERR_CAPACITY;
-  }
   const double* area = d_coords + 3 * (size_t)d.nlat;
-  const int grid = 148 * 4;
+  const int grid = 148 * 6;
   if (dtype == WBK_F32) {
     WBK_CUDA_CHECK(cudaFuncSetAttribute(events_raster_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     WBK_LAUNCH(KID_EVENTS_RASTER, events_raster_kernel<float>, dim3(grid), dim3(RS_THREADS), smem, st, d, ctx->x, d_job_off, d_pt_off,
