@@ -512,6 +512,65 @@ __device__ __forceinline__ bool chord_violation(int px, int py, int qx, int qy, 
   return false;
 }
 
+// np.sum of a contiguous float64 slice, bit for bit: NumPy's pairwise summation (blocks of <= 128 elements with
+// eight interleaved accumulators, recursive halving rounded down to multiples of 8).  The reference picks the
+// longest streamer of a group with np.argmax over such sums (streamer_index.py:240-247); near ties between
+// shifted base-point pairs are common on coarse grids, so the summation order matters.
+__device__ inline double np_sum_leaf(const double* a, int n) {
+  if (n < 8) {
+    double res = 0.0;
+    for (int i = 0; i < n; ++i) res = __dadd_rn(res, a[i]);
+    return res;
+  }
+  double r[8];
+  for (int j = 0; j < 8; ++j) r[j] = a[j];
+  int i = 8;
+  for (; i < n - (n % 8); i += 8)
+    for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], a[i + j]);
+  double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                         __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+  for (; i < n; ++i) res = __dadd_rn(res, a[i]);
+  return res;
+}
+
+__device__ inline double np_pairwise_sum(const double* a, int n) {
+  struct Frame { int off, n, stage; double left; };
+  Frame st[24];
+  int sp = 0;
+  st[sp++] = Frame{0, n, 0, 0.0};
+  double result = 0.0;
+  bool have = false;
+  while (sp > 0) {
+    Frame& f = st[sp - 1];
+    if (f.stage == 0) {
+      if (f.n <= 128) {
+        result = np_sum_leaf(a + f.off, f.n);
+        have = true;
+        --sp;
+      } else {
+        int n2 = f.n / 2;
+        n2 -= n2 % 8;
+        f.stage = 1;
+        st[sp++] = Frame{f.off, n2, 0, 0.0};
+        have = false;
+      }
+    } else if (f.stage == 1) {  // left half done
+      int n2 = f.n / 2;
+      n2 -= n2 % 8;
+      f.left = result;
+      f.stage = 2;
+      st[sp++] = Frame{f.off + n2, f.n - n2, 0, 0.0};
+      have = false;
+    } else {  // right half done
+      result = __dadd_rn(f.left, result);
+      have = true;
+      --sp;
+    }
+  }
+  (void)have;
+  return result;
+}
+
 // ordered compaction of src[0..P) with flag[] into dst; returns the new count to every thread
 __device__ inline int compact_pairs(const u64* src, u64* dst, const int* flag, int* scanb, int P, int* sscan) {
   const int tid = wbk_tid(), nt = wbk_nthreads();
@@ -748,14 +807,17 @@ __global__ void __launch_bounds__(ST_THREADS) streamer_cascade_kernel(WbkDev d, 
       for (int a = tid; a < P; a += nt) {
         const u64 k = cur[a];
         const int i1 = (int)(k >> 32), i2 = (int)(((u32)k) >> 1);
-        const double len = (pfx[base + i2] - pfx[base + i1]) + on[base + i1];
+        const double len = np_pairwise_sum(on + base + i1, i2 - i1 + 1);  // on[ind1 : ind2 + 1].sum()
+        scanb[a] = 0;
+        reinterpret_cast<double*>(oth)[a] = len;  // `oth` is free until the winners are written
         atomicMax(&hk[label[a]], (u64)__double_as_longlong(len));
       }
       __syncthreads();
       for (int a = tid; a < P; a += nt) {
         const u64 k = cur[a];
         const int i1 = (int)(k >> 32), i2 = (int)(((u32)k) >> 1);
-        const double len = (pfx[base + i2] - pfx[base + i1]) + on[base + i1];
+        const double len = reinterpret_cast<const double*>(oth)[a];
+        (void)i1; (void)i2;
         if ((u64)__double_as_longlong(len) == hk[label[a]]) atomicMin(&hv1[label[a]], (u32)a);
       }
       __syncthreads();

@@ -480,7 +480,7 @@ extern "C" int wbk_flip(const void* d_in, void* d_out, int dtype, int ntime, int
 // ------------------------------------------------------------------------------------------
 #define SYN_MAX_BLOB 32
 struct SynthParams {
-  double A, k, tilt, c, env0, env1, env_speed, blob_amp, sh_shift;
+  double A, k, tilt, c, env0, env1, env_speed, blob_amp, sh_shift, A2, k2, c2, tilt2;
   int n_blob;
   double lat0[2][SYN_MAX_BLOB], lon0[2][SYN_MAX_BLOB], rad[2][SYN_MAX_BLOB];
 };
@@ -490,7 +490,8 @@ __device__ __forceinline__ double synth_background(double alat, double lam_deg, 
   double lam = lam_deg * d2r;
   double env = p.env0 + p.env1 * cos(lam - p.env_speed * hours * d2r);
   double phase = p.k * (lam - p.c * hours * d2r) + p.tilt * (alat - 45.0) / 10.0 + 0.7 * sin(2.0 * lam);
-  double phi = alat - p.A * env * sin(phase);
+  double phase2 = p.k2 * (lam - p.c2 * hours * d2r) + p.tilt2 * (alat - 45.0) / 10.0;
+  double phi = alat - p.A * env * sin(phase) - p.A2 * sin(phase2);
   double s = sin(phi * d2r) / sin(45.0 * d2r);
   double a = fabs(s);
   double r = 2.0 * a * a * a;
@@ -535,8 +536,9 @@ extern "C" int wbk_synth_pv(void* d_out, int dtype, int ntime, int nlat, int nlo
   }
   if (ntime == 0) return WBK_OK;
   SynthParams p;
-  p.A = 11.0; p.k = 6.0; p.tilt = 1.6; p.c = 0.5; p.env0 = 0.6; p.env1 = 0.4; p.env_speed = 1.5;
-  p.blob_amp = 3.0; p.sh_shift = 37.0; p.n_blob = n_blob;
+  // frozen recipe: keep in sync with wavebreaking_b200/synthetic.py PARAMS
+  p.A = 12.0; p.k = 7.0; p.tilt = 2.6; p.c = 0.5; p.env0 = 0.6; p.env1 = 0.4; p.env_speed = 1.5;
+  p.blob_amp = 3.0; p.sh_shift = 37.0; p.A2 = 4.5; p.k2 = 19.0; p.c2 = 1.1; p.tilt2 = 2.0; p.n_blob = n_blob;
   for (int h = 0; h < 2; ++h)
     for (int b = 0; b < n_blob; ++b) {
       p.lat0[h][b] = h_blobs[(h * n_blob + b) * 3 + 0];
