@@ -228,7 +228,7 @@ int wbk_batch_fetch(wbk_ctx* ctx, const int* d_pt_off, const uint32_t* d_pts, in
  * library).  wbk_prof_enable(1) starts collecting, wbk_prof_read synchronises the device and returns, for
  * kernel id k < WBK_PROF_NKERNELS, the number of launches and the summed duration in milliseconds since
  * the last wbk_prof_reset().  Names: wbk_prof_name(k). */
-#define WBK_PROF_NKERNELS 24
+#define WBK_PROF_NKERNELS 32
 int wbk_prof_enable(int on);
 int wbk_prof_reset(void);
 int wbk_prof_read(int* h_launches, double* h_ms);

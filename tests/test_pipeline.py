@@ -49,13 +49,6 @@ def test_detector_gpu_one_degree(gpu):
 
 
 @pytest.mark.gpu
-def test_detector_gpu_quarter_degree(gpu):
-    res, want = _run(721, 1440, 1, [2.0], step_hours=1.0)
-    _compare(res, want)
-    assert len(res.tables["streamers"]) > 0
-
-
-@pytest.mark.gpu
 def test_detector_gpu_batch_invariance(gpu):
     """Size-independent property at the benchmark shape: a batch of T steps == T batches of one step."""
     lat, lon = synthetic.grid_coords(721, 1440)

@@ -132,7 +132,7 @@ class Library:
         self.check(getattr(self.cdll, name)(*args))
 
 
-PROF_NKERNELS = 24
+PROF_NKERNELS = 32
 
 
 def prof_read(lib):

@@ -48,7 +48,11 @@ struct WbkIdx {
   int NB;                    // blocks of PT points per contour (capacity)
   int* blk_x;                // [J*SC][NB][2] column range of every block of a full-width contour
   u64* pairs_b;              // [J][PC]
-  int *flag, *scanb, *label; // [J][PC]
+  int* flag;                 // [J][SC][PC] keep flags of the touch kernel
+  int *scanb, *label;        // [J][PC]
+  u64 *hm1, *hm2;            // [J][2*PC] smallest / second smallest pair key of a duplicate group
+  int* cnt1;                 // [J][SC] pairs left after check_duplicates
+  int* touch_off;            // [J*SC + 1] chunk offsets of the touch kernel
   u64* hk;                   // [J][2*PC]
   u32 *hv1, *hv2;            // [J][2*PC]
   int* ev_int;               // [3][J][EC][WBK_EV_INTS]

@@ -25,12 +25,16 @@ size_t wbk_index_layout(struct wbk_ctx* ctx, unsigned char* base, size_t off) {
   x.pair_count = (int*)take(J * SC * 4);
   x.tile_off = (int*)take((J * SC + 1) * 4);
   x.pairs_b = (u64*)take(J * PC * 8);
-  x.flag = (int*)take(J * PC * 4);
+  x.flag = (int*)take(J * SC * PC * 4);
   x.scanb = (int*)take(J * PC * 4);
   x.label = (int*)take(J * PC * 4);
   x.hk = (u64*)take(J * 2 * PC * 8);
   x.hv1 = (u32*)take(J * 2 * PC * 4);
   x.hv2 = (u32*)take(J * 2 * PC * 4);
+  x.hm1 = (u64*)take(J * 2 * PC * 8);
+  x.hm2 = (u64*)take(J * 2 * PC * 8);
+  x.cnt1 = (int*)take(J * SC * 4);
+  x.touch_off = (int*)take((J * SC + 1) * 4);
   x.ev_int = (int*)take(3 * J * EC * WBK_EV_INTS * 4);
   x.ev_f64 = (double*)take(3 * J * EC * WBK_EV_F64 * 8);
   x.ev_count = (int*)take(3 * J * 4);
@@ -278,9 +282,9 @@ __global__ void __launch_bounds__(OT_THREADS) overturning_kernel(WbkDev d, WbkId
 // ------------------------------------------------------------------------------------------ streamers
 #define ST_THREADS 1024
 #define PT 128           // pair-scan tile edge
-#define CS_PTS 16384     // contour points staged in shared memory by the cascade
-#define CS_SORT 8192     // candidate pairs sorted in shared memory
-#define CS_SMEM ((size_t)CS_PTS * 4 + (size_t)(CS_PTS / 32) * 16 + (size_t)CS_SORT * 8)
+#define CS_SORT 16384    // surviving pairs sorted in shared memory
+#define CS_SMEM ((size_t)CS_SORT * 8)
+#define TOUCH_CHUNK 2048 // chords per CTA work item of the touch kernel
 #define PS_THREADS 256
 #define EARTH_R 6371.0
 
@@ -583,163 +587,243 @@ __device__ inline int compact_pairs(const u64* src, u64* dst, const int* flag, i
   return total;
 }
 
-// filter cascade of streamer_index.py:160-264, one CTA per job (its full-width contours in turn)
-__global__ void __launch_bounds__(ST_THREADS) streamer_cascade_kernel(WbkDev d, WbkIdx x, PackedSet ps,
-                                                                      const double* __restrict__ on,
-                                                                      const double* __restrict__ pfx, int J) {
+// ---------------------------------------------------------------------------------------- filter cascade
+// streamer_index.py:160-264 in three kernels:
+//   A  streamer_dedupe_kernel  (CTA per job)   check_duplicates on the unsorted candidate list
+//   B  streamer_touch_kernel   (whole GPU)     check_intersections: every chord against the contour through a
+//                                              spatial bin index of the contour segments in shared memory
+//   C  streamer_finish_kernel  (CTA per job)   sort the survivors, check_overlapping, check_groups, events
+// The reference's "while len(df) > 1" gating is kept: a stage only runs if more than one pair is left.
+
+// A: rows equal after x % nlon -> drop the second of each group in row-major (i, j) order (:160-183).  The pair
+// key (i << 32 | j << 1 | near) orders exactly like (i, j), so no sort is needed here.
+__global__ void __launch_bounds__(ST_THREADS) streamer_dedupe_kernel(WbkDev d, WbkIdx x, PackedSet ps) {
   const int job = blockIdx.x;
   if (job >= ps.njobs) return;
-  const int tid = threadIdx.x, nt = blockDim.x, lane = wbk_lane(), warp = wbk_warp(), nwarps = nt >> 5;
+  const int tid = threadIdx.x, nt = blockDim.x;
   const int nlon = d.nlon;
   __shared__ int sscan[40];
-  __shared__ int s_nev;
+  u64* B = x.pairs_b + (size_t)job * x.PC;
+  int* scanb = x.scanb + (size_t)job * x.PC;
+  int* label = x.label + (size_t)job * x.PC;
+  u64* hk = x.hk + (size_t)job * 2 * x.PC;
+  u64* m1 = x.hm1 + (size_t)job * 2 * x.PC;
+  u64* m2 = x.hm2 + (size_t)job * 2 * x.PC;
+  const int nsel = x.nsel[job];
+  for (int si = 0; si < x.SC; ++si) {
+    const int slot = job * x.SC + si;
+    if (si >= nsel) {
+      if (tid == 0) {
+        x.cnt1[slot] = 0;
+        x.touch_off[slot] = 0;
+      }
+      continue;
+    }
+    const int c = x.sel[slot];
+    const int base = ps.pt_off[c];
+    const u32* pts = ps.pts + base;
+    int P = x.pair_count[slot];
+    if (P > x.PC) {
+      if (tid == 0) {
+        atomicOr(&d.status[job], (int)WBK_ST_PAIR_OVERFLOW);
+        x.cnt1[slot] = 0;
+        x.touch_off[slot] = 0;
+      }
+      continue;  // uniform
+    }
+    u64* A = x.pairs + (size_t)slot * x.PC;
+    int* flag = x.flag + (size_t)slot * x.PC;
+    if (P > 1) {
+      const u32 dcap = wbk_pow2_ceil((u32)(2 * P));
+      for (u32 a = tid; a < dcap; a += nt) {
+        hk[a] = ~0ull;
+        m1[a] = ~0ull;
+        m2[a] = ~0ull;
+      }
+      __syncthreads();
+      for (int a = tid; a < P; a += nt) {
+        const u64 k = A[a];
+        const u32 pi = pts[(u32)(k >> 32)], pj = pts[((u32)k) >> 1];
+        const u64 key = ((u64)wbk_pack_xy(wbk_px(pi) % nlon, wbk_py(pi)) << 32) | (u64)wbk_pack_xy(wbk_px(pj) % nlon, wbk_py(pj));
+        const u32 sl = wbk_hash_slot64(hk, dcap, key, nullptr);
+        label[a] = (int)sl;
+        atomicMin(&m1[sl], k);
+      }
+      __syncthreads();
+      for (int a = tid; a < P; a += nt) {
+        const u64 k = A[a];
+        if (m1[label[a]] != k) atomicMin(&m2[label[a]], k);
+      }
+      __syncthreads();
+      for (int a = tid; a < P; a += nt) flag[a] = m2[label[a]] == A[a] ? 0 : 1;
+      __syncthreads();
+      P = compact_pairs(A, B, flag, scanb, P, sscan);
+      for (int a = tid; a < P; a += nt) A[a] = B[a];
+      __syncthreads();
+    }
+    if (tid == 0) {
+      x.cnt1[slot] = P;
+      x.touch_off[slot] = P > 1 ? (P + TOUCH_CHUNK - 1) / TOUCH_CHUNK : 0;
+    }
+  }
+}
+
+// exclusive scan of the touch-chunk counts over all (job, sel) slots (single CTA)
+__global__ void __launch_bounds__(1024) touch_scan_kernel(WbkIdx x, int nslots) {
+  __shared__ int sscan[40];
+  const int total = wbk_block_excl_scan(x.touch_off, nslots, sscan);
+  if (threadIdx.x == 0) x.touch_off[nslots] = total;
+}
+
+// B: keep chords that only touch the contour (:185-200).  Each CTA takes one chunk of chords of one contour,
+// bins the contour's segments into TB x TB lattice cells (CSR in shared memory) and lets every thread test its
+// chords against the segments of the bins its bounding box overlaps.  Exact integer predicates.
+#define TB_SHIFT 5                 // 32 x 32 cells per bin
+#define TOUCH_THREADS 256
+#define TOUCH_MAXSEG 20480         // CSR capacity (segment incidences) in shared memory
+
+__global__ void __launch_bounds__(TOUCH_THREADS) streamer_touch_kernel(WbkDev d, WbkIdx x, PackedSet ps, int nslots) {
   WBK_DYN_SMEM(unsigned char, dsm);
-  u32* spts = reinterpret_cast<u32*>(dsm);                                   // [CS_PTS] contour points
-  int* sbb = reinterpret_cast<int*>(dsm + (size_t)CS_PTS * 4);               // [CS_PTS / 32][4] block boxes
-  u64* ssort = reinterpret_cast<u64*>(dsm + (size_t)CS_PTS * 4 + (size_t)(CS_PTS / 32) * 16);  // [CS_SORT]
+  const int nbx = (d.W >> TB_SHIFT) + 1, nby = (d.nlat >> TB_SHIFT) + 1;
+  const int nbins = nbx * nby;
+  int* boff = reinterpret_cast<int*>(dsm);                       // [nbins + 1]
+  int* bcur = boff + nbins + 1;                                  // [nbins] fill cursors
+  unsigned short* bseg = reinterpret_cast<unsigned short*>(bcur + nbins);  // [TOUCH_MAXSEG]
+  __shared__ int sscan[40];
+  __shared__ int s_total;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int total = x.touch_off[nslots];
+  for (int w = blockIdx.x; w < total; w += gridDim.x) {
+    int lo = 0, hi = nslots - 1;
+    while (lo < hi) {
+      int mid = (lo + hi + 1) >> 1;
+      if (x.touch_off[mid] <= w) lo = mid; else hi = mid - 1;
+    }
+    const int slot = lo, chunk = w - x.touch_off[slot];
+    const int c = x.sel[slot];
+    const int base = ps.pt_off[c], n = ps.pt_off[c + 1] - base;
+    const u32* pts = ps.pts + base;
+    const int P = x.cnt1[slot];
+    const u64* A = x.pairs + (size_t)slot * x.PC;
+    int* flag = x.flag + (size_t)slot * x.PC;
+    // ---- bin index of the n-1 segments (a segment goes into every bin its bounding box overlaps)
+    __syncthreads();
+    for (int b = tid; b < nbins; b += nt) boff[b] = 0;
+    __syncthreads();
+    const bool use_bins = n <= 65535;
+    if (use_bins) {
+      for (int s0 = tid; s0 < n - 1; s0 += nt) {
+        const u32 pa = pts[s0], pb = pts[s0 + 1];
+        const int bx0 = min(wbk_px(pa), wbk_px(pb)) >> TB_SHIFT, bx1 = max(wbk_px(pa), wbk_px(pb)) >> TB_SHIFT;
+        const int by0 = min(wbk_py(pa), wbk_py(pb)) >> TB_SHIFT, by1 = max(wbk_py(pa), wbk_py(pb)) >> TB_SHIFT;
+        for (int by = by0; by <= by1; ++by)
+          for (int bx = bx0; bx <= bx1; ++bx) atomicAdd(&boff[by * nbx + bx], 1);
+      }
+    }
+    __syncthreads();
+    const int ninc = wbk_block_excl_scan(boff, nbins, sscan);
+    if (tid == 0) {
+      boff[nbins] = ninc;
+      s_total = ninc;
+    }
+    for (int b = tid; b < nbins; b += nt) bcur[b] = boff[b];
+    __syncthreads();
+    const bool binned = use_bins && s_total <= TOUCH_MAXSEG;
+    if (binned) {
+      for (int s0 = tid; s0 < n - 1; s0 += nt) {
+        const u32 pa = pts[s0], pb = pts[s0 + 1];
+        const int bx0 = min(wbk_px(pa), wbk_px(pb)) >> TB_SHIFT, bx1 = max(wbk_px(pa), wbk_px(pb)) >> TB_SHIFT;
+        const int by0 = min(wbk_py(pa), wbk_py(pb)) >> TB_SHIFT, by1 = max(wbk_py(pa), wbk_py(pb)) >> TB_SHIFT;
+        for (int by = by0; by <= by1; ++by)
+          for (int bx = bx0; bx <= bx1; ++bx) bseg[atomicAdd(&bcur[by * nbx + bx], 1)] = (unsigned short)s0;
+      }
+    }
+    __syncthreads();
+    // ---- chords of this chunk
+    const u32 e0 = pts[0], e1 = pts[n - 1];
+    const int e0x = wbk_px(e0), e0y = wbk_py(e0), e1x = wbk_px(e1), e1y = wbk_py(e1);
+    const int a_end = min(P, (chunk + 1) * TOUCH_CHUNK);
+    for (int a = chunk * TOUCH_CHUNK + tid; a < a_end; a += nt) {
+      const u64 k = A[a];
+      const u32 pi = pts[(u32)(k >> 32)], pj = pts[((u32)k) >> 1];
+      const int px = wbk_px(pi), py = wbk_py(pi), qx = wbk_px(pj), qy = wbk_py(pj);
+      const int x0 = min(px, qx), x1 = max(px, qx), y0 = min(py, qy), y1 = max(py, qy);
+      bool bad = false;
+      if (binned) {
+        for (int by = y0 >> TB_SHIFT; by <= (y1 >> TB_SHIFT) && !bad; ++by)
+          for (int bx = x0 >> TB_SHIFT; bx <= (x1 >> TB_SHIFT) && !bad; ++bx) {
+            const int b = by * nbx + bx;
+            for (int q = boff[b]; q < boff[b + 1]; ++q) {
+              const int s0 = bseg[q];
+              const u32 pa = pts[s0], pb = pts[s0 + 1];
+              const int ax = wbk_px(pa), ay = wbk_py(pa), bxx = wbk_px(pb), byy = wbk_py(pb);
+              if (max(ax, bxx) < x0 || min(ax, bxx) > x1 || max(ay, byy) < y0 || min(ay, byy) > y1) continue;
+              if (chord_violation(px, py, qx, qy, ax, ay, bxx, byy, e0x, e0y, e1x, e1y)) {
+                bad = true;
+                break;
+              }
+            }
+          }
+      } else {
+        for (int s0 = 0; s0 < n - 1 && !bad; ++s0) {
+          const u32 pa = pts[s0], pb = pts[s0 + 1];
+          const int ax = wbk_px(pa), ay = wbk_py(pa), bxx = wbk_px(pb), byy = wbk_py(pb);
+          if (max(ax, bxx) < x0 || min(ax, bxx) > x1 || max(ay, byy) < y0 || min(ay, byy) > y1) continue;
+          bad = chord_violation(px, py, qx, qy, ax, ay, bxx, byy, e0x, e0y, e1x, e1y);
+        }
+      }
+      flag[a] = bad ? 0 : 1;
+    }
+  }
+}
+
+// C: survivors -> row-major order, check_overlapping, check_groups, events (:202-272)
+__global__ void __launch_bounds__(ST_THREADS) streamer_finish_kernel(WbkDev d, WbkIdx x, PackedSet ps,
+                                                                     const double* __restrict__ on, int J) {
+  const int job = blockIdx.x;
+  if (job >= ps.njobs) return;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  __shared__ int sscan[40];
+  __shared__ int s_nev;
+  WBK_DYN_SMEM(u64, ssort);  // [CS_SORT]
   if (tid == 0) s_nev = 0;
   __syncthreads();
   u64* B = x.pairs_b + (size_t)job * x.PC;
-  int* flag = x.flag + (size_t)job * x.PC;
   int* scanb = x.scanb + (size_t)job * x.PC;
   int* label = x.label + (size_t)job * x.PC;
   u64* hk = x.hk + (size_t)job * 2 * x.PC;
   u32* hv1 = x.hv1 + (size_t)job * 2 * x.PC;
-  u32* hv2 = x.hv2 + (size_t)job * 2 * x.PC;
 
   const int nsel = x.nsel[job];
   for (int si = 0; si < nsel; ++si) {
     const int slot = job * x.SC + si;
     const int c = x.sel[slot];
-    const int base = ps.pt_off[c], n = ps.pt_off[c + 1] - base;
-    int P = x.pair_count[slot];
-    if (P > x.PC) {
-      if (tid == 0) atomicOr(&d.status[job], (int)WBK_ST_PAIR_OVERFLOW);
-      continue;  // uniform
-    }
-    // stage the contour in shared memory (L2 latency would dominate the chord x segment tests) together with
-    // the bounding box of every run of 32 segments
-    const bool staged = n <= CS_PTS;
+    const int base = ps.pt_off[c];
     const u32* pts = ps.pts + base;
-    __syncthreads();
-    if (staged && P > 1) {
-      for (int k = tid; k < n; k += nt) spts[k] = pts[k];
-      __syncthreads();
-      const int nb = (n - 1 + 31) >> 5;
-      for (int bb = warp; bb < nb; bb += nwarps) {
-        const int k = bb * 32 + lane;
-        int x0 = 0x7fffffff, y0 = 0x7fffffff, x1 = -1, y1 = -1;
-        if (k < n) {
-          const u32 pp = spts[k];
-          x0 = x1 = wbk_px(pp);
-          y0 = y1 = wbk_py(pp);
-        }
-        if (lane == 0 && k + 32 < n) {  // the run's last segment ends at point k + 32
-          const u32 pp = spts[k + 32];
-          x0 = min(x0, wbk_px(pp)); x1 = max(x1, wbk_px(pp)); y0 = min(y0, wbk_py(pp)); y1 = max(y1, wbk_py(pp));
-        }
-        x0 = wbk_warp_min(x0); y0 = wbk_warp_min(y0); x1 = wbk_warp_max(x1); y1 = wbk_warp_max(y1);
-        if (lane == 0) {
-          sbb[4 * bb] = x0; sbb[4 * bb + 1] = y0; sbb[4 * bb + 2] = x1; sbb[4 * bb + 3] = y1;
-        }
-      }
-      __syncthreads();
-      pts = spts;
-    }
+    int P = x.cnt1[slot];
     u64* A = x.pairs + (size_t)slot * x.PC;
-    // row-major order of np.nonzero: sort by (i, j)
-    const u32 p2 = wbk_pow2_ceil((u32)(P > 0 ? P : 1));
-    if (p2 <= CS_SORT) {
-      for (u32 a = tid; a < p2; a += nt) ssort[a] = (int)a < P ? A[a] : ~0ull;
-      __syncthreads();
-      wbk_block_bitonic_sort(ssort, p2);
-      for (int a = tid; a < P; a += nt) A[a] = ssort[a];
-      __syncthreads();
-    } else {
-      for (u32 a = P + tid; a < p2; a += nt) A[a] = ~0ull;
-      __syncthreads();
-      wbk_block_bitonic_sort(A, p2);
-    }
+    int* flag = x.flag + (size_t)slot * x.PC;
     u64* cur = A;
     u64* oth = B;
-
-    // (1) check_duplicates (:160-183): rows equal after x % nlon -> drop the second of each group
-    if (P > 1) {
-      const u32 dcap = wbk_pow2_ceil((u32)(2 * P));
-      for (u32 a = tid; a < dcap; a += nt) {
-        hk[a] = ~0ull;
-        hv1[a] = WBK_NONE;
-        hv2[a] = WBK_NONE;
-      }
-      __syncthreads();
-      for (int a = tid; a < P; a += nt) {
-        const u64 k = cur[a];
-        const u32 pi = pts[(u32)(k >> 32)], pj = pts[((u32)k) >> 1];
-        const u64 key = ((u64)wbk_pack_xy(wbk_px(pi) % nlon, wbk_py(pi)) << 32) | (u64)wbk_pack_xy(wbk_px(pj) % nlon, wbk_py(pj));
-        const u32 sl = wbk_hash_slot64(hk, dcap, key, nullptr);
-        label[a] = (int)sl;
-        atomicMin(&hv1[sl], (u32)a);
-      }
-      __syncthreads();
-      for (int a = tid; a < P; a += nt)
-        if (hv1[label[a]] != (u32)a) atomicMin(&hv2[label[a]], (u32)a);
-      __syncthreads();
-      for (int a = tid; a < P; a += nt) flag[a] = hv2[label[a]] == (u32)a ? 0 : 1;
-      __syncthreads();
+    __syncthreads();
+    if (P > 1) {  // check_intersections ran: keep the chords flagged by the touch kernel
       P = compact_pairs(cur, oth, flag, scanb, P, sscan);
       u64* t = cur; cur = oth; oth = t;
     }
-    // (2) check_intersections (:185-200): keep chords that only touch the contour
-    if (P > 1) {
-      const u32 e0 = pts[0], e1 = pts[n - 1];
-      const int e0x = wbk_px(e0), e0y = wbk_py(e0), e1x = wbk_px(e1), e1y = wbk_py(e1);
-      for (int a = warp; a < P; a += nwarps) {
-        const u64 k = cur[a];
-        const u32 pi = pts[(u32)(k >> 32)], pj = pts[((u32)k) >> 1];
-        const int px = wbk_px(pi), py = wbk_py(pi), qx = wbk_px(pj), qy = wbk_py(pj);
-        const int bx0 = min(px, qx), bx1 = max(px, qx), by0 = min(py, qy), by1 = max(py, qy);
-        int bad = 0;
-        if (staged) {
-          const int nb = (n - 1 + 31) >> 5;
-          for (int b0 = 0; b0 < nb && !bad; b0 += 32) {
-            const int bb = b0 + lane;
-            const bool hit = bb < nb && !(sbb[4 * bb + 2] < bx0 || sbb[4 * bb] > bx1 || sbb[4 * bb + 3] < by0 || sbb[4 * bb + 1] > by1);
-            u32 mask = __ballot_sync(WBK_FULL, hit);
-            while (mask) {
-              const int hb = b0 + __ffs((int)mask) - 1;
-              mask &= mask - 1;
-              const int s = hb * 32 + lane;
-              int v = 0;
-              if (s < n - 1) {
-                const u32 pa = pts[s], pb = pts[s + 1];
-                const int ax = wbk_px(pa), ay = wbk_py(pa), bx = wbk_px(pb), by = wbk_py(pb);
-                if (!(max(ax, bx) < bx0 || min(ax, bx) > bx1 || max(ay, by) < by0 || min(ay, by) > by1))
-                  v = chord_violation(px, py, qx, qy, ax, ay, bx, by, e0x, e0y, e1x, e1y) ? 1 : 0;
-              }
-              if (__any_sync(WBK_FULL, v)) {
-                bad = 1;
-                break;
-              }
-            }
-          }
-        } else {
-          for (int s0 = 0; s0 < n - 1; s0 += 32) {
-            const int s = s0 + lane;
-            if (s < n - 1) {
-              const u32 pa = pts[s], pb = pts[s + 1];
-              const int ax = wbk_px(pa), ay = wbk_py(pa), bx = wbk_px(pb), by = wbk_py(pb);
-              if (!(max(ax, bx) < bx0 || min(ax, bx) > bx1 || max(ay, by) < by0 || min(ay, by) > by1))
-                bad |= chord_violation(px, py, qx, qy, ax, ay, bx, by, e0x, e0y, e1x, e1y) ? 1 : 0;
-            }
-            if (__any_sync(WBK_FULL, bad)) break;
-          }
-          bad = __any_sync(WBK_FULL, bad);
-        }
-        if (lane == 0) flag[a] = bad ? 0 : 1;
+    // row-major order of np.nonzero: sort by (i, j)
+    {
+      const u32 p2 = wbk_pow2_ceil((u32)(P > 0 ? P : 1));
+      if (p2 <= CS_SORT) {
+        for (u32 a = tid; a < p2; a += nt) ssort[a] = (int)a < P ? cur[a] : ~0ull;
+        __syncthreads();
+        wbk_block_bitonic_sort(ssort, p2);
+        for (int a = tid; a < P; a += nt) cur[a] = ssort[a];
+        __syncthreads();
+      } else {
+        for (u32 a = P + tid; a < p2; a += nt) cur[a] = ~0ull;
+        __syncthreads();
+        wbk_block_bitonic_sort(cur, p2);
       }
-      __syncthreads();
-      P = compact_pairs(cur, oth, flag, scanb, P, sscan);
-      u64* t = cur; cur = oth; oth = t;
     }
     // (3) check_overlapping (:202-222): drop [ind1, ind2] fully covered by another pair
     if (P > 1) {
@@ -905,8 +989,23 @@ extern "C" int wbk_index_run(wbk_ctx* ctx, int njobs, int nlevels, const int* d_
     WBK_LAUNCH_CHECK();
     WBK_LAUNCH(KID_PAIR_SCAN, pair_scan_kernel, dim3(148 * 8), dim3(PS_THREADS), 0, st, d, x, ps, ct, (const double*)pfx, *prm, nslots);
     WBK_LAUNCH_CHECK();
-    WBK_CUDA_CHECK(cudaFuncSetAttribute(streamer_cascade_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CS_SMEM));
-    WBK_LAUNCH(KID_CASCADE, streamer_cascade_kernel, dim3(njobs), dim3(ST_THREADS), CS_SMEM, st, d, x, ps, (const double*)on, (const double*)pfx, J);
+    WBK_LAUNCH(KID_CASCADE, streamer_dedupe_kernel, dim3(njobs), dim3(ST_THREADS), 0, st, d, x, ps);
+    WBK_LAUNCH_CHECK();
+    WBK_LAUNCH(KID_TILE_SCAN, touch_scan_kernel, dim3(1), dim3(1024), 0, st, x, nslots);
+    WBK_LAUNCH_CHECK();
+    {
+      const int nbins = ((d.W >> TB_SHIFT) + 1) * ((d.nlat >> TB_SHIFT) + 1);
+      const size_t tsmem = (size_t)(2 * nbins + 1) * sizeof(int) + (size_t)TOUCH_MAXSEG * sizeof(unsigned short);
+      if (tsmem > 200 * 1024) {
+        wbk_set_error("wbk_index_run: grid too large for the touch-kernel bin index");
+        return WBK_ERR_CAPACITY;
+      }
+      WBK_CUDA_CHECK(cudaFuncSetAttribute(streamer_touch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+      WBK_LAUNCH(KID_TOUCH, streamer_touch_kernel, dim3(148 * 4), dim3(TOUCH_THREADS), tsmem, st, d, x, ps, nslots);
+      WBK_LAUNCH_CHECK();
+    }
+    WBK_CUDA_CHECK(cudaFuncSetAttribute(streamer_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CS_SMEM));
+    WBK_LAUNCH(KID_FINISH, streamer_finish_kernel, dim3(njobs), dim3(ST_THREADS), CS_SMEM, st, d, x, ps, (const double*)on, J);
     WBK_LAUNCH_CHECK();
   }
   return WBK_OK;
