@@ -851,36 +851,73 @@ __global__ void __launch_bounds__(ST_THREADS) streamer_finish_kernel(WbkDev d, W
     // (4) check_groups (:224-251): chords that intersect describe one streamer; keep the longest
     int nout = P;
     if (P > 1) {
-      for (int a = tid; a < P; a += nt) label[a] = a;
+      // chord end points and labels live in shared memory (the sort buffer is free now) when they fit
+      const bool in_smem = P <= CS_SORT * 2 / 3;
+      u32* cp = reinterpret_cast<u32*>(ssort);         // [P] packed point p of chord a
+      u32* cq = cp + P;                                 // [P] packed point q
+      int* slab = reinterpret_cast<int*>(cq + P);       // [P] component labels
+      int* lab = in_smem ? slab : label;
+      __syncthreads();
+      for (int a = tid; a < P; a += nt) {
+        lab[a] = a;
+        if (in_smem) {
+          const u64 ka = cur[a];
+          cp[a] = pts[(u32)(ka >> 32)];
+          cq[a] = pts[((u32)ka) >> 1];
+        }
+      }
       __syncthreads();
       while (true) {
         int changed = 0;
         for (int a = tid; a < P; a += nt) {
-          const u64 ka = cur[a];
-          const u32 pa = pts[(u32)(ka >> 32)], qa = pts[((u32)ka) >> 1];
-          int m = label[a];
+          u32 pa, qa;
+          if (in_smem) {
+            pa = cp[a];
+            qa = cq[a];
+          } else {
+            const u64 ka = cur[a];
+            pa = pts[(u32)(ka >> 32)];
+            qa = pts[((u32)ka) >> 1];
+          }
+          const int ax0 = min(wbk_px(pa), wbk_px(qa)), ax1 = max(wbk_px(pa), wbk_px(qa));
+          const int ay0 = min(wbk_py(pa), wbk_py(qa)), ay1 = max(wbk_py(pa), wbk_py(qa));
+          int m = lab[a];
           for (int b = 0; b < P; ++b) {
-            const int lb = label[b];
+            const int lb = lab[b];
             if (lb >= m) continue;
-            const u64 kb = cur[b];
-            const u32 pb = pts[(u32)(kb >> 32)], qb = pts[((u32)kb) >> 1];
+            u32 pb, qb;
+            if (in_smem) {
+              pb = cp[b];
+              qb = cq[b];
+            } else {
+              const u64 kb = cur[b];
+              pb = pts[(u32)(kb >> 32)];
+              qb = pts[((u32)kb) >> 1];
+            }
+            if (max(wbk_px(pb), wbk_px(qb)) < ax0 || min(wbk_px(pb), wbk_px(qb)) > ax1 ||
+                max(wbk_py(pb), wbk_py(qb)) < ay0 || min(wbk_py(pb), wbk_py(qb)) > ay1)
+              continue;
             if (seg_intersect(wbk_px(pa), wbk_py(pa), wbk_px(qa), wbk_py(qa), wbk_px(pb), wbk_py(pb), wbk_px(qb), wbk_py(qb)))
               m = lb;
           }
-          if (m < label[a]) {
-            atomicMin(&label[a], m);
+          if (m < lab[a]) {
+            atomicMin(&lab[a], m);
             changed = 1;
           }
         }
         __syncthreads();
         for (int a = tid; a < P; a += nt) {  // pointer jumping
-          const int l = label[a], ll = label[l];
+          const int l = lab[a], ll = lab[l];
           if (ll < l) {
-            label[a] = ll;
+            lab[a] = ll;
             changed = 1;
           }
         }
         if (!__syncthreads_or(changed)) break;
+      }
+      if (in_smem) {
+        for (int a = tid; a < P; a += nt) label[a] = slab[a];
+        __syncthreads();
       }
       // winner of every component: max of on[ind1 : ind2 + 1].sum(), first index on ties
       for (int a = tid; a < P; a += nt) {
