@@ -810,7 +810,35 @@ __global__ void __launch_bounds__(ST_THREADS) streamer_finish_kernel(WbkDev d, W
       P = compact_pairs(cur, oth, flag, scanb, P, sscan);
       u64* t = cur; cur = oth; oth = t;
     }
-    // row-major order of np.nonzero: sort by (i, j)
+    // (3) check_overlapping (:202-222): drop [ind1, ind2] fully covered by another pair.  Order-free form:
+    // best[i] = largest ind2 among the pairs with ind1 == i, PM = running maximum of best; a pair is covered iff
+    // a pair with a smaller ind1 reaches at least as far (PM[ind1-1] >= ind2) or one with the same ind1 reaches
+    // further (best[ind1] > ind2; pairs are unique).
+    if (P > 1) {
+      const int n = ps.pt_off[c + 1] - base;
+      int* best = reinterpret_cast<int*>(x.hm1 + (size_t)job * 2 * x.PC);  // >= 4 * PC ints >= n
+      int* pm = best + n;
+      for (int i = tid; i < n; i += nt) best[i] = -1;
+      __syncthreads();
+      for (int a = tid; a < P; a += nt) {
+        const u64 k = cur[a];
+        atomicMax(&best[(int)(k >> 32)], (int)(((u32)k) >> 1));
+      }
+      __syncthreads();
+      for (int i = tid; i < n; i += nt) pm[i] = best[i];
+      __syncthreads();
+      wbk_block_incl_max_scan(pm, n, sscan);
+      for (int a = tid; a < P; a += nt) {
+        const u64 k = cur[a];
+        const int i1 = (int)(k >> 32), i2 = (int)(((u32)k) >> 1);
+        const bool covered = (i1 > 0 && pm[i1 - 1] >= i2) || best[i1] > i2;
+        flag[a] = covered ? 0 : 1;
+      }
+      __syncthreads();
+      P = compact_pairs(cur, oth, flag, scanb, P, sscan);
+      u64* t = cur; cur = oth; oth = t;
+    }
+    // row-major order of np.nonzero for what is left: sort by (i, j)
     {
       const u32 p2 = wbk_pow2_ceil((u32)(P > 0 ? P : 1));
       if (p2 <= CS_SORT) {
@@ -824,29 +852,6 @@ __global__ void __launch_bounds__(ST_THREADS) streamer_finish_kernel(WbkDev d, W
         __syncthreads();
         wbk_block_bitonic_sort(cur, p2);
       }
-    }
-    // (3) check_overlapping (:202-222): drop [ind1, ind2] fully covered by another pair
-    if (P > 1) {
-      for (int a = tid; a < P; a += nt) {
-        const u64 k = cur[a];
-        scanb[a] = (int)(((u32)k) >> 1);  // ind2
-        const bool rs = a == 0 || (u32)(cur[a - 1] >> 32) != (u32)(k >> 32);
-        label[a] = rs ? a : 0;
-      }
-      __syncthreads();
-      wbk_block_incl_max_scan(scanb, P, sscan);  // prefix max of ind2
-      wbk_block_incl_max_scan(label, P, sscan);  // row start of every pair
-      for (int a = tid; a < P; a += nt) {
-        const u64 k = cur[a];
-        const int i2 = (int)(((u32)k) >> 1);
-        const int rs = label[a];
-        bool covered = rs > 0 && scanb[rs - 1] >= i2;
-        if (a + 1 < P && (u32)(cur[a + 1] >> 32) == (u32)(k >> 32)) covered = true;
-        flag[a] = covered ? 0 : 1;
-      }
-      __syncthreads();
-      P = compact_pairs(cur, oth, flag, scanb, P, sscan);
-      u64* t = cur; cur = oth; oth = t;
     }
     // (4) check_groups (:224-251): chords that intersect describe one streamer; keep the longest
     int nout = P;

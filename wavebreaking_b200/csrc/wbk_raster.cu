@@ -182,6 +182,8 @@ __global__ void __launch_bounds__(1024) event_list_kernel(WbkIdx x, int J, int n
 }
 
 #define RS_THREADS 256
+#define RS_EVENT_ROWCAP 512  // row-buffer columns of the event rasteriser (wider events are scanned in chunks)
+#define RS_RING_CAP 4096     // ring vertices staged in shared memory per event
 
 template <typename T>
 __global__ void __launch_bounds__(RS_THREADS)
@@ -222,22 +224,26 @@ events_raster_kernel(WbkDev d, WbkIdx x, const int* __restrict__ job_off, const 
       rv.n = ev[2] - ev[1] + 1;
       rv.bx0 = rv.by0 = rv.bx1 = rv.by1 = 0;
     }
-    // bounding box of the vertices
+    // bounding box of the vertices (rings that fit are staged in shared memory: every row scans all edges)
     if (tid == 0) {
       s_box[0] = 0x7fffffff; s_box[1] = 0x7fffffff; s_box[2] = -1; s_box[3] = -1;
     }
     __syncthreads();
     {
+      u32* sring = reinterpret_cast<u32*>(sm + (size_t)nwarps * 2 * rowcap);
+      const bool stage = rv.packed != nullptr && rv.n <= RS_RING_CAP;
       int x0 = 0x7fffffff, y0 = 0x7fffffff, x1 = -1, y1 = -1;
       for (int k = tid; k < rv.n; k += blockDim.x) {
         int vx, vy;
         rv.get(k, vx, vy);
+        if (stage) sring[k] = rv.packed[k];
         x0 = min(x0, vx); x1 = max(x1, vx); y0 = min(y0, vy); y1 = max(y1, vy);
       }
       x0 = wbk_warp_min(x0); y0 = wbk_warp_min(y0); x1 = wbk_warp_max(x1); y1 = wbk_warp_max(y1);
       if (lane == 0) {
         atomicMin(&s_box[0], x0); atomicMin(&s_box[1], y0); atomicMax(&s_box[2], x1); atomicMax(&s_box[3], y1);
       }
+      if (stage) rv.packed = sring;
     }
     __syncthreads();
     const int vx0 = s_box[0], vy0 = s_box[1], vx1 = s_box[2], vy1 = s_box[3];
@@ -587,7 +593,7 @@ split_raster_kernel(WbkIdx x, int nlat, int nlon, int ntime, int8_t* __restrict_
 }
 
 static int raster_rowcap(int W) { return (W + 2 + 31) & ~31; }
-#define RS_EVENT_ROWCAP 512  // row-buffer columns of the event rasteriser (wider events are scanned in chunks)
+
 
 extern "C" int wbk_events_raster(wbk_ctx* ctx, const int* d_job_off, const int* d_pt_off, const uint32_t* d_pts,
                                  const double* d_coords, const void* d_data, int dtype, const void* d_intensity,
@@ -612,7 +618,7 @@ extern "C" int wbk_events_raster(wbk_ctx* ctx, const int* d_job_off, const int* 
   const double r_flag = d_flags ? ((prm->dlon + prm->dlat) / 2.0 / 2.0) / prm->dlon : r_prop;  // degrees -> cells
   const int rowcap = raster_rowcap(d.W) < RS_EVENT_ROWCAP ? raster_rowcap(d.W) : RS_EVENT_ROWCAP;
   int nwarps = RS_THREADS / 32;
-  const size_t smem = (size_t)nwarps * 2 * rowcap * sizeof(int);
+  const size_t smem = (size_t)nwarps * 2 * rowcap * sizeof(int) + (size_t)RS_RING_CAP * sizeof(u32);
   const double* area = d_coords + 3 * (size_t)d.nlat;
   const int grid = 148 * 6;
   if (dtype == WBK_F32) {
