@@ -43,7 +43,8 @@ size_t layout(WbkDev& d, const wbk_caps& c, int nlat, int nlon, int add, unsigne
 
 bool caps_ok(const wbk_caps* c, int nlat, int nlon, int add) {
   return c && c->max_jobs >= 1 && c->seg_cap >= 16 && c->contour_cap >= 4 && c->sel_cap >= 1 && c->pair_cap >= 16 &&
-         c->event_cap >= 1 && nlat >= 2 && nlon >= 2 && add >= 0 && nlon + add < 65536 && nlat < 65536;
+         c->event_cap >= 1 && nlat >= 2 && nlon >= 2 && add >= 0 && nlon + add < 65536 && nlat < 65536 &&
+         (long long)c->max_jobs * c->sel_cap <= 16384 && c->seg_cap + c->contour_cap <= 65536;
 }
 }  // namespace
 

@@ -45,6 +45,8 @@ struct WbkIdx {
   u64* pairs;                // [J][SC][PC]  candidate pairs (i << 32 | j)
   int* pair_count;           // [J][SC]
   int* tile_off;             // [J*SC + 1]
+  int TLC;                   // capacity of the active-tile list
+  u32* tile_list;            // [TLC] active pair-scan tiles of the batch: slot << 18 | bi << 9 | bj
   int NB;                    // blocks of PT points per contour (capacity)
   int* blk_x;                // [J*SC][NB][2] column range of every block of a full-width contour
   u64* pairs_b;              // [J][PC]

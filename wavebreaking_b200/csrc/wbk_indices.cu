@@ -31,6 +31,9 @@ size_t wbk_index_layout(struct wbk_ctx* ctx, unsigned char* base, size_t off) {
   x.hk = (u64*)take(J * 2 * PC * 8);
   x.hv1 = (u32*)take(J * 2 * PC * 4);
   x.hv2 = (u32*)take(J * 2 * PC * 4);
+  x.TLC = (int)(J * SC * 256 > (size_t)1 << 24 ? (size_t)1 << 24 : J * SC * 256);
+  if ((size_t)x.TLC < J * (PC / 16)) x.TLC = (int)(J * (PC / 16));
+  x.tile_list = (u32*)take((size_t)x.TLC * 4);
   x.hm1 = (u64*)take(J * 2 * PC * 8);
   x.hm2 = (u64*)take(J * 2 * PC * 8);
   x.cnt1 = (int*)take(J * SC * 4);
@@ -375,6 +378,26 @@ __global__ void __launch_bounds__(ST_THREADS) streamer_prep_kernel(WbkDev d, Wbk
         bx[2 * b + 1] = mx;
       }
     }
+    __syncthreads();  // block column ranges are read below
+    // active tiles: (bi <= bj) whose column ranges are at most 120 apart (streamer_index.py:157); appended to the
+    // batch-wide work list of the pair scan as slot << 18 | bi << 9 | bj
+    {
+      const int slot = job * x.SC + si;
+      const int* bx = x.blk_x + (size_t)slot * x.NB * 2;
+      const int ntile = T * (T + 1) / 2;
+      for (int q = tid; q < ntile; q += nt) {
+        int t = q, bi = 0;
+        while (t >= T - bi) {
+          t -= T - bi;
+          ++bi;
+        }
+        const int bj = bi + t;
+        if (bx[2 * bj] - bx[2 * bi + 1] > 120 || bx[2 * bi] - bx[2 * bj + 1] > 120) continue;
+        const int pos = atomicAdd(&x.total[0], 1);
+        if (pos < x.TLC) x.tile_list[pos] = ((u32)slot << 18) | ((u32)bi << 9) | (u32)bj;
+        else atomicOr(&d.status[job], (int)WBK_ST_PAIR_OVERFLOW);
+      }
+    }
     if (tid == 0) x.tile_off[(size_t)job * x.SC + si] = T * (T + 1) / 2;
   }
 }
@@ -401,32 +424,15 @@ __global__ void __launch_bounds__(PS_THREADS) pair_scan_kernel(WbkDev d, WbkIdx 
   __shared__ float fla[2][PT], flo[2][PT], fco[2][PT];
   __shared__ double sla[2][PT], slo[2][PT], sco[2][PT], spf[2][PT];
   const int tid = threadIdx.x, nlon = d.nlon;
-  const int total = x.tile_off[nslots];
+  const int total = min(x.total[0], x.TLC);
   const double sthr = sin(prm.geo_dis / (2.0 * EARTH_R));
   const float hthr = (float)(sthr * sthr);
   const float h_lo = hthr * 0.9999f, h_hi = hthr * 1.0001f;
   for (int w = blockIdx.x; w < total; w += gridDim.x) {
-    // slot = last index with tile_off[slot] <= w
-    int lo = 0, hi = nslots - 1;
-    while (lo < hi) {
-      int mid = (lo + hi + 1) >> 1;
-      if (x.tile_off[mid] <= w) lo = mid; else hi = mid - 1;
-    }
-    const int slot = lo;
+    const u32 tl = x.tile_list[w];
+    const int slot = (int)(tl >> 18), bi = (int)((tl >> 9) & 511u), bj = (int)(tl & 511u);
     const int c = x.sel[slot];
     const int base = ps.pt_off[c], n = ps.pt_off[c + 1] - base;
-    const int T = (n + PT - 1) / PT;
-    int t = w - x.tile_off[slot], bi = 0;
-    while (t >= T - bi) {
-      t -= T - bi;
-      ++bi;
-    }
-    const int bj = bi + t;
-    {
-      const int* bx = x.blk_x + (size_t)slot * x.NB * 2;
-      const int imin = bx[2 * bi], imax = bx[2 * bi + 1], jmin = bx[2 * bj], jmax = bx[2 * bj + 1];
-      if (jmin - imax > 120 || imin - jmax > 120) continue;  // uniform for the CTA
-    }
     {
       const int which = tid >> 7, k = tid & (PT - 1);
       const int idx = (which ? bj : bi) * PT + k;
@@ -1025,9 +1031,8 @@ extern "C" int wbk_index_run(wbk_ctx* ctx, int njobs, int nlevels, const int* d_
     double* on = d_work;
     double* pfx = d_work + npoints;
     const int nslots = njobs * x.SC;
+    WBK_CUDA_CHECK(cudaMemsetAsync(x.total, 0, sizeof(int), st));
     WBK_LAUNCH(KID_STREAMER_PREP, streamer_prep_kernel, dim3(njobs), dim3(ST_THREADS), 0, st, d, x, ps, ct, on, pfx);
-    WBK_LAUNCH_CHECK();
-    WBK_LAUNCH(KID_TILE_SCAN, tile_scan_kernel, dim3(1), dim3(1024), 0, st, x, nslots);
     WBK_LAUNCH_CHECK();
     WBK_LAUNCH(KID_PAIR_SCAN, pair_scan_kernel, dim3(148 * 8), dim3(PS_THREADS), 0, st, d, x, ps, ct, (const double*)pfx, *prm, nslots);
     WBK_LAUNCH_CHECK();

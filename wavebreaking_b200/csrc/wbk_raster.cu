@@ -82,7 +82,8 @@ __device__ inline double dd_block_sum(DD v, double* scratch /* >= 66 doubles */)
 // of (bx0 + i, y) (for points not on the boundary) and flg[i] has bit 0 / bit 1 set if the point is on the
 // boundary or closer than sqrt(r2a) / sqrt(r2b) to an edge.  R = floor(max radius).
 __device__ inline void raster_scan_row(const RingView& rv, int y, int bx0, int bw, int* acc, u32* flg, double r2a,
-                                       double r2b, double rmax, int R) {
+                                       double r2b, double rmax, int R, const unsigned short* elist = nullptr,
+                                       int ecount = 0) {
   const int lane = wbk_lane();
   for (int i = lane; i < bw; i += 32) {
     acc[i] = 0;
@@ -90,9 +91,11 @@ __device__ inline void raster_scan_row(const RingView& rv, int y, int bx0, int b
   }
   __syncwarp();
   const int n = rv.n;
-  for (int e0 = 0; e0 < n; e0 += 32) {
-    const int e = e0 + lane;
-    if (e < n) {
+  const int nscan = elist ? ecount : n;  // with a row bucket only the edges that can touch this row are visited
+  for (int e0 = 0; e0 < nscan; e0 += 32) {
+    const int q = e0 + lane;
+    if (q < nscan) {
+      const int e = elist ? (int)elist[q] : q;
       int xa, ya, xb, yb;
       rv.get(e, xa, ya);
       rv.get(e + 1 == n ? 0 : e + 1, xb, yb);
@@ -184,6 +187,8 @@ __global__ void __launch_bounds__(1024) event_list_kernel(WbkIdx x, int J, int n
 #define RS_THREADS 256
 #define RS_EVENT_ROWCAP 512  // row-buffer columns of the event rasteriser (wider events are scanned in chunks)
 #define RS_RING_CAP 4096     // ring vertices staged in shared memory per event
+#define RS_ROWS_CAP 1024     // lattice rows of an event's bounding box that get an edge bucket
+#define RS_EDGE_CAP 12288    // edge incidences in the row buckets
 
 template <typename T>
 __global__ void __launch_bounds__(RS_THREADS)
@@ -194,6 +199,7 @@ events_raster_kernel(WbkDev d, WbkIdx x, const int* __restrict__ job_off, const 
   WBK_DYN_SMEM(int, sm);
   __shared__ double red[72];
   __shared__ int s_box[5];
+  __shared__ int s_scan[40];
   const int tid = threadIdx.x, lane = wbk_lane(), warp = wbk_warp(), nwarps = blockDim.x >> 5;
   int* acc = sm + (size_t)warp * 2 * rowcap;
   u32* flg = reinterpret_cast<u32*>(acc + rowcap);
@@ -253,11 +259,47 @@ events_raster_kernel(WbkDev d, WbkIdx x, const int* __restrict__ job_off, const 
     const int bx0 = max(vx0 - R - 1, 0), bx1 = min(vx1 + R + 1, W - 1);
     const int by0 = max(vy0 - R - 1, 0), by1 = min(vy1 + R + 1, nlat - 1);
     const int bw = bx1 - bx0 + 1;
+    // row buckets: edge e is listed under every lattice row it can touch (its y-span widened by R), so a row
+    // visits a handful of edges instead of the whole ring
+    const int nrows = by1 - by0 + 1;
+    int* rcount = reinterpret_cast<int*>(sm + (size_t)nwarps * 2 * rowcap + RS_RING_CAP);  // [RS_ROWS_CAP + 1]
+    int* rcur = rcount + RS_ROWS_CAP + 1;                                                   // [RS_ROWS_CAP]
+    unsigned short* redge = reinterpret_cast<unsigned short*>(rcur + RS_ROWS_CAP);          // [RS_EDGE_CAP]
+    bool bucketed = rv.n <= 65535 && nrows <= RS_ROWS_CAP && rv.n > 64;
+    if (bucketed) {
+      for (int i = tid; i <= nrows; i += blockDim.x) rcount[i] = 0;
+      __syncthreads();
+      for (int e = tid; e < rv.n; e += blockDim.x) {
+        int xa, ya, xb, yb;
+        rv.get(e, xa, ya);
+        rv.get(e + 1 == rv.n ? 0 : e + 1, xb, yb);
+        const int lo = max(min(ya, yb) - R, by0), hi = min(max(ya, yb) + R, by1);
+        for (int y = lo; y <= hi; ++y) atomicAdd(&rcount[y - by0], 1);
+      }
+      __syncthreads();
+      const int ninc = wbk_block_excl_scan(rcount, nrows, s_scan);
+      if (tid == 0) rcount[nrows] = ninc;
+      for (int i = tid; i < nrows; i += blockDim.x) rcur[i] = rcount[i];
+      __syncthreads();
+      bucketed = rcount[nrows] <= RS_EDGE_CAP;  // uniform
+      if (bucketed) {
+        for (int e = tid; e < rv.n; e += blockDim.x) {
+          int xa, ya, xb, yb;
+          rv.get(e, xa, ya);
+          rv.get(e + 1 == rv.n ? 0 : e + 1, xb, yb);
+          const int lo = max(min(ya, yb) - R, by0), hi = min(max(ya, yb) + R, by1);
+          for (int y = lo; y <= hi; ++y) redge[atomicAdd(&rcur[y - by0], 1)] = (unsigned short)e;
+        }
+      }
+      __syncthreads();
+    }
     DD s_a = {0, 0}, s_v = {0, 0}, s_i = {0, 0}, s_x = {0, 0}, s_y = {0, 0}, s_n = {0, 0};
     for (int y = by0 + warp; y <= by1; y += nwarps) {
+     const unsigned short* elist = bucketed ? redge + rcount[y - by0] : nullptr;
+     const int ecount = bucketed ? rcount[y - by0 + 1] - rcount[y - by0] : 0;
      for (int cx0 = bx0; cx0 <= bx1; cx0 += rowcap) {  // wide events: the row is scanned in column chunks
       const int cw = min(rowcap, bx1 - cx0 + 1);
-      raster_scan_row(rv, y, cx0, cw, acc, flg, r2_prop, r2_flag, rmax, R);
+      raster_scan_row(rv, y, cx0, cw, acc, flg, r2_prop, r2_flag, rmax, R, elist, ecount);
       const double a = area[y];
       const size_t rowbase = ((size_t)t * nlat + y) * nlon;
       for (int i = lane; i < cw; i += 32) {
@@ -618,7 +660,8 @@ extern "C" int wbk_events_raster(wbk_ctx* ctx, const int* d_job_off, const int* 
   const double r_flag = d_flags ? ((prm->dlon + prm->dlat) / 2.0 / 2.0) / prm->dlon : r_prop;  // degrees -> cells
   const int rowcap = raster_rowcap(d.W) < RS_EVENT_ROWCAP ? raster_rowcap(d.W) : RS_EVENT_ROWCAP;
   int nwarps = RS_THREADS / 32;
-  const size_t smem = (size_t)nwarps * 2 * rowcap * sizeof(int) + (size_t)RS_RING_CAP * sizeof(u32);
+  const size_t smem = (size_t)nwarps * 2 * rowcap * sizeof(int) + (size_t)RS_RING_CAP * sizeof(u32) +
+                      (size_t)(2 * RS_ROWS_CAP + 1) * sizeof(int) + (size_t)RS_EDGE_CAP * sizeof(unsigned short);
   const double* area = d_coords + 3 * (size_t)d.nlat;
   const int grid = 148 * 6;
   if (dtype == WBK_F32) {
