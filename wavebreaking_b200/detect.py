@@ -22,8 +22,8 @@ def default_caps(nlat, nlon, add, njobs):
     """Arena capacities that fit smooth geophysical fields with headroom (regrown on overflow)."""
     W = nlon + add
     p2 = lambda v: 1 << max(4, int(np.ceil(np.log2(max(v, 2)))))
-    return dict(max_jobs=int(njobs), seg_cap=p2(8 * (W + nlat)), contour_cap=p2(max(256, W // 2)), sel_cap=4,
-                pair_cap=p2(16 * W), event_cap=256)
+    return dict(max_jobs=int(njobs), seg_cap=p2(8 * (W + nlat)), contour_cap=p2(max(256, W // 2)), sel_cap=2,
+                pair_cap=p2(48 * W), event_cap=256)
 
 
 class Context:

@@ -87,6 +87,7 @@ class _Slot:
         self.stream = torch.cuda.Stream(device=dev) if lib.is_cuda else None
         self.done = torch.cuda.Event() if lib.is_cuda else None
         self.pending = None   # (raw, ntime, flags_dev, flags_host, gmax)
+        self.grow_seen = 0
 
     def close(self):
         self.ctx.close()
@@ -113,13 +114,21 @@ class Detector:
         self.coords = detect.coord_tables(self.lat, self.lon, self.dlon, self.dlat, self.lib)
         self._slots = {}
         self._grow = {}
+        self._grow_version = 0
 
     # ------------------------------------------------------------------ slots
     def _slot(self, T, index=0):
         key = (int(T), int(index))
         s = self._slots.get(key)
+        if s is not None and s.pending is None and s.grow_seen != self._grow_version:
+            # another slot had to regrow its arenas: adopt the larger capacities before the next batch overflows too
+            if self.lib.is_cuda:
+                torch.cuda.synchronize()
+            s.close()
+            s = None
         if s is None:
             s = _Slot(self, T, self._grow)
+            s.grow_seen = self._grow_version
             self._slots[key] = s
         return s
 
@@ -277,6 +286,7 @@ class Detector:
         if status & _lib.ST_FETCH_OVERFLOW:
             grow["cap_e"], grow["cap_r"] = slot.cap_e * 2, slot.cap_r * 2
         self._grow = grow
+        self._grow_version += 1
         if len(grow) and max(grow.values()) > (1 << 28):
             raise _lib.WbkError(_lib.ERR_CAPACITY, "arenas still overflow after repeated regrowth (status {})".format(status))
         key = next(k for k, v in self._slots.items() if v is slot)
@@ -284,6 +294,7 @@ class Detector:
             torch.cuda.synchronize()
         slot.close()
         new = _Slot(self, slot.T, grow)
+        new.grow_seen = self._grow_version
         self._slots[key] = new
         self.submit(new, pend["raw"], flags_out=pend["flags"], flags_host=pend["flags_host"], gmax_nx=pend["gmax"],
                     smoothed=pend["smoothed"], intensity=pend["intensity"])
