@@ -34,17 +34,22 @@ UNIT = "time steps/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=None, help="default: 20 (b200) / 2 (reference)")
+    ap.add_argument("--warmup", type=int, default=None, help="default: 3 (b200) / 1 (reference)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=296, help="time steps per step (2 per SM)")
     ap.add_argument("--nlat", type=int, default=721)
     ap.add_argument("--nlon", type=int, default=1440)
     ap.add_argument("--passes", type=int, default=5)
-    ap.add_argument("--cpu-sample", type=int, default=6, help="time steps of the CPU baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=1, help="time steps of the CPU baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.steps is None:
+        a.steps = 20 if a.impl == "b200" else 2
+    if a.warmup is None:
+        a.warmup = 3 if a.impl == "b200" else 1
+    return a
 
 
 def workload_config(a):

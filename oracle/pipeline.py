@@ -363,13 +363,19 @@ def streamer_basepoints(points, grid, geo_dis=800, cont_dis=1500, diagnostics=No
         return df[keep]
 
     def check_overlapping(df):  # :202-222
-        ranges = [range(int(r.ind1), int(r.ind2 + 1)) for r in df.itertuples()]
-        drop = set(
-            a
-            for a, b in itertools.permutations(df.index, r=2)
-            if (ranges[a][0] in ranges[b] and ranges[a][-1] in ranges[b])
-        )
-        return df.drop(drop)
+        # the reference walks itertools.permutations(df.index, 2) in pure Python (O(P^2), ~5e8 iterations for
+        # the 2e4 candidates of a 0.25-degree contour); the same predicate is evaluated here with chunked numpy
+        # broadcasting so that the oracle stays usable as a CPU baseline at that size (identical result)
+        i1 = df.ind1.values.astype(np.int64)
+        i2 = df.ind2.values.astype(np.int64)
+        idx = np.arange(len(df))
+        drop = np.zeros(len(df), dtype=bool)
+        for s0 in range(0, len(df), 512):
+            a1, a2, ai = i1[s0:s0 + 512, None], i2[s0:s0 + 512, None], idx[s0:s0 + 512, None]
+            inside = (i1[None, :] <= a1) & (a1 <= i2[None, :]) & (i1[None, :] <= a2) & (a2 <= i2[None, :])
+            inside &= ai != idx[None, :]
+            drop[s0:s0 + 512] = inside.any(axis=1)
+        return df.drop(df.index[drop])
 
     def check_groups(df):  # :224-251
         index_combinations = np.asarray(
