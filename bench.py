@@ -212,6 +212,7 @@ def run_reference(a):
     value = a.steps * per_step / dt
     cfg = workload_config(a)
     cfg["time_steps_per_step"] = per_step
+    cfg["l2"] = "n/a (CPU arm)"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": 1000.0 * dt / a.steps, "higher_is_better": True, "scaling": "weak",

@@ -45,8 +45,8 @@ extern "C" {
 /* per-job status bits (job = one (time step, contour level)) */
 #define WBK_ST_SEG_OVERFLOW 1       /* more marching-squares segments than seg_cap */
 #define WBK_ST_CONTOUR_OVERFLOW 2   /* more contours than contour_cap */
-#define WBK_ST_LATTICE_VERTEX 4     /* a contour vertex fell exactly on a grid vertex (value == level):
-                                       skimage joins such points by float equality; result flagged */
+#define WBK_ST_LATTICE_VERTEX 4     /* informational: a contour vertex fell exactly on a grid vertex (value == level);
+                                       the job was linked by the sequential, skimage-exact linker */
 #define WBK_ST_PAIR_OVERFLOW 8      /* more streamer candidate pairs than pair_cap */
 #define WBK_ST_EVENT_OVERFLOW 16    /* more events than event_cap */
 #define WBK_ST_SEL_OVERFLOW 32      /* more full-width contours than sel_cap */

@@ -107,3 +107,51 @@ def test_contours_gpu_noisy(gpu):
     want = P.calculate_contours(sm, [2, -2], grid, 120, original_coordinates=False)
     assert len(want) > 50
     compare_contours(cs, want, grid, [2, -2])
+
+
+# ------------------------------------------------------------------ contour vertices exactly on grid vertices
+def _int_grid(nlat, nlon):
+    lat = np.linspace(-60.0, 60.0, nlat)
+    lon = np.arange(nlon) * (360.0 / nlon)
+    return P.Grid(lon, lat, synthetic.time_axis(1, 6))
+
+
+def test_lattice_vertices_skimage_vector_emu(emu):
+    """skimage's test_float field: the level passes exactly through four grid vertices."""
+    x, y = np.mgrid[-1:1:5j, -1:1:5j]
+    r = np.sqrt(x ** 2 + y ** 2)[None]
+    grid = _int_grid(5, 5)
+    cs = detect.contours(spatial.to_device(r), [0.5], 0)
+    want = P.calculate_contours(r, [0.5], grid, 0, original_coordinates=False)
+    assert cs.status[0] & 4
+    compare_contours(cs, want, grid, [0.5])
+    assert len(want) == 1 and cs.contour_points(0).tolist() == [[3, 2], [2, 1], [1, 2], [2, 3]]
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_lattice_vertices_random_integer_fields_emu(emu, seed):
+    """Integer-valued fields with an integer level: many vertices on grid points, saddles and touching rings."""
+    rng = np.random.default_rng(seed)
+    nlat, nlon = 14, 24
+    f = rng.integers(0, 4, size=(1, nlat, nlon)).astype(np.float64)
+    # smooth a little so that longer contours exist, keep many exact hits of the level
+    f = np.round((f + np.roll(f, 1, 2) + np.roll(f, 1, 1)) / 3.0 * 2.0) / 2.0
+    grid = _int_grid(nlat, nlon)
+    for level, add_deg in ((1.0, 0), (1.5, 0), (2.0, 120)):
+        cs = detect.contours(spatial.to_device(f), [level], int(add_deg / grid.dlon))
+        want = P.calculate_contours(f, [level], grid, add_deg, original_coordinates=False)
+        compare_contours(cs, want, grid, [level])
+
+
+@pytest.mark.gpu
+def test_lattice_vertices_gpu(gpu):
+    rng = np.random.default_rng(11)
+    f = rng.integers(0, 4, size=(2, 40, 72)).astype(np.float64)
+    f = np.round((f + np.roll(f, 1, 2) + np.roll(f, 1, 1)) / 3.0 * 2.0) / 2.0
+    lat = np.linspace(-60.0, 60.0, 40)
+    lon = np.arange(72) * 5.0
+    grid = P.Grid(lon, lat, synthetic.time_axis(2, 6))
+    cs = detect.contours(spatial.to_device(f), [1.0, 2.0], 24)
+    want = P.calculate_contours(f, [1.0, 2.0], grid, 120, original_coordinates=False)
+    assert np.all(cs.status & 4)
+    compare_contours(cs, want, grid, [1.0, 2.0])

@@ -255,10 +255,6 @@ def _contour_batches(c, levels, periodic_add):
     out = []
     for t0 in range(0, c.ntime, tb):
         cs = detect.contours(c.tensor[t0:t0 + tb], levels, add)
-        if np.any(cs.status & _lib.ST_LATTICE_VERTEX):
-            logger.warning("a contour vertex fell exactly on a grid vertex (field value == level) in %d job(s); "
-                           "skimage joins such points by float equality and the result may differ there",
-                           int(np.count_nonzero(cs.status & _lib.ST_LATTICE_VERTEX)))
         out.append((t0, cs))
     return out
 

@@ -104,6 +104,7 @@ struct LevelPack {
   double v[WBK_MAX_LEVELS];
 };
 
+#define WBK_VERTEX_ID 0x80000000u  // point id of a contour vertex that coincides with a grid vertex
 #define MS_THREADS 256
 #define MS_ROWS 16
 
@@ -208,6 +209,12 @@ __device__ __noinline__ void ms_emit_hits(const WbkDev& d, const T* __restrict__
       pxy[2] = wbk_pack_xy(cc, (int)rint(yl));
       pxy[3] = wbk_pack_xy(cc + 1, (int)rint(yr));
       const bool von[4] = {xt == rint(xt), xb == rint(xb), yl == rint(yl), yr == rint(yr)};
+      // a point that falls exactly on a grid vertex is identified by that vertex: skimage joins by float
+      // equality, so all edges meeting there share the point (handled by the sequential linker)
+      if (von[0]) pid[0] = WBK_VERTEX_ID | (u32)(r0 * W + (int)xt);
+      if (von[1]) pid[1] = WBK_VERTEX_ID | (u32)((r0 + 1) * W + (int)xb);
+      if (von[2]) pid[2] = WBK_VERTEX_ID | (u32)((int)yl * W + cc);
+      if (von[3]) pid[3] = WBK_VERTEX_ID | (u32)((int)yr * W + cc + 1);
       for (int s2 = 0; s2 < nseg; ++s2) {
         const int fe = (code >> (4 * s2)) & 3, te = (code >> (4 * s2 + 2)) & 3;
         lattice = lattice || von[fe] || von[te];
@@ -346,130 +353,305 @@ __global__ void __launch_bounds__(WBK_CONTOUR_THREADS) contour_link_kernel(WbkDe
   }
   if (n == 0) return;
 
-  // ---- P1: hash  from-edge -> segment
-  u32* k32 = reinterpret_cast<u32*>(hkeys);
-  const u32 hcap = wbk_pow2_ceil((u32)(2 * n) < 64u ? 64u : (u32)(2 * n));
-  u32* v32 = k32 + hcap;  // hkeys region holds 2*HC u32 >= 2*hcap
-  for (u32 i = tid; i < hcap; i += nt) k32[i] = WBK_NONE;
-  for (int s = tid; s < n; s += nt) {
-    prv[s] = WBK_NONE;
-    cminrid[s] = WBK_NONE;
-    cnseg[s] = 0;
-    cflag[s] = 0;
-  }
-  __syncthreads();
-  for (int s = tid; s < n; s += nt) wbk_hash_insert32(k32, v32, hcap, fpid[s], (u32)s);
-  __syncthreads();
-  // ---- P2: links
-  for (int s = tid; s < n; s += nt) {
-    u32 nx = wbk_hash_find32(k32, v32, hcap, tpid[s]);
-    nxt[s] = nx;
-    if (nx != WBK_NONE) prv[nx] = (u32)s;
-  }
-  __syncthreads();
-  // ---- P3: pointer doubling with max(rid): detects rings and their largest raster id
-  for (int s = tid; s < n; s += nt) w64[s] = ((u64)rid[s] << 32) | (u64)nxt[s];
-  __syncthreads();
-  const int rounds = wbk_log2_ceil((u32)n) + 1;
-  for (int it = 0; it < rounds; ++it) {
+  int nh = 0, nraw = 0;
+  const bool degenerate = (d.status[job] & WBK_ST_LATTICE_VERTEX) != 0;
+  if (!degenerate) {
+    // ---- P1: hash  from-edge -> segment
+    u32* k32 = reinterpret_cast<u32*>(hkeys);
+    const u32 hcap = wbk_pow2_ceil((u32)(2 * n) < 64u ? 64u : (u32)(2 * n));
+    u32* v32 = k32 + hcap;  // hkeys region holds 2*HC u32 >= 2*hcap
+    for (u32 i = tid; i < hcap; i += nt) k32[i] = WBK_NONE;
+    for (int s = tid; s < n; s += nt) {
+      prv[s] = WBK_NONE;
+      cminrid[s] = WBK_NONE;
+      cnseg[s] = 0;
+      cflag[s] = 0;
+    }
+    __syncthreads();
+    for (int s = tid; s < n; s += nt) wbk_hash_insert32(k32, v32, hcap, fpid[s], (u32)s);
+    __syncthreads();
+    // ---- P2: links
+    for (int s = tid; s < n; s += nt) {
+      u32 nx = wbk_hash_find32(k32, v32, hcap, tpid[s]);
+      nxt[s] = nx;
+      if (nx != WBK_NONE) prv[nx] = (u32)s;
+    }
+    __syncthreads();
+    // ---- P3: pointer doubling with max(rid): detects rings and their largest raster id
+    for (int s = tid; s < n; s += nt) w64[s] = ((u64)rid[s] << 32) | (u64)nxt[s];
+    __syncthreads();
+    const int rounds = wbk_log2_ceil((u32)n) + 1;
+    for (int it = 0; it < rounds; ++it) {
+      for (int s = tid; s < n; s += nt) {
+        u64 w = w64[s];
+        u32 p = (u32)w;
+        if (p != WBK_NONE) {
+          u64 w2 = w64[p];
+          u32 v = (u32)(w >> 32), v2 = (u32)(w2 >> 32);
+          w64[s] = ((u64)(v > v2 ? v : v2) << 32) | (u64)(u32)w2;
+        }
+      }
+      __syncthreads();
+    }
+    // ---- P4: cut every ring after its largest-id segment
     for (int s = tid; s < n; s += nt) {
       u64 w = w64[s];
-      u32 p = (u32)w;
-      if (p != WBK_NONE) {
-        u64 w2 = w64[p];
-        u32 v = (u32)(w >> 32), v2 = (u32)(w2 >> 32);
-        w64[s] = ((u64)(v > v2 ? v : v2) << 32) | (u64)(u32)w2;
+      if ((u32)w != WBK_NONE && (u32)(w >> 32) == rid[s]) {
+        u32 h = nxt[s];
+        cflag[h] = 1;  // ring: closed contour starting at h
+        prv[h] = WBK_NONE;
+        // nxt[s] stays (not used below)
       }
     }
     __syncthreads();
-  }
-  // ---- P4: cut every ring after its largest-id segment
-  for (int s = tid; s < n; s += nt) {
-    u64 w = w64[s];
-    if ((u32)w != WBK_NONE && (u32)(w >> 32) == rid[s]) {
-      u32 h = nxt[s];
-      cflag[h] = 1;  // ring: closed contour starting at h
-      prv[h] = WBK_NONE;
-      // nxt[s] stays (not used below)
-    }
-  }
-  __syncthreads();
-  // ---- P5: rank from the head by pointer jumping along prv
-  for (int s = tid; s < n; s += nt) {
-    u32 p = prv[s];
-    w64[s] = (p == WBK_NONE) ? (u64)(u32)s : (((u64)1 << 32) | (u64)p);
-  }
-  __syncthreads();
-  while (true) {
-    int changed = 0;
+    // ---- P5: rank from the head by pointer jumping along prv
     for (int s = tid; s < n; s += nt) {
-      u64 w = w64[s];
-      u32 p = (u32)w;
-      if (p != (u32)s) {
-        u64 w2 = w64[p];
-        u32 p2 = (u32)w2;
-        if (p2 != p) {
-          w64[s] = ((((w >> 32) + (w2 >> 32)) << 32) | (u64)p2);
-          changed = 1;
+      u32 p = prv[s];
+      w64[s] = (p == WBK_NONE) ? (u64)(u32)s : (((u64)1 << 32) | (u64)p);
+    }
+    __syncthreads();
+    while (true) {
+      int changed = 0;
+      for (int s = tid; s < n; s += nt) {
+        u64 w = w64[s];
+        u32 p = (u32)w;
+        if (p != (u32)s) {
+          u64 w2 = w64[p];
+          u32 p2 = (u32)w2;
+          if (p2 != p) {
+            w64[s] = ((((w >> 32) + (w2 >> 32)) << 32) | (u64)p2);
+            changed = 1;
+          }
         }
       }
+      if (!__syncthreads_or(changed)) break;
     }
-    if (!__syncthreads_or(changed)) break;
-  }
-  // ---- P6: per-contour statistics keyed by the head segment
-  for (int s = tid; s < n; s += nt) {
-    u32 h = (u32)w64[s];
-    atomicMin(&cminrid[h], rid[s]);
-    atomicAdd(&cnseg[h], 1u);
-    if (h == (u32)s) {
-      int k = atomicAdd(&s_nheads, 1);
-      if (k < CC) sortkeys[k] = (u64)s;  // temporarily the head id
+    // ---- P6: per-contour statistics keyed by the head segment
+    for (int s = tid; s < n; s += nt) {
+      u32 h = (u32)w64[s];
+      atomicMin(&cminrid[h], rid[s]);
+      atomicAdd(&cnseg[h], 1u);
+      if (h == (u32)s) {
+        int k = atomicAdd(&s_nheads, 1);
+        if (k < CC) sortkeys[k] = (u64)s;  // temporarily the head id
+      }
     }
-  }
-  __syncthreads();
-  const int nh = s_nheads;
-  if (nh > CC) {
-    if (tid == 0) atomicOr(&d.status[job], (int)WBK_ST_CONTOUR_OVERFLOW);
-    return;
-  }
-  // ---- P7: contour order = ascending smallest raster id
-  const u32 np2 = wbk_pow2_ceil((u32)nh);
-  for (u32 i = tid; i < np2; i += nt) {
-    if ((int)i < nh) {
-      u32 h = (u32)sortkeys[i];
-      sortkeys[i] = ((u64)cminrid[h] << 32) | (u64)h;
-    } else {
-      sortkeys[i] = ~0ull;
+    __syncthreads();
+    nh = s_nheads;
+    if (nh > CC) {
+      if (tid == 0) atomicOr(&d.status[job], (int)WBK_ST_CONTOUR_OVERFLOW);
+      return;
     }
-  }
-  __syncthreads();
-  wbk_block_bitonic_sort(sortkeys, np2);
-  for (int k = tid; k < nh; k += nt) {
-    u32 h = (u32)sortkeys[k];
-    cidx[h] = (u32)k;
-    craw_n[k] = (int)cnseg[h] + 1;
-    craw_off[k] = (int)cnseg[h] + 1;
-    cclosed[k] = (int)cflag[h];
-    cnuniq[k] = 0;
-    cdrop[k] = 0;
-    cymin[k] = 0x7fffffff;
-    cymax[k] = -1;
-  }
-  __syncthreads();
-  const int nraw = wbk_block_excl_scan(craw_off, nh, sscan);  // == n + nh
-  if (tid == 0) craw_off[nh] = nraw;
-  // ---- P8: raw (rounded) points in contour order
-  for (int s = tid; s < n; s += nt) {
-    u64 w = w64[s];
-    u32 h = (u32)w;
-    int k = (int)cidx[h];
-    int pos = craw_off[k] + (int)(w >> 32) + 1;
-    raw[pos] = txy[s];
-    rawc[pos] = (u32)k;
-    if (h == (u32)s) {
-      raw[craw_off[k]] = fxy[s];
-      rawc[craw_off[k]] = (u32)k;
+    // ---- P7: contour order = ascending smallest raster id
+    const u32 np2 = wbk_pow2_ceil((u32)nh);
+    for (u32 i = tid; i < np2; i += nt) {
+      if ((int)i < nh) {
+        u32 h = (u32)sortkeys[i];
+        sortkeys[i] = ((u64)cminrid[h] << 32) | (u64)h;
+      } else {
+        sortkeys[i] = ~0ull;
+      }
     }
+    __syncthreads();
+    wbk_block_bitonic_sort(sortkeys, np2);
+    for (int k = tid; k < nh; k += nt) {
+      u32 h = (u32)sortkeys[k];
+      cidx[h] = (u32)k;
+      craw_n[k] = (int)cnseg[h] + 1;
+      craw_off[k] = (int)cnseg[h] + 1;
+      cclosed[k] = (int)cflag[h];
+      cnuniq[k] = 0;
+      cdrop[k] = 0;
+      cymin[k] = 0x7fffffff;
+      cymax[k] = -1;
+    }
+    __syncthreads();
+    nraw = wbk_block_excl_scan(craw_off, nh, sscan);  // == n + nh
+    if (tid == 0) craw_off[nh] = nraw;
+    // ---- P8: raw (rounded) points in contour order
+    for (int s = tid; s < n; s += nt) {
+      u64 w = w64[s];
+      u32 h = (u32)w;
+      int k = (int)cidx[h];
+      int pos = craw_off[k] + (int)(w >> 32) + 1;
+      raw[pos] = txy[s];
+      rawc[pos] = (u32)k;
+      if (h == (u32)s) {
+        raw[craw_off[k]] = fxy[s];
+        rawc[craw_off[k]] = (u32)k;
+      }
+    }
+
+  } else {
+    // ------------------------------------------------------------------------------------------------
+    // Sequential linker for jobs in which a contour vertex coincides with a grid vertex (a field value equal
+    // to the level): skimage's _assemble_contours joins segments through dicts keyed by the float point, so
+    // several segments can meet in one point and the outcome depends on the raster order.  The same
+    // dict / deque procedure is replayed here by one thread on canonical point ids (vertex id or edge id).
+    // ------------------------------------------------------------------------------------------------
+    const u32 np2s = wbk_pow2_ceil((u32)n);
+    if (4 * n > S || (int)np2s > S) {  // tables are sized for n <= S / 4: ask for a larger arena
+      if (tid == 0) atomicOr(&d.status[job], (int)WBK_ST_SEG_OVERFLOW);
+      return;
+    }
+    for (u32 i = tid; i < np2s; i += nt) w64[i] = (int)i < n ? (((u64)rid[i] << 32) | (u64)i) : ~0ull;
+    __syncthreads();
+    wbk_block_bitonic_sort(w64, np2s);
+    const u32 tcap = wbk_pow2_ceil((u32)(4 * n) < 64u ? 64u : (u32)(4 * n));  // <= HC / 2
+    u32* st_k = reinterpret_cast<u32*>(hkeys);
+    u32* st_v = st_k + tcap;
+    u32* en_k = st_v + tcap;
+    u32* en_v = en_k + tcap;
+    for (u32 i = tid; i < tcap; i += nt) {
+      st_k[i] = WBK_NONE;
+      en_k[i] = WBK_NONE;
+    }
+    __syncthreads();
+    u32* nd_next = nxt;      // nodes (points of the partial contours): <= 2n
+    u32* nd_prev = prv;
+    u32* nd_xy = cminrid;
+    u32* nd_pid = cnseg;
+    u32* c_head = cidx;      // partial contours in creation order: <= n
+    u32* c_tail = cflag;
+    u32* c_alive = slot;
+    int* c_cnt = scan;
+    if (tid == 0) {
+      const u32 TOMB = 0xfffffffeu;
+      auto tpop = [&](u32* keys, u32* vals, u32 key) -> u32 {
+        u32 h = wbk_hash32(key) & (tcap - 1);
+        while (true) {
+          const u32 k = keys[h];
+          if (k == key) {
+            keys[h] = TOMB;
+            return vals[h];
+          }
+          if (k == WBK_NONE) return WBK_NONE;
+          h = (h + 1) & (tcap - 1);
+        }
+      };
+      auto tput = [&](u32* keys, u32* vals, u32 key, u32 val) {
+        u32 h = wbk_hash32(key) & (tcap - 1);
+        u32 first_free = WBK_NONE;
+        while (true) {
+          const u32 k = keys[h];
+          if (k == key) {
+            vals[h] = val;
+            return;
+          }
+          if (k == TOMB && first_free == WBK_NONE) first_free = h;
+          if (k == WBK_NONE) {
+            if (first_free == WBK_NONE) first_free = h;
+            keys[first_free] = key;
+            vals[first_free] = val;
+            return;
+          }
+          h = (h + 1) & (tcap - 1);
+        }
+      };
+      u32 nn = 0, nc = 0;
+      auto new_node = [&](u32 pid, u32 xy) -> u32 {
+        nd_pid[nn] = pid;
+        nd_xy[nn] = xy;
+        nd_next[nn] = WBK_NONE;
+        nd_prev[nn] = WBK_NONE;
+        return nn++;
+      };
+      for (int q = 0; q < n; ++q) {
+        const int s2 = (int)(u32)w64[q];
+        const u32 f = fpid[s2], t = tpid[s2];
+        if (f == t) continue;  // degenerate segment
+        const u32 tail = tpop(st_k, st_v, t);
+        const u32 head = tpop(en_k, en_v, f);
+        if (tail != WBK_NONE && head != WBK_NONE) {
+          if (tail == head) {  // close the ring: add the end point
+            const u32 nd = new_node(t, txy[s2]);
+            nd_prev[nd] = c_tail[head];
+            nd_next[c_tail[head]] = nd;
+            c_tail[head] = nd;
+            c_cnt[head] += 1;
+          } else {
+            // joined sequence = head ++ tail; the contour that was created first survives
+            const u32 keep = tail > head ? head : tail, dead = tail > head ? tail : head;
+            const u32 hh = c_head[head], ht = c_tail[head], th = c_head[tail], tt = c_tail[tail];
+            nd_next[ht] = th;
+            nd_prev[th] = ht;
+            c_head[keep] = hh;
+            c_tail[keep] = tt;
+            c_cnt[keep] = c_cnt[head] + c_cnt[tail];
+            c_alive[dead] = 0;
+            if (keep == tail) tpop(st_k, st_v, nd_pid[hh]);
+            tput(st_k, st_v, nd_pid[hh], keep);
+            tput(en_k, en_v, nd_pid[tt], keep);
+          }
+        } else if (tail == WBK_NONE && head == WBK_NONE) {
+          const u32 a0 = new_node(f, fxy[s2]), a1 = new_node(t, txy[s2]);
+          nd_next[a0] = a1;
+          nd_prev[a1] = a0;
+          c_head[nc] = a0;
+          c_tail[nc] = a1;
+          c_alive[nc] = 1;
+          c_cnt[nc] = 2;
+          tput(st_k, st_v, f, nc);
+          tput(en_k, en_v, t, nc);
+          ++nc;
+        } else if (head == WBK_NONE) {  // prepend the from-point to `tail`
+          const u32 nd = new_node(f, fxy[s2]);
+          nd_next[nd] = c_head[tail];
+          nd_prev[c_head[tail]] = nd;
+          c_head[tail] = nd;
+          c_cnt[tail] += 1;
+          tput(st_k, st_v, f, tail);
+        } else {  // append the to-point to `head`
+          const u32 nd = new_node(t, txy[s2]);
+          nd_prev[nd] = c_tail[head];
+          nd_next[c_tail[head]] = nd;
+          c_tail[head] = nd;
+          c_cnt[head] += 1;
+          tput(en_k, en_v, t, head);
+        }
+      }
+      // surviving contours in creation order
+      int k = 0, off = 0;
+      for (u32 c2 = 0; c2 < nc; ++c2) {
+        if (!c_alive[c2]) continue;
+        if (k < CC) {
+          sortkeys[k] = (u64)c2;
+          craw_off[k] = off;
+          craw_n[k] = c_cnt[c2];
+          cclosed[k] = nd_pid[c_head[c2]] == nd_pid[c_tail[c2]] ? 1 : 0;
+          cnuniq[k] = 0;
+          cdrop[k] = 0;
+          cymin[k] = 0x7fffffff;
+          cymax[k] = -1;
+        }
+        off += c_cnt[c2];
+        ++k;
+      }
+      s_nheads = k;
+      s_ncand = off;  // borrowed: total raw points (reset below)
+    }
+    __syncthreads();
+    nh = s_nheads;
+    nraw = s_ncand;
+    __syncthreads();
+    if (tid == 0) s_ncand = 0;
+    if (nh > CC || nraw > R) {
+      if (tid == 0) atomicOr(&d.status[job], (int)WBK_ST_CONTOUR_OVERFLOW);
+      return;
+    }
+    if (tid == 0) craw_off[nh] = nraw;
+    // one thread per contour walks its list
+    for (int k = tid; k < nh; k += nt) {
+      u32 nd = c_head[(u32)sortkeys[k]];
+      int pos = craw_off[k];
+      while (nd != WBK_NONE) {
+        raw[pos] = nd_xy[nd];
+        rawc[pos] = (u32)k;
+        ++pos;
+        nd = nd_next[nd];
+      }
+    }
+    __syncthreads();
   }
   // ---- P9: keep-first dedupe of the rounded points inside every contour
   const u32 dcap = wbk_pow2_ceil((u32)(2 * nraw) < 64u ? 64u : (u32)(2 * nraw));

@@ -402,16 +402,6 @@ __global__ void __launch_bounds__(ST_THREADS) streamer_prep_kernel(WbkDev d, Wbk
   }
 }
 
-// exclusive scan of the tile counts over all (job, sel) slots (single CTA)
-__global__ void __launch_bounds__(1024) tile_scan_kernel(WbkIdx x, int nslots) {
-  __shared__ int sscan[40];
-  const int total = wbk_block_excl_scan(x.tile_off, nslots, sscan);
-  if (threadIdx.x == 0) {
-    x.tile_off[nslots] = total;
-    x.total[0] = total;
-  }
-}
-
 // tiled pair scan: geo < geo_dis and cont > cont_dis and |x1 - x2| <= 120 (streamer_index.py:130-157),
 // without materialising the N x N matrices.  Persistent CTAs stride over the (contour, tile) work list; tiles
 // whose column ranges are more than 120 apart are skipped.  The haversine test is decided in fp32 on
