@@ -48,7 +48,7 @@ struct WbkIdx {
   int TLC;                   // capacity of the active-tile list
   u32* tile_list;            // [TLC] active pair-scan tiles of the batch: slot << 18 | bi << 9 | bj
   int NB;                    // blocks of PT points per contour (capacity)
-  int* blk_x;                // [J*SC][NB][2] column range of every block of a full-width contour
+  int* blk_x;                // [J*SC][NB][4] column / row range of every block of a full-width contour
   u64* pairs_b;              // [J][PC]
   int* flag;                 // [J][SC][PC] keep flags of the touch kernel
   int *scanb, *label;        // [J][PC]

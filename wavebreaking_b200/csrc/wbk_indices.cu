@@ -44,7 +44,7 @@ size_t wbk_index_layout(struct wbk_ctx* ctx, unsigned char* base, size_t off) {
   x.ev_off = (int*)take((3 * J + 1) * 4);
   x.total = (int*)take(64);
   x.NB = (c.seg_cap + c.contour_cap + PT_HOST - 1) / PT_HOST;
-  x.blk_x = (int*)take(J * SC * (size_t)x.NB * 2 * 4);
+  x.blk_x = (int*)take(J * SC * (size_t)x.NB * 4 * 4);
   x.SPV = (int)(J * 4096 < (size_t)1 << 26 ? J * 4096 : (size_t)1 << 26);
   x.SPR = (int)(J * 32);
   x.split_xy = (int*)take((size_t)x.SPV * 2 * 4);
@@ -336,7 +336,8 @@ __device__ inline void block_incl_scan_f64(double* data, int n, double* scratch 
 
 // along-contour distances on[k] and their prefix sums for every full-width contour; tile counts
 __global__ void __launch_bounds__(ST_THREADS) streamer_prep_kernel(WbkDev d, WbkIdx x, PackedSet ps, CoordTabs ct,
-                                                                   double* on, double* pfx) {
+                                                                   double* on, double* pfx, double prm_dlon,
+                                                                   double geo_dis) {
   const int job = blockIdx.x;
   if (job >= ps.njobs) return;
   __shared__ double sscan[40];
@@ -364,18 +365,24 @@ __global__ void __launch_bounds__(ST_THREADS) streamer_prep_kernel(WbkDev d, Wbk
     const int T = (n + PT - 1) / PT;
     // column range of every PT-point block (tile skipping in the pair scan)
     for (int b = wbk_warp(); b < T; b += (nt >> 5)) {
-      int mn = 0x7fffffff, mx = -1;
+      int mn = 0x7fffffff, mx = -1, yn = 0x7fffffff, yx = -1;
       for (int k = b * PT + wbk_lane(); k < min(n, (b + 1) * PT); k += 32) {
-        const int px = wbk_px(ps.pts[base + k]);
-        mn = min(mn, px);
-        mx = max(mx, px);
+        const u32 pp = ps.pts[base + k];
+        mn = min(mn, wbk_px(pp));
+        mx = max(mx, wbk_px(pp));
+        yn = min(yn, wbk_py(pp));
+        yx = max(yx, wbk_py(pp));
       }
       mn = wbk_warp_min(mn);
       mx = wbk_warp_max(mx);
+      yn = wbk_warp_min(yn);
+      yx = wbk_warp_max(yx);
       if (wbk_lane() == 0 && b < x.NB) {
-        int* bx = x.blk_x + ((size_t)job * x.SC + si) * x.NB * 2;
-        bx[2 * b] = mn;
-        bx[2 * b + 1] = mx;
+        int* bx = x.blk_x + ((size_t)job * x.SC + si) * x.NB * 4;
+        bx[4 * b] = mn;
+        bx[4 * b + 1] = mx;
+        bx[4 * b + 2] = yn;
+        bx[4 * b + 3] = yx;
       }
     }
     __syncthreads();  // block column ranges are read below
@@ -383,8 +390,9 @@ __global__ void __launch_bounds__(ST_THREADS) streamer_prep_kernel(WbkDev d, Wbk
     // batch-wide work list of the pair scan as slot << 18 | bi << 9 | bj
     {
       const int slot = job * x.SC + si;
-      const int* bx = x.blk_x + (size_t)slot * x.NB * 2;
+      const int* bx = x.blk_x + (size_t)slot * x.NB * 4;
       const int ntile = T * (T + 1) / 2;
+      const double d2r = 0.017453292519943295;
       for (int q = tid; q < ntile; q += nt) {
         int t = q, bi = 0;
         while (t >= T - bi) {
@@ -392,7 +400,19 @@ __global__ void __launch_bounds__(ST_THREADS) streamer_prep_kernel(WbkDev d, Wbk
           ++bi;
         }
         const int bj = bi + t;
-        if (bx[2 * bj] - bx[2 * bi + 1] > 120 || bx[2 * bi] - bx[2 * bj + 1] > 120) continue;
+        const int xgap = max(max(bx[4 * bj] - bx[4 * bi + 1], bx[4 * bi] - bx[4 * bj + 1]), 0);
+        if (xgap > 120) continue;  // |x1 - x2| <= 120 can not hold (streamer_index.py:157)
+        // lower bound of the great-circle distance between the two blocks' bounding boxes: the latitude gap, and
+        // the longitude gap at the most poleward latitude (h >= cos^2(lat_max) sin^2(dlon/2)); tiles that cannot
+        // reach geo_dis are left out (1e-6 relative slack; x gaps <= 120 columns are never folded)
+        const int ygap = max(max(bx[4 * bj + 2] - bx[4 * bi + 3], bx[4 * bi + 2] - bx[4 * bj + 3]), 0);
+        const double lat_lo = ct.lat_deg[min(bx[4 * bi + 2], bx[4 * bj + 2])], lat_hi = ct.lat_deg[max(bx[4 * bi + 3], bx[4 * bj + 3])];
+        const double amax = fmax(fabs(lat_lo), fabs(lat_hi));
+        const double dlat = fabs(ct.lat_deg[1] - ct.lat_deg[0]) * ygap * d2r;
+        const double dlon = prm_dlon * xgap * d2r;
+        const double lb_lat = EARTH_R * dlat;
+        const double lb_lon = 2.0 * EARTH_R * asin(fmin(1.0, cos(fmin(amax, 90.0) * d2r) * sin(fmin(0.5 * dlon, 1.5707963267948966))));
+        if (fmax(lb_lat, lb_lon) > geo_dis * 1.000001) continue;
         const int pos = atomicAdd(&x.total[0], 1);
         if (pos < x.TLC) x.tile_list[pos] = ((u32)slot << 18) | ((u32)bi << 9) | (u32)bj;
         else atomicOr(&d.status[job], (int)WBK_ST_PAIR_OVERFLOW);
@@ -1022,7 +1042,8 @@ extern "C" int wbk_index_run(wbk_ctx* ctx, int njobs, int nlevels, const int* d_
     double* pfx = d_work + npoints;
     const int nslots = njobs * x.SC;
     WBK_CUDA_CHECK(cudaMemsetAsync(x.total, 0, sizeof(int), st));
-    WBK_LAUNCH(KID_STREAMER_PREP, streamer_prep_kernel, dim3(njobs), dim3(ST_THREADS), 0, st, d, x, ps, ct, on, pfx);
+    WBK_LAUNCH(KID_STREAMER_PREP, streamer_prep_kernel, dim3(njobs), dim3(ST_THREADS), 0, st, d, x, ps, ct, on, pfx, prm->dlon,
+               prm->geo_dis);
     WBK_LAUNCH_CHECK();
     WBK_LAUNCH(KID_PAIR_SCAN, pair_scan_kernel, dim3(148 * 8), dim3(PS_THREADS), 0, st, d, x, ps, ct, (const double*)pfx, *prm, nslots);
     WBK_LAUNCH_CHECK();

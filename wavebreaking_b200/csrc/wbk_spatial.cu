@@ -57,6 +57,9 @@ __device__ __forceinline__ double smooth_finish(double v) {
 #define SM_TILE 64                     // tile edge = SM_NB bands x SM_PER rows = 32 lanes x 2 columns
 #define SM_NB (SM_TILE / SM_PER)       // bands (= warps) per CTA
 #define SM_STRIP_THREADS (32 * SM_NB)
+#ifndef SM_MIN_CTAS
+#define SM_MIN_CTAS 3                  // resident CTAs per SM the register budget is sized for
+#endif
 
 template <int P, int RFIRST, int RREST, bool SAFE>
 __device__ __forceinline__ void smooth_strip_passes(double (&vx)[SM_PER], double (&vy)[SM_PER],
@@ -106,7 +109,7 @@ __device__ __forceinline__ void smooth_strip_passes(double (&vx)[SM_PER], double
 // Persistent CTAs stride over the (time, tile row, tile column) list; the raw values of the NEXT tile are
 // requested before the current tile is computed, so the DRAM latency hides behind the FP64 work.
 template <int P, typename TIn, typename TOut, int RMODE>
-__global__ void __launch_bounds__(SM_STRIP_THREADS, 2)
+__global__ void __launch_bounds__(SM_STRIP_THREADS, SM_MIN_CTAS)
 smooth_fused_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, int nlat, int nlon, int nan_border, int tiles_x,
                     int tiles_y, int ntime) {
   constexpr int OUTW = SM_TILE - 2 * P;  // valid outputs per tile edge
@@ -187,7 +190,7 @@ static int launch_smooth_p(const void* in, void* out, int ntime, int nlat, int n
   constexpr int OUTW = SM_TILE - 2 * P;
   const int tiles_x = (nlon + OUTW - 1) / OUTW, tiles_y = (nlat + OUTW - 1) / OUTW;
   const long long ntiles = (long long)tiles_x * tiles_y * ntime;
-  const int grid = (int)(ntiles < 148 * 2 ? ntiles : 148 * 2);  // persistent: 2 CTAs per SM
+  const int grid = (int)(ntiles < 148 * SM_MIN_CTAS ? ntiles : 148 * SM_MIN_CTAS);  // persistent CTAs
   WBK_LAUNCH(KID_SMOOTH, (smooth_fused_kernel<P, TIn, TOut, RMODE>), dim3(grid), dim3(SM_STRIP_THREADS), 0, st, (const TIn*)in,
              (TOut*)out, nlat, nlon, nan_border, tiles_x, tiles_y, ntime);
   WBK_LAUNCH_CHECK();
