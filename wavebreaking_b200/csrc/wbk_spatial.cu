@@ -58,7 +58,7 @@ __device__ __forceinline__ double smooth_finish(double v) {
 #define SM_NB (SM_TILE / SM_PER)       // bands (= warps) per CTA
 #define SM_STRIP_THREADS (32 * SM_NB)
 #ifndef SM_MIN_CTAS
-#define SM_MIN_CTAS 3                  // resident CTAs per SM the register budget is sized for
+#define SM_MIN_CTAS 2                  // resident CTAs per SM the register budget is sized for
 #endif
 
 template <int P, int RFIRST, int RREST, bool SAFE>
