@@ -52,10 +52,11 @@ struct WbkIdx {
   u64* pairs_b;              // [J][PC]
   int* flag;                 // [J][SC][PC] keep flags of the touch kernel
   int *scanb, *label;        // [J][PC]
-  u64 *hm1, *hm2;            // [J][2*PC] smallest / second smallest pair key of a duplicate group
+  u64 *hm1, *hm2;            // [J][SC][2*PC] smallest / second smallest pair key of a duplicate group
   int* cnt1;                 // [J][SC] pairs left after check_duplicates
   int* touch_off;            // [J*SC + 1] chunk offsets of the touch kernel
-  u64* hk;                   // [J][2*PC]
+  u64* pairs2;               // [J][SC][PC]  pairs left after check_duplicates (unordered)
+  u64* hk;                   // [J][SC][2*PC]
   u32 *hv1, *hv2;            // [J][2*PC]
   int* ev_int;               // [3][J][EC][WBK_EV_INTS]
   double* ev_f64;            // [3][J][EC][WBK_EV_F64]

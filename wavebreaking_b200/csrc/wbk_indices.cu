@@ -28,14 +28,15 @@ size_t wbk_index_layout(struct wbk_ctx* ctx, unsigned char* base, size_t off) {
   x.flag = (int*)take(J * SC * PC * 4);
   x.scanb = (int*)take(J * PC * 4);
   x.label = (int*)take(J * PC * 4);
-  x.hk = (u64*)take(J * 2 * PC * 8);
+  x.hk = (u64*)take(J * SC * 2 * PC * 8);
   x.hv1 = (u32*)take(J * 2 * PC * 4);
   x.hv2 = (u32*)take(J * 2 * PC * 4);
   x.TLC = (int)(J * SC * 256 > (size_t)1 << 24 ? (size_t)1 << 24 : J * SC * 256);
   if ((size_t)x.TLC < J * (PC / 16)) x.TLC = (int)(J * (PC / 16));
   x.tile_list = (u32*)take((size_t)x.TLC * 4);
-  x.hm1 = (u64*)take(J * 2 * PC * 8);
-  x.hm2 = (u64*)take(J * 2 * PC * 8);
+  x.hm1 = (u64*)take(J * SC * 2 * PC * 8);
+  x.hm2 = (u64*)take(J * SC * 2 * PC * 8);
+  x.pairs2 = (u64*)take(J * SC * PC * 8);
   x.cnt1 = (int*)take(J * SC * 4);
   x.touch_off = (int*)take((J * SC + 1) * 4);
   x.ev_int = (int*)take(3 * J * EC * WBK_EV_INTS * 4);
@@ -612,74 +613,62 @@ __device__ inline int compact_pairs(const u64* src, u64* dst, const int* flag, i
 // The reference's "while len(df) > 1" gating is kept: a stage only runs if more than one pair is left.
 
 // A: rows equal after x % nlon -> drop the second of each group in row-major (i, j) order (:160-183).  The pair
-// key (i << 32 | j << 1 | near) orders exactly like (i, j), so no sort is needed here.
-__global__ void __launch_bounds__(ST_THREADS) streamer_dedupe_kernel(WbkDev d, WbkIdx x, PackedSet ps) {
-  const int job = blockIdx.x;
-  if (job >= ps.njobs) return;
-  const int tid = threadIdx.x, nt = blockDim.x;
-  const int nlon = d.nlon;
-  __shared__ int sscan[40];
-  u64* B = x.pairs_b + (size_t)job * x.PC;
-  int* scanb = x.scanb + (size_t)job * x.PC;
-  int* label = x.label + (size_t)job * x.PC;
-  u64* hk = x.hk + (size_t)job * 2 * x.PC;
-  u64* m1 = x.hm1 + (size_t)job * 2 * x.PC;
-  u64* m2 = x.hm2 + (size_t)job * 2 * x.PC;
-  const int nsel = x.nsel[job];
-  for (int si = 0; si < x.SC; ++si) {
-    const int slot = job * x.SC + si;
-    if (si >= nsel) {
-      if (tid == 0) {
-        x.cnt1[slot] = 0;
-        x.touch_off[slot] = 0;
-      }
-      continue;
-    }
-    const int c = x.sel[slot];
-    const int base = ps.pt_off[c];
-    const u32* pts = ps.pts + base;
-    int P = x.pair_count[slot];
-    if (P > x.PC) {
-      if (tid == 0) {
-        atomicOr(&d.status[job], (int)WBK_ST_PAIR_OVERFLOW);
-        x.cnt1[slot] = 0;
-        x.touch_off[slot] = 0;
-      }
-      continue;  // uniform
-    }
-    u64* A = x.pairs + (size_t)slot * x.PC;
-    int* flag = x.flag + (size_t)slot * x.PC;
-    if (P > 1) {
-      const u32 dcap = wbk_pow2_ceil((u32)(2 * P));
-      for (u32 a = tid; a < dcap; a += nt) {
-        hk[a] = ~0ull;
-        m1[a] = ~0ull;
-        m2[a] = ~0ull;
-      }
-      __syncthreads();
-      for (int a = tid; a < P; a += nt) {
-        const u64 k = A[a];
-        const u32 pi = pts[(u32)(k >> 32)], pj = pts[((u32)k) >> 1];
-        const u64 key = ((u64)wbk_pack_xy(wbk_px(pi) % nlon, wbk_py(pi)) << 32) | (u64)wbk_pack_xy(wbk_px(pj) % nlon, wbk_py(pj));
-        const u32 sl = wbk_hash_slot64(hk, dcap, key, nullptr);
-        label[a] = (int)sl;
-        atomicMin(&m1[sl], k);
-      }
-      __syncthreads();
-      for (int a = tid; a < P; a += nt) {
-        const u64 k = A[a];
-        if (m1[label[a]] != k) atomicMin(&m2[label[a]], k);
-      }
-      __syncthreads();
-      for (int a = tid; a < P; a += nt) flag[a] = m2[label[a]] == A[a] ? 0 : 1;
-      __syncthreads();
-      P = compact_pairs(A, B, flag, scanb, P, sscan);
-      for (int a = tid; a < P; a += nt) A[a] = B[a];
-      __syncthreads();
-    }
-    if (tid == 0) {
+// key (i << 32 | j << 1 | near) orders exactly like (i, j), so no sort is needed here: per duplicate group the
+// smallest and second smallest key are found through a per-slot hash table, the second smallest is dropped.
+// Four grid-wide phases (DD_PARTS CTAs per contour): 0 clear the table, 1 insert + smallest key, 2 second smallest,
+// 3 compaction (unordered; the survivors are sorted later) into pairs2.
+#define DD_PARTS 8
+template <int PHASE>
+__global__ void __launch_bounds__(256) streamer_dedupe_kernel(WbkDev d, WbkIdx x, PackedSet ps) {
+  const int slot = blockIdx.x / DD_PARTS, part = blockIdx.x % DD_PARTS;
+  const int job = slot / x.SC, si = slot - job * x.SC;
+  if (job >= ps.njobs || si >= x.nsel[job]) return;
+  const int P = x.pair_count[slot];
+  if (P > x.PC) {
+    if (PHASE == 0 && part == 0 && threadIdx.x == 0) atomicOr(&d.status[job], (int)WBK_ST_PAIR_OVERFLOW);
+    return;
+  }
+  const u64* A = x.pairs + (size_t)slot * x.PC;
+  u64* A2 = x.pairs2 + (size_t)slot * x.PC;
+  const int stride = DD_PARTS * blockDim.x, first = part * blockDim.x + threadIdx.x;
+  if (P <= 1) {  // nothing to filter (streamer_index.py:261): pass the pair on
+    if (PHASE == 3 && first == 0) {
+      if (P == 1) A2[0] = A[0];
       x.cnt1[slot] = P;
-      x.touch_off[slot] = P > 1 ? (P + TOUCH_CHUNK - 1) / TOUCH_CHUNK : 0;
+    }
+    return;
+  }
+  const int nlon = d.nlon;
+  const u32* pts = ps.pts + ps.pt_off[x.sel[slot]];
+  int* sl_of = x.flag + (size_t)slot * x.PC;  // table slot of every pair (the touch kernel reuses this array)
+  u64* hk = x.hk + (size_t)slot * 2 * x.PC;
+  u64* m1 = x.hm1 + (size_t)slot * 2 * x.PC;
+  u64* m2 = x.hm2 + (size_t)slot * 2 * x.PC;
+  const u32 dcap = wbk_pow2_ceil((u32)(2 * P));
+  if (PHASE == 0) {
+    for (u32 i = first; i < dcap; i += stride) {
+      hk[i] = ~0ull;
+      m1[i] = ~0ull;
+      m2[i] = ~0ull;
+    }
+  } else if (PHASE == 1) {
+    for (int a = first; a < P; a += stride) {
+      const u64 k = A[a];
+      const u32 pi = pts[(u32)(k >> 32)], pj = pts[((u32)k) >> 1];
+      const u64 key = ((u64)wbk_pack_xy(wbk_px(pi) % nlon, wbk_py(pi)) << 32) | (u64)wbk_pack_xy(wbk_px(pj) % nlon, wbk_py(pj));
+      const u32 sl = wbk_hash_slot64(hk, dcap, key, nullptr);
+      sl_of[a] = (int)sl;
+      atomicMin(&m1[sl], k);
+    }
+  } else if (PHASE == 2) {
+    for (int a = first; a < P; a += stride) {
+      const u64 k = A[a];
+      if (m1[sl_of[a]] != k) atomicMin(&m2[sl_of[a]], k);
+    }
+  } else {
+    for (int a = first; a < P; a += stride) {
+      const u64 k = A[a];
+      if (m2[sl_of[a]] != k) A2[atomicAdd(&x.cnt1[slot], 1)] = k;
     }
   }
 }
@@ -687,6 +676,11 @@ __global__ void __launch_bounds__(ST_THREADS) streamer_dedupe_kernel(WbkDev d, W
 // exclusive scan of the touch-chunk counts over all (job, sel) slots (single CTA)
 __global__ void __launch_bounds__(1024) touch_scan_kernel(WbkIdx x, int nslots) {
   __shared__ int sscan[40];
+  for (int s2 = threadIdx.x; s2 < nslots; s2 += blockDim.x) {
+    const int P = x.cnt1[s2];
+    x.touch_off[s2] = P > 1 ? (P + TOUCH_CHUNK - 1) / TOUCH_CHUNK : 0;
+  }
+  __syncthreads();
   const int total = wbk_block_excl_scan(x.touch_off, nslots, sscan);
   if (threadIdx.x == 0) x.touch_off[nslots] = total;
 }
@@ -720,7 +714,7 @@ __global__ void __launch_bounds__(TOUCH_THREADS) streamer_touch_kernel(WbkDev d,
     const int base = ps.pt_off[c], n = ps.pt_off[c + 1] - base;
     const u32* pts = ps.pts + base;
     const int P = x.cnt1[slot];
-    const u64* A = x.pairs + (size_t)slot * x.PC;
+    const u64* A = x.pairs2 + (size_t)slot * x.PC;
     int* flag = x.flag + (size_t)slot * x.PC;
     // ---- bin index of the n-1 segments (a segment goes into every bin its bounding box overlaps)
     __syncthreads();
@@ -817,7 +811,7 @@ __global__ void __launch_bounds__(ST_THREADS) streamer_finish_kernel(WbkDev d, W
     const int base = ps.pt_off[c];
     const u32* pts = ps.pts + base;
     int P = x.cnt1[slot];
-    u64* A = x.pairs + (size_t)slot * x.PC;
+    u64* A = x.pairs2 + (size_t)slot * x.PC;
     int* flag = x.flag + (size_t)slot * x.PC;
     u64* cur = A;
     u64* oth = B;
@@ -1047,7 +1041,11 @@ extern "C" int wbk_index_run(wbk_ctx* ctx, int njobs, int nlevels, const int* d_
     WBK_LAUNCH_CHECK();
     WBK_LAUNCH(KID_PAIR_SCAN, pair_scan_kernel, dim3(148 * 8), dim3(PS_THREADS), 0, st, d, x, ps, ct, (const double*)pfx, *prm, nslots);
     WBK_LAUNCH_CHECK();
-    WBK_LAUNCH(KID_CASCADE, streamer_dedupe_kernel, dim3(njobs), dim3(ST_THREADS), 0, st, d, x, ps);
+    WBK_CUDA_CHECK(cudaMemsetAsync(x.cnt1, 0, sizeof(int) * nslots, st));
+    WBK_LAUNCH(KID_CASCADE, streamer_dedupe_kernel<0>, dim3(nslots * DD_PARTS), dim3(256), 0, st, d, x, ps);
+    WBK_LAUNCH(KID_CASCADE, streamer_dedupe_kernel<1>, dim3(nslots * DD_PARTS), dim3(256), 0, st, d, x, ps);
+    WBK_LAUNCH(KID_CASCADE, streamer_dedupe_kernel<2>, dim3(nslots * DD_PARTS), dim3(256), 0, st, d, x, ps);
+    WBK_LAUNCH(KID_CASCADE, streamer_dedupe_kernel<3>, dim3(nslots * DD_PARTS), dim3(256), 0, st, d, x, ps);
     WBK_LAUNCH_CHECK();
     WBK_LAUNCH(KID_TILE_SCAN, touch_scan_kernel, dim3(1), dim3(1024), 0, st, x, nslots);
     WBK_LAUNCH_CHECK();
