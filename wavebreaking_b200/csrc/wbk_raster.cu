@@ -32,6 +32,14 @@ __device__ __forceinline__ long long ceil_div_ll(long long n, long long d) {  //
   return n >= 0 ? (n + d - 1) / d : -((-n) / d);
 }
 
+__device__ __forceinline__ int ceil_div_i(int n, int d) {  // d != 0
+  if (d < 0) {
+    n = -n;
+    d = -d;
+  }
+  return n >= 0 ? (n + d - 1) / d : -((-n) / d);
+}
+
 // double-double accumulation (error-free TwoSum): the area-weighted sums come out correctly rounded in
 // practice, like the compensated (Kahan) group sums of pandas that the reference relies on
 // (index_utils.py:94-102) -- the truncated centre-of-mass quotient is sensitive to the last bit.
@@ -105,7 +113,10 @@ __device__ inline void raster_scan_row(const RingView& rv, int y, int bx0, int b
         // winding contribution: lattice points strictly left of the crossing get +-1
         if (dy != 0 && lo <= y && y < hi) {
           const int s = dy > 0 ? 1 : -1;
-          const long long cx = (long long)xa + ceil_div_ll((long long)dx * (y - ya), (long long)dy);
+          // |dx|, |y - ya| < 2^15 on grids below 32768 points per axis: the product fits an int
+          const bool small = (dx < 32768 && dx > -32768 && dy < 32768 && dy > -32768);
+          const long long cx = small ? (long long)(xa + ceil_div_i(dx * (y - ya), dy))
+                                     : (long long)xa + ceil_div_ll((long long)dx * (y - ya), (long long)dy);
           const long long idx = cx - bx0;
           if (idx > 0) {
             atomicAdd(&acc[0], s);
@@ -120,10 +131,13 @@ __device__ inline void raster_scan_row(const RingView& rv, int y, int bx0, int b
             cl = min(xa, xb) - R;
             ch = max(xa, xb) + R;
           } else {
-            const double xc = (double)xa + (double)dx * (double)(y - ya) / (double)dy;
-            const double hw = rmax * sqrt((double)len2) / fabs((double)dy) + rmax + 1e-6;
-            cl = max((int)ceil(xc - hw), min(xa, xb) - R - 1);
-            ch = min((int)floor(xc + hw), max(xa, xb) + R + 1);
+            // candidate columns around the edge's abscissa on this row (float with a generous margin: every
+            // candidate is tested exactly below)
+            const float ady = fabsf((float)dy);
+            const float xc = (float)xa + (float)dx * (float)(y - ya) / (float)dy;
+            const float hw = (float)rmax * sqrtf((float)len2) / ady + (float)rmax + 1.0f + 1e-3f * fabsf(xc);
+            cl = max((int)floorf(xc - hw), min(xa, xb) - R - 1);
+            ch = min((int)ceilf(xc + hw), max(xa, xb) + R + 1);
           }
           cl = max(cl, bx0);
           ch = min(ch, bx0 + bw - 1);
@@ -302,23 +316,33 @@ events_raster_kernel(WbkDev d, WbkIdx x, const int* __restrict__ job_off, const 
       raster_scan_row(rv, y, cx0, cw, acc, flg, r2_prop, r2_flag, rmax, R, elist, ecount);
       const double a = area[y];
       const size_t rowbase = ((size_t)t * nlat + y) * nlon;
+      int row_members = 0;
       for (int i = lane; i < cw; i += 32) {
         const bool in = acc[i] != 0;
         const u32 f = flg[i];
         const int px = cx0 + i;
         if (in || (f & 1u)) {
-          const int xf = px % nlon;
-          dd_add(s_a, a);
+          const int xf = px < nlon ? px : (px < 2 * nlon ? px - nlon : px % nlon);
+          // sum(a) and sum(y * a) have one value per row: counted here, added once per row below
           dd_add(s_v, __dmul_rn(a, (double)data[rowbase + xf]));
           if (intensity) dd_add(s_i, __dmul_rn(a, (double)intensity[rowbase + xf]));
           dd_add(s_x, __dmul_rn((double)px, a));
-          dd_add(s_y, __dmul_rn((double)y, a));
-          dd_add(s_n, 1.0);
+          ++row_members;
         }
         if (flags && split != 1 && (in || (f & 2u))) {
           const int xf = px - shift;
           if (xf >= 0 && xf < nlon) flags[(((size_t)kind * ntime + t) * nlat + y) * nlon + xf] = 1;
         }
+      }
+      if (row_members) {
+        // n identical addends: n * value is exact in double-double (two-product by FMA), like adding them one by one
+        const double nrm = (double)row_members;
+        const double ya = __dmul_rn((double)y, a);
+        const double pa = __dmul_rn(nrm, a), pa_lo = __fma_rn(nrm, a, -pa);
+        const double py = __dmul_rn(nrm, ya), py_lo = __fma_rn(nrm, ya, -py);
+        dd_merge(s_a, pa, pa_lo);
+        dd_merge(s_y, py, py_lo);
+        dd_add(s_n, nrm);
       }
       __syncwarp();
      }
