@@ -98,3 +98,12 @@ def test_smoothing_of_extreme_values_is_exact_emu(emu):
     got = spatial.smooth(f, 3).numpy()
     assert np.array_equal(np.isnan(got), np.isnan(want))
     assert np.array_equal(np.nan_to_num(got, posinf=1e308, neginf=-1e308), np.nan_to_num(want, posinf=1e308, neginf=-1e308))
+
+
+def test_detector_descending_latitude_emu(emu):
+    lat, lon = synthetic.grid_coords(46, 90)
+    raw = synthetic.pv_field(46, 90, np.arange(2) * 6.0)
+    a = pipeline.Detector(lat, lon, levels=[2.0]).run_batch(spatial.to_device(raw))
+    d = pipeline.Detector(lat[::-1].copy(), lon, levels=[2.0]).run_batch(spatial.to_device(raw[:, ::-1, :].copy()))
+    assert pipeline.summarize(a) == pipeline.summarize(d)
+    assert np.array_equal(a.flags.numpy(), d.flags.numpy())

@@ -202,10 +202,10 @@ __global__ void __launch_bounds__(1024) event_list_kernel(WbkIdx x, int J, int n
 #define RS_EVENT_ROWCAP 512  // row-buffer columns of the event rasteriser (wider events are scanned in chunks)
 #define RS_RING_CAP 4096     // ring vertices staged in shared memory per event
 #define RS_ROWS_CAP 1024     // lattice rows of an event's bounding box that get an edge bucket
-#define RS_EDGE_CAP 12288    // edge incidences in the row buckets
+#define RS_EDGE_CAP 8192     // edge incidences in the row buckets
 
 template <typename T>
-__global__ void __launch_bounds__(RS_THREADS)
+__global__ void __launch_bounds__(RS_THREADS, 3)
 events_raster_kernel(WbkDev d, WbkIdx x, const int* __restrict__ job_off, const int* __restrict__ pt_off,
                      const u32* __restrict__ pts, const double* __restrict__ area, const T* __restrict__ data,
                      const T* __restrict__ intensity, int8_t* __restrict__ flags, int ntime, int nlevels, int J,
@@ -687,7 +687,7 @@ extern "C" int wbk_events_raster(wbk_ctx* ctx, const int* d_job_off, const int* 
   const size_t smem = (size_t)nwarps * 2 * rowcap * sizeof(int) + (size_t)RS_RING_CAP * sizeof(u32) +
                       (size_t)(2 * RS_ROWS_CAP + 1) * sizeof(int) + (size_t)RS_EDGE_CAP * sizeof(unsigned short);
   const double* area = d_coords + 3 * (size_t)d.nlat;
-  const int grid = 148 * 6;
+  const int grid = 148 * 9;
   if (dtype == WBK_F32) {
     WBK_CUDA_CHECK(cudaFuncSetAttribute(events_raster_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     WBK_LAUNCH(KID_EVENTS_RASTER, events_raster_kernel<float>, dim3(grid), dim3(RS_THREADS), smem, st, d, ctx->x, d_job_off, d_pt_off,

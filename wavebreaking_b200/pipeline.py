@@ -66,6 +66,7 @@ class _Slot:
         self.sm_f32 = None
         self.sm_tmp = torch.empty(shape, dtype=f64, device=dev) if det.passes > _lib.SMOOTH_MAX_FUSED else None
         self.raw_dev = None  # allocated on first host submit
+        self.flipped = None
         self.job_off = torch.empty(J + 1, dtype=i32, device=dev)
         self.pt_off = torch.empty(self.cap_c + 1, dtype=i32, device=dev)
         self.meta = torch.empty((self.cap_c, 4), dtype=i32, device=dev)
@@ -101,6 +102,14 @@ class Detector:
         self.lib = _lib.get()
         self.lat = np.asarray(lat, dtype=np.float64)
         self.lon = np.asarray(lon, dtype=np.float64)
+        # descending coordinates (ERA5 latitudes): batches are flipped on the device after the upload
+        # (utils/data_utils.py:196-213); all results refer to the ascending orientation
+        self.flip_lat = bool(len(self.lat) > 1 and self.lat[0] > self.lat[-1])
+        self.flip_lon = bool(len(self.lon) > 1 and self.lon[0] > self.lon[-1])
+        if self.flip_lat:
+            self.lat = self.lat[::-1].copy()
+        if self.flip_lon:
+            self.lon = self.lon[::-1].copy()
         self.nlat, self.nlon = len(self.lat), len(self.lon)
         self.dlon = float(abs(self.lon[1] - self.lon[0]))
         self.dlat = float(abs(self.lat[1] - self.lat[0]))
@@ -166,6 +175,12 @@ class Detector:
                 slot.raw_dev[:nt].copy_(raw, non_blocking=True)
                 raw = slot.raw_dev[:nt]
             raw = raw.contiguous()
+            if self.flip_lat or self.flip_lon:
+                if slot.flipped is None or slot.flipped.dtype != raw.dtype:
+                    slot.flipped = torch.empty((slot.T, self.nlat, self.nlon), dtype=raw.dtype, device=lib.device)
+                lib.call("wbk_flip", _lib.ptr(raw), _lib.ptr(slot.flipped), _lib.dtype_code(raw.dtype), nt, self.nlat,
+                         self.nlon, int(self.flip_lat), int(self.flip_lon), st)
+                raw = slot.flipped[:nt]
             if intensity is not None:
                 intensity = intensity.to(lib.device).contiguous()
             if smoothed is not None:

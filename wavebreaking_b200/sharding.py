@@ -88,3 +88,14 @@ def run_sharded(detector, raw_full_or_shard, ntime_total=None, is_shard=False):
     if g != res.gmax_nx:
         res = detector.run_batch(shard, gmax_nx=g)
     return t0, t1, res
+
+
+def track_sharded(local_events, dst=0, **kwargs):
+    """``track_events`` across ranks: event tables are gathered on ``dst`` in time order and tracked there
+    (events.py:113-241 links t to (t, t + time_range], i.e. across shard boundaries too); other ranks get None."""
+    from . import tracking
+
+    merged = gather_frames(local_events, dst=dst)
+    if merged is None:
+        return None
+    return tracking.track_events(merged, **kwargs)
