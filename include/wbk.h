@@ -129,6 +129,12 @@ int wbk_destroy(wbk_ctx* ctx);
  */
 int wbk_contours(wbk_ctx* ctx, const void* d_field, int dtype, int ntime, const double* h_levels, int nlevels,
                  void* stream);
+/* calculate_smoothed_field + calculate_contours in one pass over the field (float32 under NumPy >= 2 promotion or
+ * float64 input, float64 smoothed output, 1..WBK_SMOOTH_MAX_FUSED passes): the marching-squares stage runs on the
+ * smoothed tiles while they are still on chip, so the smoothed field is written once and not re-read.  Results are
+ * identical to wbk_smooth followed by wbk_contours. */
+int wbk_smooth_contours(wbk_ctx* ctx, const void* d_in, int in_dtype, double* d_smoothed, int ntime, int passes,
+                        const double* h_levels, int nlevels, void* stream);
 /* per-job results of the last wbk_contours (synchronises the stream): number of contours, number
  * of contour points, status bits (WBK_ST_*), and the batch-wide maximum number of distinct
  * columns of a contour (exp_lon.max() / dlon).  Arrays have ntime*nlevels entries. */

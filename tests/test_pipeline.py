@@ -62,3 +62,34 @@ def test_detector_gpu_batch_invariance(gpu):
             sel = whole.tables[kind].job == t
             assert int(sel.sum()) == len(one.tables[kind])
             assert np.array_equal(whole.tables[kind].sums[sel], one.tables[kind].sums)
+
+
+def _same_result(a, b):
+    assert pipeline.summarize(a) == pipeline.summarize(b)
+    assert np.array_equal(a.flags.cpu().numpy(), b.flags.cpu().numpy())
+    ha, hb = a.contours.host(), b.contours.host()
+    for k in ("x", "y", "closed", "nx", "job"):
+        assert np.array_equal(ha[k], hb[k]), k
+    for kind in detect.KINDS:
+        assert np.array_equal(a.tables[kind].sums, b.tables[kind].sums)
+
+
+@pytest.mark.parametrize("shape,dtype,passes", [((46, 90), np.float32, 5), ((57, 112), np.float64, 3), ((71, 140), np.float32, 8)])
+def test_fused_smoothing_contours_equals_separate_emu(emu, shape, dtype, passes):
+    """wbk_smooth_contours == wbk_smooth + wbk_contours (tile seams, odd shapes, both dtypes)."""
+    nlat, nlon = shape
+    lat, lon = synthetic.grid_coords(nlat, nlon)
+    raw = synthetic.pv_field(nlat, nlon, np.arange(2) * 6.0, dtype=np.float64)
+    raw = np.ascontiguousarray(raw).astype(dtype)
+    a = pipeline.Detector(lat, lon, levels=[2.0, -2.0], passes=passes, fuse=True).run_batch(spatial.to_device(raw))
+    b = pipeline.Detector(lat, lon, levels=[2.0, -2.0], passes=passes, fuse=False).run_batch(spatial.to_device(raw))
+    _same_result(a, b)
+
+
+@pytest.mark.gpu
+def test_fused_smoothing_contours_equals_separate_gpu(gpu):
+    lat, lon = synthetic.grid_coords(721, 1440)
+    raw = spatial.synth_pv(3, 721, 1440, hour0=100.0, hour_step=50.0)
+    a = pipeline.Detector(lat, lon, levels=[2.0, 1.5], fuse=True).run_batch(raw)
+    b = pipeline.Detector(lat, lon, levels=[2.0, 1.5], fuse=False).run_batch(raw)
+    _same_result(a, b)

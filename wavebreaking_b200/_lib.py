@@ -70,6 +70,7 @@ _SIGNATURES = {
     "wbk_create": (c_int, [POINTER(c_void_p), POINTER(Caps), c_int, c_int, c_int, c_void_p, c_size_t]),
     "wbk_destroy": (c_int, [c_void_p]),
     "wbk_contours": (c_int, [c_void_p, c_void_p, c_int, c_int, POINTER(c_double), c_int, c_void_p]),
+    "wbk_smooth_contours": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, POINTER(c_double), c_int, c_void_p]),
     "wbk_contours_counts": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int), c_void_p]),
     "wbk_contours_pack": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p]),

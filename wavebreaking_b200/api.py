@@ -463,7 +463,7 @@ def calculate_cutoffs(data, contour_level, contours=None, min_exp=5, intensity=N
 def to_xarray(data, events, flag="ones", name="flag", *args, **kwargs):
     """Flag the grid cells covered by events (processing/events.py:37-110)."""
     c = _Canon(data, kwargs, need_values=False)
-    if c.dlon != c.dlat:
+    if abs(c.dlon - c.dlat) > 1e-9 * abs(c.dlon):
         raise ValueError("to_xarray needs dlon == dlat (the buffer radius of events.py:75-78 is isotropic in degrees)")
     if flag != "ones":
         try:

@@ -2,6 +2,7 @@
 // skimage's order, rounding + keep-first dedupe, length and periodic-duplicate filters.
 // Reference: wavebreaking/indices/contour_index.py:86-194 (skimage.measure.find_contours inside).
 #include "wbk_ctx.cuh"
+#include "wbk_ms.cuh"
 
 // ------------------------------------------------------------------------------------------ context
 namespace {
@@ -100,136 +101,30 @@ extern "C" int wbk_destroy(wbk_ctx* ctx) {
 // strip (the right neighbour comes from a warp shuffle); squares of the periodic extension
 // (columns >= nlon) are emitted by the thread that owns the matching base column, so the extension
 // costs no extra reads.  Segments are appended to the job's arena with warp-aggregated atomics.
-struct LevelPack {
-  double v[WBK_MAX_LEVELS];
-};
-
-#define WBK_VERTEX_ID 0x80000000u  // point id of a contour vertex that coincides with a grid vertex
-#define MS_THREADS 256
-#define MS_ROWS 16
-
-__device__ __forceinline__ double ms_fraction(double from_value, double to_value, double level) {
-  if (to_value == from_value) return 0.0;
-  return __ddiv_rn(__dsub_rn(level, from_value), __dsub_rn(to_value, from_value));
-}
-
-// edges: 0 top, 1 bottom, 2 left, 3 right;  code = from | to << 2 (first segment) | second << 4 | n << 8
-__device__ __forceinline__ int ms_case_code(int c) {
-  // (from, to) per case, fully_connected = 'low'
-  switch (c) {
-    case 1: return (0 | 2 << 2) | (1 << 8);
-    case 2: return (3 | 0 << 2) | (1 << 8);
-    case 3: return (3 | 2 << 2) | (1 << 8);
-    case 4: return (2 | 1 << 2) | (1 << 8);
-    case 5: return (0 | 1 << 2) | (1 << 8);
-    case 6: return (3 | 0 << 2) | ((2 | 1 << 2) << 4) | (2 << 8);
-    case 7: return (3 | 1 << 2) | (1 << 8);
-    case 8: return (1 | 3 << 2) | (1 << 8);
-    case 9: return (0 | 2 << 2) | ((1 | 3 << 2) << 4) | (2 << 8);
-    case 10: return (1 | 0 << 2) | (1 << 8);
-    case 11: return (1 | 2 << 2) | (1 << 8);
-    case 12: return (2 | 3 << 2) | (1 << 8);
-    case 13: return (0 | 3 << 2) | (1 << 8);
-    case 14: return (2 | 0 << 2) | (1 << 8);
-    default: return 0;
-  }
-}
-
-// Emission of the marching-squares kernel: the hits (squares crossed by a contour) of one warp strip are
-// compacted first, then every lane builds the segments of ONE hit exactly as skimage does (float coordinates,
-// np.round) and appends them to the job's arena with a warp-aggregated atomic.  The four corner values are
-// re-read from global memory (L1 / L2 hits: the strip has just been loaded).
+// Emission of the stand-alone kernel: the hits of one warp strip are compacted, every lane then handles ONE hit;
+// the four corner values are re-read from global memory (L1 / L2 hits: the strip has just been loaded).
 template <typename T>
 __device__ __noinline__ void ms_emit_hits(const WbkDev& d, const T* __restrict__ src, const u32* __restrict__ masks,
                                           int nrows, int job, int r_begin, int col_base, double level) {
   const int lane = wbk_lane();
-  const int W = d.W, nlon = d.nlon;
+  const int nlon = d.nlon;
   int total = 0;
   for (int i = 0; i < nrows; ++i) total += __popc(masks[i]);
   for (int h0 = 0; h0 < total; h0 += 32) {
     const int h = h0 + lane;
-    int nemit = 0, code = 0, r0 = 0, c0 = 0, ncopy = 1;
+    int r0 = 0, c0 = 0, mi = 0, sl = 0;
     double ul = 0, ur = 0, ll = 0, lr = 0;
-    if (h < total) {
-      // locate hit h: row i, then the k-th set bit of its mask
-      int cum = 0, i = 0;
-      for (; i < nrows; ++i) {
-        const int c = __popc(masks[i]);
-        if (h < cum + c) break;
-        cum += c;
-      }
-      u32 m = masks[i];
-      for (int k = h - cum; k > 0; --k) m &= m - 1;
-      const int src_lane = __ffs((int)m) - 1;
-      r0 = r_begin + i;
-      c0 = col_base + src_lane;
+    const bool active = h < total && ms_locate_hit(masks, nrows, h, mi, sl);
+    if (active) {
+      r0 = r_begin + mi;
+      c0 = col_base + sl;
       const int cr = c0 + 1 == nlon ? 0 : c0 + 1;
       ul = (double)src[(size_t)r0 * nlon + c0];
       ur = (double)src[(size_t)r0 * nlon + cr];
       ll = (double)src[(size_t)(r0 + 1) * nlon + c0];
       lr = (double)src[(size_t)(r0 + 1) * nlon + cr];
-      const int sq = (ul > level ? 1 : 0) | (ur > level ? 2 : 0) | (ll > level ? 4 : 0) | (lr > level ? 8 : 0);
-      code = ms_case_code(sq);
-      ncopy = (c0 + nlon <= W - 2) ? 2 : 1;
-      nemit = (code >> 8) * ncopy;
     }
-    // warp-aggregated slot allocation
-    const int incl = wbk_warp_incl_scan(nemit);
-    const int tot = __shfl_sync(WBK_FULL, incl, 31);
-    int base = 0;
-    if (lane == 31) base = atomicAdd(&d.seg_count[job], tot);
-    base = __shfl_sync(WBK_FULL, base, 31);
-    if (nemit == 0) continue;
-    int slot = base + incl - nemit;
-    const int nseg = code >> 8;
-    bool lattice = false;
-    // only the edges this square uses are interpolated (identical expression from both adjacent squares)
-    double frac[4];
-    bool need[4] = {false, false, false, false};
-    for (int s2 = 0; s2 < nseg; ++s2) {
-      need[(code >> (4 * s2)) & 3] = true;
-      need[(code >> (4 * s2 + 2)) & 3] = true;
-    }
-    frac[0] = need[0] ? ms_fraction(ul, ur, level) : 0.0;
-    frac[1] = need[1] ? ms_fraction(ll, lr, level) : 0.0;
-    frac[2] = need[2] ? ms_fraction(ul, ll, level) : 0.0;
-    frac[3] = need[3] ? ms_fraction(ur, lr, level) : 0.0;
-    for (int copy = 0; copy < ncopy; ++copy) {
-      const int cc = c0 + copy * nlon;  // column of the square on the extended grid
-      // float coordinates exactly as skimage builds them, then np.round (half to even)
-      const double xt = __dadd_rn((double)cc, frac[0]), xb = __dadd_rn((double)cc, frac[1]);
-      const double yl = __dadd_rn((double)r0, frac[2]), yr = __dadd_rn((double)r0, frac[3]);
-      u32 pid[4], pxy[4];
-      pid[0] = 2u * (u32)(r0 * W + cc);             // top: horizontal edge (r0, cc)
-      pid[1] = 2u * (u32)((r0 + 1) * W + cc);       // bottom: horizontal edge (r0+1, cc)
-      pid[2] = 2u * (u32)(r0 * W + cc) + 1u;        // left: vertical edge (r0, cc)
-      pid[3] = 2u * (u32)(r0 * W + cc + 1) + 1u;    // right: vertical edge (r0, cc+1)
-      pxy[0] = wbk_pack_xy((int)rint(xt), r0);
-      pxy[1] = wbk_pack_xy((int)rint(xb), r0 + 1);
-      pxy[2] = wbk_pack_xy(cc, (int)rint(yl));
-      pxy[3] = wbk_pack_xy(cc + 1, (int)rint(yr));
-      const bool von[4] = {xt == rint(xt), xb == rint(xb), yl == rint(yl), yr == rint(yr)};
-      // a point that falls exactly on a grid vertex is identified by that vertex: skimage joins by float
-      // equality, so all edges meeting there share the point (handled by the sequential linker)
-      if (von[0]) pid[0] = WBK_VERTEX_ID | (u32)(r0 * W + (int)xt);
-      if (von[1]) pid[1] = WBK_VERTEX_ID | (u32)((r0 + 1) * W + (int)xb);
-      if (von[2]) pid[2] = WBK_VERTEX_ID | (u32)((int)yl * W + cc);
-      if (von[3]) pid[3] = WBK_VERTEX_ID | (u32)((int)yr * W + cc + 1);
-      for (int s2 = 0; s2 < nseg; ++s2) {
-        const int fe = (code >> (4 * s2)) & 3, te = (code >> (4 * s2 + 2)) & 3;
-        lattice = lattice || von[fe] || von[te];
-        if (slot < d.S) {
-          const size_t o = (size_t)job * d.S + slot;
-          d.rid[o] = 2u * (u32)(r0 * (W - 1) + cc) + (u32)s2;
-          d.fpid[o] = pid[fe];
-          d.tpid[o] = pid[te];
-          d.fxy[o] = pxy[fe];
-          d.txy[o] = pxy[te];
-        }
-        ++slot;
-      }
-    }
-    if (lattice) atomicOr(&d.status[job], (int)WBK_ST_LATTICE_VERTEX);
+    ms_emit_squares(d, job, active, r0, c0, ul, ur, ll, lr, level);
   }
 }
 
@@ -820,6 +715,38 @@ extern "C" int wbk_contours(wbk_ctx* ctx, const void* d_field, int dtype, int nt
     return WBK_ERR_INVALID;
   }
   WBK_LAUNCH_CHECK();
+  WBK_LAUNCH(KID_CONTOUR_LINK, contour_link_kernel, dim3(njobs), dim3(WBK_CONTOUR_THREADS), 0, st, d, njobs);
+  WBK_LAUNCH_CHECK();
+  return WBK_OK;
+}
+
+int wbk_launch_smooth_ms(const void* d_in, int in_dtype, double* d_out, int ntime, int nlat, int nlon, int passes,
+                         const WbkDev& dev, const LevelPack& lv, int nlevels, cudaStream_t st);  // wbk_spatial.cu
+
+extern "C" int wbk_smooth_contours(wbk_ctx* ctx, const void* d_in, int in_dtype, double* d_smoothed, int ntime,
+                                   int passes, const double* h_levels, int nlevels, void* stream) {
+  if (!ctx || !d_in || !d_smoothed || !h_levels || ntime < 0 || nlevels < 1 || nlevels > WBK_MAX_LEVELS ||
+      passes < 1 || passes > WBK_SMOOTH_MAX_FUSED || ctx->d.nlat < 4) {
+    wbk_set_error("wbk_smooth_contours: invalid argument (1..%d passes, 1..%d levels)", WBK_SMOOTH_MAX_FUSED, WBK_MAX_LEVELS);
+    return WBK_ERR_INVALID;
+  }
+  const int njobs = ntime * nlevels;
+  if (njobs > ctx->caps.max_jobs) {
+    wbk_set_error("wbk_smooth_contours: %d jobs exceed max_jobs=%d", njobs, ctx->caps.max_jobs);
+    return WBK_ERR_CAPACITY;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  ctx->njobs = njobs;
+  ctx->nlevels = nlevels;
+  if (njobs == 0) return WBK_OK;
+  WbkDev& d = ctx->d;
+  WBK_CUDA_CHECK(cudaMemsetAsync(d.seg_count, 0, sizeof(int) * njobs, st));
+  WBK_CUDA_CHECK(cudaMemsetAsync(d.status, 0, sizeof(int) * njobs, st));
+  WBK_CUDA_CHECK(cudaMemsetAsync(d.max_nx, 0, sizeof(int), st));
+  LevelPack lv;
+  for (int i = 0; i < WBK_MAX_LEVELS; ++i) lv.v[i] = i < nlevels ? h_levels[i] : 0.0;
+  const int rc = wbk_launch_smooth_ms(d_in, in_dtype, d_smoothed, ntime, d.nlat, d.nlon, passes, d, lv, nlevels, st);
+  if (rc != WBK_OK) return rc;
   WBK_LAUNCH(KID_CONTOUR_LINK, contour_link_kernel, dim3(njobs), dim3(WBK_CONTOUR_THREADS), 0, st, d, njobs);
   WBK_LAUNCH_CHECK();
   return WBK_OK;

@@ -3,6 +3,7 @@
 #include "wbk_common.cuh"
 
 #define WBK_MAX_LEVELS 16
+#define WBK_VERTEX_ID 0x80000000u  // point id of a contour vertex that coincides with a grid vertex
 #define WBK_CONTOUR_THREADS 1024
 
 // Device-side view of the arenas (passed to kernels by value).  Per-job arrays have a fixed

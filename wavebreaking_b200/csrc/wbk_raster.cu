@@ -674,7 +674,7 @@ extern "C" int wbk_events_raster(wbk_ctx* ctx, const int* d_job_off, const int* 
   if (d_flags && ntime > 0)
     WBK_CUDA_CHECK(cudaMemsetAsync(d_flags, 0, (size_t)3 * ntime * d.nlat * d.nlon, st));
   if (njobs == 0) return WBK_OK;
-  if (d_flags && prm->dlon != prm->dlat) {
+  if (d_flags && fabs(prm->dlon - prm->dlat) > 1e-9 * fabs(prm->dlon)) {
     wbk_set_error("wbk_events_raster: to_xarray flags need dlon == dlat (buffer radius is isotropic in degrees)");
     return WBK_ERR_INVALID;
   }

@@ -2,6 +2,7 @@
 // momentum flux, orientation flip, synthetic PV generator.
 // Reference: wavebreaking/processing/spatial.py:27-128, utils/data_utils.py:196-213.
 #include "wbk_common.cuh"
+#include "wbk_ms.cuh"
 
 // ------------------------------------------------------------------------------------------
 // K1: fused `passes` x (5-point stencil / 6), periodic in longitude AND latitude
@@ -108,12 +109,17 @@ __device__ __forceinline__ void smooth_strip_passes(double (&vx)[SM_PER], double
 
 // Persistent CTAs stride over the (time, tile row, tile column) list; the raw values of the NEXT tile are
 // requested before the current tile is computed, so the DRAM latency hides behind the FP64 work.
-template <int P, typename TIn, typename TOut, int RMODE>
+// With FUSE the kernel also runs the marching-squares segment stage (contour_index.py:103) on the finished tile while
+// it is still on chip (the tile is parked in shared memory), so the contour stage does not re-read the smoothed
+// field: tiles then advance by one cell less (a square needs its right / lower neighbours in the same tile).
+template <int P, typename TIn, typename TOut, int RMODE, bool FUSE>
 __global__ void __launch_bounds__(SM_STRIP_THREADS, SM_MIN_CTAS)
 smooth_fused_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, int nlat, int nlon, int nan_border, int tiles_x,
-                    int tiles_y, int ntime) {
-  constexpr int OUTW = SM_TILE - 2 * P;  // valid outputs per tile edge
+                    int tiles_y, int ntime, const __grid_constant__ WbkDev dev, const __grid_constant__ LevelPack levels,
+                    int nlevels) {
+  constexpr int OUTW = SM_TILE - 2 * P - (FUSE ? 1 : 0);  // tile stride (valid outputs per tile edge: 64 - 2P)
   __shared__ double halo[2][SM_NB][2][SM_TILE];  // [parity][band][top/bottom][column]
+  WBK_DYN_SMEM(double, tile);                    // FUSE: [64][64] finished tile, then SM_NB x 16 hit masks
   const int lane = wbk_lane(), band = wbk_warp();
   const int r_base = band * SM_PER;
   const size_t plane = (size_t)nlat * nlon;
@@ -181,7 +187,64 @@ smooth_fused_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, int nlat
       if (c_lo >= P && c_lo < SM_TILE - P && ox0 < nlon) dst[(size_t)gy * nlon + ox0] = (TOut)(nanrow ? qnan : vx[i]);
       if (c_lo + 1 >= P && c_lo + 1 < SM_TILE - P && ox1 < nlon) dst[(size_t)gy * nlon + ox1] = (TOut)(nanrow ? qnan : vy[i]);
     }
-    __syncthreads();  // the halo buffers are reused by the next tile
+    if (FUSE) {
+      // ---- marching squares on the finished tile (squares whose upper-left corner is in tile rows / columns
+      //      [P, P + OUTW); all four corners are valid cells of this tile)
+      u32* masks = reinterpret_cast<u32*>(tile + SM_TILE * SM_TILE) + band * 2 * SM_PER;
+#pragma unroll
+      for (int i = 0; i < SM_PER; ++i) {
+        const int r = r_base + i, gy = y0 + r;
+        const bool nanrow = nan_border > 0 && gy >= 0 && gy < nlat && (gy < nan_border || gy >= nlat - nan_border);
+        *reinterpret_cast<double2*>(&tile[r * SM_TILE + c_lo]) = make_double2(nanrow ? qnan : vx[i], nanrow ? qnan : vy[i]);
+      }
+      __syncthreads();
+      for (int l = 0; l < nlevels; ++l) {
+        const double level = levels.v[l];
+        u32 any_hits = 0;
+#pragma unroll
+        for (int i = 0; i < SM_PER; ++i) {
+          const int r = r_base + i, gy = y0 + r;
+          const bool row_ok = r >= P && r < P + OUTW && gy >= 0 && gy + 1 <= nlat - 1;
+#pragma unroll
+          for (int par = 0; par < 2; ++par) {
+            const int c = c_lo + par, gx = x0 + c;
+            int sq = 0;
+            if (row_ok && c >= P && c < P + OUTW && gx >= 0 && gx <= nlon - 1 && gx <= dev.W - 2) {
+              const double ul = tile[r * SM_TILE + c], ur = tile[r * SM_TILE + c + 1];
+              const double ll = tile[(r + 1) * SM_TILE + c], lr = tile[(r + 1) * SM_TILE + c + 1];
+              if (!(ul != ul || ur != ur || ll != ll || lr != lr)) {
+                sq = (ul > level ? 1 : 0) | (ur > level ? 2 : 0) | (ll > level ? 4 : 0) | (lr > level ? 8 : 0);
+                if (sq == 15) sq = 0;
+              }
+            }
+            const u32 hits = __ballot_sync(WBK_FULL, sq != 0);
+            if (lane == 0) masks[2 * i + par] = hits;
+            any_hits |= hits;
+          }
+        }
+        if (any_hits) {  // warp-uniform
+          __syncwarp();
+          int total = 0;
+          for (int m = 0; m < 2 * SM_PER; ++m) total += __popc(masks[m]);
+          for (int h0 = 0; h0 < total; h0 += 32) {
+            const int h = h0 + lane;
+            int mi = 0, sl = 0, r0 = 0, c0 = 0;
+            double ul = 0, ur = 0, ll = 0, lr = 0;
+            const bool active = h < total && ms_locate_hit(masks, 2 * SM_PER, h, mi, sl);
+            if (active) {
+              const int r = r_base + (mi >> 1), c = 2 * sl + (mi & 1);
+              r0 = y0 + r;
+              c0 = x0 + c;
+              ul = tile[r * SM_TILE + c]; ur = tile[r * SM_TILE + c + 1];
+              ll = tile[(r + 1) * SM_TILE + c]; lr = tile[(r + 1) * SM_TILE + c + 1];
+            }
+            ms_emit_squares(dev, bt * nlevels + l, active, r0, c0, ul, ur, ll, lr, level);
+          }
+          __syncwarp();
+        }
+      }
+    }
+    __syncthreads();  // the halo buffers (and the parked tile) are reused by the next tile
   }
 }
 
@@ -191,10 +254,52 @@ static int launch_smooth_p(const void* in, void* out, int ntime, int nlat, int n
   const int tiles_x = (nlon + OUTW - 1) / OUTW, tiles_y = (nlat + OUTW - 1) / OUTW;
   const long long ntiles = (long long)tiles_x * tiles_y * ntime;
   const int grid = (int)(ntiles < 148 * SM_MIN_CTAS ? ntiles : 148 * SM_MIN_CTAS);  // persistent CTAs
-  WBK_LAUNCH(KID_SMOOTH, (smooth_fused_kernel<P, TIn, TOut, RMODE>), dim3(grid), dim3(SM_STRIP_THREADS), 0, st, (const TIn*)in,
-             (TOut*)out, nlat, nlon, nan_border, tiles_x, tiles_y, ntime);
+  WbkDev none = {};
+  LevelPack lv = {};
+  WBK_LAUNCH(KID_SMOOTH, (smooth_fused_kernel<P, TIn, TOut, RMODE, false>), dim3(grid), dim3(SM_STRIP_THREADS), 0, st,
+             (const TIn*)in, (TOut*)out, nlat, nlon, nan_border, tiles_x, tiles_y, ntime, none, lv, 0);
   WBK_LAUNCH_CHECK();
   return WBK_OK;
+}
+
+// fused smoothing + marching squares (float64 output); the segment arenas of `dev` must have been reset
+template <int P, typename TIn, int RMODE>
+static int launch_smooth_ms_p(const void* in, double* out, int ntime, int nlat, int nlon, const WbkDev& dev,
+                              const LevelPack& lv, int nlevels, cudaStream_t st) {
+  constexpr int OUTW = SM_TILE - 2 * P - 1;
+  const int tiles_x = (nlon + OUTW - 1) / OUTW, tiles_y = (nlat + OUTW - 1) / OUTW;
+  const long long ntiles = (long long)tiles_x * tiles_y * ntime;
+  const int grid = (int)(ntiles < 148 * SM_MIN_CTAS ? ntiles : 148 * SM_MIN_CTAS);
+  const size_t smem = (size_t)SM_TILE * SM_TILE * sizeof(double) + (size_t)SM_NB * 2 * SM_PER * sizeof(u32);
+  WBK_CUDA_CHECK(cudaFuncSetAttribute(smooth_fused_kernel<P, TIn, double, RMODE, true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  WBK_LAUNCH(KID_SMOOTH_MS, (smooth_fused_kernel<P, TIn, double, RMODE, true>), dim3(grid), dim3(SM_STRIP_THREADS), smem, st,
+             (const TIn*)in, out, nlat, nlon, 2, tiles_x, tiles_y, ntime, dev, lv, nlevels);
+  WBK_LAUNCH_CHECK();
+  return WBK_OK;
+}
+
+template <typename TIn, int RMODE>
+static int launch_smooth_ms(const void* in, double* out, int ntime, int nlat, int nlon, int passes, const WbkDev& dev,
+                            const LevelPack& lv, int nlevels, cudaStream_t st) {
+  switch (passes) {
+    case 1: return launch_smooth_ms_p<1, TIn, RMODE>(in, out, ntime, nlat, nlon, dev, lv, nlevels, st);
+    case 2: return launch_smooth_ms_p<2, TIn, RMODE>(in, out, ntime, nlat, nlon, dev, lv, nlevels, st);
+    case 3: return launch_smooth_ms_p<3, TIn, RMODE>(in, out, ntime, nlat, nlon, dev, lv, nlevels, st);
+    case 4: return launch_smooth_ms_p<4, TIn, RMODE>(in, out, ntime, nlat, nlon, dev, lv, nlevels, st);
+    case 5: return launch_smooth_ms_p<5, TIn, RMODE>(in, out, ntime, nlat, nlon, dev, lv, nlevels, st);
+    case 6: return launch_smooth_ms_p<6, TIn, RMODE>(in, out, ntime, nlat, nlon, dev, lv, nlevels, st);
+    case 7: return launch_smooth_ms_p<7, TIn, RMODE>(in, out, ntime, nlat, nlon, dev, lv, nlevels, st);
+    case 8: return launch_smooth_ms_p<8, TIn, RMODE>(in, out, ntime, nlat, nlon, dev, lv, nlevels, st);
+  }
+  return WBK_ERR_INVALID;
+}
+
+// used by wbk_smooth_contours (wbk_contours.cu)
+int wbk_launch_smooth_ms(const void* d_in, int in_dtype, double* d_out, int ntime, int nlat, int nlon, int passes,
+                         const WbkDev& dev, const LevelPack& lv, int nlevels, cudaStream_t st) {
+  if (in_dtype == WBK_F32) return launch_smooth_ms<float, WBK_ROUND_FIRST>(d_in, d_out, ntime, nlat, nlon, passes, dev, lv, nlevels, st);
+  return launch_smooth_ms<double, WBK_ROUND_NONE>(d_in, d_out, ntime, nlat, nlon, passes, dev, lv, nlevels, st);
 }
 
 template <typename TIn, typename TOut, int RMODE>

@@ -98,7 +98,7 @@ class Detector:
     """Holds the grid, thresholds and the reusable slots of one detection configuration."""
 
     def __init__(self, lat, lon, levels=(2.0,), periodic_add=120, passes=5, which=detect.KINDS, geo_dis=800.0,
-                 cont_dis=1500.0, range_group=5.0, ot_min_exp=5.0, co_min_exp=5.0, want_flags=True):
+                 cont_dis=1500.0, range_group=5.0, ot_min_exp=5.0, co_min_exp=5.0, want_flags=True, fuse=True):
         self.lib = _lib.get()
         self.lat = np.asarray(lat, dtype=np.float64)
         self.lon = np.asarray(lon, dtype=np.float64)
@@ -120,6 +120,7 @@ class Detector:
         self.params = dict(geo_dis=geo_dis, cont_dis=cont_dis, range_group=range_group, ot_min_exp=ot_min_exp,
                            co_min_exp=co_min_exp)
         self.want_flags = want_flags
+        self.fuse = bool(fuse)  # smoothing + marching squares in one kernel when the pass count allows
         self.coords = detect.coord_tables(self.lat, self.lon, self.dlon, self.dlat, self.lib)
         self._slots = {}
         self._grow = {}
@@ -183,6 +184,10 @@ class Detector:
                 raw = slot.flipped[:nt]
             if intensity is not None:
                 intensity = intensity.to(lib.device).contiguous()
+            h = slot.ctx.handle
+            L = len(self.levels)
+            lv = self.levels.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+            fused = False
             if smoothed is not None:
                 sm = smoothed
             elif self.passes > 0:
@@ -193,14 +198,17 @@ class Detector:
                     sm, rmode = slot.sm_f32[:nt], _lib.ROUND_ALL
                 else:
                     sm, rmode = slot.sm[:nt], (_lib.ROUND_FIRST if f32 else _lib.ROUND_NONE)
-                lib.call("wbk_smooth", _lib.ptr(raw), _lib.dtype_code(raw.dtype), _lib.ptr(sm), _lib.dtype_code(sm.dtype),
-                         _lib.ptr(slot.sm_tmp), nt, self.nlat, self.nlon, self.passes, rmode, st)
+                if self.fuse and sm.dtype == torch.float64 and self.passes <= _lib.SMOOTH_MAX_FUSED and self.nlat >= 4:
+                    lib.call("wbk_smooth_contours", h, _lib.ptr(raw), _lib.dtype_code(raw.dtype), _lib.ptr(sm), nt,
+                             self.passes, lv, L, st)
+                    fused = True
+                else:
+                    lib.call("wbk_smooth", _lib.ptr(raw), _lib.dtype_code(raw.dtype), _lib.ptr(sm),
+                             _lib.dtype_code(sm.dtype), _lib.ptr(slot.sm_tmp), nt, self.nlat, self.nlon, self.passes, rmode, st)
             else:
                 sm = raw
-            h = slot.ctx.handle
-            L = len(self.levels)
-            lib.call("wbk_contours", h, _lib.ptr(sm), _lib.dtype_code(sm.dtype), nt,
-                     self.levels.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), L, st)
+            if not fused:
+                lib.call("wbk_contours", h, _lib.ptr(sm), _lib.dtype_code(sm.dtype), nt, lv, L, st)
             lib.call("wbk_contours_pack_auto", h, _lib.ptr(slot.job_off), _lib.ptr(slot.pt_off), _lib.ptr(slot.meta),
                      _lib.ptr(slot.pts), slot.cap_c, slot.cap_p, st)
             if intensity is not None and intensity.dtype != sm.dtype:
