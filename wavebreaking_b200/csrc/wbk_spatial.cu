@@ -191,36 +191,54 @@ smooth_fused_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, int nlat
       // ---- marching squares on the finished tile (squares whose upper-left corner is in tile rows / columns
       //      [P, P + OUTW); all four corners are valid cells of this tile)
       u32* masks = reinterpret_cast<u32*>(tile + SM_TILE * SM_TILE) + band * 2 * SM_PER;
+      unsigned char* bits = reinterpret_cast<unsigned char*>(tile + SM_TILE * SM_TILE) + SM_NB * 2 * SM_PER * sizeof(u32);
+      double fx[SM_PER], fy[SM_PER];  // final values of this lane's cells (NaN border applied)
 #pragma unroll
       for (int i = 0; i < SM_PER; ++i) {
         const int r = r_base + i, gy = y0 + r;
         const bool nanrow = nan_border > 0 && gy >= 0 && gy < nlat && (gy < nan_border || gy >= nlat - nan_border);
-        *reinterpret_cast<double2*>(&tile[r * SM_TILE + c_lo]) = make_double2(nanrow ? qnan : vx[i], nanrow ? qnan : vy[i]);
+        fx[i] = nanrow ? qnan : vx[i];
+        fy[i] = nanrow ? qnan : vy[i];
+        *reinterpret_cast<double2*>(&tile[r * SM_TILE + c_lo]) = make_double2(fx[i], fy[i]);
       }
-      __syncthreads();
       for (int l = 0; l < nlevels; ++l) {
         const double level = levels.v[l];
+        // one comparison per cell: bit 0 = value > level, bit 2 = NaN; the squares are classified from these bytes
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < SM_PER; ++i) {
+          const unsigned bxv = (fx[i] > level ? 1u : 0u) | (fx[i] != fx[i] ? 4u : 0u);
+          const unsigned byv = (fy[i] > level ? 1u : 0u) | (fy[i] != fy[i] ? 4u : 0u);
+          *reinterpret_cast<unsigned short*>(&bits[(r_base + i) * SM_TILE + c_lo]) = (unsigned short)(bxv | (byv << 8));
+        }
+        __syncthreads();
         u32 any_hits = 0;
+        // bytes of columns c_lo .. c_lo+2 of a row (the third belongs to the next lane)
+        auto row_bits = [&](int r) -> unsigned {
+          const unsigned a2 = *reinterpret_cast<const unsigned short*>(&bits[r * SM_TILE + c_lo]);
+          const unsigned b1 = c_lo + 2 < SM_TILE ? bits[r * SM_TILE + c_lo + 2] : 4u;
+          return a2 | (b1 << 16);
+        };
+        unsigned up = row_bits(r_base);
 #pragma unroll
         for (int i = 0; i < SM_PER; ++i) {
           const int r = r_base + i, gy = y0 + r;
+          const unsigned dn = r + 1 < SM_TILE ? row_bits(r + 1) : 0x040404u;
           const bool row_ok = r >= P && r < P + OUTW && gy >= 0 && gy + 1 <= nlat - 1;
 #pragma unroll
           for (int par = 0; par < 2; ++par) {
             const int c = c_lo + par, gx = x0 + c;
-            int sq = 0;
-            if (row_ok && c >= P && c < P + OUTW && gx >= 0 && gx <= nlon - 1 && gx <= dev.W - 2) {
-              const double ul = tile[r * SM_TILE + c], ur = tile[r * SM_TILE + c + 1];
-              const double ll = tile[(r + 1) * SM_TILE + c], lr = tile[(r + 1) * SM_TILE + c + 1];
-              if (!(ul != ul || ur != ur || ll != ll || lr != lr)) {
-                sq = (ul > level ? 1 : 0) | (ur > level ? 2 : 0) | (ll > level ? 4 : 0) | (lr > level ? 8 : 0);
-                if (sq == 15) sq = 0;
-              }
-            }
+            const unsigned ul = (up >> (8 * par)) & 0xffu, ur = (up >> (8 * par + 8)) & 0xffu;
+            const unsigned ll = (dn >> (8 * par)) & 0xffu, lr = (dn >> (8 * par + 8)) & 0xffu;
+            int sq = (int)((ul & 1u) | ((ur & 1u) << 1) | ((ll & 1u) << 2) | ((lr & 1u) << 3));
+            if (((ul | ur | ll | lr) & 4u) || sq == 15 || !row_ok || c < P || c >= P + OUTW || gx < 0 || gx > nlon - 1 ||
+                gx > dev.W - 2)
+              sq = 0;
             const u32 hits = __ballot_sync(WBK_FULL, sq != 0);
             if (lane == 0) masks[2 * i + par] = hits;
             any_hits |= hits;
           }
+          up = dn;
         }
         if (any_hits) {  // warp-uniform
           __syncwarp();
@@ -270,7 +288,8 @@ static int launch_smooth_ms_p(const void* in, double* out, int ntime, int nlat, 
   const int tiles_x = (nlon + OUTW - 1) / OUTW, tiles_y = (nlat + OUTW - 1) / OUTW;
   const long long ntiles = (long long)tiles_x * tiles_y * ntime;
   const int grid = (int)(ntiles < 148 * SM_MIN_CTAS ? ntiles : 148 * SM_MIN_CTAS);
-  const size_t smem = (size_t)SM_TILE * SM_TILE * sizeof(double) + (size_t)SM_NB * 2 * SM_PER * sizeof(u32);
+  const size_t smem = (size_t)SM_TILE * SM_TILE * sizeof(double) + (size_t)SM_NB * 2 * SM_PER * sizeof(u32) +
+                      (size_t)SM_TILE * SM_TILE;  // parked tile, hit masks, comparison bytes
   WBK_CUDA_CHECK(cudaFuncSetAttribute(smooth_fused_kernel<P, TIn, double, RMODE, true>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   WBK_LAUNCH(KID_SMOOTH_MS, (smooth_fused_kernel<P, TIn, double, RMODE, true>), dim3(grid), dim3(SM_STRIP_THREADS), smem, st,
