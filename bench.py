@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=1, help="time steps of the CPU baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--concurrent", action="store_true", help="device-resident leg: one CUDA stream per slot")
     a = ap.parse_args()
     if a.steps is None:
         a.steps = 20 if a.impl == "b200" else 2
@@ -277,7 +278,7 @@ def run_b200(a):
     # ---- device-resident leg (value)
     stats = {"segments": 0, "points": 0, "pairs": 0}
     depth = 3
-    for res in det.stream((slabs[s % nslab] for s in range(W)), depth=depth, shared_stream=True):
+    for res in det.stream((slabs[s % nslab] for s in range(W)), depth=depth, shared_stream=not a.concurrent):
         pass
     barrier()
     launches0 = lib.cdll.wbk_launch_count()
@@ -288,7 +289,7 @@ def run_b200(a):
     ev0.record()
     t_wall0 = time.perf_counter()
     counts = []
-    for res in det.stream((slabs[(W + s) % nslab] for s in range(K)), depth=depth, shared_stream=True):
+    for res in det.stream((slabs[(W + s) % nslab] for s in range(K)), depth=depth, shared_stream=not a.concurrent):
         counts.append(pipeline.summarize(res))
     torch.cuda.synchronize()
     wall_ms = (time.perf_counter() - t_wall0) * 1000.0
