@@ -22,8 +22,8 @@ __device__ __forceinline__ int wrap_idx(int i, int n) {
 
 // periodic index for values that are at most one period outside (falls back to the modulo otherwise)
 __device__ __forceinline__ int wrap_near(int i, int n) {
-  i = i < 0 ? i + n : (i >= n ? i - n : i);
-  if (i < 0 || i >= n) i = wrap_idx(i, n);
+  while (i < 0) i += n;
+  while (i >= n) i -= n;
   return i;
 }
 
@@ -123,45 +123,94 @@ smooth_fused_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, int nlat
   const int lane = wbk_lane(), band = wbk_warp();
   const int r_base = band * SM_PER;
   const size_t plane = (size_t)nlat * nlon;
-  const long long ntiles = (long long)tiles_x * tiles_y * ntime;
+  const unsigned ntiles = (unsigned)tiles_x * (unsigned)tiles_y * (unsigned)ntime;  // < 2^31 (chunked by the launcher)
+  const unsigned utx = (unsigned)tiles_x, uty = (unsigned)tiles_y;
 
-  auto load_tile = [&](long long w, TIn (&tx)[SM_PER], TIn (&ty)[SM_PER]) {
-    const int bx = (int)(w % tiles_x);
-    const long long q = w / tiles_x;
-    const int by = (int)(q % tiles_y), bt = (int)(q / tiles_y);
-    const int x0 = bx * OUTW - P, y0 = by * OUTW - P;
+  // tile coordinates advance incrementally by the grid stride (no division in the loop)
+  const unsigned g_q = gridDim.x / utx, g_bx = gridDim.x - g_q * utx;
+  const unsigned g_bt = g_q / uty, g_by = g_q - g_bt * uty;
+  unsigned nbx, nby, nbt;  // tile that is loaded next
+  {
+    const unsigned q = blockIdx.x / utx;
+    nbx = blockIdx.x - q * utx;
+    nbt = q / uty;
+    nby = q - nbt * uty;
+  }
+
+  auto load_tile = [&](unsigned bx, unsigned by, unsigned bt, TIn (&tx)[SM_PER], TIn (&ty)[SM_PER]) {
+    const int x0 = (int)bx * OUTW - P, y0 = (int)by * OUTW - P;
     const TIn* src = in + plane * bt;
     const int gx0 = wrap_near(x0 + 2 * lane, nlon), gx1 = wrap_near(x0 + 2 * lane + 1, nlon);
-    int gy = wrap_near(y0 + r_base, nlat);
-    const TIn* row = src + (size_t)gy * nlon;
+    const int gy0 = y0 + r_base;
+    if (gy0 >= 0 && gy0 + SM_PER <= nlat) {  // warp-uniform: the band does not cross the latitude wrap
+      const TIn* p0 = src + (size_t)gy0 * nlon + gx0;
+      const int d1 = gx1 - gx0;
 #pragma unroll
-    for (int i = 0; i < SM_PER; ++i) {
-      tx[i] = row[gx0];
-      ty[i] = row[gx1];
-      ++gy;
-      row += nlon;
-      if (gy == nlat) {  // periodic in latitude too (scipy mode="wrap")
-        gy = 0;
-        row = src;
+      for (int i = 0; i < SM_PER; ++i) {
+        tx[i] = p0[0];
+        ty[i] = p0[d1];
+        p0 += nlon;
+      }
+    } else {
+      int gy = wrap_near(gy0, nlat);
+      const TIn* row = src + (size_t)gy * nlon;
+#pragma unroll
+      for (int i = 0; i < SM_PER; ++i) {
+        tx[i] = row[gx0];
+        ty[i] = row[gx1];
+        ++gy;
+        row += nlon;
+        if (gy == nlat) {  // periodic in latitude too (scipy mode="wrap")
+          gy = 0;
+          row = src;
+        }
       }
     }
   };
 
   TIn tx[SM_PER], ty[SM_PER];
-  long long w = blockIdx.x;
-  if (w < ntiles) load_tile(w, tx, ty);
+  unsigned w = blockIdx.x;
+  if (w < ntiles) load_tile(nbx, nby, nbt, tx, ty);
   for (; w < ntiles; w += gridDim.x) {
+    const int x0 = (int)nbx * OUTW - P, y0 = (int)nby * OUTW - P, bt = (int)nbt;  // the tile computed now
     double vx[SM_PER], vy[SM_PER];
     int unsafe = 0;
+    if (sizeof(TIn) == 4) {
+      // float input: only NaN / Inf leave the range div6_fast is valid for (x * 0 is NaN exactly for those)
+      float acc = 0.0f;
 #pragma unroll
-    for (int i = 0; i < SM_PER; ++i) {
-      vx[i] = (double)tx[i];
-      vy[i] = (double)ty[i];
-      const double ax = fabs(vx[i]), ay = fabs(vy[i]);
-      unsafe |= !(ax <= 1e290) || (ax < 1e-150 && ax != 0.0) || !(ay <= 1e290) || (ay < 1e-150 && ay != 0.0);
+      for (int i = 0; i < SM_PER; ++i) {
+        acc = fmaf((float)tx[i], 0.0f, acc);
+        acc = fmaf((float)ty[i], 0.0f, acc);
+        vx[i] = (double)tx[i];
+        vy[i] = (double)ty[i];
+      }
+      unsafe = !(acc == 0.0f);
+#ifdef __CUDA_ARCH__
+      asm volatile("" : "+r"(nbx) : "f"(acc));  // keep the check ahead of the prefetch (no copies of the raw tile)
+#endif
+    } else {
+#pragma unroll
+      for (int i = 0; i < SM_PER; ++i) {
+        vx[i] = (double)tx[i];
+        vy[i] = (double)ty[i];
+        const double ax = fabs(vx[i]), ay = fabs(vy[i]);
+        unsafe |= !(ax <= 1e290) || (ax < 1e-150 && ax != 0.0) || !(ay <= 1e290) || (ay < 1e-150 && ay != 0.0);
+      }
     }
-    // prefetch the next tile of this CTA
-    if (w + gridDim.x < ntiles) load_tile(w + gridDim.x, tx, ty);
+    // advance to and prefetch the next tile of this CTA
+    nbx += g_bx;
+    if (nbx >= utx) {
+      nbx -= utx;
+      ++nby;
+    }
+    nby += g_by;
+    if (nby >= uty) {
+      nby -= uty;
+      ++nbt;
+    }
+    nbt += g_bt;
+    if (w + gridDim.x < ntiles) load_tile(nbx, nby, nbt, tx, ty);
     const int slow = __syncthreads_or(unsafe);
 
     constexpr int RFIRST = RMODE == WBK_ROUND_ALL ? 2 : (RMODE == WBK_ROUND_FIRST ? 1 : 0);
@@ -170,22 +219,31 @@ smooth_fused_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, int nlat
     else smooth_strip_passes<P, RFIRST, RREST, false>(vx, vy, halo, lane, band, r_base);
 
     // write the valid interior: tile rows / columns [P, 64 - P)
-    const int bx = (int)(w % tiles_x);
-    const long long q = w / tiles_x;
-    const int by = (int)(q % tiles_y), bt = (int)(q / tiles_y);
-    const int x0 = bx * OUTW - P, y0 = by * OUTW - P;
-    TOut* dst = out + plane * bt;
     const int c_lo = 2 * lane;
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    // the NaN border (spatial.py:106-107) only concerns bands at the top / bottom of the grid (warp-uniform)
+    if (nan_border > 0 && (y0 + r_base < nan_border || y0 + r_base + SM_PER > nlat - nan_border)) {
 #pragma unroll
-    for (int i = 0; i < SM_PER; ++i) {
-      const int r = r_base + i;
-      const int gy = y0 + r;
-      if (r < P || r >= SM_TILE - P || gy >= nlat) continue;
-      const bool nanrow = nan_border > 0 && (gy < nan_border || gy >= nlat - nan_border);
-      const int ox0 = x0 + c_lo, ox1 = ox0 + 1;
-      if (c_lo >= P && c_lo < SM_TILE - P && ox0 < nlon) dst[(size_t)gy * nlon + ox0] = (TOut)(nanrow ? qnan : vx[i]);
-      if (c_lo + 1 >= P && c_lo + 1 < SM_TILE - P && ox1 < nlon) dst[(size_t)gy * nlon + ox1] = (TOut)(nanrow ? qnan : vy[i]);
+      for (int i = 0; i < SM_PER; ++i) {
+        const int gy = y0 + r_base + i;
+        if (gy < nan_border || (gy >= nlat - nan_border && gy < nlat)) vx[i] = vy[i] = qnan;
+      }
+    }
+    {
+      const int ox0 = x0 + c_lo;
+      const bool ok0 = c_lo >= P && c_lo < SM_TILE - P && ox0 < nlon;
+      const bool ok1 = c_lo + 1 >= P && c_lo + 1 < SM_TILE - P && ox0 + 1 < nlon;
+      TOut* dp = out + plane * bt + ((long long)(y0 + r_base) * nlon + ox0);
+      int rows_left = nlat - (y0 + r_base);  // rows of this band that exist in the grid
+#pragma unroll
+      for (int i = 0; i < SM_PER; ++i) {
+        const int r = r_base + i;
+        if (r >= P && r < SM_TILE - P && i < rows_left) {  // warp-uniform
+          if (ok0) dp[0] = (TOut)vx[i];
+          if (ok1) dp[1] = (TOut)vy[i];
+        }
+        dp += nlon;
+      }
     }
     if (FUSE) {
       // ---- marching squares on the finished tile (squares whose upper-left corner is in tile rows / columns
@@ -195,10 +253,9 @@ smooth_fused_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, int nlat
       double fx[SM_PER], fy[SM_PER];  // final values of this lane's cells (NaN border applied)
 #pragma unroll
       for (int i = 0; i < SM_PER; ++i) {
-        const int r = r_base + i, gy = y0 + r;
-        const bool nanrow = nan_border > 0 && gy >= 0 && gy < nlat && (gy < nan_border || gy >= nlat - nan_border);
-        fx[i] = nanrow ? qnan : vx[i];
-        fy[i] = nanrow ? qnan : vy[i];
+        const int r = r_base + i;
+        fx[i] = vx[i];
+        fy[i] = vy[i];
         *reinterpret_cast<double2*>(&tile[r * SM_TILE + c_lo]) = make_double2(fx[i], fy[i]);
       }
       for (int l = 0; l < nlevels; ++l) {
@@ -270,13 +327,20 @@ template <int P, typename TIn, typename TOut, int RMODE>
 static int launch_smooth_p(const void* in, void* out, int ntime, int nlat, int nlon, int nan_border, cudaStream_t st) {
   constexpr int OUTW = SM_TILE - 2 * P;
   const int tiles_x = (nlon + OUTW - 1) / OUTW, tiles_y = (nlat + OUTW - 1) / OUTW;
-  const long long ntiles = (long long)tiles_x * tiles_y * ntime;
-  const int grid = (int)(ntiles < 148 * SM_MIN_CTAS ? ntiles : 148 * SM_MIN_CTAS);  // persistent CTAs
   WbkDev none = {};
   LevelPack lv = {};
-  WBK_LAUNCH(KID_SMOOTH, (smooth_fused_kernel<P, TIn, TOut, RMODE, false>), dim3(grid), dim3(SM_STRIP_THREADS), 0, st,
-             (const TIn*)in, (TOut*)out, nlat, nlon, nan_border, tiles_x, tiles_y, ntime, none, lv, 0);
-  WBK_LAUNCH_CHECK();
+  // the kernel indexes tiles with 32 bits: very long series go in chunks of time steps
+  const long long per_step = (long long)tiles_x * tiles_y;
+  const int max_t = (int)((1LL << 30) / per_step) > 0 ? (int)((1LL << 30) / per_step) : 1;
+  for (int t0 = 0; t0 < ntime; t0 += max_t) {
+    const int nt = ntime - t0 < max_t ? ntime - t0 : max_t;
+    const long long ntiles = per_step * nt;
+    const int grid = (int)(ntiles < 148 * SM_MIN_CTAS ? ntiles : 148 * SM_MIN_CTAS);  // persistent CTAs
+    const size_t off = (size_t)t0 * nlat * nlon;
+    WBK_LAUNCH(KID_SMOOTH, (smooth_fused_kernel<P, TIn, TOut, RMODE, false>), dim3(grid), dim3(SM_STRIP_THREADS), 0, st,
+               (const TIn*)in + off, (TOut*)out + off, nlat, nlon, nan_border, tiles_x, tiles_y, nt, none, lv, 0);
+    WBK_LAUNCH_CHECK();
+  }
   return WBK_OK;
 }
 
@@ -287,6 +351,10 @@ static int launch_smooth_ms_p(const void* in, double* out, int ntime, int nlat, 
   constexpr int OUTW = SM_TILE - 2 * P - 1;
   const int tiles_x = (nlon + OUTW - 1) / OUTW, tiles_y = (nlat + OUTW - 1) / OUTW;
   const long long ntiles = (long long)tiles_x * tiles_y * ntime;
+  if (ntiles > (1LL << 30)) {
+    wbk_set_error("wbk_smooth_contours: batch too long (%lld tiles), split the time axis", ntiles);
+    return WBK_ERR_INVALID;
+  }
   const int grid = (int)(ntiles < 148 * SM_MIN_CTAS ? ntiles : 148 * SM_MIN_CTAS);
   const size_t smem = (size_t)SM_TILE * SM_TILE * sizeof(double) + (size_t)SM_NB * 2 * SM_PER * sizeof(u32) +
                       (size_t)SM_TILE * SM_TILE;  // parked tile, hit masks, comparison bytes
