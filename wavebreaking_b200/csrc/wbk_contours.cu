@@ -132,7 +132,7 @@ template <typename T>
 __global__ void __launch_bounds__(MS_THREADS, 3)
 ms_segments_kernel(const T* __restrict__ field, const __grid_constant__ WbkDev d, const __grid_constant__ LevelPack levels,
                    int nlevels) {
-  __shared__ u32 smask[MS_THREADS / 32][MS_ROWS];
+  __shared__ u32 smask[MS_THREADS / 32][WBK_MAX_LEVELS][MS_ROWS];
   const int nlat = d.nlat, nlon = d.nlon, W = d.W;
   // every warp covers 31 base columns; lane 31 only supplies the right neighbour of lane 30 (so no thread
   // needs a second, uncoalesced load) -- column nlon wraps to column 0 (periodic extension)
@@ -150,41 +150,49 @@ ms_segments_kernel(const T* __restrict__ field, const __grid_constant__ WbkDev d
 
   // all rows of the strip are requested before any is used (MS_ROWS + 1 independent loads in flight)
   T vals[MS_ROWS + 1];
+  {
+    const T* p = src + (size_t)r_begin * nlon + csrc;
+    const int nrows_ld = r_end - r_begin + 1;  // block-uniform
 #pragma unroll
-  for (int i = 0; i <= MS_ROWS; ++i) {
-    const int r = r_begin + i;
-    vals[i] = (loads && r <= r_end) ? src[(size_t)r * nlon + csrc] : (T)0;
+    for (int i = 0; i <= MS_ROWS; ++i) {
+      vals[i] = (loads && i < nrows_ld) ? *p : (T)0;
+      p += nlon;
+    }
   }
+  // lanes whose base square (r0, c0)-(r0+1, c0+1) exists; bit c of a row mask belongs to column col_base + c
+  const u32 sqmask = __ballot_sync(WBK_FULL, own_base);
+  u32 level_hits = 0;  // bit l: this warp strip holds contour squares of level l (warp-uniform)
   for (int l = 0; l < nlevels; ++l) {
     const double level = levels.v[l];
     const T tl = (T)level;
     const bool exact_level = (double)tl == level;  // compare in T when the level is representable (always for f64)
-    // packed comparison bits of the own column: bit0 value > level, bit2 NaN
-    int mu = 0;
-    {
-      const T v = vals[0];
-      mu = ((exact_level ? v > tl : (double)v > level) ? 1 : 0) | (v != v ? 4 : 0);
-    }
-    u32 any_hits = 0;
+    // one ballot per row turns the comparisons into 32-column bit rows (uniform across the warp); lane i keeps
+    // the rows of strip row i, fetches row i + 1 from its neighbour and classifies the 31 squares of that row with a
+    // handful of bit operations: a contour square has corner bits that are neither all set nor all clear, no NaN
+    u32 myg = 0, myn = 0;
 #pragma unroll
-    for (int i = 0; i < MS_ROWS; ++i) {
-      const int r0 = r_begin + i;
-      const T v = vals[i + 1];
-      const int ml = ((exact_level ? v > tl : (double)v > level) ? 1 : 0) | (v != v ? 4 : 0);
-      const int m = mu | (ml << 1);  // bit0 upper, bit1 lower, bits 2/3 NaN
-      const int mr = __shfl_down_sync(WBK_FULL, m, 1);
-      int sq = (m & 1) | ((mr & 1) << 1) | ((m & 2) << 1) | ((mr & 2) << 2);
-      if (((m | mr) & 12) || !own_base || sq == 15 || r0 >= r_end) sq = 0;
-      const u32 hits = __ballot_sync(WBK_FULL, sq != 0);
-      if (lane == 0) smask[warp][i] = hits;
-      any_hits |= hits;
-      mu = ml;
+    for (int i = 0; i <= MS_ROWS; ++i) {
+      const T v = vals[i];
+      const u32 g = __ballot_sync(WBK_FULL, exact_level ? v > tl : (double)v > level);
+      const u32 n = __ballot_sync(WBK_FULL, v != v);
+      if (lane == i) {
+        myg = g;
+        myn = n;
+      }
     }
-    if (any_hits) {  // warp-uniform
-      __syncwarp();
-      ms_emit_hits<T>(d, src, smask[warp], MS_ROWS, t * nlevels + l, r_begin, col_base, level);
-      __syncwarp();
-    }
+    const u32 gl = __shfl_down_sync(WBK_FULL, myg, 1), nl = __shfl_down_sync(WBK_FULL, myn, 1);
+    const u32 both = myg & gl, either = myg | gl, nn = myn | nl;
+    u32 hits = ((either | (either >> 1)) & ~(both & (both >> 1))) & ~(nn | (nn >> 1)) & sqmask;
+    if (lane >= MS_ROWS || r_begin + lane >= r_end) hits = 0;
+    if (lane < MS_ROWS) smask[warp][l][lane] = hits;
+    if (__ballot_sync(WBK_FULL, hits != 0)) level_hits |= 1u << l;
+  }
+  // emission after the scan (the strip values are dead by now: no registers live across the call)
+  if (level_hits) {
+    __syncwarp();
+    for (int l = 0; l < nlevels; ++l)
+      if ((level_hits >> l) & 1u)
+        ms_emit_hits<T>(d, src, smask[warp][l], MS_ROWS, t * nlevels + l, r_begin, col_base, levels.v[l]);
   }
 }
 

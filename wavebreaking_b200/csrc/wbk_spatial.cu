@@ -62,7 +62,9 @@ __device__ __forceinline__ double smooth_finish(double v) {
 #define SM_MIN_CTAS 2                  // resident CTAs per SM the register budget is sized for
 #endif
 
-template <int P, int RFIRST, int RREST, bool SAFE>
+// EDGE: 1 = top band of the tile, 2 = bottom band: their outermost k rows are not needed any more after pass k
+// (only rows [k, 64-k) of the tile feed the valid interior), so they are skipped; 0 = middle band.
+template <int P, int RFIRST, int RREST, bool SAFE, int EDGE>
 __device__ __forceinline__ void smooth_strip_passes(double (&vx)[SM_PER], double (&vy)[SM_PER],
                                                     double (*halo)[SM_NB][2][SM_TILE], int lane, int band, int r_base) {
 #pragma unroll
@@ -78,7 +80,7 @@ __device__ __forceinline__ void smooth_strip_passes(double (&vx)[SM_PER], double
 #pragma unroll
     for (int i = 0; i < SM_PER; ++i) {
       const double cx = vx[i], cy = vy[i];
-      {  // rows outside [k, 64-k) are computed too (no longer needed, but branch-free)
+      if (!((EDGE == 1 && i < k) || (EDGE == 2 && i >= SM_PER - k))) {
         const double sx = i + 1 < SM_PER ? vx[i + 1] : south.x;
         const double sy = i + 1 < SM_PER ? vy[i + 1] : south.y;
         const double wv = __shfl_up_sync(WBK_FULL, cy, 1);    // column 2l-1 (lane 0: unused halo garbage)
@@ -215,8 +217,10 @@ smooth_fused_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, int nlat
 
     constexpr int RFIRST = RMODE == WBK_ROUND_ALL ? 2 : (RMODE == WBK_ROUND_FIRST ? 1 : 0);
     constexpr int RREST = RMODE == WBK_ROUND_ALL ? 2 : 0;
-    if (!slow) smooth_strip_passes<P, RFIRST, RREST, true>(vx, vy, halo, lane, band, r_base);
-    else smooth_strip_passes<P, RFIRST, RREST, false>(vx, vy, halo, lane, band, r_base);
+    if (slow) smooth_strip_passes<P, RFIRST, RREST, false, 0>(vx, vy, halo, lane, band, r_base);
+    else if (band == 0) smooth_strip_passes<P, RFIRST, RREST, true, 1>(vx, vy, halo, lane, band, r_base);
+    else if (band == SM_NB - 1) smooth_strip_passes<P, RFIRST, RREST, true, 2>(vx, vy, halo, lane, band, r_base);
+    else smooth_strip_passes<P, RFIRST, RREST, true, 0>(vx, vy, halo, lane, band, r_base);
 
     // write the valid interior: tile rows / columns [P, 64 - P)
     const int c_lo = 2 * lane;
