@@ -129,7 +129,7 @@ __device__ __noinline__ void ms_emit_hits(const WbkDev& d, const T* __restrict__
 }
 
 template <typename T>
-__global__ void __launch_bounds__(MS_THREADS, 3)
+__global__ void __launch_bounds__(MS_THREADS, MS_MIN_CTAS)
 ms_segments_kernel(const T* __restrict__ field, const __grid_constant__ WbkDev d, const __grid_constant__ LevelPack levels,
                    int nlevels) {
   __shared__ u32 smask[MS_THREADS / 32][WBK_MAX_LEVELS][MS_ROWS];

@@ -288,7 +288,6 @@ __global__ void __launch_bounds__(OT_THREADS) overturning_kernel(WbkDev d, WbkId
 #define PT 128           // pair-scan tile edge
 #define CS_SORT 16384    // surviving pairs sorted in shared memory
 #define CS_SMEM ((size_t)CS_SORT * 8)
-#define TOUCH_CHUNK 2048 // chords per CTA work item of the touch kernel
 #define PS_THREADS 256
 #define EARTH_R 6371.0
 
@@ -673,52 +672,57 @@ __global__ void __launch_bounds__(256) streamer_dedupe_kernel(WbkDev d, WbkIdx x
   }
 }
 
-// exclusive scan of the touch-chunk counts over all (job, sel) slots (single CTA)
-__global__ void __launch_bounds__(1024) touch_scan_kernel(WbkIdx x, int nslots) {
-  __shared__ int sscan[40];
-  for (int s2 = threadIdx.x; s2 < nslots; s2 += blockDim.x) {
-    const int P = x.cnt1[s2];
-    x.touch_off[s2] = P > 1 ? (P + TOUCH_CHUNK - 1) / TOUCH_CHUNK : 0;
-  }
-  __syncthreads();
-  const int total = wbk_block_excl_scan(x.touch_off, nslots, sscan);
-  if (threadIdx.x == 0) x.touch_off[nslots] = total;
-}
-
-// B: keep chords that only touch the contour (:185-200).  Each CTA takes one chunk of chords of one contour,
-// bins the contour's segments into TB x TB lattice cells (CSR in shared memory) and lets every thread test its
-// chords against the segments of the bins its bounding box overlaps.  Exact integer predicates.
-#define TB_SHIFT 5                 // 32 x 32 cells per bin
-#define TOUCH_THREADS 256
+// B: check_intersections (:185-200) restricted to the chords that can still matter.  check_overlapping (:202-222)
+// keeps only the maximal index ranges among the chords that touch, so a chord covered by a chord that is known to
+// touch never needs the (expensive) geometric test.  Two rounds per contour, one CTA per (job, selected contour):
+//   round 1: the maximal ranges M1 of ALL candidates are tested -> C1 = those that touch;
+//   round 2: candidates covered by a member of C1 are dropped untested, the rest (ranges that were only covered by
+//            failed chords) is tested.
+// max(T) = max(C1 u T(round 2)): dropped chords are covered by a touching chord, hence neither maximal themselves nor
+// needed to cover anything (cover is transitive).  The survivors (unordered) replace the candidate list; the finish
+// kernel applies the order-free overlap filter to them.  Typical 0.25-degree contour: 26 k candidates, 120 + 390 tests.
+// The geometric test: the contour's segments are binned into TB x TB lattice cells (CSR in shared memory), a chord
+// is tested against the segments of the bins its line passes through.  Exact integer predicates.
+#define TB_SHIFT 4                 // 16 x 16 cells per bin
+#define TOUCH_THREADS 1024
+#define TOUCH_MAXPTS 12288        // contour points staged in shared memory
 #define TOUCH_MAXSEG 20480         // CSR capacity (segment incidences) in shared memory
 
 __global__ void __launch_bounds__(TOUCH_THREADS) streamer_touch_kernel(WbkDev d, WbkIdx x, PackedSet ps, int nslots) {
   WBK_DYN_SMEM(unsigned char, dsm);
   const int nbx = (d.W >> TB_SHIFT) + 1, nby = (d.nlat >> TB_SHIFT) + 1;
   const int nbins = nbx * nby;
-  int* boff = reinterpret_cast<int*>(dsm);                       // [nbins + 1]
-  int* bcur = boff + nbins + 1;                                  // [nbins] fill cursors
-  unsigned short* bseg = reinterpret_cast<unsigned short*>(bcur + nbins);  // [TOUCH_MAXSEG]
+  int* boff = reinterpret_cast<int*>(dsm);                       // [nbins + 1]: bin starts, after the fill bin ends
+  u32* spts = reinterpret_cast<u32*>(boff + nbins + 1);           // [TOUCH_MAXPTS]
+  unsigned short* bseg = reinterpret_cast<unsigned short*>(spts + TOUCH_MAXPTS);  // [TOUCH_MAXSEG]
   __shared__ int sscan[40];
-  __shared__ int s_total;
+  __shared__ int s_total, s_cnt;
   const int tid = threadIdx.x, nt = blockDim.x;
-  const int total = x.touch_off[nslots];
-  for (int w = blockIdx.x; w < total; w += gridDim.x) {
-    int lo = 0, hi = nslots - 1;
-    while (lo < hi) {
-      int mid = (lo + hi + 1) >> 1;
-      if (x.touch_off[mid] <= w) lo = mid; else hi = mid - 1;
-    }
-    const int slot = lo, chunk = w - x.touch_off[slot];
+  const int lane = wbk_lane(), warp = wbk_warp(), nwarps = nt >> 5;
+  for (int slot = blockIdx.x; slot < nslots; slot += gridDim.x) {
+    const int job = slot / x.SC, si = slot - job * x.SC;
+    if (job >= ps.njobs || si >= x.nsel[job]) continue;
+    const int P = x.cnt1[slot];
+    if (P <= 1 || P > x.PC) continue;  // nothing to filter (streamer_index.py:261) / overflow already reported
     const int c = x.sel[slot];
     const int base = ps.pt_off[c], n = ps.pt_off[c + 1] - base;
-    const u32* pts = ps.pts + base;
-    const int P = x.cnt1[slot];
-    const u64* A = x.pairs2 + (size_t)slot * x.PC;
-    int* flag = x.flag + (size_t)slot * x.PC;
+    const u32* gpts = ps.pts + base;
+    const u32* pts = n <= TOUCH_MAXPTS ? spts : gpts;  // the contour, in shared memory when it fits
+    u64* A = x.pairs2 + (size_t)slot * x.PC;
+    int* flag = x.flag + (size_t)slot * x.PC;    // 0 dropped / untested, 1 touches, 2 to be tested, 3 failed
+    int* best = reinterpret_cast<int*>(x.hm1 + (size_t)slot * 2 * x.PC);  // 4 * PC ints (dedupe tables are dead)
+    int* pm = best + n;
+    int* wl = reinterpret_cast<int*>(x.pairs + (size_t)slot * x.PC);      // work list (the raw pair list is dead)
+    u64* stage = x.hm2 + (size_t)slot * 2 * x.PC;
+    if (2 * (size_t)n > 4 * (size_t)x.PC) {
+      if (tid == 0) atomicOr(&d.status[job], (int)WBK_ST_PAIR_OVERFLOW);
+      continue;
+    }
     // ---- bin index of the n-1 segments (a segment goes into every bin its bounding box overlaps)
     __syncthreads();
     for (int b = tid; b < nbins; b += nt) boff[b] = 0;
+    if (n <= TOUCH_MAXPTS)
+      for (int i = tid; i < n; i += nt) spts[i] = gpts[i];
     __syncthreads();
     const bool use_bins = n <= 65535;
     if (use_bins) {
@@ -736,7 +740,6 @@ __global__ void __launch_bounds__(TOUCH_THREADS) streamer_touch_kernel(WbkDev d,
       boff[nbins] = ninc;
       s_total = ninc;
     }
-    for (int b = tid; b < nbins; b += nt) bcur[b] = boff[b];
     __syncthreads();
     const bool binned = use_bins && s_total <= TOUCH_MAXSEG;
     if (binned) {
@@ -745,45 +748,98 @@ __global__ void __launch_bounds__(TOUCH_THREADS) streamer_touch_kernel(WbkDev d,
         const int bx0 = min(wbk_px(pa), wbk_px(pb)) >> TB_SHIFT, bx1 = max(wbk_px(pa), wbk_px(pb)) >> TB_SHIFT;
         const int by0 = min(wbk_py(pa), wbk_py(pb)) >> TB_SHIFT, by1 = max(wbk_py(pa), wbk_py(pb)) >> TB_SHIFT;
         for (int by = by0; by <= by1; ++by)
-          for (int bx = bx0; bx <= bx1; ++bx) bseg[atomicAdd(&bcur[by * nbx + bx], 1)] = (unsigned short)s0;
+          for (int bx = bx0; bx <= bx1; ++bx) bseg[atomicAdd(&boff[by * nbx + bx], 1)] = (unsigned short)s0;
       }
     }
-    __syncthreads();
-    // ---- chords of this chunk
+    __syncthreads();  // boff[b] is now the END of bin b (= start of bin b + 1)
     const u32 e0 = pts[0], e1 = pts[n - 1];
     const int e0x = wbk_px(e0), e0y = wbk_py(e0), e1x = wbk_px(e1), e1y = wbk_py(e1);
-    const int a_end = min(P, (chunk + 1) * TOUCH_CHUNK);
-    for (int a = chunk * TOUCH_CHUNK + tid; a < a_end; a += nt) {
-      const u64 k = A[a];
-      const u32 pi = pts[(u32)(k >> 32)], pj = pts[((u32)k) >> 1];
-      const int px = wbk_px(pi), py = wbk_py(pi), qx = wbk_px(pj), qy = wbk_py(pj);
-      const int x0 = min(px, qx), x1 = max(px, qx), y0 = min(py, qy), y1 = max(py, qy);
-      bool bad = false;
-      if (binned) {
-        for (int by = y0 >> TB_SHIFT; by <= (y1 >> TB_SHIFT) && !bad; ++by)
-          for (int bx = x0 >> TB_SHIFT; bx <= (x1 >> TB_SHIFT) && !bad; ++bx) {
-            const int b = by * nbx + bx;
-            for (int q = boff[b]; q < boff[b + 1]; ++q) {
-              const int s0 = bseg[q];
-              const u32 pa = pts[s0], pb = pts[s0 + 1];
-              const int ax = wbk_px(pa), ay = wbk_py(pa), bxx = wbk_px(pb), byy = wbk_py(pb);
-              if (max(ax, bxx) < x0 || min(ax, bxx) > x1 || max(ay, byy) < y0 || min(ay, byy) > y1) continue;
-              if (chord_violation(px, py, qx, qy, ax, ay, bxx, byy, e0x, e0y, e1x, e1y)) {
-                bad = true;
-                break;
-              }
-            }
-          }
-      } else {
-        for (int s0 = 0; s0 < n - 1 && !bad; ++s0) {
-          const u32 pa = pts[s0], pb = pts[s0 + 1];
-          const int ax = wbk_px(pa), ay = wbk_py(pa), bxx = wbk_px(pb), byy = wbk_py(pb);
-          if (max(ax, bxx) < x0 || min(ax, bxx) > x1 || max(ay, byy) < y0 || min(ay, byy) > y1) continue;
-          bad = chord_violation(px, py, qx, qy, ax, ay, bxx, byy, e0x, e0y, e1x, e1y);
+
+    for (int round = 0; round < 2; ++round) {
+      // ---- best[i] = furthest ind2 of the reference set starting at ind1 == i, pm = running maximum
+      for (int i = tid; i < n; i += nt) best[i] = -1;
+      if (tid == 0) s_cnt = 0;
+      __syncthreads();
+      for (int a = tid; a < P; a += nt) {
+        if (round == 0 || flag[a] == 1) {
+          const u64 k = A[a];
+          atomicMax(&best[(int)(k >> 32)], (int)(((u32)k) >> 1));
         }
       }
-      flag[a] = bad ? 0 : 1;
+      __syncthreads();
+      for (int i = tid; i < n; i += nt) pm[i] = best[i];
+      __syncthreads();
+      wbk_block_incl_max_scan(pm, n, sscan);
+      // ---- work list: round 0 the maximal candidates, round 1 the untested candidates no touching chord covers
+      for (int a = tid; a < P; a += nt) {
+        if (round == 1 && flag[a] != 0) continue;
+        const u64 k = A[a];
+        const int i1 = (int)(k >> 32), i2 = (int)(((u32)k) >> 1);
+        const bool covered = (i1 > 0 && pm[i1 - 1] >= i2) || (round == 0 ? best[i1] > i2 : best[i1] >= i2);
+        if (!covered) wl[atomicAdd(&s_cnt, 1)] = a;
+        flag[a] = covered ? 0 : 2;
+      }
+      __syncthreads();
+      const int m = s_cnt;
+      // ---- geometric test of the listed chords: one warp per chord, lanes over the segments of a bin
+      for (int w = warp; w < m; w += nwarps) {
+        const int a = wl[w];
+        const u64 k = A[a];
+        const u32 pi = pts[(u32)(k >> 32)], pj = pts[((u32)k) >> 1];
+        const int px = wbk_px(pi), py = wbk_py(pi), qx = wbk_px(pj), qy = wbk_py(pj);
+        const int x0 = min(px, qx), x1 = max(px, qx), y0 = min(py, qy), y1 = max(py, qy);
+        bool bad = false;
+        if (binned) {
+          const int ux = qx - px, uy = qy - py;
+          const int sdx = -(uy << TB_SHIFT), sdy = ux << TB_SHIFT;
+          for (int by = y0 >> TB_SHIFT; by <= (y1 >> TB_SHIFT) && !bad; ++by)
+            for (int bx = x0 >> TB_SHIFT; bx <= (x1 >> TB_SHIFT) && !bad; ++bx) {
+              // skip bins whose (closed) cell rectangle lies strictly on one side of the chord's line: a segment can
+              // only meet the chord inside a bin the chord passes through
+              const int s00 = ux * ((by << TB_SHIFT) - py) - uy * ((bx << TB_SHIFT) - px);
+              const int s10 = s00 + sdx, s01 = s00 + sdy, s11 = s10 + sdy;
+              if (min(min(s00, s10), min(s01, s11)) > 0 || max(max(s00, s10), max(s01, s11)) < 0) continue;
+              const int b = by * nbx + bx;
+              const int q1 = boff[b];
+              for (int q0 = b ? boff[b - 1] : 0; q0 < q1 && !bad; q0 += 32) {  // warp-uniform loop
+                bool hit = false;
+                const int q = q0 + lane;
+                if (q < q1) {
+                  const int s0 = bseg[q];
+                  const u32 pa = pts[s0], pb = pts[s0 + 1];
+                  const int ax = wbk_px(pa), ay = wbk_py(pa), bxx = wbk_px(pb), byy = wbk_py(pb);
+                  if (!(max(ax, bxx) < x0 || min(ax, bxx) > x1 || max(ay, byy) < y0 || min(ay, byy) > y1))
+                    hit = chord_violation(px, py, qx, qy, ax, ay, bxx, byy, e0x, e0y, e1x, e1y);
+                }
+                bad = __any_sync(WBK_FULL, hit);
+              }
+            }
+        } else {
+          for (int s00 = 0; s00 < n - 1 && !bad; s00 += 32) {
+            bool hit = false;
+            const int s0 = s00 + lane;
+            if (s0 < n - 1) {
+              const u32 pa = pts[s0], pb = pts[s0 + 1];
+              const int ax = wbk_px(pa), ay = wbk_py(pa), bxx = wbk_px(pb), byy = wbk_py(pb);
+              if (!(max(ax, bxx) < x0 || min(ax, bxx) > x1 || max(ay, byy) < y0 || min(ay, byy) > y1))
+                hit = chord_violation(px, py, qx, qy, ax, ay, bxx, byy, e0x, e0y, e1x, e1y);
+            }
+            bad = __any_sync(WBK_FULL, hit);
+          }
+        }
+        if (lane == 0) flag[a] = bad ? 3 : 1;
+      }
+      __syncthreads();
     }
+    // ---- the touching chords (unordered) replace the candidate list
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+    for (int a = tid; a < P; a += nt)
+      if (flag[a] == 1) stage[atomicAdd(&s_cnt, 1)] = A[a];
+    __syncthreads();
+    const int ns = s_cnt;
+    for (int a = tid; a < ns; a += nt) A[a] = stage[a];
+    if (tid == 0) x.cnt1[slot] = ns;
   }
 }
 
@@ -816,10 +872,8 @@ __global__ void __launch_bounds__(ST_THREADS) streamer_finish_kernel(WbkDev d, W
     u64* cur = A;
     u64* oth = B;
     __syncthreads();
-    if (P > 1) {  // check_intersections ran: keep the chords flagged by the touch kernel
-      P = compact_pairs(cur, oth, flag, scanb, P, sscan);
-      u64* t = cur; cur = oth; oth = t;
-    }
+    // (2) check_intersections already ran (streamer_touch_kernel): the list holds the touching chords that are
+    // not covered by another touching chord of the first round
     // (3) check_overlapping (:202-222): drop [ind1, ind2] fully covered by another pair.  Order-free form:
     // best[i] = largest ind2 among the pairs with ind1 == i, PM = running maximum of best; a pair is covered iff
     // a pair with a smaller ind1 reaches at least as far (PM[ind1-1] >= ind2) or one with the same ind1 reaches
@@ -1047,17 +1101,16 @@ extern "C" int wbk_index_run(wbk_ctx* ctx, int njobs, int nlevels, const int* d_
     WBK_LAUNCH(KID_CASCADE, streamer_dedupe_kernel<2>, dim3(nslots * DD_PARTS), dim3(256), 0, st, d, x, ps);
     WBK_LAUNCH(KID_CASCADE, streamer_dedupe_kernel<3>, dim3(nslots * DD_PARTS), dim3(256), 0, st, d, x, ps);
     WBK_LAUNCH_CHECK();
-    WBK_LAUNCH(KID_TILE_SCAN, touch_scan_kernel, dim3(1), dim3(1024), 0, st, x, nslots);
-    WBK_LAUNCH_CHECK();
     {
       const int nbins = ((d.W >> TB_SHIFT) + 1) * ((d.nlat >> TB_SHIFT) + 1);
-      const size_t tsmem = (size_t)(2 * nbins + 1) * sizeof(int) + (size_t)TOUCH_MAXSEG * sizeof(unsigned short);
+      const size_t tsmem = (size_t)(nbins + 1 + TOUCH_MAXPTS) * sizeof(int) + (size_t)TOUCH_MAXSEG * sizeof(unsigned short);
       if (tsmem > 200 * 1024) {
         wbk_set_error("wbk_index_run: grid too large for the touch-kernel bin index");
         return WBK_ERR_CAPACITY;
       }
       WBK_CUDA_CHECK(cudaFuncSetAttribute(streamer_touch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
-      WBK_LAUNCH(KID_TOUCH, streamer_touch_kernel, dim3(148 * 4), dim3(TOUCH_THREADS), tsmem, st, d, x, ps, nslots);
+      const int tgrid = nslots < 148 * 2 ? nslots : 148 * 2;
+      WBK_LAUNCH(KID_TOUCH, streamer_touch_kernel, dim3(tgrid), dim3(TOUCH_THREADS), tsmem, st, d, x, ps, nslots);
       WBK_LAUNCH_CHECK();
     }
     WBK_CUDA_CHECK(cudaFuncSetAttribute(streamer_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CS_SMEM));

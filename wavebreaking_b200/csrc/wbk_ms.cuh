@@ -10,6 +10,9 @@ struct LevelPack {
 
 #define MS_THREADS 256
 #define MS_ROWS 16
+#ifndef MS_MIN_CTAS
+#define MS_MIN_CTAS 3
+#endif
 
 __device__ __forceinline__ double ms_fraction(double from_value, double to_value, double level) {
   if (to_value == from_value) return 0.0;
