@@ -362,6 +362,33 @@ __global__ void __launch_bounds__(ST_THREADS) streamer_prep_kernel(WbkDev d, Wbk
     }
     __syncthreads();
     block_incl_scan_f64(pfx + base, n, sscan);
+    // twin of every point: the point of this contour with the same y whose x differs by nlon (its periodic copy),
+    // -1 if there is none.  Rows that are equal after x % nlon (check_duplicates, streamer_index.py:160-183) can only
+    // pair a point with itself or its twin, so the pair scan resolves duplicate groups on the fly.
+    {
+      const int slot = job * x.SC + si;
+      int* tw = x.flag + (size_t)slot * x.PC;
+      if (n > x.PC) {
+        if (tid == 0) atomicOr(&d.status[job], (int)WBK_ST_PAIR_OVERFLOW);
+        for (int k = tid; k < min(n, x.PC); k += nt) tw[k] = -1;
+      } else {
+        const u32 cap = wbk_pow2_ceil((u32)(2 * n));
+        u32* hkeys = reinterpret_cast<u32*>(x.hk + (size_t)slot * 2 * x.PC);
+        u32* hvals = hkeys + cap;
+        for (u32 i = tid; i < cap; i += nt) hkeys[i] = WBK_NONE;
+        __syncthreads();
+        for (int k = tid; k < n; k += nt) wbk_hash_insert32(hkeys, hvals, cap, ps.pts[base + k], (u32)k);
+        __syncthreads();
+        for (int k = tid; k < n; k += nt) {
+          const u32 p = ps.pts[base + k];
+          const int px = wbk_px(p), py = wbk_py(p);
+          u32 t = WBK_NONE;
+          if (px + nlon < 65536) t = wbk_hash_find32(hkeys, hvals, cap, wbk_pack_xy(px + nlon, py));
+          if (t == WBK_NONE && px >= nlon) t = wbk_hash_find32(hkeys, hvals, cap, wbk_pack_xy(px - nlon, py));
+          tw[k] = t == WBK_NONE ? -1 : (int)t;
+        }
+      }
+    }
     const int T = (n + PT - 1) / PT;
     // column range of every PT-point block (tile skipping in the pair scan)
     for (int b = wbk_warp(); b < T; b += (nt >> 5)) {
@@ -430,7 +457,7 @@ __global__ void __launch_bounds__(ST_THREADS) streamer_prep_kernel(WbkDev d, Wbk
 __global__ void __launch_bounds__(PS_THREADS) pair_scan_kernel(WbkDev d, WbkIdx x, PackedSet ps, CoordTabs ct,
                                                                const double* __restrict__ pfx, wbk_index_params prm,
                                                                int nslots) {
-  __shared__ int sx[2][PT];
+  __shared__ int sx[2][PT], stw[2][PT];
   __shared__ float fla[2][PT], flo[2][PT], fco[2][PT];
   __shared__ double sla[2][PT], slo[2][PT], sco[2][PT], spf[2][PT];
   const int tid = threadIdx.x, nlon = d.nlon;
@@ -454,6 +481,7 @@ __global__ void __launch_bounds__(PS_THREADS) pair_scan_kernel(WbkDev d, WbkIdx 
         sla[which][k] = la; slo[which][k] = lo2; sco[which][k] = co;
         fla[which][k] = (float)la; flo[which][k] = (float)lo2; fco[which][k] = (float)co;
         spf[which][k] = pfx[base + idx];
+        stw[which][k] = idx < x.PC ? x.flag[(size_t)slot * x.PC + idx] : -1;
       }
     }
     __syncthreads();
@@ -481,8 +509,28 @@ __global__ void __launch_bounds__(PS_THREADS) pair_scan_kernel(WbkDev d, WbkIdx 
             if (!(dist < prm.geo_dis)) continue;
             near |= fabs(dist - prm.geo_dis) <= 1e-9 * prm.geo_dis;
           }
-          const int k = atomicAdd(&x.pair_count[slot], 1);
-          if (k < x.PC) x.pairs[(size_t)slot * x.PC + k] = ((u64)(u32)i << 32) | ((u64)(u32)j << 1) | (u64)near;
+          // check_duplicates (:160-183): the rows equal to (i, j) after x % nlon are the candidates among
+          // (tw i, tw j), (i, tw j), (tw i, j); they share the geographic positions, so only the index order, the
+          // 120-column rule and the along-contour distance decide.  The second row of a group (row-major) is dropped.
+          const int ti = stw[0][ii], tj = stw[1][jj];
+          if (ti >= 0 || tj >= 0) {
+            int smaller = 0;
+            const int cc[3] = {ti, i, ti}, dd[3] = {tj, tj, j};
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+              const int ci = cc[q], dj = dd[q];
+              if (ci < 0 || dj < 0 || ci >= dj) continue;
+              int ddx = wbk_px(ps.pts[base + ci]) - wbk_px(ps.pts[base + dj]);
+              if (ddx < 0) ddx = -ddx;
+              if (ddx > 120) continue;
+              if (!(__dsub_rn(pfx[base + dj], pfx[base + ci]) > prm.cont_dis)) continue;
+              if (ci < i || (ci == i && dj < j)) ++smaller;
+            }
+            if (smaller == 1) continue;
+          }
+          const int k = atomicAdd(&x.cnt1[slot], 1);
+          if (k < x.PC) x.pairs2[(size_t)slot * x.PC + k] = ((u64)(u32)i << 32) | ((u64)(u32)j << 1) | (u64)near;
+          else atomicOr(&d.status[slot / x.SC], (int)WBK_ST_PAIR_OVERFLOW);
         }
       }
     }
@@ -604,73 +652,12 @@ __device__ inline int compact_pairs(const u64* src, u64* dst, const int* flag, i
 }
 
 // ---------------------------------------------------------------------------------------- filter cascade
-// streamer_index.py:160-264 in three kernels:
-//   A  streamer_dedupe_kernel  (CTA per job)   check_duplicates on the unsorted candidate list
-//   B  streamer_touch_kernel   (whole GPU)     check_intersections: every chord against the contour through a
-//                                              spatial bin index of the contour segments in shared memory
-//   C  streamer_finish_kernel  (CTA per job)   sort the survivors, check_overlapping, check_groups, events
+// streamer_index.py:160-264:
+//   A  check_duplicates        resolved inside pair_scan_kernel through the twin index of every point
+//   B  streamer_touch_kernel   (CTA per contour) check_intersections on the chords that can survive
+//                                              check_overlapping, through a bin index of the contour's segments
+//   C  streamer_finish_kernel  (CTA per job)   check_overlapping, sort, check_groups, events
 // The reference's "while len(df) > 1" gating is kept: a stage only runs if more than one pair is left.
-
-// A: rows equal after x % nlon -> drop the second of each group in row-major (i, j) order (:160-183).  The pair
-// key (i << 32 | j << 1 | near) orders exactly like (i, j), so no sort is needed here: per duplicate group the
-// smallest and second smallest key are found through a per-slot hash table, the second smallest is dropped.
-// Four grid-wide phases (DD_PARTS CTAs per contour): 0 clear the table, 1 insert + smallest key, 2 second smallest,
-// 3 compaction (unordered; the survivors are sorted later) into pairs2.
-#define DD_PARTS 8
-template <int PHASE>
-__global__ void __launch_bounds__(256) streamer_dedupe_kernel(WbkDev d, WbkIdx x, PackedSet ps) {
-  const int slot = blockIdx.x / DD_PARTS, part = blockIdx.x % DD_PARTS;
-  const int job = slot / x.SC, si = slot - job * x.SC;
-  if (job >= ps.njobs || si >= x.nsel[job]) return;
-  const int P = x.pair_count[slot];
-  if (P > x.PC) {
-    if (PHASE == 0 && part == 0 && threadIdx.x == 0) atomicOr(&d.status[job], (int)WBK_ST_PAIR_OVERFLOW);
-    return;
-  }
-  const u64* A = x.pairs + (size_t)slot * x.PC;
-  u64* A2 = x.pairs2 + (size_t)slot * x.PC;
-  const int stride = DD_PARTS * blockDim.x, first = part * blockDim.x + threadIdx.x;
-  if (P <= 1) {  // nothing to filter (streamer_index.py:261): pass the pair on
-    if (PHASE == 3 && first == 0) {
-      if (P == 1) A2[0] = A[0];
-      x.cnt1[slot] = P;
-    }
-    return;
-  }
-  const int nlon = d.nlon;
-  const u32* pts = ps.pts + ps.pt_off[x.sel[slot]];
-  int* sl_of = x.flag + (size_t)slot * x.PC;  // table slot of every pair (the touch kernel reuses this array)
-  u64* hk = x.hk + (size_t)slot * 2 * x.PC;
-  u64* m1 = x.hm1 + (size_t)slot * 2 * x.PC;
-  u64* m2 = x.hm2 + (size_t)slot * 2 * x.PC;
-  const u32 dcap = wbk_pow2_ceil((u32)(2 * P));
-  if (PHASE == 0) {
-    for (u32 i = first; i < dcap; i += stride) {
-      hk[i] = ~0ull;
-      m1[i] = ~0ull;
-      m2[i] = ~0ull;
-    }
-  } else if (PHASE == 1) {
-    for (int a = first; a < P; a += stride) {
-      const u64 k = A[a];
-      const u32 pi = pts[(u32)(k >> 32)], pj = pts[((u32)k) >> 1];
-      const u64 key = ((u64)wbk_pack_xy(wbk_px(pi) % nlon, wbk_py(pi)) << 32) | (u64)wbk_pack_xy(wbk_px(pj) % nlon, wbk_py(pj));
-      const u32 sl = wbk_hash_slot64(hk, dcap, key, nullptr);
-      sl_of[a] = (int)sl;
-      atomicMin(&m1[sl], k);
-    }
-  } else if (PHASE == 2) {
-    for (int a = first; a < P; a += stride) {
-      const u64 k = A[a];
-      if (m1[sl_of[a]] != k) atomicMin(&m2[sl_of[a]], k);
-    }
-  } else {
-    for (int a = first; a < P; a += stride) {
-      const u64 k = A[a];
-      if (m2[sl_of[a]] != k) A2[atomicAdd(&x.cnt1[slot], 1)] = k;
-    }
-  }
-}
 
 // B: check_intersections (:185-200) restricted to the chords that can still matter.  check_overlapping (:202-222)
 // keeps only the maximal index ranges among the chords that touch, so a chord covered by a chord that is known to
@@ -1093,13 +1080,8 @@ extern "C" int wbk_index_run(wbk_ctx* ctx, int njobs, int nlevels, const int* d_
     WBK_LAUNCH(KID_STREAMER_PREP, streamer_prep_kernel, dim3(njobs), dim3(ST_THREADS), 0, st, d, x, ps, ct, on, pfx, prm->dlon,
                prm->geo_dis);
     WBK_LAUNCH_CHECK();
-    WBK_LAUNCH(KID_PAIR_SCAN, pair_scan_kernel, dim3(148 * 8), dim3(PS_THREADS), 0, st, d, x, ps, ct, (const double*)pfx, *prm, nslots);
-    WBK_LAUNCH_CHECK();
     WBK_CUDA_CHECK(cudaMemsetAsync(x.cnt1, 0, sizeof(int) * nslots, st));
-    WBK_LAUNCH(KID_CASCADE, streamer_dedupe_kernel<0>, dim3(nslots * DD_PARTS), dim3(256), 0, st, d, x, ps);
-    WBK_LAUNCH(KID_CASCADE, streamer_dedupe_kernel<1>, dim3(nslots * DD_PARTS), dim3(256), 0, st, d, x, ps);
-    WBK_LAUNCH(KID_CASCADE, streamer_dedupe_kernel<2>, dim3(nslots * DD_PARTS), dim3(256), 0, st, d, x, ps);
-    WBK_LAUNCH(KID_CASCADE, streamer_dedupe_kernel<3>, dim3(nslots * DD_PARTS), dim3(256), 0, st, d, x, ps);
+    WBK_LAUNCH(KID_PAIR_SCAN, pair_scan_kernel, dim3(148 * 8), dim3(PS_THREADS), 0, st, d, x, ps, ct, (const double*)pfx, *prm, nslots);
     WBK_LAUNCH_CHECK();
     {
       const int nbins = ((d.W >> TB_SHIFT) + 1) * ((d.nlat >> TB_SHIFT) + 1);
