@@ -100,6 +100,20 @@ def test_smoothing_of_extreme_values_is_exact_emu(emu):
     assert np.array_equal(np.nan_to_num(got, posinf=1e308, neginf=-1e308), np.nan_to_num(want, posinf=1e308, neginf=-1e308))
 
 
+def test_smoothing_of_non_finite_float32_is_exact_emu(emu):
+    """float32 input: tiles holding NaN / Inf leave the fast exact-division path (one fused x*0 check per tile)."""
+    rng = np.random.default_rng(3)
+    f = rng.standard_normal((2, 70, 140)).astype(np.float32)
+    f[0, 12, 17] = np.inf
+    f[0, 50, 120] = -np.inf
+    f[1, 33, 3] = np.nan
+    want = P.smooth_field(f, 5)
+    got = spatial.smooth(f, 5).numpy()
+    assert got.dtype == want.dtype
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    assert np.array_equal(np.nan_to_num(got, posinf=1e308, neginf=-1e308), np.nan_to_num(want, posinf=1e308, neginf=-1e308))
+
+
 def test_detector_descending_latitude_emu(emu):
     lat, lon = synthetic.grid_coords(46, 90)
     raw = synthetic.pv_field(46, 90, np.arange(2) * 6.0)
