@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=1, help="time steps of the CPU baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--depth", type=int, default=3, help="batches in flight (slots / streams)")
     ap.add_argument("--serial", action="store_true", help="device-resident leg on ONE stream (no kernel overlap)")
     a = ap.parse_args()
     if a.steps is None:
@@ -277,7 +278,7 @@ def run_b200(a):
 
     # ---- device-resident leg (value)
     stats = {"segments": 0, "points": 0, "pairs": 0}
-    depth = 3
+    depth = a.depth
 
     def timed_region(shared_stream):
         """K batches, 3 in flight; returns (ms, per-kernel profile, launches, per-batch counts)."""

@@ -47,7 +47,8 @@ struct WbkIdx {
   int* pair_count;           // [J][SC]
   int* tile_off;             // [J*SC + 1]
   int TLC;                   // capacity of the active-tile list
-  u32* tile_list;            // [TLC] active pair-scan tiles of the batch: slot << 18 | bi << 9 | bj
+  u64* tile_list;            // [TLC] active pair-scan tiles of the batch: slot << 40 | bi << 20 | bj
+  double* blk_pf;            // [J][SC][NB][2] min / max along-contour prefix of every block of PT points
   int NB;                    // blocks of PT points per contour (capacity)
   int* blk_x;                // [J*SC][NB][4] column / row range of every block of a full-width contour
   u64* pairs_b;              // [J][PC]

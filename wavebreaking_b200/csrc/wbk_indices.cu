@@ -4,7 +4,7 @@
 #include "wbk_ctx.cuh"
 
 // ------------------------------------------------------------------------------------------ arenas
-#define PT_HOST 128  // == PT, the pair-scan tile edge
+#define PT_HOST 32   // == PT, the pair-scan tile edge
 size_t wbk_index_layout(struct wbk_ctx* ctx, unsigned char* base, size_t off) {
   WbkIdx& x = ctx->x;
   const wbk_caps& c = ctx->caps;
@@ -33,7 +33,7 @@ size_t wbk_index_layout(struct wbk_ctx* ctx, unsigned char* base, size_t off) {
   x.hv2 = (u32*)take(J * 2 * PC * 4);
   x.TLC = (int)(J * SC * 256 > (size_t)1 << 24 ? (size_t)1 << 24 : J * SC * 256);
   if ((size_t)x.TLC < J * (PC / 16)) x.TLC = (int)(J * (PC / 16));
-  x.tile_list = (u32*)take((size_t)x.TLC * 4);
+  x.tile_list = (u64*)take((size_t)x.TLC * 8);
   x.hm1 = (u64*)take(J * SC * 2 * PC * 8);
   x.hm2 = (u64*)take(J * SC * 2 * PC * 8);
   x.pairs2 = (u64*)take(J * SC * PC * 8);
@@ -46,6 +46,7 @@ size_t wbk_index_layout(struct wbk_ctx* ctx, unsigned char* base, size_t off) {
   x.total = (int*)take(64);
   x.NB = (c.seg_cap + c.contour_cap + PT_HOST - 1) / PT_HOST;
   x.blk_x = (int*)take(J * SC * (size_t)x.NB * 4 * 4);
+  x.blk_pf = (double*)take(J * SC * (size_t)x.NB * 2 * 8);
   x.SPV = (int)(J * 4096 < (size_t)1 << 26 ? J * 4096 : (size_t)1 << 26);
   x.SPR = (int)(J * 32);
   x.split_xy = (int*)take((size_t)x.SPV * 2 * 4);
@@ -285,7 +286,7 @@ __global__ void __launch_bounds__(OT_THREADS) overturning_kernel(WbkDev d, WbkId
 
 // ------------------------------------------------------------------------------------------ streamers
 #define ST_THREADS 1024
-#define PT 128           // pair-scan tile edge
+#define PT 32            // pair-scan tile edge (one point per lane)
 #define CS_SORT 16384    // surviving pairs sorted in shared memory
 #define CS_SMEM ((size_t)CS_SORT * 8)
 #define PS_THREADS 256
@@ -337,7 +338,7 @@ __device__ inline void block_incl_scan_f64(double* data, int n, double* scratch 
 // along-contour distances on[k] and their prefix sums for every full-width contour; tile counts
 __global__ void __launch_bounds__(ST_THREADS) streamer_prep_kernel(WbkDev d, WbkIdx x, PackedSet ps, CoordTabs ct,
                                                                    double* on, double* pfx, double prm_dlon,
-                                                                   double geo_dis) {
+                                                                   double geo_dis, double cont_dis) {
   const int job = blockIdx.x;
   if (job >= ps.njobs) return;
   __shared__ double sscan[40];
@@ -390,58 +391,72 @@ __global__ void __launch_bounds__(ST_THREADS) streamer_prep_kernel(WbkDev d, Wbk
       }
     }
     const int T = (n + PT - 1) / PT;
-    // column range of every PT-point block (tile skipping in the pair scan)
+    // column / row range and along-contour prefix range of every PT-point block (tile skipping in the pair scan)
     for (int b = wbk_warp(); b < T; b += (nt >> 5)) {
       int mn = 0x7fffffff, mx = -1, yn = 0x7fffffff, yx = -1;
+      double pmin = 1e300, pmax = -1e300;
       for (int k = b * PT + wbk_lane(); k < min(n, (b + 1) * PT); k += 32) {
         const u32 pp = ps.pts[base + k];
         mn = min(mn, wbk_px(pp));
         mx = max(mx, wbk_px(pp));
         yn = min(yn, wbk_py(pp));
         yx = max(yx, wbk_py(pp));
+        const double pf = pfx[base + k];
+        pmin = fmin(pmin, pf);
+        pmax = fmax(pmax, pf);
       }
       mn = wbk_warp_min(mn);
       mx = wbk_warp_max(mx);
       yn = wbk_warp_min(yn);
       yx = wbk_warp_max(yx);
+#pragma unroll
+      for (int dd = 16; dd > 0; dd >>= 1) {
+        pmin = fmin(pmin, __shfl_xor_sync(WBK_FULL, pmin, dd));
+        pmax = fmax(pmax, __shfl_xor_sync(WBK_FULL, pmax, dd));
+      }
       if (wbk_lane() == 0 && b < x.NB) {
         int* bx = x.blk_x + ((size_t)job * x.SC + si) * x.NB * 4;
         bx[4 * b] = mn;
         bx[4 * b + 1] = mx;
         bx[4 * b + 2] = yn;
         bx[4 * b + 3] = yx;
+        double* bp = x.blk_pf + ((size_t)job * x.SC + si) * x.NB * 2;
+        bp[2 * b] = pmin;
+        bp[2 * b + 1] = pmax;
       }
     }
-    __syncthreads();  // block column ranges are read below
-    // active tiles: (bi <= bj) whose column ranges are at most 120 apart (streamer_index.py:157); appended to the
-    // batch-wide work list of the pair scan as slot << 18 | bi << 9 | bj
+    __syncthreads();  // block ranges are read below
+    // active tiles (bi <= bj): column ranges at most 120 apart (streamer_index.py:157), some pair further than
+    // cont_dis along the contour, bounding boxes within geo_dis; appended to the batch-wide work list of the pair
+    // scan as slot << 40 | bi << 20 | bj
     {
       const int slot = job * x.SC + si;
       const int* bx = x.blk_x + (size_t)slot * x.NB * 4;
-      const int ntile = T * (T + 1) / 2;
+      const double* bp = x.blk_pf + (size_t)slot * x.NB * 2;
       const double d2r = 0.017453292519943295;
-      for (int q = tid; q < ntile; q += nt) {
-        int t = q, bi = 0;
-        while (t >= T - bi) {
-          t -= T - bi;
-          ++bi;
-        }
-        const int bj = bi + t;
+      const double dlat_deg = fabs(ct.lat_deg[1] - ct.lat_deg[0]);
+      const long long nsq = (long long)T * T;
+      for (long long q = tid; q < nsq; q += nt) {
+        const int bi = (int)(q / T), bj = (int)(q - (long long)bi * T);
+        if (bj < bi) continue;
         const int xgap = max(max(bx[4 * bj] - bx[4 * bi + 1], bx[4 * bi] - bx[4 * bj + 1]), 0);
         if (xgap > 120) continue;  // |x1 - x2| <= 120 can not hold (streamer_index.py:157)
+        // cont(i, j) = pfx[j] - pfx[i] <= max pfx(bj) - min pfx(bi) (the rounded subtraction is monotone)
+        if (!(__dsub_rn(bp[2 * bj + 1], bp[2 * bi]) > cont_dis)) continue;
         // lower bound of the great-circle distance between the two blocks' bounding boxes: the latitude gap, and
         // the longitude gap at the most poleward latitude (h >= cos^2(lat_max) sin^2(dlon/2)); tiles that cannot
         // reach geo_dis are left out (1e-6 relative slack; x gaps <= 120 columns are never folded)
         const int ygap = max(max(bx[4 * bj + 2] - bx[4 * bi + 3], bx[4 * bi + 2] - bx[4 * bj + 3]), 0);
-        const double lat_lo = ct.lat_deg[min(bx[4 * bi + 2], bx[4 * bj + 2])], lat_hi = ct.lat_deg[max(bx[4 * bi + 3], bx[4 * bj + 3])];
-        const double amax = fmax(fabs(lat_lo), fabs(lat_hi));
-        const double dlat = fabs(ct.lat_deg[1] - ct.lat_deg[0]) * ygap * d2r;
-        const double dlon = prm_dlon * xgap * d2r;
-        const double lb_lat = EARTH_R * dlat;
-        const double lb_lon = 2.0 * EARTH_R * asin(fmin(1.0, cos(fmin(amax, 90.0) * d2r) * sin(fmin(0.5 * dlon, 1.5707963267948966))));
-        if (fmax(lb_lat, lb_lon) > geo_dis * 1.000001) continue;
+        if (EARTH_R * (dlat_deg * ygap * d2r) > geo_dis * 1.000001) continue;
+        if (xgap > 0) {
+          const double lat_lo = ct.lat_deg[min(bx[4 * bi + 2], bx[4 * bj + 2])], lat_hi = ct.lat_deg[max(bx[4 * bi + 3], bx[4 * bj + 3])];
+          const double amax = fmax(fabs(lat_lo), fabs(lat_hi));
+          const double dlon = prm_dlon * xgap * d2r;
+          const double lb_lon = 2.0 * EARTH_R * asin(fmin(1.0, cos(fmin(amax, 90.0) * d2r) * sin(fmin(0.5 * dlon, 1.5707963267948966))));
+          if (lb_lon > geo_dis * 1.000001) continue;
+        }
         const int pos = atomicAdd(&x.total[0], 1);
-        if (pos < x.TLC) x.tile_list[pos] = ((u32)slot << 18) | ((u32)bi << 9) | (u32)bj;
+        if (pos < x.TLC) x.tile_list[pos] = ((u64)(u32)slot << 40) | ((u64)(u32)bi << 20) | (u64)(u32)bj;
         else atomicOr(&d.status[job], (int)WBK_ST_PAIR_OVERFLOW);
       }
     }
@@ -450,91 +465,99 @@ __global__ void __launch_bounds__(ST_THREADS) streamer_prep_kernel(WbkDev d, Wbk
 }
 
 // tiled pair scan: geo < geo_dis and cont > cont_dis and |x1 - x2| <= 120 (streamer_index.py:130-157),
-// without materialising the N x N matrices.  Persistent CTAs stride over the (contour, tile) work list; tiles
-// whose column ranges are more than 120 apart are skipped.  The haversine test is decided in fp32 on
+// without materialising the N x N matrices.  One WARP per 32 x 32 tile of the batch-wide active-tile list (lane = the
+// point i of block bi, the 32 points of block bj are broadcast from shared memory); warps stride over the list on
+// their own, no block barrier.  The haversine test is decided in fp32 on
 // h = sin^2(dlat/2) + cos cos sin^2(dlon/2) against sin^2(geo_dis / 2R) with a 1e-4 relative margin; only pairs
 // inside the margin evaluate the reference's fp64 expression (and carry the near-threshold flag).
+#define PS_WARPS (PS_THREADS / 32)
 __global__ void __launch_bounds__(PS_THREADS) pair_scan_kernel(WbkDev d, WbkIdx x, PackedSet ps, CoordTabs ct,
                                                                const double* __restrict__ pfx, wbk_index_params prm,
                                                                int nslots) {
-  __shared__ int sx[2][PT], stw[2][PT];
-  __shared__ float fla[2][PT], flo[2][PT], fco[2][PT];
-  __shared__ double sla[2][PT], slo[2][PT], sco[2][PT], spf[2][PT];
-  const int tid = threadIdx.x, nlon = d.nlon;
+  __shared__ float4 sj4[PS_WARPS][PT];   // packed point (bits), lat, lon, cos(lat) of block bj in fp32
+  __shared__ double sjpf[PS_WARPS][PT];  // along-contour prefix of block bj
+  const int lane = wbk_lane(), warp = wbk_warp(), nlon = d.nlon;
   const int total = min(x.total[0], x.TLC);
   const double sthr = sin(prm.geo_dis / (2.0 * EARTH_R));
   const float hthr = (float)(sthr * sthr);
   const float h_lo = hthr * 0.9999f, h_hi = hthr * 1.0001f;
-  for (int w = blockIdx.x; w < total; w += gridDim.x) {
-    const u32 tl = x.tile_list[w];
-    const int slot = (int)(tl >> 18), bi = (int)((tl >> 9) & 511u), bj = (int)(tl & 511u);
+  const int nwarps_grid = gridDim.x * PS_WARPS;
+  for (int w = blockIdx.x * PS_WARPS + warp; w < total; w += nwarps_grid) {
+    const u64 tl = x.tile_list[w];
+    const int slot = (int)(tl >> 40), bi = (int)((tl >> 20) & 0xfffffu), bj = (int)(tl & 0xfffffu);
     const int c = x.sel[slot];
     const int base = ps.pt_off[c], n = ps.pt_off[c + 1] - base;
-    {
-      const int which = tid >> 7, k = tid & (PT - 1);
-      const int idx = (which ? bj : bi) * PT + k;
-      if (idx < n) {
-        const u32 p = ps.pts[base + idx];
-        const int py = wbk_py(p), pxx = wbk_px(p);
-        const double la = ct.lat_rad[py], lo2 = ct.lon_rad[pxx % nlon], co = ct.cos_lat[py];
-        sx[which][k] = pxx;
-        sla[which][k] = la; slo[which][k] = lo2; sco[which][k] = co;
-        fla[which][k] = (float)la; flo[which][k] = (float)lo2; fco[which][k] = (float)co;
-        spf[which][k] = pfx[base + idx];
-        stw[which][k] = idx < x.PC ? x.flag[(size_t)slot * x.PC + idx] : -1;
-      }
+    const int i = bi * PT + lane, j0 = bj * PT + lane;
+    __syncwarp();  // the previous tile's readers are done
+    if (j0 < n) {
+      const u32 p = ps.pts[base + j0];
+      const int py = wbk_py(p);
+      sj4[warp][lane] = make_float4(__uint_as_float(p), (float)ct.lat_rad[py], (float)ct.lon_rad[wbk_px(p) % nlon],
+                                    (float)ct.cos_lat[py]);
+      sjpf[warp][lane] = pfx[base + j0];
     }
-    __syncthreads();
-    {
-      const int ii = tid & (PT - 1), half = tid >> 7;
-      const int i = bi * PT + ii;
-      if (i < n) {
-        const int xi = sx[0][ii];
-        const float lai = fla[0][ii], loi = flo[0][ii], ci = fco[0][ii];
-        const double pfi = spf[0][ii];
-        for (int jj = half * (PT / 2); jj < (half + 1) * (PT / 2); ++jj) {
-          const int j = bj * PT + jj;
-          if (j >= n || j <= i) continue;
-          int dxi = xi - sx[1][jj];
-          if (dxi < 0) dxi = -dxi;
-          if (dxi > 120) continue;  // hard-coded index units (streamer_index.py:157)
-          const double cont = __dsub_rn(spf[1][jj], pfi);
-          if (!(cont > prm.cont_dis)) continue;
-          const float s0 = __sinf(0.5f * (lai - fla[1][jj])), s1 = __sinf(0.5f * (loi - flo[1][jj]));
-          const float h = s0 * s0 + ci * fco[1][jj] * s1 * s1;
-          if (h > h_hi) continue;
-          int near = fabs(cont - prm.cont_dis) <= 1e-9 * prm.cont_dis;
-          if (h >= h_lo) {  // inside the margin: the reference's fp64 expression decides
-            const double dist = hav_km(sla[0][ii], slo[0][ii], sco[0][ii], sla[1][jj], slo[1][jj], sco[1][jj]);
-            if (!(dist < prm.geo_dis)) continue;
-            near |= fabs(dist - prm.geo_dis) <= 1e-9 * prm.geo_dis;
-          }
-          // check_duplicates (:160-183): the rows equal to (i, j) after x % nlon are the candidates among
-          // (tw i, tw j), (i, tw j), (tw i, j); they share the geographic positions, so only the index order, the
-          // 120-column rule and the along-contour distance decide.  The second row of a group (row-major) is dropped.
-          const int ti = stw[0][ii], tj = stw[1][jj];
-          if (ti >= 0 || tj >= 0) {
-            int smaller = 0;
-            const int cc[3] = {ti, i, ti}, dd[3] = {tj, tj, j};
-#pragma unroll
-            for (int q = 0; q < 3; ++q) {
-              const int ci = cc[q], dj = dd[q];
-              if (ci < 0 || dj < 0 || ci >= dj) continue;
-              int ddx = wbk_px(ps.pts[base + ci]) - wbk_px(ps.pts[base + dj]);
-              if (ddx < 0) ddx = -ddx;
-              if (ddx > 120) continue;
-              if (!(__dsub_rn(pfx[base + dj], pfx[base + ci]) > prm.cont_dis)) continue;
-              if (ci < i || (ci == i && dj < j)) ++smaller;
-            }
-            if (smaller == 1) continue;
-          }
-          const int k = atomicAdd(&x.cnt1[slot], 1);
-          if (k < x.PC) x.pairs2[(size_t)slot * x.PC + k] = ((u64)(u32)i << 32) | ((u64)(u32)j << 1) | (u64)near;
-          else atomicOr(&d.status[slot / x.SC], (int)WBK_ST_PAIR_OVERFLOW);
+    u32 pi = 0;
+    float lai = 0.f, loi = 0.f, ci = 0.f;
+    double pfi = 0.0;
+    int ti = -1;
+    if (i < n) {
+      pi = ps.pts[base + i];
+      const int py = wbk_py(pi);
+      lai = (float)ct.lat_rad[py];
+      loi = (float)ct.lon_rad[wbk_px(pi) % nlon];
+      ci = (float)ct.cos_lat[py];
+      pfi = pfx[base + i];
+      ti = i < x.PC ? x.flag[(size_t)slot * x.PC + i] : -1;
+    }
+    __syncwarp();
+    if (i < n) {
+      const int xi = wbk_px(pi);
+      const int nj = min(PT, n - bj * PT);
+      for (int jj = 0; jj < nj; ++jj) {
+        const int j = bj * PT + jj;
+        if (j <= i) continue;
+        const float4 q4 = sj4[warp][jj];
+        const u32 pj = __float_as_uint(q4.x);
+        int dxi = xi - wbk_px(pj);
+        if (dxi < 0) dxi = -dxi;
+        if (dxi > 120) continue;  // hard-coded index units (streamer_index.py:157)
+        const double cont = __dsub_rn(sjpf[warp][jj], pfi);
+        if (!(cont > prm.cont_dis)) continue;
+        const float s0 = __sinf(0.5f * (lai - q4.y)), s1 = __sinf(0.5f * (loi - q4.z));
+        const float h = s0 * s0 + ci * q4.w * s1 * s1;
+        if (h > h_hi) continue;
+        int near = fabs(cont - prm.cont_dis) <= 1e-9 * prm.cont_dis;
+        if (h >= h_lo) {  // inside the margin: the reference's fp64 expression decides
+          const int yi = wbk_py(pi), yj = wbk_py(pj);
+          const double dist = hav_km(ct.lat_rad[yi], ct.lon_rad[xi % nlon], ct.cos_lat[yi], ct.lat_rad[yj],
+                                     ct.lon_rad[wbk_px(pj) % nlon], ct.cos_lat[yj]);
+          if (!(dist < prm.geo_dis)) continue;
+          near |= fabs(dist - prm.geo_dis) <= 1e-9 * prm.geo_dis;
         }
+        // check_duplicates (:160-183): the rows equal to (i, j) after x % nlon are the candidates among
+        // (tw i, tw j), (i, tw j), (tw i, j); they share the geographic positions, so only the index order, the
+        // 120-column rule and the along-contour distance decide.  The second row of a group (row-major) is dropped.
+        const int tj = j < x.PC ? x.flag[(size_t)slot * x.PC + j] : -1;
+        if (ti >= 0 || tj >= 0) {
+          int smaller = 0;
+          const int cc[3] = {ti, i, ti}, dd[3] = {tj, tj, j};
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            const int ci2 = cc[q], dj = dd[q];
+            if (ci2 < 0 || dj < 0 || ci2 >= dj) continue;
+            int ddx = wbk_px(ps.pts[base + ci2]) - wbk_px(ps.pts[base + dj]);
+            if (ddx < 0) ddx = -ddx;
+            if (ddx > 120) continue;
+            if (!(__dsub_rn(pfx[base + dj], pfx[base + ci2]) > prm.cont_dis)) continue;
+            if (ci2 < i || (ci2 == i && dj < j)) ++smaller;
+          }
+          if (smaller == 1) continue;
+        }
+        const int k = atomicAdd(&x.cnt1[slot], 1);
+        if (k < x.PC) x.pairs2[(size_t)slot * x.PC + k] = ((u64)(u32)i << 32) | ((u64)(u32)j << 1) | (u64)near;
+        else atomicOr(&d.status[slot / x.SC], (int)WBK_ST_PAIR_OVERFLOW);
       }
     }
-    __syncthreads();
   }
 }
 
@@ -1078,7 +1101,7 @@ extern "C" int wbk_index_run(wbk_ctx* ctx, int njobs, int nlevels, const int* d_
     const int nslots = njobs * x.SC;
     WBK_CUDA_CHECK(cudaMemsetAsync(x.total, 0, sizeof(int), st));
     WBK_LAUNCH(KID_STREAMER_PREP, streamer_prep_kernel, dim3(njobs), dim3(ST_THREADS), 0, st, d, x, ps, ct, on, pfx, prm->dlon,
-               prm->geo_dis);
+               prm->geo_dis, prm->cont_dis);
     WBK_LAUNCH_CHECK();
     WBK_CUDA_CHECK(cudaMemsetAsync(x.cnt1, 0, sizeof(int) * nslots, st));
     WBK_LAUNCH(KID_PAIR_SCAN, pair_scan_kernel, dim3(148 * 8), dim3(PS_THREADS), 0, st, d, x, ps, ct, (const double*)pfx, *prm, nslots);
