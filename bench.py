@@ -41,7 +41,7 @@ def parse_args():
     ap.add_argument("--nlat", type=int, default=721)
     ap.add_argument("--nlon", type=int, default=1440)
     ap.add_argument("--passes", type=int, default=5)
-    ap.add_argument("--cpu-sample", type=int, default=1, help="time steps of the CPU baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=3, help="time steps of the CPU baseline sample (~4-8 s each)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--depth", type=int, default=3, help="batches in flight (slots / streams)")

@@ -86,6 +86,43 @@ __device__ inline double dd_block_sum(DD v, double* scratch /* >= 66 doubles */)
   return scratch[64];
 }
 
+// six double-double sums at once (one pair of barriers instead of six): out[k] to every thread.
+// scratch: >= 6 * 2 * 32 + 6 doubles
+__device__ inline void dd_block_sum6(DD (&v)[6], double* scratch, double (&out)[6]) {
+  const int lane = wbk_lane(), warp = wbk_warp(), nwarps = wbk_nthreads() >> 5;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      const double oh = __shfl_xor_sync(WBK_FULL, v[k].hi, d), ol = __shfl_xor_sync(WBK_FULL, v[k].lo, d);
+      dd_merge(v[k], oh, ol);
+    }
+  }
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      scratch[(k * 32 + warp) * 2] = v[k].hi;
+      scratch[(k * 32 + warp) * 2 + 1] = v[k].lo;
+    }
+  }
+  __syncthreads();
+  if (warp < 6) {  // warp k reduces sum k (same lane order as dd_block_sum: deterministic)
+    DD w;
+    w.hi = lane < nwarps ? scratch[(warp * 32 + lane) * 2] : 0.0;
+    w.lo = lane < nwarps ? scratch[(warp * 32 + lane) * 2 + 1] : 0.0;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      const double oh = __shfl_xor_sync(WBK_FULL, w.hi, d), ol = __shfl_xor_sync(WBK_FULL, w.lo, d);
+      dd_merge(w, oh, ol);
+    }
+    if (lane == 0) scratch[384 + warp] = __dadd_rn(w.hi, w.lo);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 6; ++k) out[k] = scratch[384 + k];
+}
+
 // Warp-cooperative scan of lattice row y over columns [bx0, bx0 + bw): on return acc[i] is the winding number
 // of (bx0 + i, y) (for points not on the boundary) and flg[i] has bit 0 / bit 1 set if the point is on the
 // boundary or closer than sqrt(r2a) / sqrt(r2b) to an edge.  R = floor(max radius).
@@ -211,7 +248,7 @@ events_raster_kernel(WbkDev d, WbkIdx x, const int* __restrict__ job_off, const 
                      const T* __restrict__ intensity, int8_t* __restrict__ flags, int ntime, int nlevels, int J,
                      int njobs, double r2_prop, double r2_flag, int rowcap) {
   WBK_DYN_SMEM(int, sm);
-  __shared__ double red[72];
+  __shared__ double red[392];
   __shared__ int s_box[5];
   __shared__ int s_scan[40];
   const int tid = threadIdx.x, lane = wbk_lane(), warp = wbk_warp(), nwarps = blockDim.x >> 5;
@@ -347,10 +384,11 @@ events_raster_kernel(WbkDev d, WbkIdx x, const int* __restrict__ job_off, const 
       __syncwarp();
      }
     }
-    const double t_a = dd_block_sum(s_a, red), t_v = dd_block_sum(s_v, red), t_i = dd_block_sum(s_i, red);
-    const double t_x = dd_block_sum(s_x, red), t_y = dd_block_sum(s_y, red), t_n = dd_block_sum(s_n, red);
+    DD sums6[6] = {s_a, s_v, s_i, s_x, s_y, s_n};
+    double tot6[6];
+    dd_block_sum6(sums6, red, tot6);
     if (tid == 0) {
-      evf[0] = t_a; evf[1] = t_v; evf[2] = t_i; evf[3] = t_x; evf[4] = t_y; evf[5] = t_n;
+      evf[0] = tot6[0]; evf[1] = tot6[1]; evf[2] = tot6[2]; evf[3] = tot6[3]; evf[4] = tot6[4]; evf[5] = tot6[5];
       if (kind != WBK_EV_OVERTURNING) {
         ev[3] = vx0; ev[4] = vy0; ev[5] = vx1; ev[6] = vy1;
       }
