@@ -350,7 +350,7 @@ class Detector:
         self.submit(slot, raw_host, flags_host=flags_host)
         return self.collect(slot)
 
-    def stream(self, batches, depth=3, flags_host=None, shared_stream=False):
+    def stream(self, batches, depth=3, flags_host=None, shared_stream=False, gmax_nx=None):
         """Pipelined execution: yields one BatchResult per input batch, in order.
 
         ``batches``: iterable of device or pinned-host tensors of (at most) equal length.  ``depth`` batches are
@@ -358,6 +358,9 @@ class Detector:
         handling overlap.  With ``shared_stream`` all slots enqueue on ONE side stream: kernels of different
         batches do not overlap each other, the host merely runs ahead (device-resident inputs).
         ``flags_host``: optional list of pinned int8 buffers, one per slot.
+        ``gmax_nx``: the global ``exp_lon.max()`` in columns (streamer_index.py:106 takes it over ALL dates); by
+        default every batch uses its own maximum, which is the same value as soon as each batch holds a
+        circumglobal contour.
         The flag grids / contour set of a result are only valid until its slot is reused (``depth`` batches later).
         """
         common = None
@@ -373,7 +376,7 @@ class Detector:
                 yield self.collect(inflight.pop(0))
             slot = self._slot(int(raw.shape[0]), idx)
             fh = flags_host[idx] if flags_host is not None else None
-            inflight.append(self.submit(slot, raw, flags_host=fh, stream=common))
+            inflight.append(self.submit(slot, raw, flags_host=fh, stream=common, gmax_nx=gmax_nx))
             i += 1
         while inflight:
             yield self.collect(inflight.pop(0))
