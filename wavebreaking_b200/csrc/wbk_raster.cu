@@ -123,6 +123,12 @@ __device__ inline void dd_block_sum6(DD (&v)[6], double* scratch, double (&out)[
   for (int k = 0; k < 6; ++k) out[k] = scratch[384 + k];
 }
 
+// column of the extended grid -> column of the real grid (x % nlon without the division: W < a few nlon)
+__device__ __forceinline__ int fold_x(int px, int nlon) {
+  while (px >= nlon) px -= nlon;
+  return px;
+}
+
 // Warp-cooperative scan of lattice row y over columns [bx0, bx0 + bw): on return acc[i] is the winding number
 // of (bx0 + i, y) (for points not on the boundary) and flg[i] has bit 0 / bit 1 set if the point is on the
 // boundary or closer than sqrt(r2a) / sqrt(r2b) to an edge.  R = floor(max radius).
@@ -163,6 +169,14 @@ __device__ inline void raster_scan_row(const RingView& rv, int y, int bx0, int b
         // boundary / near-edge candidates of this row
         if (y >= lo - R && y <= hi + R) {
           const long long len2 = (long long)dx * dx + (long long)dy * dy;
+          if (len2 <= 2 && rmax * rmax <= 0.5) {
+            // unit step of a contour ring with radii <= sqrt(1/2): every lattice point off the edge is at least
+            // 1/sqrt(2) away, so only the end points qualify; the start vertex is marked here, the end vertex is the
+            // start of the next edge
+            const int idx = xa - bx0;
+            if (ya == y && idx >= 0 && idx < bw) atomicOr(&flg[idx], 3u);
+            continue;
+          }
           int cl, ch;
           if (dy == 0) {
             cl = min(xa, xb) - R;
@@ -240,6 +254,7 @@ __global__ void __launch_bounds__(1024) event_list_kernel(WbkIdx x, int J, int n
 #define RS_RING_CAP 4096     // ring vertices staged in shared memory per event
 #define RS_ROWS_CAP 1024     // lattice rows of an event's bounding box that get an edge bucket
 #define RS_EDGE_CAP 8192     // edge incidences in the row buckets
+#define RS_PRE 4             // 32-column groups of a row whose field values are prefetched before the scan
 
 template <typename T>
 __global__ void __launch_bounds__(RS_THREADS, 3)
@@ -248,7 +263,6 @@ events_raster_kernel(WbkDev d, WbkIdx x, const int* __restrict__ job_off, const 
                      const T* __restrict__ intensity, int8_t* __restrict__ flags, int ntime, int nlevels, int J,
                      int njobs, double r2_prop, double r2_flag, int rowcap) {
   WBK_DYN_SMEM(int, sm);
-  __shared__ double red[392];
   __shared__ int s_box[5];
   __shared__ int s_scan[40];
   const int tid = threadIdx.x, lane = wbk_lane(), warp = wbk_warp(), nwarps = blockDim.x >> 5;
@@ -350,18 +364,27 @@ events_raster_kernel(WbkDev d, WbkIdx x, const int* __restrict__ job_off, const 
      const int ecount = bucketed ? rcount[y - by0 + 1] - rcount[y - by0] : 0;
      for (int cx0 = bx0; cx0 <= bx1; cx0 += rowcap) {  // wide events: the row is scanned in column chunks
       const int cw = min(rowcap, bx1 - cx0 + 1);
+      const size_t rowbase = ((size_t)t * nlat + y) * nlon;
+      // the field values of the row's first RS_PRE * 32 columns are requested before the scan, so their DRAM latency
+      // hides behind it (otherwise every 32-column step of the member loop waits for a load on its own)
+      T dpre[RS_PRE];
+#pragma unroll
+      for (int k = 0; k < RS_PRE; ++k) {
+        const int px = cx0 + lane + 32 * k;
+        const int xf = fold_x(px, nlon);
+        dpre[k] = lane + 32 * k < cw ? data[rowbase + xf] : (T)0;
+      }
       raster_scan_row(rv, y, cx0, cw, acc, flg, r2_prop, r2_flag, rmax, R, elist, ecount);
       const double a = area[y];
-      const size_t rowbase = ((size_t)t * nlat + y) * nlon;
       int row_members = 0;
-      for (int i = lane; i < cw; i += 32) {
+      auto visit = [&](int i, double dv) {
         const bool in = acc[i] != 0;
         const u32 f = flg[i];
         const int px = cx0 + i;
         if (in || (f & 1u)) {
-          const int xf = px < nlon ? px : (px < 2 * nlon ? px - nlon : px % nlon);
+          const int xf = fold_x(px, nlon);
           // sum(a) and sum(y * a) have one value per row: counted here, added once per row below
-          dd_add(s_v, __dmul_rn(a, (double)data[rowbase + xf]));
+          dd_add(s_v, __dmul_rn(a, dv));
           if (intensity) dd_add(s_i, __dmul_rn(a, (double)intensity[rowbase + xf]));
           dd_add(s_x, __dmul_rn((double)px, a));
           ++row_members;
@@ -370,6 +393,14 @@ events_raster_kernel(WbkDev d, WbkIdx x, const int* __restrict__ job_off, const 
           const int xf = px - shift;
           if (xf >= 0 && xf < nlon) flags[(((size_t)kind * ntime + t) * nlat + y) * nlon + xf] = 1;
         }
+      };
+#pragma unroll
+      for (int k = 0; k < RS_PRE; ++k)
+        if (lane + 32 * k < cw) visit(lane + 32 * k, (double)dpre[k]);
+      for (int i = lane + 32 * RS_PRE; i < cw; i += 32) {
+        const int px = cx0 + i;
+        const int xf = fold_x(px, nlon);
+        visit(i, (double)data[rowbase + xf]);
       }
       if (row_members) {
         // n identical addends: n * value is exact in double-double (two-product by FMA), like adding them one by one
@@ -386,7 +417,7 @@ events_raster_kernel(WbkDev d, WbkIdx x, const int* __restrict__ job_off, const 
     }
     DD sums6[6] = {s_a, s_v, s_i, s_x, s_y, s_n};
     double tot6[6];
-    dd_block_sum6(sums6, red, tot6);
+    dd_block_sum6(sums6, reinterpret_cast<double*>(sm), tot6);  // the row buffers are free by now
     if (tid == 0) {
       evf[0] = tot6[0]; evf[1] = tot6[1]; evf[2] = tot6[2]; evf[3] = tot6[3]; evf[4] = tot6[4]; evf[5] = tot6[5];
       if (kind != WBK_EV_OVERTURNING) {
