@@ -321,8 +321,12 @@ events_raster_kernel(WbkDev d, WbkIdx x, const int* __restrict__ job_off, const 
     // 0: all vertices on the real grid, 1: straddles the last meridian (host clips), 2: entirely in the extension
     const int split = vx1 < nlon ? 0 : (vx0 >= nlon ? 2 : 1);
     const int shift = split == 2 ? nlon : 0;
-    const int bx0 = max(vx0 - R - 1, 0), bx1 = min(vx1 + R + 1, W - 1);
-    const int by0 = max(vy0 - R - 1, 0), by1 = min(vy1 + R + 1, nlat - 1);
+    // overturning boxes with radii below one cell: the members are exactly the lattice points of the closed box
+    // (every other lattice point is at least one cell away), no winding / near-edge scan needed
+    const bool boxfast = kind == WBK_EV_OVERTURNING && rmax < 1.0;
+    const int mrg = boxfast ? 0 : R + 1;
+    const int bx0 = max(vx0 - mrg, 0), bx1 = min(vx1 + mrg, W - 1);
+    const int by0 = max(vy0 - mrg, 0), by1 = min(vy1 + mrg, nlat - 1);
     const int bw = bx1 - bx0 + 1;
     // row buckets: edge e is listed under every lattice row it can touch (its y-span widened by R), so a row
     // visits a handful of edges instead of the whole ring
@@ -374,12 +378,12 @@ events_raster_kernel(WbkDev d, WbkIdx x, const int* __restrict__ job_off, const 
         const int xf = fold_x(px, nlon);
         dpre[k] = lane + 32 * k < cw ? data[rowbase + xf] : (T)0;
       }
-      raster_scan_row(rv, y, cx0, cw, acc, flg, r2_prop, r2_flag, rmax, R, elist, ecount);
+      if (!boxfast) raster_scan_row(rv, y, cx0, cw, acc, flg, r2_prop, r2_flag, rmax, R, elist, ecount);
       const double a = area[y];
       int row_members = 0;
       auto visit = [&](int i, double dv) {
-        const bool in = acc[i] != 0;
-        const u32 f = flg[i];
+        const bool in = boxfast || acc[i] != 0;
+        const u32 f = boxfast ? 3u : flg[i];
         const int px = cx0 + i;
         if (in || (f & 1u)) {
           const int xf = fold_x(px, nlon);
