@@ -69,7 +69,8 @@ struct WbkIdx {
   int SPV, SPR;              // vertex pool / ring list capacities
   int* split_xy;             // [SPV][2] vertex pool (chain scratch and final folded, truncated pieces)
   int* split_ring;           // [SPR][4] start, len, time index, kind
-  int* split_count;          // [0] vertex cursor, [1] ring cursor, [2] overflow flag
+  int* split_count;          // [0] vertex cursor, [1] ring cursor, [2] overflow flag, [3] split_list cursor
+  int* split_list;           // [SPR] events (index in ev_off order) that straddle the last meridian
 };
 
 struct wbk_ctx {

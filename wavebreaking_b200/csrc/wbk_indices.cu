@@ -52,6 +52,7 @@ size_t wbk_index_layout(struct wbk_ctx* ctx, unsigned char* base, size_t off) {
   x.split_xy = (int*)take((size_t)x.SPV * 2 * 4);
   x.split_ring = (int*)take((size_t)x.SPR * 4 * 4);
   x.split_count = (int*)take(64);
+  x.split_list = (int*)take((size_t)x.SPR * 4);
   return (o + 255) & ~(size_t)255;
 }
 
@@ -369,10 +370,22 @@ __global__ void __launch_bounds__(ST_THREADS) streamer_prep_kernel(WbkDev d, Wbk
     {
       const int slot = job * x.SC + si;
       int* tw = x.flag + (size_t)slot * x.PC;
-      if (n > x.PC) {
+      // fp32 record of every point for the pair scan (packed point bits, lat, lon, cos lat): one coalesced 16-byte
+      // load per lane and tile instead of a chain of dependent table lookups; lives in the (not yet used) pair arena
+      float4* rec = reinterpret_cast<float4*>(x.pairs + (size_t)slot * x.PC);
+      if (n > x.PC / 2) {
         if (tid == 0) atomicOr(&d.status[job], (int)WBK_ST_PAIR_OVERFLOW);
-        for (int k = tid; k < min(n, x.PC); k += nt) tw[k] = -1;
+        for (int k = tid; k < min(n, x.PC / 2); k += nt) {
+          tw[k] = -1;
+          rec[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       } else {
+        for (int k = tid; k < n; k += nt) {
+          const u32 p = ps.pts[base + k];
+          const int py = wbk_py(p);
+          rec[k] = make_float4(__uint_as_float(p), (float)ct.lat_rad[py], (float)ct.lon_rad[wbk_px(p) % nlon],
+                               (float)ct.cos_lat[py]);
+        }
         const u32 cap = wbk_pow2_ceil((u32)(2 * n));
         u32* hkeys = reinterpret_cast<u32*>(x.hk + (size_t)slot * 2 * x.PC);
         u32* hvals = hkeys + cap;
@@ -488,29 +501,28 @@ __global__ void __launch_bounds__(PS_THREADS) pair_scan_kernel(WbkDev d, WbkIdx 
     const int c = x.sel[slot];
     const int base = ps.pt_off[c], n = ps.pt_off[c + 1] - base;
     const int i = bi * PT + lane, j0 = bj * PT + lane;
+    const float4* rec = reinterpret_cast<const float4*>(x.pairs + (size_t)slot * x.PC);  // streamer_prep_kernel
+    const bool has_rec = n <= x.PC / 2;
     __syncwarp();  // the previous tile's readers are done
-    if (j0 < n) {
-      const u32 p = ps.pts[base + j0];
-      const int py = wbk_py(p);
-      sj4[warp][lane] = make_float4(__uint_as_float(p), (float)ct.lat_rad[py], (float)ct.lon_rad[wbk_px(p) % nlon],
-                                    (float)ct.cos_lat[py]);
+    if (j0 < n && has_rec) {
+      sj4[warp][lane] = rec[j0];
       sjpf[warp][lane] = pfx[base + j0];
     }
     u32 pi = 0;
     float lai = 0.f, loi = 0.f, ci = 0.f;
     double pfi = 0.0;
     int ti = -1;
-    if (i < n) {
-      pi = ps.pts[base + i];
-      const int py = wbk_py(pi);
-      lai = (float)ct.lat_rad[py];
-      loi = (float)ct.lon_rad[wbk_px(pi) % nlon];
-      ci = (float)ct.cos_lat[py];
+    if (i < n && has_rec) {
+      const float4 r4 = rec[i];
+      pi = __float_as_uint(r4.x);
+      lai = r4.y;
+      loi = r4.z;
+      ci = r4.w;
       pfi = pfx[base + i];
-      ti = i < x.PC ? x.flag[(size_t)slot * x.PC + i] : -1;
+      ti = x.flag[(size_t)slot * x.PC + i];
     }
     __syncwarp();
-    if (i < n) {
+    if (i < n && has_rec) {  // without records the job carries WBK_ST_PAIR_OVERFLOW and is re-run with larger arenas
       const int xi = wbk_px(pi);
       const int nj = min(PT, n - bj * PT);
       for (int jj = 0; jj < nj; ++jj) {

@@ -428,6 +428,11 @@ events_raster_kernel(WbkDev d, WbkIdx x, const int* __restrict__ job_off, const 
         ev[3] = vx0; ev[4] = vy0; ev[5] = vx1; ev[6] = vy1;
       }
       ev[8] = split;
+      if (split == 1 && flags) {  // work list of the meridian split
+        const int pos = atomicAdd(&x.split_count[3], 1);
+        if (pos < x.SPR) x.split_list[pos] = w;
+        else atomicExch(&x.split_count[2], 1);
+      }
     }
     __syncthreads();
   }
@@ -653,33 +658,48 @@ __device__ void split_clip_side(const RingView& rv, int c, bool keep_le, int nlo
   }
 }
 
-__global__ void split_events_kernel(WbkDev d, WbkIdx x, const int* __restrict__ pt_off, const u32* __restrict__ pts,
-                                    int nlevels, int J, int njobs) {
-  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per listed event: the lanes stage the ring in shared memory, lane 0 runs the (sequential, tiny) clipping.
+#define SPLIT_WARPS 4
+#define SPLIT_STAGE 2048  // ring vertices staged per warp
+__global__ void __launch_bounds__(32 * SPLIT_WARPS)
+split_events_kernel(WbkDev d, WbkIdx x, const int* __restrict__ pt_off, const u32* __restrict__ pts, int nlevels, int J,
+                    int njobs) {
+  __shared__ u32 sring[SPLIT_WARPS][SPLIT_STAGE];
+  const int lane = wbk_lane(), warp = wbk_warp();
   const int nlist = 3 * njobs;
-  if (w >= x.ev_off[nlist]) return;
-  int lo = 0, hi = nlist - 1;
-  while (lo < hi) {
-    int mid = (lo + hi + 1) >> 1;
-    if (x.ev_off[mid] <= w) lo = mid; else hi = mid - 1;
+  const int count = min(x.split_count[3], x.SPR);
+  for (int q = blockIdx.x * SPLIT_WARPS + warp; q < count; q += gridDim.x * SPLIT_WARPS) {
+    const int w = x.split_list[q];
+    int lo = 0, hi = nlist - 1;
+    while (lo < hi) {
+      int mid = (lo + hi + 1) >> 1;
+      if (x.ev_off[mid] <= w) lo = mid; else hi = mid - 1;
+    }
+    const int kind = lo / njobs, job = lo - kind * njobs, e = w - x.ev_off[lo];
+    const int* ev = x.ev_int + (((size_t)kind * J + job) * x.EC + e) * WBK_EV_INTS;
+    RingView rv;
+    rv.xy = nullptr;
+    if (kind == WBK_EV_OVERTURNING) {
+      rv.packed = nullptr;
+      rv.bx0 = ev[3]; rv.by0 = ev[4]; rv.bx1 = ev[5]; rv.by1 = ev[6];
+      rv.n = 4;
+    } else {
+      rv.packed = pts + pt_off[ev[0]] + ev[1];
+      rv.n = ev[2] - ev[1] + 1;
+      rv.bx0 = rv.by0 = rv.bx1 = rv.by1 = 0;
+      __syncwarp();
+      if (rv.n <= SPLIT_STAGE) {
+        for (int k = lane; k < rv.n; k += 32) sring[warp][k] = rv.packed[k];
+        rv.packed = sring[warp];
+      }
+      __syncwarp();
+    }
+    if (lane == 0) {
+      const int t = job / nlevels;
+      split_clip_side(rv, d.nlon - 1, true, d.nlon, t, kind, x);
+      split_clip_side(rv, d.nlon, false, d.nlon, t, kind, x);
+    }
   }
-  const int kind = lo / njobs, job = lo - kind * njobs, e = w - x.ev_off[lo];
-  const int* ev = x.ev_int + (((size_t)kind * J + job) * x.EC + e) * WBK_EV_INTS;
-  if (ev[8] != 1) return;
-  RingView rv;
-  rv.xy = nullptr;
-  if (kind == WBK_EV_OVERTURNING) {
-    rv.packed = nullptr;
-    rv.bx0 = ev[3]; rv.by0 = ev[4]; rv.bx1 = ev[5]; rv.by1 = ev[6];
-    rv.n = 4;
-  } else {
-    rv.packed = pts + pt_off[ev[0]] + ev[1];
-    rv.n = ev[2] - ev[1] + 1;
-    rv.bx0 = rv.by0 = rv.bx1 = rv.by1 = 0;
-  }
-  const int t = job / nlevels;
-  split_clip_side(rv, d.nlon - 1, true, d.nlon, t, kind, x);
-  split_clip_side(rv, d.nlon, false, d.nlon, t, kind, x);
 }
 
 // rasterise the split pieces (real grid, r = 1/2 cell: processing/events.py:75-79) into the flag grids
@@ -751,6 +771,7 @@ extern "C" int wbk_events_raster(wbk_ctx* ctx, const int* d_job_off, const int* 
     wbk_set_error("wbk_events_raster: to_xarray flags need dlon == dlat (buffer radius is isotropic in degrees)");
     return WBK_ERR_INVALID;
   }
+  WBK_CUDA_CHECK(cudaMemsetAsync(ctx->x.split_count, 0, 16, st));  // cursors of the meridian split (filled by the rasteriser)
   WBK_LAUNCH(KID_EVENT_LIST, event_list_kernel, dim3(1), dim3(1024), 0, st, ctx->x, J, njobs);
   WBK_LAUNCH_CHECK();
   const double r_prop = (prm->dlon + prm->dlat) / 2.0 / 2.0;  // index units (index_utils.py:47-50)
@@ -778,9 +799,7 @@ extern "C" int wbk_events_raster(wbk_ctx* ctx, const int* d_job_off, const int* 
   WBK_LAUNCH_CHECK();
   if (d_flags) {
     // events straddling the last meridian: clip on the device, rasterise the pieces
-    WBK_CUDA_CHECK(cudaMemsetAsync(ctx->x.split_count, 0, 16, st));
-    const int max_events = 3 * njobs * ctx->x.EC;
-    WBK_LAUNCH(KID_SPLIT, split_events_kernel, dim3((max_events + 127) / 128), dim3(128), 0, st, d, ctx->x, d_pt_off,
+    WBK_LAUNCH(KID_SPLIT, split_events_kernel, dim3(148 * 2), dim3(32 * SPLIT_WARPS), 0, st, d, ctx->x, d_pt_off,
                (const u32*)d_pts, ctx->nlevels, J, njobs);
     WBK_LAUNCH_CHECK();
     const int rc2 = raster_rowcap(d.nlon);
