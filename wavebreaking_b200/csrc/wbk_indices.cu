@@ -484,11 +484,13 @@ __global__ void __launch_bounds__(ST_THREADS) streamer_prep_kernel(WbkDev d, Wbk
 // h = sin^2(dlat/2) + cos cos sin^2(dlon/2) against sin^2(geo_dis / 2R) with a 1e-4 relative margin; only pairs
 // inside the margin evaluate the reference's fp64 expression (and carry the near-threshold flag).
 #define PS_WARPS (PS_THREADS / 32)
+#define PS_BUF 256
 __global__ void __launch_bounds__(PS_THREADS) pair_scan_kernel(WbkDev d, WbkIdx x, PackedSet ps, CoordTabs ct,
                                                                const double* __restrict__ pfx, wbk_index_params prm,
                                                                int nslots) {
   __shared__ float4 sj4[PS_WARPS][PT];   // packed point (bits), lat, lon, cos(lat) of block bj in fp32
   __shared__ double sjpf[PS_WARPS][PT];  // along-contour prefix of block bj
+  __shared__ u64 sbuf[PS_WARPS][PS_BUF];  // candidates of the current tile
   const int lane = wbk_lane(), warp = wbk_warp(), nlon = d.nlon;
   const int total = min(x.total[0], x.TLC);
   const double sthr = sin(prm.geo_dis / (2.0 * EARTH_R));
@@ -522,54 +524,85 @@ __global__ void __launch_bounds__(PS_THREADS) pair_scan_kernel(WbkDev d, WbkIdx 
       ti = x.flag[(size_t)slot * x.PC + i];
     }
     __syncwarp();
-    if (i < n && has_rec) {  // without records the job carries WBK_ST_PAIR_OVERFLOW and is re-run with larger arenas
-      const int xi = wbk_px(pi);
-      const int nj = min(PT, n - bj * PT);
-      for (int jj = 0; jj < nj; ++jj) {
-        const int j = bj * PT + jj;
-        if (j <= i) continue;
+    // candidates are collected in a per-warp buffer and appended with ONE atomic per flush (an atomic with a return
+    // value inside the loop would stall the warp for a round trip to L2 per candidate)
+    const bool act = i < n && has_rec;  // without records the job carries WBK_ST_PAIR_OVERFLOW and is re-run
+    const int xi = wbk_px(pi);
+    const int nj = min(PT, n - bj * PT);
+    int cnt = 0;
+    auto flush = [&]() {
+      int basep = 0;
+      if (lane == 0) basep = atomicAdd(&x.cnt1[slot], cnt);
+      basep = __shfl_sync(WBK_FULL, basep, 0);
+      for (int k = lane; k < cnt; k += 32) {
+        if (basep + k < x.PC) x.pairs2[(size_t)slot * x.PC + basep + k] = sbuf[warp][k];
+        else atomicOr(&d.status[slot / x.SC], (int)WBK_ST_PAIR_OVERFLOW);
+      }
+      cnt = 0;
+      __syncwarp();
+    };
+    for (int jj = 0; jj < nj; ++jj) {
+      const int j = bj * PT + jj;
+      bool cand = false;
+      u64 key = 0;
+      if (act && j > i) {
         const float4 q4 = sj4[warp][jj];
         const u32 pj = __float_as_uint(q4.x);
         int dxi = xi - wbk_px(pj);
         if (dxi < 0) dxi = -dxi;
-        if (dxi > 120) continue;  // hard-coded index units (streamer_index.py:157)
         const double cont = __dsub_rn(sjpf[warp][jj], pfi);
-        if (!(cont > prm.cont_dis)) continue;
-        const float s0 = __sinf(0.5f * (lai - q4.y)), s1 = __sinf(0.5f * (loi - q4.z));
-        const float h = s0 * s0 + ci * q4.w * s1 * s1;
-        if (h > h_hi) continue;
-        int near = fabs(cont - prm.cont_dis) <= 1e-9 * prm.cont_dis;
-        if (h >= h_lo) {  // inside the margin: the reference's fp64 expression decides
-          const int yi = wbk_py(pi), yj = wbk_py(pj);
-          const double dist = hav_km(ct.lat_rad[yi], ct.lon_rad[xi % nlon], ct.cos_lat[yi], ct.lat_rad[yj],
-                                     ct.lon_rad[wbk_px(pj) % nlon], ct.cos_lat[yj]);
-          if (!(dist < prm.geo_dis)) continue;
-          near |= fabs(dist - prm.geo_dis) <= 1e-9 * prm.geo_dis;
-        }
-        // check_duplicates (:160-183): the rows equal to (i, j) after x % nlon are the candidates among
-        // (tw i, tw j), (i, tw j), (tw i, j); they share the geographic positions, so only the index order, the
-        // 120-column rule and the along-contour distance decide.  The second row of a group (row-major) is dropped.
-        const int tj = j < x.PC ? x.flag[(size_t)slot * x.PC + j] : -1;
-        if (ti >= 0 || tj >= 0) {
-          int smaller = 0;
-          const int cc[3] = {ti, i, ti}, dd[3] = {tj, tj, j};
+        // hard-coded 120 index units (streamer_index.py:157), cont > cont_dis (:138)
+        if (dxi <= 120 && cont > prm.cont_dis) {
+          const float s0 = __sinf(0.5f * (lai - q4.y)), s1 = __sinf(0.5f * (loi - q4.z));
+          const float h = s0 * s0 + ci * q4.w * s1 * s1;
+          if (!(h > h_hi)) {
+            int near = fabs(cont - prm.cont_dis) <= 1e-9 * prm.cont_dis;
+            bool ok = true;
+            if (h >= h_lo) {  // inside the margin: the reference's fp64 expression decides
+              const int yi = wbk_py(pi), yj = wbk_py(pj);
+              const double dist = hav_km(ct.lat_rad[yi], ct.lon_rad[xi % nlon], ct.cos_lat[yi], ct.lat_rad[yj],
+                                         ct.lon_rad[wbk_px(pj) % nlon], ct.cos_lat[yj]);
+              ok = dist < prm.geo_dis;
+              near |= fabs(dist - prm.geo_dis) <= 1e-9 * prm.geo_dis;
+            }
+            if (ok) {
+              // check_duplicates (:160-183): the rows equal to (i, j) after x % nlon are the candidates among
+              // (tw i, tw j), (i, tw j), (tw i, j); they share the geographic positions, so only the index order,
+              // the 120-column rule and the along-contour distance decide.  The second row of a group (row-major)
+              // is dropped.
+              const int tj = x.flag[(size_t)slot * x.PC + j];
+              if (ti >= 0 || tj >= 0) {
+                int smaller = 0;
+                const int cc[3] = {ti, i, ti}, dd[3] = {tj, tj, j};
 #pragma unroll
-          for (int q = 0; q < 3; ++q) {
-            const int ci2 = cc[q], dj = dd[q];
-            if (ci2 < 0 || dj < 0 || ci2 >= dj) continue;
-            int ddx = wbk_px(ps.pts[base + ci2]) - wbk_px(ps.pts[base + dj]);
-            if (ddx < 0) ddx = -ddx;
-            if (ddx > 120) continue;
-            if (!(__dsub_rn(pfx[base + dj], pfx[base + ci2]) > prm.cont_dis)) continue;
-            if (ci2 < i || (ci2 == i && dj < j)) ++smaller;
+                for (int q = 0; q < 3; ++q) {
+                  const int ci2 = cc[q], dj = dd[q];
+                  if (ci2 < 0 || dj < 0 || ci2 >= dj) continue;
+                  int ddx = wbk_px(ps.pts[base + ci2]) - wbk_px(ps.pts[base + dj]);
+                  if (ddx < 0) ddx = -ddx;
+                  if (ddx > 120) continue;
+                  if (!(__dsub_rn(pfx[base + dj], pfx[base + ci2]) > prm.cont_dis)) continue;
+                  if (ci2 < i || (ci2 == i && dj < j)) ++smaller;
+                }
+                ok = smaller != 1;
+              }
+              if (ok) {
+                cand = true;
+                key = ((u64)(u32)i << 32) | ((u64)(u32)j << 1) | (u64)near;
+              }
+            }
           }
-          if (smaller == 1) continue;
         }
-        const int k = atomicAdd(&x.cnt1[slot], 1);
-        if (k < x.PC) x.pairs2[(size_t)slot * x.PC + k] = ((u64)(u32)i << 32) | ((u64)(u32)j << 1) | (u64)near;
-        else atomicOr(&d.status[slot / x.SC], (int)WBK_ST_PAIR_OVERFLOW);
+      }
+      const u32 m = __ballot_sync(WBK_FULL, cand);
+      if (m) {  // warp-uniform
+        if (cand) sbuf[warp][cnt + __popc(m & ((1u << lane) - 1u))] = key;
+        cnt += __popc(m);
+        __syncwarp();
+        if (cnt > PS_BUF - 32) flush();
       }
     }
+    if (cnt) flush();
   }
 }
 
