@@ -403,11 +403,18 @@ def run_b200(a):
 
 
 def main():
+    # stdout carries exactly ONE line (the JSON): everything libraries print there (the NCCL version banner ...) is
+    # sent to stderr by pointing fd 1 at fd 2 for the run; the JSON line goes to the saved real stdout
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)
     else:
         run_b200(a)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":
