@@ -56,7 +56,7 @@ struct WbkIdx {
   int *scanb, *label;        // [J][PC]
   u64 *hm1, *hm2;            // [J][SC][2*PC] smallest / second smallest pair key of a duplicate group
   int* cnt1;                 // [J][SC] pairs left after check_duplicates
-  int* touch_off;            // [J*SC + 1] chunk offsets of the touch kernel
+  int* touch_off;            // [J*SC + 1] (unused since the touch kernel runs one CTA per contour)
   u64* pairs2;               // [J][SC][PC]  pairs left after check_duplicates (unordered)
   u64* hk;                   // [J][SC][2*PC]
   u32 *hv1, *hv2;            // [J][2*PC]

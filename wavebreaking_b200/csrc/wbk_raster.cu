@@ -57,36 +57,8 @@ __device__ __forceinline__ void dd_merge(DD& a, double hi, double lo) {
   dd_add(a, hi);
   a.lo = __dadd_rn(a.lo, lo);
 }
-// deterministic block-wide double-double sum; result (rounded to double) to every thread
-__device__ inline double dd_block_sum(DD v, double* scratch /* >= 66 doubles */) {
-  const int lane = wbk_lane(), warp = wbk_warp(), nwarps = wbk_nthreads() >> 5;
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) {
-    const double oh = __shfl_xor_sync(WBK_FULL, v.hi, d), ol = __shfl_xor_sync(WBK_FULL, v.lo, d);
-    dd_merge(v, oh, ol);
-  }
-  __syncthreads();
-  if (lane == 0) {
-    scratch[2 * warp] = v.hi;
-    scratch[2 * warp + 1] = v.lo;
-  }
-  __syncthreads();
-  if (warp == 0) {
-    DD w;
-    w.hi = lane < nwarps ? scratch[2 * lane] : 0.0;
-    w.lo = lane < nwarps ? scratch[2 * lane + 1] : 0.0;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-      const double oh = __shfl_xor_sync(WBK_FULL, w.hi, d), ol = __shfl_xor_sync(WBK_FULL, w.lo, d);
-      dd_merge(w, oh, ol);
-    }
-    if (lane == 0) scratch[64] = __dadd_rn(w.hi, w.lo);
-  }
-  __syncthreads();
-  return scratch[64];
-}
-
-// six double-double sums at once (one pair of barriers instead of six): out[k] to every thread.
+// deterministic block-wide double-double sums, six at once (one pair of barriers): out[k] (rounded to double) to
+// every thread.
 // scratch: >= 6 * 2 * 32 + 6 doubles
 __device__ inline void dd_block_sum6(DD (&v)[6], double* scratch, double (&out)[6]) {
   const int lane = wbk_lane(), warp = wbk_warp(), nwarps = wbk_nthreads() >> 5;
@@ -107,7 +79,7 @@ __device__ inline void dd_block_sum6(DD (&v)[6], double* scratch, double (&out)[
     }
   }
   __syncthreads();
-  if (warp < 6) {  // warp k reduces sum k (same lane order as dd_block_sum: deterministic)
+  if (warp < 6) {  // warp k reduces sum k (fixed lane order: deterministic)
     DD w;
     w.hi = lane < nwarps ? scratch[(warp * 32 + lane) * 2] : 0.0;
     w.lo = lane < nwarps ? scratch[(warp * 32 + lane) * 2 + 1] : 0.0;
