@@ -346,10 +346,13 @@ events_raster_kernel(WbkDev d, WbkIdx x, const int* __restrict__ job_off, const 
       T dpre[RS_PRE];
 #pragma unroll
       for (int k = 0; k < RS_PRE; ++k) {
-        const int px = cx0 + lane + 32 * k;
-        const int xf = fold_x(px, nlon);
-        dpre[k] = lane + 32 * k < cw ? data[rowbase + xf] : (T)0;
+        dpre[k] = (T)0;
+        if (32 * k < cw) {  // warp-uniform
+          const int px = cx0 + lane + 32 * k;
+          if (lane + 32 * k < cw) dpre[k] = data[rowbase + fold_x(px, nlon)];
+        }
       }
+      int8_t* frow = flags ? flags + (((size_t)kind * ntime + t) * nlat + y) * nlon : nullptr;
       if (!boxfast) raster_scan_row(rv, y, cx0, cw, acc, flg, r2_prop, r2_flag, rmax, R, elist, ecount);
       const double a = area[y];
       int row_members = 0;
@@ -365,9 +368,9 @@ events_raster_kernel(WbkDev d, WbkIdx x, const int* __restrict__ job_off, const 
           dd_add(s_x, __dmul_rn((double)px, a));
           ++row_members;
         }
-        if (flags && split != 1 && (in || (f & 2u))) {
+        if (frow && split != 1 && (in || (f & 2u))) {
           const int xf = px - shift;
-          if (xf >= 0 && xf < nlon) flags[(((size_t)kind * ntime + t) * nlat + y) * nlon + xf] = 1;
+          if (xf >= 0 && xf < nlon) frow[xf] = 1;
         }
       };
 #pragma unroll
