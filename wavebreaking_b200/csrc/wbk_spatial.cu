@@ -323,7 +323,9 @@ smooth_fused_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, int nlat
         }
       }
     }
-    __syncthreads();  // the halo buffers (and the parked tile) are reused by the next tile
+    // the halo buffers are reused by the next tile: its __syncthreads_or (before the first pass) already orders that;
+    // only the parked tile of the fused variant needs a barrier of its own
+    if (FUSE) __syncthreads();
   }
 }
 
