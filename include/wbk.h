@@ -35,6 +35,7 @@ extern "C" {
 
 #define WBK_F32 0
 #define WBK_F64 1
+#define WBK_I16 2 /* packed NetCDF shorts (input of wbk_smooth / wbk_smooth_contours / wbk_orient only) */
 
 /* rounding of the smoothing passes (scipy keeps the input dtype, the division by
  * np.sum(weights) promotes float32 to float64 under NumPy >= 2) */
@@ -67,10 +68,28 @@ int wbk_device_count(void);
  *   (out_dtype: F64 for ROUND_NONE / ROUND_FIRST, F32 for ROUND_ALL; passes == 0 needs
  *   out_dtype == in_dtype).  d_tmp (same size as d_out) is needed only if
  *   passes > WBK_SMOOTH_MAX_FUSED, else may be NULL.
+ *
+ * opts (may be NULL) describes how d_in is stored; the result is always in the ascending orientation:
+ *   flip_lat / flip_lon   the latitude / longitude coordinate of d_in is descending
+ *                         (utils/data_utils.py:196-213 correct_dimension_orientation; ERA5 files are lat-descending):
+ *                         the kernel reads row nlat-1-y / column nlon-1-x, no re-sorted copy is made;
+ *   scale, offset, fill   in_dtype == WBK_I16 only: CF packing of NetCDF files, decoded the way xarray does,
+ *                         float64(v) * scale_factor + add_offset (two roundings), v == fill -> NaN when has_fill
+ *                         (round_mode must be WBK_ROUND_NONE and out_dtype WBK_F64).
  */
 #define WBK_SMOOTH_MAX_FUSED 8
+typedef struct wbk_smooth_opts {
+  int flip_lat, flip_lon;
+  double scale, offset;
+  int has_fill, fill;
+} wbk_smooth_opts;
 int wbk_smooth(const void* d_in, int in_dtype, void* d_out, int out_dtype, void* d_tmp, int ntime, int nlat,
-               int nlon, int passes, int round_mode, void* stream);
+               int nlon, int passes, int round_mode, const wbk_smooth_opts* opts, void* stream);
+
+/* orientation fix (and int16 decode) alone: d_out[t, y, x] = decode(d_in[t, flip_lat ? nlat-1-y : y,
+ * flip_lon ? nlon-1-x : x]); output dtype = in_dtype, float64 for WBK_I16 */
+int wbk_orient(const void* d_in, int in_dtype, void* d_out, int ntime, int nlat, int nlon, const wbk_smooth_opts* opts,
+               void* stream);
 
 /* spatial.py:103 with user-supplied weights / mode: ONE pass of
  * scipy.ndimage.convolve(in, weights, mode, cval=0) (output dtype = dtype, accumulation in
@@ -129,12 +148,14 @@ int wbk_destroy(wbk_ctx* ctx);
  */
 int wbk_contours(wbk_ctx* ctx, const void* d_field, int dtype, int ntime, const double* h_levels, int nlevels,
                  void* stream);
-/* calculate_smoothed_field + calculate_contours in one pass over the field (float32 under NumPy >= 2 promotion or
- * float64 input, float64 smoothed output, 1..WBK_SMOOTH_MAX_FUSED passes): the marching-squares stage runs on the
- * smoothed tiles while they are still on chip, so the smoothed field is written once and not re-read.  Results are
- * identical to wbk_smooth followed by wbk_contours. */
+/* calculate_smoothed_field + calculate_contours without re-reading the smoothed field (float32 under NumPy >= 2
+ * promotion, float64 or packed int16 input; float64 smoothed output; 1..WBK_SMOOTH_MAX_FUSED passes): the smoothing
+ * kernel leaves, next to the smoothed field, two bits per cell and level ("value > level", "is NaN"; ballots of the
+ * values it holds in registers) and the marching-squares stage classifies the squares on those bit planes, fetching
+ * the four corner values only for the squares a contour crosses.  Results are identical to wbk_smooth followed by
+ * wbk_contours.  opts: as for wbk_smooth. */
 int wbk_smooth_contours(wbk_ctx* ctx, const void* d_in, int in_dtype, double* d_smoothed, int ntime, int passes,
-                        const double* h_levels, int nlevels, void* stream);
+                        const double* h_levels, int nlevels, const wbk_smooth_opts* opts, void* stream);
 /* per-job results of the last wbk_contours (synchronises the stream): number of contours, number
  * of contour points, status bits (WBK_ST_*), and the batch-wide maximum number of distinct
  * columns of a contour (exp_lon.max() / dlon).  Arrays have ntime*nlevels entries. */
@@ -193,6 +214,17 @@ int wbk_events_raster(wbk_ctx* ctx, const int* d_job_off, const int* d_pt_off, c
                       const double* d_coords, const void* d_data, int dtype, const void* d_intensity, int ntime,
                       int8_t* d_flags, const wbk_index_params* params, void* stream);
 
+/* Near-threshold decisions of the streamer pair scan of the last wbk_index_run (streamer_index.py:130-139): every
+ * pair (i < j, |x_i - x_j| <= 120) for which `geo < geo_dis` or `cont > cont_dis` was decided within 1e-9 (relative)
+ * of its threshold while the other test passed or was in its band too -- the pairs that were KEPT and the pairs that
+ * were REJECTED.  (CUDA's sin / asin differ from glibc's by <= 2 ulp, so these are the only pairs whose membership
+ * may differ from the reference.)  Inside the band `cont` is summed in the reference's order (on[i+1] + ... + on[j]).
+ * Record = 4 ints: job, contour (index into the packed set), i, j | kept << 28 | geo_in_band << 29 | cont_in_band << 30.
+ * Copies min(cap, WBK_NEAR_CAP) records to d_recs and the number of decisions seen to *d_count (device memory,
+ * asynchronous). */
+#define WBK_NEAR_CAP 4096
+int wbk_near_list(wbk_ctx* ctx, int* d_recs, int cap, int* d_count, void* stream);
+
 /* per-kind, per-job event counts of the last wbk_index_run (synchronises): h_counts [3][njobs] */
 int wbk_events_counts(wbk_ctx* ctx, int* h_counts, int* h_status, void* stream);
 /* events of one kind, job-major in reference row order: h_ints [n][WBK_EV_INTS], h_f64 [n][WBK_EV_F64], h_job [n] */
@@ -242,12 +274,37 @@ const char* wbk_prof_name(int k);
 /* total number of kernel launches issued by the library in this process (always counted) */
 long long wbk_launch_count(void);
 
-/* wavebreaking/processing/events.py:205-214 track_events(method="by_overlap"): areas of event pairs.
+/* ---------------------------------------------------------------------------------------------
+ * wavebreaking/processing/events.py:113-241 track_events.  Events are sorted by date on the host; everything
+ * that scales with the number of event pairs runs here.
+ *
+ * wbk_track_candidates (events.py:160-181): d_lo / d_hi [n] give, per event i, the index window [lo, hi) of the
+ * events j with 0 < date_j - date_i <= time_range.  Appends every (i, j) of the windows whose integer bounding
+ * boxes d_bbox [n][4] = x0, y0, x1, y1 intersect (d_bbox NULL: all of them) to d_pairs [cap][2], in no particular
+ * order; *d_count receives the number found (> cap: the caller retries with a larger buffer). */
+int wbk_track_candidates(const int* d_lo, const int* d_hi, const int* d_bbox, int n, int* d_pairs, int cap,
+                         int* d_count, void* stream);
+
+/* events.py:205-214 with overlap = 0 (`inter.area / union.area > 0`), decided exactly for lattice polygons
+ * (integer vertices in [0, 4096)).  d_edges [V][4]: for every vertex its edge x0, y0, x1, y1 to the next vertex of
+ * its ring; d_vsign [V]: orientation of the vertex's ring (+1 counter-clockwise, -1 clockwise, 0 degenerate);
+ * ring r = vertices [d_ring_off[r], d_ring_off[r+1]), polygon p = rings [d_poly_off[p], d_poly_off[p+1]) (non-zero
+ * winding over all rings).  d_result[k]: bit 0 = the polygons of pair k share a region of positive area, bit 1 =
+ * their boundaries touch without crossing (decided piece by piece). */
+int wbk_track_overlap_exact(const int* d_edges, const int* d_vsign, const int* d_ring_off, const int* d_poly_off,
+                            const int* d_pairs, int npairs, int* d_result, void* stream);
+
+/* events.py:205-214 for overlap > 0: float64 areas of event pairs.
  * Polygons are given as rings of double (x, y) vertices: polygon p = rings [d_poly_off[p], d_poly_off[p+1]),
  * ring r = vertices [d_ring_off[r], d_ring_off[r+1]) of d_xy (open rings).  For pair k = (d_pairs[2k],
  * d_pairs[2k+1]) writes d_out[3k..3k+2] = area(A), area(B), area(A n B). */
 int wbk_track_overlap(const double* d_xy, const int* d_ring_off, const int* d_poly_off, const int* d_pairs, int npairs,
                       double* d_out, void* stream);
+
+/* events.py:187-201 by_distance: sklearn's haversine (unit sphere, radians) of the rows d_rad [n][2] of every
+ * pair, in sklearn's operand order; d_out [npairs].  CUDA's libm differs from glibc's by <= 2 ulp: the caller
+ * re-decides pairs within 1e-9 of its threshold on the host. */
+int wbk_track_distance(const double* d_rad, const int* d_pairs, int npairs, double* d_out, void* stream);
 
 #ifdef __cplusplus
 }

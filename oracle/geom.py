@@ -351,3 +351,78 @@ def overlap_areas(rings_a, rings_b):
         area[1] += h[inb].sum()
         area[2] += h[ina & inb].sum()
     return float(area[0]), float(area[1]), float(area[2])
+
+
+# --------------------------------------------------------------------------- exact overlap decision
+def overlap_positive_exact(rings_a, rings_b):
+    """True iff the (multi)polygons A and B (lattice rings, non-zero winding) share a region of positive area --
+    what ``geom1.intersection(geom2).area > 0`` means in ``processing/events.py:205-214`` (GEOS returns an empty or
+    lower-dimensional intersection for polygons that merely touch).
+
+    Exact rational slab decomposition, independent of the product's crossing / touching rules: between two
+    consecutive abscissae of the vertices and edge-edge intersection points no two edges cross, so the edges
+    spanning the slab are ordered by their ordinate at the slab centre and the winding numbers of A and B are swept
+    upwards; a slab piece where both are non-zero and whose centre height is positive proves the overlap.
+    ``fractions.Fraction`` throughout; only the part of the plane where the bounding boxes intersect is swept.
+    """
+    def edges_of(rings):
+        out = []
+        for ring in rings:
+            ring = [(int(x), int(y)) for x, y in np.asarray(ring).reshape(-1, 2)]
+            for i in range(len(ring)):
+                a, b = ring[i], ring[(i + 1) % len(ring)]
+                if a != b:
+                    out.append((a[0], a[1], b[0], b[1]))
+        return out
+
+    ea, eb = edges_of(rings_a), edges_of(rings_b)
+    if not ea or not eb:
+        return False
+    xa0, xa1 = min(min(e[0], e[2]) for e in ea), max(max(e[0], e[2]) for e in ea)
+    xb0, xb1 = min(min(e[0], e[2]) for e in eb), max(max(e[0], e[2]) for e in eb)
+    xl, xr = max(xa0, xb0), min(xa1, xb1)
+    if xl >= xr:
+        return False
+    edges = [(e, 0) for e in ea] + [(e, 1) for e in eb]
+    # only non-vertical edges that reach into (xl, xr) matter
+    edges = [(e, o) for e, o in edges if e[0] != e[2] and min(e[0], e[2]) < xr and max(e[0], e[2]) > xl]
+    E = np.array([e for e, _ in edges], dtype=np.int64).reshape(-1, 4)
+    xs = {Fraction(xl), Fraction(xr)}
+    for e, _ in edges:
+        for x in (e[0], e[2]):
+            if xl < x < xr:
+                xs.add(Fraction(x))
+    # intersection abscissae of every pair of these edges (integer prefilter, exact rational points)
+    n = len(edges)
+    if n > 1:
+        x1, y1, x2, y2 = (E[:, k][:, None] for k in range(4))
+        x3, y3, x4, y4 = (E[:, k][None, :] for k in range(4))
+        den = (x1 - x2) * (y3 - y4) - (y1 - y2) * (x3 - x4)
+        tn = (x1 - x3) * (y3 - y4) - (y1 - y3) * (x3 - x4)
+        un = (x1 - x3) * (y1 - y2) - (y1 - y3) * (x1 - x2)
+        sg = np.sign(den)
+        hit = (den != 0) & (tn * sg > 0) & (tn * sg < den * sg) & (un * sg > 0) & (un * sg < den * sg)
+        for i, j in zip(*np.nonzero(np.triu(hit, 1))):
+            x = Fraction(int(E[i, 0])) + Fraction(int(tn[i, j]), int(den[i, j])) * int(E[i, 2] - E[i, 0])
+            if xl < x < xr:
+                xs.add(x)
+    xs = sorted(xs)
+    for a, b in zip(xs[:-1], xs[1:]):
+        xm = (a + b) / 2
+        span = []
+        for (x0, y0, x1_, y1_), owner in edges:
+            lo, hi = (x0, x1_) if x0 < x1_ else (x1_, x0)
+            if lo <= a and hi >= b:
+                ym = Fraction(y0) + Fraction(y1_ - y0, x1_ - x0) * (xm - x0)
+                span.append((ym, owner, 1 if x1_ > x0 else -1))
+        span.sort(key=lambda s: s[0])
+        wa = wb = 0
+        for k in range(len(span) - 1):
+            ym, owner, dw = span[k]
+            if owner == 0:
+                wa += dw
+            else:
+                wb += dw
+            if wa != 0 and wb != 0 and span[k + 1][0] > ym:
+                return True
+    return False

@@ -546,8 +546,9 @@ def to_xarray(data, events, grid, flag="ones"):
     return flagged
 
 
-def track_events(events, time_range=None, method="by_overlap", buffer=0, overlap=0, distance=1000):
-    """``track_events`` (processing/events.py:151-241); ``buffer`` must be 0 (no GEOS here)."""
+def track_events(events, time_range=None, method="by_overlap", buffer=0, overlap=0, distance=1000, _memo=None):
+    """``track_events`` (processing/events.py:151-241); ``buffer`` must be 0 (no GEOS here).
+    ``_memo`` (tests): dict that caches the per-pair areas between calls on the same table."""
     events = events.reset_index(drop=True)
     if len(events) == 0:
         raise ValueError("geopandas.GeoDataFrame is empty!")
@@ -575,8 +576,38 @@ def track_events(events, time_range=None, method="by_overlap", buffer=0, overlap
         if buffer != 0:
             raise NotImplementedError("oracle restates by_overlap for buffer=0 only")
         check = []
+        geoms = [[np.asarray(r).reshape(-1, 2) for r in g] for g in events.geometry]
+        boxes = [(min(r[:, 0].min() for r in g), min(r[:, 1].min() for r in g), max(r[:, 0].max() for r in g),
+                  max(r[:, 1].max() for r in g)) if len(g) else None for g in geoms]
+        lattice = all(np.array_equal(r, np.rint(r)) for g in geoms for r in g)
         for a, b in range_comb:
-            a1, a2, inter = geom.overlap_areas(events.geometry.iloc[a], events.geometry.iloc[b])
+            ba, bb = boxes[a], boxes[b]
+            if ba is None or bb is None:
+                check.append(False if overlap >= 0 else (ba is not None or bb is not None))
+                continue
+            if ba[2] < bb[0] or bb[2] < ba[0] or ba[3] < bb[1] or bb[3] < ba[1]:
+                # disjoint boxes: the intersection is empty, 0 / union
+                check.append(0.0 > overlap)
+                continue
+            key = (int(a), int(b))
+            if _memo is not None and key in _memo:
+                a1, a2, inter = _memo[key]
+            else:
+                if lattice:
+                    # GEOS' overlay is robust: polygons that merely touch give area 0.0, overlapping ones a positive
+                    # area.  A float64 sum is not, so the sign of the intersection area is decided exactly and the
+                    # float64 area is only evaluated where it is positive.
+                    a1 = sum(abs(geom._ring_area2([(int(x), int(y)) for x, y in r])) for r in geoms[a]) / 2.0
+                    a2 = sum(abs(geom._ring_area2([(int(x), int(y)) for x, y in r])) for r in geoms[b]) / 2.0
+                    a1, a2 = float(a1), float(a2)
+                    if geom.overlap_positive_exact(geoms[a], geoms[b]):
+                        inter = max(geom.overlap_areas(geoms[a], geoms[b])[2], np.finfo(np.float64).tiny)
+                    else:
+                        inter = 0.0
+                else:
+                    a1, a2, inter = geom.overlap_areas(geoms[a], geoms[b])
+                if _memo is not None:
+                    _memo[key] = (a1, a2, inter)
             with np.errstate(divide="ignore", invalid="ignore"):
                 check.append(np.float64(inter) / np.float64(a2 + a1 - inter) > overlap)
         combine = range_comb[np.asarray(check, dtype=bool)]

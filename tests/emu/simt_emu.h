@@ -28,6 +28,7 @@
 #define __launch_bounds__(...)
 #define __shared__ static
 #define __constant__ static
+#define __align__(n) __attribute__((aligned(n)))
 
 struct dim3 {
   unsigned x, y, z;
@@ -241,5 +242,6 @@ struct uint4 { unsigned x, y, z, w; };
 inline float __sinf(float v) { return std::sin(v); }
 inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
 inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
+inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { uint4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 inline float __uint_as_float(unsigned v) { float f; std::memcpy(&f, &v, 4); return f; }
 inline unsigned __float_as_uint(float f) { unsigned v; std::memcpy(&v, &f, 4); return v; }

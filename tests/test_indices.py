@@ -134,3 +134,46 @@ def test_indices_gpu(gpu, shape, levels, nt):
     c, want = oracle_case(grid, sm, levels)
     assert sum(len(v) for v in want.values()) > 0
     compare_events(cs, tables, flags, want, grid, levels, sm)
+
+
+def test_near_threshold_pairs_are_listed_kept_and_rejected_emu(emu):
+    """north_star: a streamer-pair difference is allowed only where a distance lies within tolerance of geo_dis /
+    cont_dis 'and such pairs are listed'.  Thresholds are placed 1e-12 (relative) above / below the distance of one
+    pair: the pair must appear in the near list of the batch both when it is kept and when it is rejected."""
+    from wavebreaking_b200 import pipeline, spatial, synthetic
+
+    nlat, nlon = 91, 180
+    lat, lon = synthetic.grid_coords(nlat, nlon)
+    raw = synthetic.pv_field(nlat, nlon, np.array([6.0]))
+    grid = P.Grid(lon, lat, synthetic.time_axis(1, 6))
+    base = pipeline.Detector(lat, lon, levels=[2.0]).run_batch(spatial.to_device(raw))
+    assert base.near_total == 0 and len(base.near) == 0
+    cs = base.contours
+    h = cs.host()
+    c = int(np.argmax(h["nx"]))  # the full-width contour
+    pts = cs.contour_points(c)
+    diag = {}
+    P.streamer_basepoints(pts, grid, diagnostics=diag)
+    on = diag["on"]
+    x = pts[:, 0]
+    # a pair well inside the cont test whose geo distance becomes the threshold, and one for the cont threshold
+    geo = P.dist.pairwise(np.radians(np.c_[lat[pts[:, 1]], lon[x % nlon]])) * 6371
+    cont = np.cumsum(np.triu(np.tile(on, (len(on), 1)), k=1), axis=1)
+    ii, jj = np.nonzero((np.abs(x[:, None] - x[None, :]) <= 120) & (cont > 2500) & (geo > 300) & (geo < 1200))
+    assert len(ii)
+    i, j = int(ii[len(ii) // 2]), int(jj[len(ii) // 2])
+    for which, value in (("geo_dis", geo[i, j]), ("cont_dis", cont[i, j])):
+        for factor, bit in ((1 + 1e-12, None), (1 - 1e-12, None)):
+            kw = {which: float(value) * factor}
+            if which == "cont_dis":
+                kw["geo_dis"] = float(geo[i, j]) * 1.5
+            res = pipeline.Detector(lat, lon, levels=[2.0], **kw).run_batch(spatial.to_device(raw))
+            rec = res.near[(res.near[:, 3] == i) & (res.near[:, 4] == j)]
+            assert len(rec) == 1, (which, factor, res.near)
+            flags = int(rec[0, 5])
+            assert flags & (2 if which == "geo_dis" else 4)
+            if which == "geo_dis":
+                assert bool(flags & 1) == (geo[i, j] < kw[which])  # kept iff strictly below the threshold
+            else:
+                assert bool(flags & 1) == (cont[i, j] > kw[which])  # the reference's row cumsum decides inside the band
+            assert res.near_total == len(res.near) >= 1

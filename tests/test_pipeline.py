@@ -93,3 +93,34 @@ def test_fused_smoothing_contours_equals_separate_gpu(gpu):
     a = pipeline.Detector(lat, lon, levels=[2.0, 1.5], fuse=True).run_batch(raw)
     b = pipeline.Detector(lat, lon, levels=[2.0, 1.5], fuse=False).run_batch(raw)
     _same_result(a, b)
+
+
+def test_stream_uses_the_global_exp_lon_maximum_emu(emu, caplog):
+    """exp_lon.max() is global over all dates (streamer_index.py:106): a batch WITHOUT a circumglobal contour must not
+    promote its widest contour to 'full width'.  Stream of two batches vs. one call on the concatenated record."""
+    import logging
+
+    nlat, nlon = 46, 90
+    lat, lon = synthetic.grid_coords(nlat, nlon)
+    raw = synthetic.pv_field(nlat, nlon, np.arange(2) * 6.0)
+    # second batch: the field is capped below the contour level over a band of longitudes, so no contour is circumglobal
+    broken = raw.copy()
+    broken[:, :, 30:40] = np.minimum(broken[:, :, 30:40], 0.5)
+    record = np.concatenate([raw, broken])
+    det = pipeline.Detector(lat, lon, levels=[2.0])
+    whole = det.run_batch(spatial.to_device(record))
+    assert whole.contours.max_nx == nlon + det.add
+    parts = [(pipeline.summarize(r), r.flags.cpu().numpy().copy()) for r in
+             det.stream([spatial.to_device(raw), spatial.to_device(broken)], depth=1)]
+    assert parts[1][0]["streamers"] == 0 and parts[1][0]["overturnings"] == 0
+    flags = np.concatenate([p[1] for p in parts], axis=1)
+    assert np.array_equal(flags, whole.flags.cpu().numpy())
+    for k in ("streamers", "overturnings", "cutoffs"):
+        assert parts[0][0][k] + parts[1][0][k] == len(whole.tables[k])
+    # per-batch maxima (the old default) give a different, wrong answer for the second batch
+    own = list(det.stream([spatial.to_device(broken)], depth=1, gmax_nx=None))[0]
+    assert pipeline.summarize(own)["cutoffs"] != parts[1][0]["cutoffs"] or pipeline.summarize(own)["streamers"] > 0
+    # a record without any circumglobal contour is reported
+    with caplog.at_level(logging.WARNING, logger="wavebreaking_b200.pipeline"):
+        list(det.stream([spatial.to_device(broken)], depth=1))
+    assert "re-run with gmax_nx" in caplog.text

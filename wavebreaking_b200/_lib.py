@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 DEFAULT_PATH = os.path.join(HERE, "libwbk.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_NODEVICE = 0, -1, -2, -3, -4
-F32, F64 = 0, 1
+F32, F64, I16 = 0, 1, 2
 ROUND_NONE, ROUND_FIRST, ROUND_ALL = 0, 1, 2
 SMOOTH_MAX_FUSED = 8
 
@@ -46,6 +46,18 @@ class Caps(ctypes.Structure):
                 ("pair_cap", c_int), ("event_cap", c_int)]
 
 
+class SmoothOpts(ctypes.Structure):
+    """wbk_smooth_opts (include/wbk.h): storage orientation / CF packing of the input field."""
+
+    _fields_ = [("flip_lat", c_int), ("flip_lon", c_int), ("scale", c_double), ("offset", c_double),
+                ("has_fill", c_int), ("fill", c_int)]
+
+
+def smooth_opts(flip_lat=False, flip_lon=False, scale=1.0, offset=0.0, fill=None):
+    return SmoothOpts(int(bool(flip_lat)), int(bool(flip_lon)), float(scale), float(offset),
+                      int(fill is not None), int(fill) if fill is not None else 0)
+
+
 class IndexParams(ctypes.Structure):
     """wbk_index_params (include/wbk.h)."""
 
@@ -56,12 +68,14 @@ class IndexParams(ctypes.Structure):
 
 EV_STREAMER, EV_OVERTURNING, EV_CUTOFF = 0, 1, 2
 EV_INTS, EV_F64 = 10, 6
+NEAR_CAP = 4096
 
 _SIGNATURES = {
     "wbk_index_run": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
                               c_void_p, POINTER(IndexParams), c_void_p]),
     "wbk_events_raster": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int,
                                   c_void_p, POINTER(IndexParams), c_void_p]),
+    "wbk_near_list": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "wbk_events_counts": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), c_void_p]),
     "wbk_events_fetch": (c_int, [c_void_p, c_int, c_int, POINTER(c_int), POINTER(c_double), POINTER(c_int), c_void_p]),
     "wbk_rasterize_rings": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double,
@@ -70,7 +84,9 @@ _SIGNATURES = {
     "wbk_create": (c_int, [POINTER(c_void_p), POINTER(Caps), c_int, c_int, c_int, c_void_p, c_size_t]),
     "wbk_destroy": (c_int, [c_void_p]),
     "wbk_contours": (c_int, [c_void_p, c_void_p, c_int, c_int, POINTER(c_double), c_int, c_void_p]),
-    "wbk_smooth_contours": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, POINTER(c_double), c_int, c_void_p]),
+    "wbk_smooth_contours": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, POINTER(c_double), c_int,
+                                    POINTER(SmoothOpts), c_void_p]),
+    "wbk_orient": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, POINTER(SmoothOpts), c_void_p]),
     "wbk_contours_counts": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int), c_void_p]),
     "wbk_contours_pack": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p]),
@@ -78,6 +94,9 @@ _SIGNATURES = {
     "wbk_batch_fetch": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                 c_int, c_void_p, c_void_p]),
     "wbk_track_overlap": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "wbk_track_candidates": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    "wbk_track_overlap_exact": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "wbk_track_distance": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "wbk_prof_enable": (c_int, [c_int]),
     "wbk_prof_reset": (c_int, []),
     "wbk_prof_read": (c_int, [POINTER(c_int), POINTER(c_double)]),
@@ -86,7 +105,8 @@ _SIGNATURES = {
     "wbk_last_error": (c_char_p, []),
     "wbk_version": (c_int, []),
     "wbk_device_count": (c_int, []),
-    "wbk_smooth": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "wbk_smooth": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                           POINTER(SmoothOpts), c_void_p]),
     "wbk_convolve2d": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, POINTER(c_double), c_int,
                                c_int, c_int, c_int, c_double, c_void_p]),
     "wbk_nan_border": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
@@ -191,4 +211,6 @@ def dtype_code(torch_dtype):
         return F32
     if torch_dtype == torch.float64:
         return F64
+    if torch_dtype == torch.int16:
+        return I16
     raise TypeError("only float32 / float64 fields are supported, got {}".format(torch_dtype))

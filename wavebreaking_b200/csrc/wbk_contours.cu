@@ -39,6 +39,8 @@ size_t layout(WbkDev& d, const wbk_caps& c, int nlat, int nlon, int add, unsigne
   d.cymax = b.take<int>(J * CC); d.cout = b.take<int>(J * CC); d.cand = b.take<int>(J * CC * 2);
   d.out_pts = b.take<u32>(J * R); d.out_tab = b.take<int>(J * CC * 4); d.out_sumy = b.take<int>(J * CC);
   d.out_nc = b.take<int>(J); d.out_np = b.take<int>(J); d.max_nx = b.take<int>(64);
+  // comparison bit planes of the fused smoothing: <= 4 words per (job, row, strip), strips of >= 48 valid columns
+  d.planes = b.take<u32>(J * 4 * (size_t)nlat * (size_t)((nlon + 47) / 48));
   return (b.off + 255) & ~(size_t)255;
 }
 
@@ -728,11 +730,123 @@ extern "C" int wbk_contours(wbk_ctx* ctx, const void* d_field, int dtype, int nt
   return WBK_OK;
 }
 
-int wbk_launch_smooth_ms(const void* d_in, int in_dtype, double* d_out, int ntime, int nlat, int nlon, int passes,
-                         const WbkDev& dev, const LevelPack& lv, int nlevels, cudaStream_t st);  // wbk_spatial.cu
+// ------------------------------------------------------------------------------------------ K3b
+// Marching squares on the comparison bit planes the smoothing kernel leaves behind (wbk_smooth.cu): the smoothed
+// field is not re-read; only the four corner values of the squares a contour actually crosses are fetched.
+// One thread per (time step, chunk of MSP_ROWS rows, strip): it turns the even / odd column words of two
+// consecutive rows into 64-column bit rows (the column right of the strip comes from the next strip's first valid
+// column, the last strip wraps to column 0 = the periodic extension) and classifies all squares of the row with
+// the same bit expression as ms_segments_kernel.  Hits are compacted per warp and emitted by ms_emit_squares.
+#define MSP_THREADS 128
+#define MSP_ROWS 8
+
+__device__ __forceinline__ u64 msp_spread(u32 v) {
+  u64 x = v;
+  x = (x | (x << 16)) & 0x0000ffff0000ffffULL;
+  x = (x | (x << 8)) & 0x00ff00ff00ff00ffULL;
+  x = (x | (x << 4)) & 0x0f0f0f0f0f0f0f0fULL;
+  x = (x | (x << 2)) & 0x3333333333333333ULL;
+  x = (x | (x << 1)) & 0x5555555555555555ULL;
+  return x;
+}
+
+struct MspGeom {
+  int nstrips, V, P, PW;  // strips per row, valid columns per strip, left halo (= passes), words per (t, row, strip)
+  int ntime, nchunks;
+};
+
+// 64-column bit row of plane word pair `w` (even, odd) of (t, row, strip s), bit j = strip column j; the bit right
+// of the last valid column is taken from the next strip
+__device__ __forceinline__ u64 msp_row(const u32* __restrict__ planes, const MspGeom& g, size_t row_base, int s, int w,
+                                       int vcols) {
+  const u32* p = planes + (row_base + s) * g.PW + w;
+  u64 m = msp_spread(p[0]) | (msp_spread(p[1]) << 1);
+  const int sn = s + 1 == g.nstrips ? 0 : s + 1;
+  const u32* q = planes + (row_base + sn) * g.PW + w;
+  const u32 nb = (q[g.P & 1] >> (g.P >> 1)) & 1u;  // strip column P of the next strip
+  const int j = g.P + vcols;                        // < 64
+  m = (m & ~(1ULL << j)) | ((u64)nb << j);
+  return m;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(MSP_THREADS)
+ms_planes_kernel(const T* __restrict__ field, const u32* __restrict__ planes, const __grid_constant__ WbkDev d,
+                 const __grid_constant__ LevelPack levels, int nlevels, const __grid_constant__ MspGeom g) {
+  __shared__ u32 smask[MSP_THREADS / 32][64];
+  const int lane = wbk_lane(), warp = wbk_warp();
+  const int nlat = d.nlat, nlon = d.nlon, W = d.W;
+  // items of one time step are padded to whole warps, so that a warp emits into ONE job per level
+  const int per_t = g.nchunks * g.nstrips, wpt = (per_t + 31) / 32;
+  const long long wglobal = (long long)blockIdx.x * (MSP_THREADS / 32) + warp;
+  if (wglobal >= (long long)g.ntime * wpt) return;  // whole warp
+  const int t = (int)(wglobal / wpt);
+  const int item0 = (int)(wglobal % wpt) * 32;  // first item of this warp within the time step
+  const bool live = item0 + lane < per_t;
+  const int it = live ? item0 + lane : 0;  // dead lanes shadow item 0 with an empty square mask
+  const int s = it % g.nstrips, chunk = it / g.nstrips;
+  const int r_begin = chunk * MSP_ROWS;
+  const int r_end = min(r_begin + MSP_ROWS, nlat - 1);  // squares r0 in [r_begin, r_end)
+  const int vcols = min(g.V, nlon - s * g.V);
+  // squares owned by this strip: strip columns [P, P + vcols) whose base square exists (c0 <= W - 2)
+  const int c_first = s * g.V;
+  int nsq = min(vcols, W - 1 - c_first);
+  if (nsq < 0 || !live) nsq = 0;
+  const u64 sqmask = nsq >= 64 ? ~0ULL : (((1ULL << nsq) - 1ULL) << g.P);
+  const size_t trow = (size_t)t * nlat;
+  const T* src = field + trow * nlon;
+
+  for (int l = 0; l < nlevels; ++l) {
+    u64 g0 = msp_row(planes, g, (trow + r_begin) * g.nstrips, s, 2 + 2 * l, vcols);
+    u64 n0 = msp_row(planes, g, (trow + r_begin) * g.nstrips, s, 0, vcols);
+    for (int r = r_begin; r < r_begin + MSP_ROWS; ++r) {  // warp-uniform trip count
+      u64 hits = 0, g1 = 0, n1 = 0;
+      if (r < r_end) {
+        g1 = msp_row(planes, g, (trow + r + 1) * g.nstrips, s, 2 + 2 * l, vcols);
+        n1 = msp_row(planes, g, (trow + r + 1) * g.nstrips, s, 0, vcols);
+        const u64 both = g0 & g1, either = g0 | g1, nn = n0 | n1;
+        hits = ((either | (either >> 1)) & ~(both & (both >> 1))) & ~(nn | (nn >> 1)) & sqmask;
+      }
+      g0 = g1;
+      n0 = n1;
+      if (!__any_sync(WBK_FULL, hits != 0)) continue;
+      __syncwarp();
+      smask[warp][2 * lane] = (u32)hits;
+      smask[warp][2 * lane + 1] = (u32)(hits >> 32);
+      __syncwarp();
+      int total = 0;
+      for (int i = 0; i < 64; ++i) total += __popc(smask[warp][i]);
+      for (int h0 = 0; h0 < total; h0 += 32) {
+        const int h = h0 + lane;
+        int mi = 0, sl = 0, r0 = 0, c0 = 0;
+        double ul = 0, ur = 0, ll = 0, lr = 0;
+        const bool active = h < total && ms_locate_hit(smask[warp], 64, h, mi, sl);
+        if (active) {  // the hit belongs to the item of lane mi >> 1 (same time step, maybe another row chunk)
+          const int hit_item = item0 + (mi >> 1);
+          const int hs = hit_item % g.nstrips, hchunk = hit_item / g.nstrips;
+          r0 = hchunk * MSP_ROWS + (r - r_begin);
+          c0 = hs * g.V + ((mi & 1) * 32 + sl) - g.P;
+          const int cr = c0 + 1 == nlon ? 0 : c0 + 1;
+          ul = (double)src[(size_t)r0 * nlon + c0];
+          ur = (double)src[(size_t)r0 * nlon + cr];
+          ll = (double)src[(size_t)(r0 + 1) * nlon + c0];
+          lr = (double)src[(size_t)(r0 + 1) * nlon + cr];
+        }
+        ms_emit_squares(d, t * nlevels + l, active, r0, c0, ul, ur, ll, lr, levels.v[l]);
+      }
+      __syncwarp();
+    }
+  }
+}
+
+int wbk_launch_smooth(const void* d_in, int in_dtype, void* d_out, int out_dtype, int ntime, int nlat, int nlon, int passes,
+                      int round_mode, int nan_border, const wbk_smooth_opts* opts, u32* d_planes, const double* h_levels,
+                      int nlevels, cudaStream_t st);  // wbk_smooth.cu
+void wbk_smooth_plane_geometry(int nlon, int passes, int* nstrips, int* V);
 
 extern "C" int wbk_smooth_contours(wbk_ctx* ctx, const void* d_in, int in_dtype, double* d_smoothed, int ntime,
-                                   int passes, const double* h_levels, int nlevels, void* stream) {
+                                   int passes, const double* h_levels, int nlevels, const wbk_smooth_opts* opts,
+                                   void* stream) {
   if (!ctx || !d_in || !d_smoothed || !h_levels || ntime < 0 || nlevels < 1 || nlevels > WBK_MAX_LEVELS ||
       passes < 1 || passes > WBK_SMOOTH_MAX_FUSED || ctx->d.nlat < 4) {
     wbk_set_error("wbk_smooth_contours: invalid argument (1..%d passes, 1..%d levels)", WBK_SMOOTH_MAX_FUSED, WBK_MAX_LEVELS);
@@ -753,8 +867,25 @@ extern "C" int wbk_smooth_contours(wbk_ctx* ctx, const void* d_in, int in_dtype,
   WBK_CUDA_CHECK(cudaMemsetAsync(d.max_nx, 0, sizeof(int), st));
   LevelPack lv;
   for (int i = 0; i < WBK_MAX_LEVELS; ++i) lv.v[i] = i < nlevels ? h_levels[i] : 0.0;
-  const int rc = wbk_launch_smooth_ms(d_in, in_dtype, d_smoothed, ntime, d.nlat, d.nlon, passes, d, lv, nlevels, st);
+  const int rmode = in_dtype == WBK_F32 ? WBK_ROUND_FIRST : WBK_ROUND_NONE;
+  int rc = wbk_launch_smooth(d_in, in_dtype, d_smoothed, WBK_F64, ntime, d.nlat, d.nlon, passes, rmode, 2, opts, d.planes,
+                             h_levels, nlevels, st);
   if (rc != WBK_OK) return rc;
+  MspGeom g;
+  wbk_smooth_plane_geometry(d.nlon, passes, &g.nstrips, &g.V);
+  g.P = passes;
+  g.PW = 2 + 2 * nlevels;
+  g.ntime = ntime;
+  g.nchunks = (d.nlat - 1 + MSP_ROWS - 1) / MSP_ROWS;
+  const long long nwarps = (long long)ntime * ((g.nchunks * g.nstrips + 31) / 32);
+  const long long nblocks = (nwarps + MSP_THREADS / 32 - 1) / (MSP_THREADS / 32);
+  if (nblocks > 0x7fffffffLL) {
+    wbk_set_error("wbk_smooth_contours: batch too long, split the time axis");
+    return WBK_ERR_INVALID;
+  }
+  WBK_LAUNCH(KID_MS_SEGMENTS, ms_planes_kernel<double>, dim3((unsigned)nblocks), dim3(MSP_THREADS), 0, st,
+             (const double*)d_smoothed, (const u32*)d.planes, d, lv, nlevels, g);
+  WBK_LAUNCH_CHECK();
   WBK_LAUNCH(KID_CONTOUR_LINK, contour_link_kernel, dim3(njobs), dim3(WBK_CONTOUR_THREADS), 0, st, d, njobs);
   WBK_LAUNCH_CHECK();
   return WBK_OK;

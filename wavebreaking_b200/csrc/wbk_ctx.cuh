@@ -36,6 +36,7 @@ struct WbkDev {
   int* out_sumy;            // [J][CC]
   int *out_nc, *out_np;     // [J]
   int* max_nx;              // [1]
+  u32* planes;              // comparison bit planes written by the fused smoothing (wbk_smooth.cu), read by ms_planes_kernel
 };
 
 // Index-stage arenas.  PC = pair_cap rounded up to a power of two, EC = event_cap.
@@ -71,6 +72,10 @@ struct WbkIdx {
   int* split_ring;           // [SPR][4] start, len, time index, kind
   int* split_count;          // [0] vertex cursor, [1] ring cursor, [2] overflow flag, [3] split_list cursor
   int* split_list;           // [SPR] events (index in ev_off order) that straddle the last meridian
+  // near-threshold decisions of the streamer pair scan (accepted AND rejected pairs): job, contour, i, j | flags << 28
+  int NRC;                   // capacity of the list
+  int* near_rec;             // [NRC][4]
+  int* near_cnt;             // [1] number of decisions seen (may exceed NRC)
 };
 
 struct wbk_ctx {

@@ -53,6 +53,9 @@ size_t wbk_index_layout(struct wbk_ctx* ctx, unsigned char* base, size_t off) {
   x.split_ring = (int*)take((size_t)x.SPR * 4 * 4);
   x.split_count = (int*)take(64);
   x.split_list = (int*)take((size_t)x.SPR * 4);
+  x.NRC = WBK_NEAR_CAP;
+  x.near_rec = (int*)take((size_t)x.NRC * 4 * sizeof(int));
+  x.near_cnt = (int*)take(64);
   return (o + 255) & ~(size_t)255;
 }
 
@@ -455,7 +458,7 @@ __global__ void __launch_bounds__(ST_THREADS) streamer_prep_kernel(WbkDev d, Wbk
         const int xgap = max(max(bx[4 * bj] - bx[4 * bi + 1], bx[4 * bi] - bx[4 * bj + 1]), 0);
         if (xgap > 120) continue;  // |x1 - x2| <= 120 can not hold (streamer_index.py:157)
         // cont(i, j) = pfx[j] - pfx[i] <= max pfx(bj) - min pfx(bi) (the rounded subtraction is monotone)
-        if (!(__dsub_rn(bp[2 * bj + 1], bp[2 * bi]) > cont_dis)) continue;
+        if (!(__dsub_rn(bp[2 * bj + 1], bp[2 * bi]) > cont_dis * (1.0 - 2e-9))) continue;  // keeps the tolerance band
         // lower bound of the great-circle distance between the two blocks' bounding boxes: the latitude gap, and
         // the longitude gap at the most poleward latitude (h >= cos^2(lat_max) sin^2(dlon/2)); tiles that cannot
         // reach geo_dis are left out (1e-6 relative slack; x gaps <= 120 columns are never folded)
@@ -486,6 +489,7 @@ __global__ void __launch_bounds__(ST_THREADS) streamer_prep_kernel(WbkDev d, Wbk
 #define PS_WARPS (PS_THREADS / 32)
 #define PS_BUF 256
 __global__ void __launch_bounds__(PS_THREADS) pair_scan_kernel(WbkDev d, WbkIdx x, PackedSet ps, CoordTabs ct,
+                                                               const double* __restrict__ on,
                                                                const double* __restrict__ pfx, wbk_index_params prm,
                                                                int nslots) {
   __shared__ float4 sj4[PS_WARPS][PT];   // packed point (bits), lat, lon, cos(lat) of block bj in fp32
@@ -550,20 +554,52 @@ __global__ void __launch_bounds__(PS_THREADS) pair_scan_kernel(WbkDev d, WbkIdx 
         const u32 pj = __float_as_uint(q4.x);
         int dxi = xi - wbk_px(pj);
         if (dxi < 0) dxi = -dxi;
-        const double cont = __dsub_rn(sjpf[warp][jj], pfi);
-        // hard-coded 120 index units (streamer_index.py:157), cont > cont_dis (:138)
-        if (dxi <= 120 && cont > prm.cont_dis) {
+        double cont = __dsub_rn(sjpf[warp][jj], pfi);
+        // hard-coded 120 index units (streamer_index.py:157), cont > cont_dis (:138).  Inside the tolerance band of
+        // the threshold the reference's own summation decides: cont[i, j] = on[i+1] + ... + on[j], left to right
+        // (streamer_index.py:133-135; a prefix difference differs from it by rounding)
+        const bool cont_near = fabs(cont - prm.cont_dis) <= 1e-9 * prm.cont_dis;
+        if (cont_near && dxi <= 120) {
+          double acc = 0.0;
+          for (int k = i + 1; k <= j; ++k) acc = __dadd_rn(acc, on[base + k]);
+          cont = acc;
+        }
+        const bool cont_ok = cont > prm.cont_dis;
+        if (dxi <= 120 && (cont_ok || cont_near)) {
           const float s0 = __sinf(0.5f * (lai - q4.y)), s1 = __sinf(0.5f * (loi - q4.z));
           const float h = s0 * s0 + ci * q4.w * s1 * s1;
           if (!(h > h_hi)) {
-            int near = fabs(cont - prm.cont_dis) <= 1e-9 * prm.cont_dis;
-            bool ok = true;
+            int near = cont_near;
+            bool ok = cont_ok;
             if (h >= h_lo) {  // inside the margin: the reference's fp64 expression decides
               const int yi = wbk_py(pi), yj = wbk_py(pj);
               const double dist = hav_km(ct.lat_rad[yi], ct.lon_rad[xi % nlon], ct.cos_lat[yi], ct.lat_rad[yj],
                                          ct.lon_rad[wbk_px(pj) % nlon], ct.cos_lat[yj]);
-              ok = dist < prm.geo_dis;
-              near |= fabs(dist - prm.geo_dis) <= 1e-9 * prm.geo_dis;
+              const bool geo_ok = dist < prm.geo_dis;
+              const bool geo_near = fabs(dist - prm.geo_dis) <= 1e-9 * prm.geo_dis;
+              near |= geo_near;
+              if (!geo_ok && !geo_near) near = 0;  // clearly too far: the cont decision does not matter
+              ok = ok && geo_ok;
+              // every decision inside a tolerance band is listed, whether the pair was kept or rejected
+              if (near) {
+                const int pos = atomicAdd(x.near_cnt, 1);
+                if (pos < x.NRC) {
+                  int* rec4 = x.near_rec + 4 * pos;
+                  rec4[0] = slot / x.SC;
+                  rec4[1] = c;
+                  rec4[2] = i;
+                  rec4[3] = j | ((ok ? 1 : 0) << 28) | ((geo_near ? 1 : 0) << 29) | ((cont_near ? 1 : 0) << 30);
+                }
+              }
+            } else if (near) {  // clearly close enough: only the cont decision is inside its band
+              const int pos = atomicAdd(x.near_cnt, 1);
+              if (pos < x.NRC) {
+                int* rec4 = x.near_rec + 4 * pos;
+                rec4[0] = slot / x.SC;
+                rec4[1] = c;
+                rec4[2] = i;
+                rec4[3] = j | ((ok ? 1 : 0) << 28) | (1 << 30);
+              }
             }
             if (ok) {
               // check_duplicates (:160-183): the rows equal to (i, j) after x % nlon are the candidates among
@@ -1145,11 +1181,12 @@ extern "C" int wbk_index_run(wbk_ctx* ctx, int njobs, int nlevels, const int* d_
     double* pfx = d_work + npoints;
     const int nslots = njobs * x.SC;
     WBK_CUDA_CHECK(cudaMemsetAsync(x.total, 0, sizeof(int), st));
+    WBK_CUDA_CHECK(cudaMemsetAsync(x.near_cnt, 0, sizeof(int), st));
     WBK_LAUNCH(KID_STREAMER_PREP, streamer_prep_kernel, dim3(njobs), dim3(ST_THREADS), 0, st, d, x, ps, ct, on, pfx, prm->dlon,
                prm->geo_dis, prm->cont_dis);
     WBK_LAUNCH_CHECK();
     WBK_CUDA_CHECK(cudaMemsetAsync(x.cnt1, 0, sizeof(int) * nslots, st));
-    WBK_LAUNCH(KID_PAIR_SCAN, pair_scan_kernel, dim3(148 * 8), dim3(PS_THREADS), 0, st, d, x, ps, ct, (const double*)pfx, *prm, nslots);
+    WBK_LAUNCH(KID_PAIR_SCAN, pair_scan_kernel, dim3(148 * 8), dim3(PS_THREADS), 0, st, d, x, ps, ct, (const double*)on, (const double*)pfx, *prm, nslots);
     WBK_LAUNCH_CHECK();
     {
       const int nbins = ((d.W >> TB_SHIFT) + 1) * ((d.nlat >> TB_SHIFT) + 1);
@@ -1167,6 +1204,18 @@ extern "C" int wbk_index_run(wbk_ctx* ctx, int njobs, int nlevels, const int* d_
     WBK_LAUNCH(KID_FINISH, streamer_finish_kernel, dim3(njobs), dim3(ST_THREADS), CS_SMEM, st, d, x, ps, (const double*)on, J);
     WBK_LAUNCH_CHECK();
   }
+  return WBK_OK;
+}
+
+extern "C" int wbk_near_list(wbk_ctx* ctx, int* d_recs, int cap, int* d_count, void* stream) {
+  if (!ctx || !d_count || cap < 0 || (cap > 0 && !d_recs)) {
+    wbk_set_error("wbk_near_list: invalid argument");
+    return WBK_ERR_INVALID;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = cap < ctx->x.NRC ? cap : ctx->x.NRC;
+  WBK_CUDA_CHECK(cudaMemcpyAsync(d_count, ctx->x.near_cnt, sizeof(int), cudaMemcpyDeviceToDevice, st));
+  if (n > 0) WBK_CUDA_CHECK(cudaMemcpyAsync(d_recs, ctx->x.near_rec, sizeof(int) * 4 * n, cudaMemcpyDeviceToDevice, st));
   return WBK_OK;
 }
 

@@ -78,7 +78,7 @@ def iter_batches(field, batch, depth=3, start=0, stop=None):
     th.join()
 
 
-def detect_file(path, lat, lon, batch=296, depth=3, shape=None, dtype=np.float32, gmax_nx=None, **detector_kwargs):
+def detect_file(path, lat, lon, batch=296, depth=3, shape=None, dtype=np.float32, gmax_nx="full", **detector_kwargs):
     """Run the whole detection path over a field file; yields ``(t0, BatchResult)`` per batch in time order.
 
     ``gmax_nx``: see ``Detector.stream`` (the reference's global ``exp_lon.max()``)."""

@@ -14,12 +14,15 @@ host<->device copies overlap with kernels (``Detector.stream``).
 """
 
 import ctypes
+import logging
 from dataclasses import dataclass
 
 import numpy as np
 import torch
 
 from . import _lib, detect, spatial
+
+logger = logging.getLogger(__name__)
 
 
 @dataclass
@@ -30,6 +33,10 @@ class BatchResult:
     flags: torch.Tensor       # int8 [3, ntime, nlat, nlon] (device, or pinned host in the end-to-end path)
     gmax_nx: int
     n_split: int = 0
+    # streamer pairs decided within 1e-9 of geo_dis / cont_dis, kept AND rejected ones (wbk_near_list):
+    # int32 [m, 6] = time step, level index, contour, i, j, flags (1 kept, 2 geo in band, 4 cont in band)
+    near: np.ndarray = None
+    near_total: int = 0
 
 
 def _pinned(shape, dtype, lib):
@@ -80,6 +87,10 @@ class _Slot:
         self.ring_pts = torch.empty(self.cap_r, dtype=i32, device=dev)
         self.summary = torch.zeros(8, dtype=i32, device=dev)
         self.h_summary = _pinned(8, i32, lib)
+        self.near = torch.zeros((_lib.NEAR_CAP, 4), dtype=i32, device=dev)
+        self.near_cnt = torch.zeros(1, dtype=i32, device=dev)
+        self.h_near = _pinned((_lib.NEAR_CAP, 4), i32, lib)
+        self.h_near_cnt = _pinned(1, i32, lib)
         self.h_ev_int = _pinned((self.cap_e, _lib.EV_INTS), i32, lib)
         self.h_ev_f64 = _pinned((self.cap_e, _lib.EV_F64), f64, lib)
         self.h_ev_job = _pinned(self.cap_e, i32, lib)
@@ -98,7 +109,8 @@ class Detector:
     """Holds the grid, thresholds and the reusable slots of one detection configuration."""
 
     def __init__(self, lat, lon, levels=(2.0,), periodic_add=120, passes=5, which=detect.KINDS, geo_dis=800.0,
-                 cont_dis=1500.0, range_group=5.0, ot_min_exp=5.0, co_min_exp=5.0, want_flags=True, fuse=False):
+                 cont_dis=1500.0, range_group=5.0, ot_min_exp=5.0, co_min_exp=5.0, want_flags=True, fuse=True,
+                 packing=None):
         self.lib = _lib.get()
         self.lat = np.asarray(lat, dtype=np.float64)
         self.lon = np.asarray(lon, dtype=np.float64)
@@ -120,10 +132,11 @@ class Detector:
         self.params = dict(geo_dis=geo_dis, cont_dis=cont_dis, range_group=range_group, ot_min_exp=ot_min_exp,
                            co_min_exp=co_min_exp)
         self.want_flags = want_flags
-        # smoothing + marching squares in one kernel (wbk_smooth_contours).  Off by default: measured on B200 the
-        # fused kernel (3.10 ms per 296 steps) is slower than the two separate ones (2.00 + 0.97 ms), because the
-        # smoothing is bound by the FP64 pipe / instruction issue, not by the memory traffic the fusion removes.
+        # smoothing that also leaves the marching-squares bit planes (wbk_smooth_contours): the contour stage then
+        # does not re-read the smoothed field.  fuse=False runs wbk_smooth + wbk_contours (same results).
         self.fuse = bool(fuse)
+        # CF packing of int16 input (scale_factor, add_offset, _FillValue or None), decoded in the smoothing loads
+        self.packing = tuple(packing) if packing is not None else (1.0, 0.0, None)
         self.coords = detect.coord_tables(self.lat, self.lon, self.dlon, self.dlat, self.lib)
         self._slots = {}
         self._grow = {}
@@ -179,17 +192,16 @@ class Detector:
                 slot.raw_dev[:nt].copy_(raw, non_blocking=True)
                 raw = slot.raw_dev[:nt]
             raw = raw.contiguous()
-            if self.flip_lat or self.flip_lon:
-                if slot.flipped is None or slot.flipped.dtype != raw.dtype:
-                    slot.flipped = torch.empty((slot.T, self.nlat, self.nlon), dtype=raw.dtype, device=lib.device)
-                lib.call("wbk_flip", _lib.ptr(raw), _lib.ptr(slot.flipped), _lib.dtype_code(raw.dtype), nt, self.nlat,
-                         self.nlon, int(self.flip_lat), int(self.flip_lon), st)
-                raw = slot.flipped[:nt]
+            raw_in = raw  # what the caller handed over (the regrow path re-submits exactly this)
             if intensity is not None:
                 intensity = intensity.to(lib.device).contiguous()
             h = slot.ctx.handle
             L = len(self.levels)
             lv = self.levels.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+            # the stored orientation (descending ERA5 latitudes, utils/data_utils.py:196-213) and the CF packing of
+            # int16 input are resolved inside the smoothing loads: no re-oriented / decoded copy of the batch
+            opts = _lib.smooth_opts(self.flip_lat, self.flip_lon, *self.packing) if (
+                self.flip_lat or self.flip_lon or raw.dtype == torch.int16) else None
             fused = False
             if smoothed is not None:
                 sm = smoothed
@@ -203,12 +215,20 @@ class Detector:
                     sm, rmode = slot.sm[:nt], (_lib.ROUND_FIRST if f32 else _lib.ROUND_NONE)
                 if self.fuse and sm.dtype == torch.float64 and self.passes <= _lib.SMOOTH_MAX_FUSED and self.nlat >= 4:
                     lib.call("wbk_smooth_contours", h, _lib.ptr(raw), _lib.dtype_code(raw.dtype), _lib.ptr(sm), nt,
-                             self.passes, lv, L, st)
+                             self.passes, lv, L, opts, st)
                     fused = True
                 else:
                     lib.call("wbk_smooth", _lib.ptr(raw), _lib.dtype_code(raw.dtype), _lib.ptr(sm),
-                             _lib.dtype_code(sm.dtype), _lib.ptr(slot.sm_tmp), nt, self.nlat, self.nlon, self.passes, rmode, st)
+                             _lib.dtype_code(sm.dtype), _lib.ptr(slot.sm_tmp), nt, self.nlat, self.nlon, self.passes,
+                             rmode, opts, st)
             else:
+                if opts is not None:  # no smoothing: orientation / decode only
+                    want = torch.float64 if raw.dtype == torch.int16 else raw.dtype
+                    if slot.flipped is None or slot.flipped.dtype != want:
+                        slot.flipped = torch.empty((slot.T, self.nlat, self.nlon), dtype=want, device=lib.device)
+                    lib.call("wbk_orient", _lib.ptr(raw), _lib.dtype_code(raw.dtype), _lib.ptr(slot.flipped), nt,
+                             self.nlat, self.nlon, opts, st)
+                    raw = slot.flipped[:nt]
                 sm = raw
             if not fused:
                 lib.call("wbk_contours", h, _lib.ptr(sm), _lib.dtype_code(sm.dtype), nt, lv, L, st)
@@ -220,6 +240,7 @@ class Detector:
             lib.call("wbk_index_run", h, nt * L, L, _lib.ptr(slot.job_off), _lib.ptr(slot.pt_off), _lib.ptr(slot.meta),
                      _lib.ptr(slot.pts), slot.cap_c, slot.cap_p, _lib.ptr(self.coords), _lib.ptr(slot.work),
                      ctypes.byref(prm), st)
+            lib.call("wbk_near_list", h, _lib.ptr(slot.near), _lib.NEAR_CAP, _lib.ptr(slot.near_cnt), st)
             flags = None
             if self.want_flags:
                 if flags_out is not None:
@@ -237,6 +258,8 @@ class Detector:
                      slot.cap_e, slot.cap_r, _lib.ptr(slot.summary), st)
             # asynchronous read-back of everything the host needs (tables are small; flags only on request)
             slot.h_summary.copy_(slot.summary, non_blocking=True)
+            slot.h_near_cnt.copy_(slot.near_cnt, non_blocking=True)
+            slot.h_near.copy_(slot.near, non_blocking=True)
             slot.h_ev_int.copy_(slot.ev_int, non_blocking=True)
             slot.h_ev_f64.copy_(slot.ev_f64, non_blocking=True)
             slot.h_ev_job.copy_(slot.ev_job, non_blocking=True)
@@ -246,7 +269,7 @@ class Detector:
                 flags_host[:, :nt].copy_(flags[:, :nt] if flags.shape[1] != nt else flags, non_blocking=True)
             if slot.done is not None:
                 slot.done.record()
-        slot.pending = dict(raw=raw, nt=nt, flags=flags, flags_host=flags_host, gmax=gmax_nx, smoothed=smoothed, sm=sm,
+        slot.pending = dict(raw=raw_in, nt=nt, flags=flags, flags_host=flags_host, gmax=gmax_nx, smoothed=smoothed, sm=sm,
                             intensity=intensity)
         return slot
 
@@ -290,8 +313,12 @@ class Detector:
             status=np.full(nt * L, status, dtype=np.int32), max_nx=max_nx, h_ncontours=None, h_npoints=None)
         flags = pend["flags_host"] if pend["flags_host"] is not None else pend["flags"]
         n_sp = int(sum(int((t.split == 1).sum()) for t in tables.values()))
+        n_near = int(slot.h_near_cnt[0]) if "streamers" in self.which else 0
+        rec = slot.h_near.numpy()[:min(n_near, _lib.NEAR_CAP)]
+        near = np.c_[rec[:, 0] // L, rec[:, 0] % L, rec[:, 1], rec[:, 2], rec[:, 3] & 0x0FFFFFFF, (rec[:, 3] >> 28) & 7]
         return BatchResult(ntime=nt, contours=cs, tables=tables, flags=flags,
-                           gmax_nx=max_nx if pend["gmax"] is None else int(pend["gmax"]), n_split=n_sp)
+                           gmax_nx=max_nx if pend["gmax"] is None else int(pend["gmax"]), n_split=n_sp,
+                           near=near.astype(np.int32), near_total=n_near)
 
     def _regrow_and_rerun(self, slot, status):
         pend = slot.pending
@@ -350,7 +377,7 @@ class Detector:
         self.submit(slot, raw_host, flags_host=flags_host)
         return self.collect(slot)
 
-    def stream(self, batches, depth=3, flags_host=None, shared_stream=False, gmax_nx=None):
+    def stream(self, batches, depth=3, flags_host=None, shared_stream=False, gmax_nx="full"):
         """Pipelined execution: yields one BatchResult per input batch, in order.
 
         ``batches``: iterable of device or pinned-host tensors of (at most) equal length.  ``depth`` batches are
@@ -358,9 +385,13 @@ class Detector:
         handling overlap.  With ``shared_stream`` all slots enqueue on ONE side stream: kernels of different
         batches do not overlap each other, the host merely runs ahead (device-resident inputs).
         ``flags_host``: optional list of pinned int8 buffers, one per slot.
-        ``gmax_nx``: the global ``exp_lon.max()`` in columns (streamer_index.py:106 takes it over ALL dates); by
-        default every batch uses its own maximum, which is the same value as soon as each batch holds a
-        circumglobal contour.
+        ``gmax_nx``: the global ``exp_lon.max()`` in columns.  The reference takes it over ALL dates of a call
+        (streamer_index.py:106, overturning_index.py:105, cutoff_index.py:90), a stream only sees one batch at a
+        time, so the default ``"full"`` uses the width of the extended grid, ``nlon + periodic_add / dlon``: the value
+        the maximum has as soon as ANY date of the record holds a circumglobal contour (a batch without one then yields
+        no streamers / overturnings, exactly like those dates do in the reference).  If no batch at all reaches the full
+        width a warning is logged with the maximum that was seen -- re-run with ``gmax_nx=<that value>`` to get the
+        reference's result for such a record.  ``None`` = every batch uses its own maximum; an int = that value.
         The flag grids / contour set of a result are only valid until its slot is reused (``depth`` batches later).
         """
         common = None
@@ -368,18 +399,31 @@ class Detector:
             if getattr(self, "_shared", None) is None:
                 self._shared = torch.cuda.Stream(device=self.lib.device)
             common = self._shared
+        full = self.nlon + self.add
+        assumed = gmax_nx == "full"
+        if assumed:
+            gmax_nx = full
+        seen_max = 0
         inflight = []
         i = 0
         for raw in batches:
             idx = i % depth
             if len(inflight) == depth:
-                yield self.collect(inflight.pop(0))
+                res = self.collect(inflight.pop(0))
+                seen_max = max(seen_max, res.contours.max_nx)
+                yield res
             slot = self._slot(int(raw.shape[0]), idx)
             fh = flags_host[idx] if flags_host is not None else None
             inflight.append(self.submit(slot, raw, flags_host=fh, stream=common, gmax_nx=gmax_nx))
             i += 1
         while inflight:
-            yield self.collect(inflight.pop(0))
+            res = self.collect(inflight.pop(0))
+            seen_max = max(seen_max, res.contours.max_nx)
+            yield res
+        if assumed and i > 0 and seen_max < full:
+            logger.warning("no contour of the %d batches spans the extended grid (%d columns; widest: %d): the "
+                           "reference's exp_lon.max() would be %d columns, re-run with gmax_nx=%d", i, full, seen_max,
+                           seen_max, seen_max)
 
 
 class _null:
@@ -395,5 +439,56 @@ def summarize(res):
     return dict(
         ntime=res.ntime, contours=res.contours.ncontours, points=res.contours.npoints,
         streamers=len(res.tables["streamers"]), overturnings=len(res.tables["overturnings"]),
-        cutoffs=len(res.tables["cutoffs"]), split=res.n_split,
+        cutoffs=len(res.tables["cutoffs"]), split=res.n_split, near=res.near_total,
     )
+
+
+def events_soup(res, kind, det):
+    """Lattice polygons of the events of one kind of a BatchResult, as ``track_events`` sees them after
+    ``transform_polygons`` (utils/index_utils.py:129-184): index coordinates of the REAL grid, folded with
+    ``x % nlon``, events that straddle the last meridian split into their pieces (a multipolygon).
+    Returns ``(tracking.PolygonSoup, com)`` with ``com`` the (lon, lat) centre-of-mass column."""
+    from . import geometry, tracking
+
+    tab = res.tables[kind]
+    n = len(tab)
+    nlon = det.nlon
+    if kind == "overturnings":
+        x0, y0, x1, y1 = (tab.box[:, k].astype(np.int64) for k in range(4))
+        xy = np.stack([np.c_[x1, y0], np.c_[x1, y1], np.c_[x0, y1], np.c_[x0, y0]], axis=1).reshape(-1, 2)
+        off = np.arange(n + 1, dtype=np.int64) * 4
+    else:
+        off = tab.rings.off - tab.rings.off[0]
+        p = tab.rings.packed
+        xy = np.c_[(p & 0xFFFF).astype(np.int64), (p >> 16).astype(np.int64)]
+    straddle = np.nonzero(tab.split == 1)[0]
+    if len(straddle) == 0:
+        xy[:, 0] %= nlon
+        soup = tracking.PolygonSoup(xy.astype(np.int32), off, np.arange(n + 1), True)
+    else:
+        # only the few events that straddle the meridian are rebuilt one by one
+        ring_xy, ring_len, poly_nr = [], [], np.ones(n, dtype=np.int64)
+        prev = 0
+        for e in straddle:
+            a, b = off[prev], off[e]
+            if b > a:
+                seg = xy[a:b].copy()
+                seg[:, 0] %= nlon
+                ring_xy.append(seg)
+                ring_len.extend(np.diff(off[prev:e + 1]).tolist())
+            pieces = geometry.transform_ring(xy[off[e]:off[e + 1]], nlon)
+            poly_nr[e] = len(pieces)
+            for pc in pieces:
+                ring_xy.append(np.asarray(pc, dtype=np.int64).reshape(-1, 2))
+                ring_len.append(len(pc))
+            prev = e + 1
+        if off[n] > off[prev]:
+            seg = xy[off[prev]:off[n]].copy()
+            seg[:, 0] %= nlon
+            ring_xy.append(seg)
+            ring_len.extend(np.diff(off[prev:n + 1]).tolist())
+        allxy = np.concatenate(ring_xy) if ring_xy else np.zeros((0, 2), dtype=np.int64)
+        soup = tracking.PolygonSoup(allxy.astype(np.int32), np.r_[0, np.cumsum(ring_len)], np.r_[0, np.cumsum(poly_nr)],
+                                    True)
+    props = detect.finish_properties(tab, det.lon, det.lat, nlon)
+    return soup, np.asarray(props["com"], dtype=np.float64).reshape(-1, 2)

@@ -65,7 +65,7 @@ def smooth(data, passes, weights=DEFAULT_WEIGHTS, mode="wrap", numpy2_promotion=
         if passes == 0:
             out = torch.empty_like(x)
             lib.call("wbk_smooth", _lib.ptr(x), _lib.dtype_code(x.dtype), _lib.ptr(out), _lib.dtype_code(out.dtype),
-                     None, ntime, nlat, nlon, 0, _lib.ROUND_NONE, st)
+                     None, ntime, nlat, nlon, 0, _lib.ROUND_NONE, None, st)
             return out
         if f32 and numpy2_promotion:
             out_dtype, rmode = torch.float64, _lib.ROUND_FIRST
@@ -76,7 +76,7 @@ def smooth(data, passes, weights=DEFAULT_WEIGHTS, mode="wrap", numpy2_promotion=
         out = torch.empty(x.shape, dtype=out_dtype, device=x.device)
         tmp = torch.empty_like(out) if passes > _lib.SMOOTH_MAX_FUSED else None
         lib.call("wbk_smooth", _lib.ptr(x), _lib.dtype_code(x.dtype), _lib.ptr(out), _lib.dtype_code(out_dtype),
-                 _lib.ptr(tmp), ntime, nlat, nlon, passes, rmode, st)
+                 _lib.ptr(tmp), ntime, nlat, nlon, passes, rmode, None, st)
         return out
     # generic weights / mode: one launch per pass
     if mode not in _MODES:
