@@ -103,8 +103,12 @@ int wbk_convolve2d(const void* d_in, int in_dtype, void* d_out, int out_dtype, i
 /* set rows {0..border-1} and {nlat-border..nlat-1} to NaN (spatial.py:106-107) */
 int wbk_nan_border(void* d_field, int dtype, int ntime, int nlat, int nlon, int border, void* stream);
 
-/* spatial.py:27-57 calculate_momentum_flux: (u - nanmean_lon(u)) * (v - nanmean_lon(v)) */
-int wbk_mflux(const void* d_u, const void* d_v, void* d_out, int dtype, int ntime, int nlat, int nlon, void* stream);
+/* spatial.py:27-57 calculate_momentum_flux: (u - nanmean_lon(u)) * (v - nanmean_lon(v)).  The zonal means follow
+ * numpy.nanmean bit for bit: pairwise summation in the data dtype when longitude is the contiguous axis of the
+ * user's array (sequential = 0), plain left-to-right summation when it is not (sequential = 1), float64 quotient
+ * rounded to the data dtype. */
+int wbk_mflux(const void* d_u, const void* d_v, void* d_out, int dtype, int ntime, int nlat, int nlon, int sequential,
+              void* stream);
 
 /* utils/data_utils.py:196-213 correct_dimension_orientation: out[t, y, x] = in[t, flip_lat ? nlat-1-y : y,
  * flip_lon ? nlon-1-x : x] */
@@ -253,13 +257,20 @@ int wbk_rasterize_rings(const int* d_xy, const int* d_ring_off, const int* d_rin
  * wbk_batch_fetch: after wbk_events_raster, gathers ALL events (kind-major, then job, then reference order)
  * into d_out_int [cap_events][WBK_EV_INTS], d_out_f64 [cap_events][WBK_EV_F64], d_out_job [cap_events], the
  * ring vertices of every streamer / cutoff event into d_ring_pts (event e = [d_ring_off[e], d_ring_off[e+1])),
- * and writes the summary record d_summary[8] = contours, points, streamers, overturnings, cutoffs,
- * OR of all status bits, max_nx, split pieces.  The caller copies these buffers to the host and synchronises once. */
+ * and writes the summary record d_summary[16] = contours, points, streamers, overturnings, cutoffs,
+ * OR of all status bits, max_nx, split pieces, marching-squares segments, streamer candidate pairs (after the pair
+ * scan), near-threshold decisions, active pair-scan tiles, 4 reserved.  The caller copies these buffers to the host
+ * and synchronises once. */
 int wbk_contours_pack_auto(wbk_ctx* ctx, int* d_job_off, int* d_pt_off, int* d_meta, uint32_t* d_pts, int cap_contours,
                            int cap_points, void* stream);
 int wbk_batch_fetch(wbk_ctx* ctx, const int* d_pt_off, const uint32_t* d_pts, int* d_out_int, double* d_out_f64,
                     int* d_out_job, int* d_ring_off, uint32_t* d_ring_pts, int cap_events, int cap_ring, int* d_summary,
                     void* stream);
+
+/* Bit-packed copy of flag grids for the device -> host link: cell c of d_flags (int8, != 0 means set) becomes bit
+ * (c & 7) of byte c >> 3 of d_packed (numpy.unpackbits(..., bitorder="little") restores the grid).  d_packed holds
+ * 4 * ceil(ncells / 32) bytes; d_flags 16-byte aligned, d_packed 4-byte aligned. */
+int wbk_pack_flags(const int8_t* d_flags, uint8_t* d_packed, long long ncells, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Per-kernel device timing (CUDA events on the launching stream around every kernel launch of the

@@ -170,90 +170,6 @@ def ring_is_simple(ring):
 
 
 # --------------------------------------------------------------------------- meridian split
-def _clip_ring_vertical(ring, c, keep_le):
-    """Faces of ``ring`` on one side of the vertical line x = c (kept side includes the line).
-
-    Returns a list of rings whose vertices are (x, Fraction(y)) tuples.  Faces are
-    separated (no bridge edges along the cut between different faces): crossings on
-    the line are sorted by y and paired (even-odd along the line), then every chain of
-    kept vertices is linked from its exit crossing to the paired entry crossing.
-    """
-    n = len(ring)
-    xs = [int(v[0]) for v in ring]
-    ys = [int(v[1]) for v in ring]
-    inside = [(x <= c) if keep_le else (x >= c) for x in xs]
-    if all(inside):
-        return [[(x, Fraction(y)) for x, y in zip(xs, ys)]]
-    if not any(inside):
-        return []
-
-    def cross_y(i, j):
-        # intersection of edge i->j with x = c (exact)
-        return Fraction(ys[i]) + Fraction((c - xs[i]) * (ys[j] - ys[i]), xs[j] - xs[i])
-
-    # start at an entry: previous outside, current inside
-    start = next(k for k in range(n) if inside[k] and not inside[k - 1])
-    chains = []  # each: dict(points=[...], y_in=..., y_out=...)
-    k = start
-    visited = 0
-    while visited < n:
-        if inside[k] and not inside[k - 1]:
-            pts = []
-            prev = (k - 1) % n
-            if xs[k] != c:
-                y_in = cross_y(prev, k)
-                pts.append((c, y_in))
-            else:
-                y_in = Fraction(ys[k])
-            j = k
-            while inside[j]:
-                pts.append((xs[j], Fraction(ys[j])))
-                j = (j + 1) % n
-                visited += 1
-            last = (j - 1) % n
-            if xs[last] != c:
-                y_out = cross_y(last, j)
-                pts.append((c, y_out))
-            else:
-                y_out = Fraction(ys[last])
-            chains.append({"pts": pts, "y_in": y_in, "y_out": y_out})
-            k = j
-        else:
-            k = (k + 1) % n
-            visited += 1
-
-    # pair the crossings along the line
-    crossings = []
-    for ci, ch in enumerate(chains):
-        crossings.append((ch["y_in"], 0, ci))  # 0 = entry
-        crossings.append((ch["y_out"], 1, ci))  # 1 = exit
-    crossings.sort(key=lambda t: (t[0], t[2], t[1]))
-    partner_of_exit = {}
-    for a in range(0, len(crossings) - 1, 2):
-        c0, c1 = crossings[a], crossings[a + 1]
-        if c0[1] == 1 and c1[1] == 0:
-            partner_of_exit[c0[2]] = c1[2]
-        elif c0[1] == 0 and c1[1] == 1:
-            partner_of_exit[c1[2]] = c0[2]
-        else:  # non-simple ring: fall back to closing every chain on itself
-            partner_of_exit = {ci: ci for ci in range(len(chains))}
-            break
-
-    faces = []
-    used = [False] * len(chains)
-    for ci in range(len(chains)):
-        if used[ci]:
-            continue
-        face = []
-        cur = ci
-        while not used[cur]:
-            used[cur] = True
-            face.extend(chains[cur]["pts"])
-            cur = partner_of_exit.get(cur, cur)
-        faces.append(face)
-    return faces
-
-
 def _ring_area2(face):
     s = Fraction(0)
     m = len(face)
@@ -264,27 +180,171 @@ def _ring_area2(face):
     return s
 
 
+def _winding(px, py, ring):
+    """Winding number of the closed ring around (px, py) (exact; the point must not lie on the ring)."""
+    w = 0
+    n = len(ring)
+    for i in range(n):
+        x0, y0 = ring[i]
+        x1, y1 = ring[(i + 1) % n]
+        cr = (x1 - x0) * (py - y0) - (y1 - y0) * (px - x0)
+        if y0 <= py < y1 and cr > 0:
+            w += 1
+        elif y1 <= py < y0 and cr < 0:
+            w -= 1
+    return w
+
+
+def _interior_point(face):
+    """A point strictly inside the simple counter-clockwise polygon ``face`` (Fraction coordinates)."""
+    n = len(face)
+    k = min(range(n), key=lambda i: face[i])  # lexicographically smallest vertex: convex
+    a, b, c = face[k - 1], face[k], face[(k + 1) % n]
+
+    def inside_tri(p):
+        d1 = (b[0] - a[0]) * (p[1] - a[1]) - (b[1] - a[1]) * (p[0] - a[0])
+        d2 = (c[0] - b[0]) * (p[1] - b[1]) - (c[1] - b[1]) * (p[0] - b[0])
+        d3 = (a[0] - c[0]) * (p[1] - c[1]) - (a[1] - c[1]) * (p[0] - c[0])
+        return d1 >= 0 and d2 >= 0 and d3 >= 0
+
+    best, best_d = None, None
+    for i, p in enumerate(face):
+        if p in (a, b, c):
+            continue
+        if inside_tri(p):
+            # distance from the line ac towards b: the vertex closest to b wins
+            d = abs((c[0] - a[0]) * (p[1] - a[1]) - (c[1] - a[1]) * (p[0] - a[0]))
+            if best is None or d > best_d:
+                best, best_d = p, d
+    if best is None:
+        return ((a[0] + b[0] + c[0]) / 3, (a[1] + b[1] + c[1]) / 3)
+    return ((b[0] + best[0]) / 2, (b[1] + best[1]) / 2)
+
+
 def split_ring_at_meridian(ring, nlon):
     """Pieces of an index-space ring after the split of ``utils/index_utils.py:148-173``.
 
-    The strip between x = nlon-1 and x = nlon is removed, the faces on either side
-    are kept as separate pieces, their coordinates are truncated to ints
-    (``:135``) and folded with ``x % nlon`` (``:139``).  Returns a list of (n, 2)
-    int arrays (open rings); an empty list stands for the empty ``Polygon()``.
+    The reference overlays the polygon boundary with the boundary of the strip between x = nlon-1 and
+    x = nlon, polygonises the union and keeps the faces that are not inside the strip and inside the
+    polygon.  This is restated literally as a PLANAR-GRAPH FACE WALK with exact rational arithmetic
+    (an independent formulation: the product clips chains against the two lines instead):
+
+    1. the polygon edges are subdivided where they cross the two vertical lines; the lines themselves are cut
+       at every node that lies on them (the strip's horizontal edges cannot separate faces of the polygon);
+    2. at every node the outgoing half-edges are sorted by angle; a face is traced by always turning to the next
+       half-edge clockwise from the one just arrived on (the face lies to the left);
+    3. bounded faces (positive area) are kept if an interior point lies outside the strip and inside the polygon
+       (non-zero winding).
+    The kept faces' coordinates are truncated to ints (``:135``) and folded with ``x % nlon`` (``:139``).  Returns a
+    list of (n, 2) int arrays (open rings, vertex order of the face walk); an empty list stands for ``Polygon()``.
     """
+    ring = [(int(x), int(y)) for x, y in np.asarray(ring).reshape(-1, 2)]
+    n = len(ring)
+    c0, c1 = nlon - 1, nlon
+    segs = set()
+    on_line = {c0: set(), c1: set()}
+
+    def node(x, y):
+        p = (Fraction(x), Fraction(y))
+        for c in (c0, c1):
+            if p[0] == c:
+                on_line[c].add(p)
+        return p
+
+    for i in range(n):
+        (x0, y0), (x1, y1) = ring[i], ring[(i + 1) % n]
+        if (x0, y0) == (x1, y1):
+            continue
+        pts = [node(x0, y0), node(x1, y1)]
+        for c in (c0, c1):
+            if min(x0, x1) < c < max(x0, x1):
+                pts.append(node(c, Fraction(y0) + Fraction((c - x0) * (y1 - y0), x1 - x0)))
+        # order along the edge
+        pts.sort(key=lambda p: (p[0] - x0) * (x1 - x0) + (p[1] - y0) * (y1 - y0))
+        for a, b in zip(pts[:-1], pts[1:]):
+            if a != b:
+                segs.add((a, b) if a < b else (b, a))
+    for c in (c0, c1):
+        line = sorted(on_line[c])
+        for a, b in zip(line[:-1], line[1:]):
+            segs.add((a, b))
+    # half-edges sorted by angle around every node
+    out = {}
+    for a, b in segs:
+        out.setdefault(a, []).append(b)
+        out.setdefault(b, []).append(a)
+
+    def angle_key(o):
+        def key(p):
+            dx, dy = p[0] - o[0], p[1] - o[1]
+            half = 0 if (dy > 0 or (dy == 0 and dx > 0)) else 1
+            return half, dx, dy
+        return key
+
+    import functools
+
+    def cmp_at(o):
+        def cmp(p, q):
+            kp, kq = angle_key(o)(p), angle_key(o)(q)
+            if kp[0] != kq[0]:
+                return -1 if kp[0] < kq[0] else 1
+            cr = kp[1] * kq[2] - kp[2] * kq[1]  # p before q (counter-clockwise) iff cross > 0
+            return -1 if cr > 0 else (1 if cr < 0 else 0)
+        return cmp
+
+    for o in out:
+        out[o].sort(key=functools.cmp_to_key(cmp_at(o)))
+    visited = set()
     pieces = []
-    for c, keep_le in ((nlon - 1, True), (nlon, False)):
-        for face in _clip_ring_vertical(ring, c, keep_le):
-            if len(face) < 3 or _ring_area2(face) == 0:
+    for a in out:
+        for b in out[a]:
+            if (a, b) in visited:
                 continue
+            face = []
+            u, v = a, b
+            while (u, v) not in visited:
+                visited.add((u, v))
+                face.append(u)
+                nb = out[v]
+                k = nb.index(u)
+                u, v = v, nb[k - 1]  # next half-edge: clockwise neighbour of the reverse edge (face on the left)
+            if len(face) < 3 or _ring_area2(face) <= 0:
+                continue  # the unbounded face (clockwise) and degenerate walks
+            px, py = _interior_point(face)
+            if c0 < px < c1:
+                continue  # inside the strip
+            if _winding(px, py, ring) == 0:
+                continue  # a hole of the overlay, not part of the polygon
             xy = np.array([[int(x) % nlon, int(y)] for x, y in face], dtype=np.int64)
-            # drop consecutive repeats created by the truncation
             keep = np.ones(len(xy), dtype=bool)
             keep[1:] = np.any(xy[1:] != xy[:-1], axis=1)
             if len(xy) > 1 and np.all(xy[0] == xy[-1]):
                 keep[-1] = False
-            pieces.append(xy[keep])
+            xy = xy[keep]
+            if len(xy) >= 3:
+                pieces.append(xy)
     return pieces
+
+
+def canonical_region(piece):
+    """Canonical vertex list of a lattice ring as a REGION: collinear vertices removed, counter-clockwise, starting at
+    the lexicographically smallest vertex (two rings that bound the same region compare equal)."""
+    p = [(int(x), int(y)) for x, y in np.asarray(piece).reshape(-1, 2)]
+    changed = True
+    while changed and len(p) >= 3:
+        changed = False
+        for i in range(len(p)):
+            a, b, c = p[i - 1], p[i], p[(i + 1) % len(p)]
+            if (b[0] - a[0]) * (c[1] - b[1]) - (b[1] - a[1]) * (c[0] - b[0]) == 0:
+                del p[i]
+                changed = True
+                break
+    if len(p) < 3:
+        return ()
+    if _ring_area2(p) < 0:
+        p = p[::-1]
+    k = p.index(min(p))
+    return tuple(p[k:] + p[:k])
 
 
 # --------------------------------------------------------------------------- overlap area
@@ -354,17 +414,10 @@ def overlap_areas(rings_a, rings_b):
 
 
 # --------------------------------------------------------------------------- exact overlap decision
-def overlap_positive_exact(rings_a, rings_b):
-    """True iff the (multi)polygons A and B (lattice rings, non-zero winding) share a region of positive area --
-    what ``geom1.intersection(geom2).area > 0`` means in ``processing/events.py:205-214`` (GEOS returns an empty or
-    lower-dimensional intersection for polygons that merely touch).
-
-    Exact rational slab decomposition, independent of the product's crossing / touching rules: between two
-    consecutive abscissae of the vertices and edge-edge intersection points no two edges cross, so the edges
-    spanning the slab are ordered by their ordinate at the slab centre and the winding numbers of A and B are swept
-    upwards; a slab piece where both are non-zero and whose centre height is positive proves the overlap.
-    ``fractions.Fraction`` throughout; only the part of the plane where the bounding boxes intersect is swept.
-    """
+def _sweep_exact(rings_a, rings_b, xl=None, xr=None, stop_at_first=False):
+    """Exact slab sweep over two ring sets (non-zero winding each): Fractions (area A, area B, area A n B) of the
+    part of the plane with xl <= x <= xr (default: everything).  With ``stop_at_first`` the sweep returns as soon
+    as a piece of positive area lies in both."""
     def edges_of(rings):
         out = []
         for ring in rings:
@@ -376,25 +429,23 @@ def overlap_positive_exact(rings_a, rings_b):
         return out
 
     ea, eb = edges_of(rings_a), edges_of(rings_b)
-    if not ea or not eb:
-        return False
-    xa0, xa1 = min(min(e[0], e[2]) for e in ea), max(max(e[0], e[2]) for e in ea)
-    xb0, xb1 = min(min(e[0], e[2]) for e in eb), max(max(e[0], e[2]) for e in eb)
-    xl, xr = max(xa0, xb0), min(xa1, xb1)
-    if xl >= xr:
-        return False
     edges = [(e, 0) for e in ea] + [(e, 1) for e in eb]
-    # only non-vertical edges that reach into (xl, xr) matter
-    edges = [(e, o) for e, o in edges if e[0] != e[2] and min(e[0], e[2]) < xr and max(e[0], e[2]) > xl]
+    edges = [(e, o) for e, o in edges if e[0] != e[2]]  # vertical edges bound no area in a vertical-slab sweep
+    if not edges:
+        return Fraction(0), Fraction(0), Fraction(0)
+    lo = min(min(e[0], e[2]) for e, _ in edges) if xl is None else xl
+    hi = max(max(e[0], e[2]) for e, _ in edges) if xr is None else xr
+    if lo >= hi:
+        return Fraction(0), Fraction(0), Fraction(0)
+    edges = [(e, o) for e, o in edges if min(e[0], e[2]) < hi and max(e[0], e[2]) > lo]
     E = np.array([e for e, _ in edges], dtype=np.int64).reshape(-1, 4)
-    xs = {Fraction(xl), Fraction(xr)}
+    xs = {Fraction(lo), Fraction(hi)}
     for e, _ in edges:
         for x in (e[0], e[2]):
-            if xl < x < xr:
+            if lo < x < hi:
                 xs.add(Fraction(x))
-    # intersection abscissae of every pair of these edges (integer prefilter, exact rational points)
     n = len(edges)
-    if n > 1:
+    if n > 1:  # intersection abscissae of every pair of edges (integer prefilter, exact rational points)
         x1, y1, x2, y2 = (E[:, k][:, None] for k in range(4))
         x3, y3, x4, y4 = (E[:, k][None, :] for k in range(4))
         den = (x1 - x2) * (y3 - y4) - (y1 - y2) * (x3 - x4)
@@ -404,18 +455,19 @@ def overlap_positive_exact(rings_a, rings_b):
         hit = (den != 0) & (tn * sg > 0) & (tn * sg < den * sg) & (un * sg > 0) & (un * sg < den * sg)
         for i, j in zip(*np.nonzero(np.triu(hit, 1))):
             x = Fraction(int(E[i, 0])) + Fraction(int(tn[i, j]), int(den[i, j])) * int(E[i, 2] - E[i, 0])
-            if xl < x < xr:
+            if lo < x < hi:
                 xs.add(x)
     xs = sorted(xs)
+    area = [Fraction(0), Fraction(0), Fraction(0)]
     for a, b in zip(xs[:-1], xs[1:]):
         xm = (a + b) / 2
         span = []
         for (x0, y0, x1_, y1_), owner in edges:
-            lo, hi = (x0, x1_) if x0 < x1_ else (x1_, x0)
-            if lo <= a and hi >= b:
+            l0, h0 = (x0, x1_) if x0 < x1_ else (x1_, x0)
+            if l0 <= a and h0 >= b:
                 ym = Fraction(y0) + Fraction(y1_ - y0, x1_ - x0) * (xm - x0)
                 span.append((ym, owner, 1 if x1_ > x0 else -1))
-        span.sort(key=lambda s: s[0])
+        span.sort(key=lambda t: t[0])
         wa = wb = 0
         for k in range(len(span) - 1):
             ym, owner, dw = span[k]
@@ -423,6 +475,44 @@ def overlap_positive_exact(rings_a, rings_b):
                 wa += dw
             else:
                 wb += dw
-            if wa != 0 and wb != 0 and span[k + 1][0] > ym:
-                return True
-    return False
+            h = (span[k + 1][0] - ym) * (b - a)  # mid-height x width = exact trapezoid area
+            if h > 0:
+                if wa != 0:
+                    area[0] += h
+                if wb != 0:
+                    area[1] += h
+                if wa != 0 and wb != 0:
+                    area[2] += h
+                    if stop_at_first:
+                        return tuple(area)
+    return tuple(area)
+
+
+def regions_equal(rings_a, rings_b):
+    """True iff the two ring sets cover the same region (exact: area(A) == area(B) == area(A n B))."""
+    a, b, ab = _sweep_exact(rings_a, rings_b)
+    return a == b == ab
+
+
+def overlap_positive_exact(rings_a, rings_b):
+    """True iff the (multi)polygons A and B (lattice rings, non-zero winding) share a region of positive area --
+    what ``geom1.intersection(geom2).area > 0`` means in ``processing/events.py:205-214`` (GEOS returns an empty or
+    lower-dimensional intersection for polygons that merely touch).
+
+    Exact rational slab decomposition (:func:`_sweep_exact`), independent of the product's crossing / touching rules:
+    between two consecutive abscissae of the vertices and edge-edge intersection points no two edges cross, so the
+    edges spanning the slab are ordered by their ordinate at the slab centre and the winding numbers of A and B are
+    swept upwards; a slab piece where both are non-zero and whose centre height is positive proves the overlap.
+    Only the part of the plane where the bounding boxes intersect is swept.
+    """
+    def xrange(rings):
+        xs = [int(x) for ring in rings for x in np.asarray(ring).reshape(-1, 2)[:, 0]]
+        return (min(xs), max(xs)) if xs else None
+
+    ra, rb = xrange(rings_a), xrange(rings_b)
+    if ra is None or rb is None:
+        return False
+    xl, xr = max(ra[0], rb[0]), min(ra[1], rb[1])
+    if xl >= xr:
+        return False
+    return _sweep_exact(rings_a, rings_b, xl, xr, stop_at_first=True)[2] > 0

@@ -218,7 +218,7 @@ def test_momentum_flux_api_emu(emu):
     data, grid, raw = demo_like(1)
     mf = wb.calculate_momentum_flux(data, data)
     assert mf.name == "mflux" and mf.values.shape == raw.shape
-    np.testing.assert_allclose(mf.values, P.momentum_flux(raw, raw), rtol=1e-4, atol=1e-5)
+    assert np.array_equal(mf.values, P.momentum_flux(raw, raw))  # bit-exact (numpy pairwise order)
 
 
 @pytest.mark.gpu
@@ -228,3 +228,32 @@ def test_api_pipeline_gpu(gpu):
     st = _check_indices(sm, want_sm, grid, index)
     tracked = wb.track_events(st, method="by_overlap")
     assert "label" in tracked.columns and tracked.label.min() == 0
+
+
+def test_supplied_contours_of_other_levels_all_take_part_emu(emu):
+    """streamer_index.py:104-108 runs the index over EVERY contour of the supplied frame; contour_index.py:221-231
+    only warns about levels that are missing -- a frame with two levels must not be filtered down to one"""
+    data, grid, raw = demo_like(2)
+    sm = wb.calculate_smoothed_field(data, 5)
+    both = wb.calculate_contours(sm, [2, -2], original_coordinates=False)
+    n2 = len(wb.calculate_streamers(sm, 2, contours=both[both.level == 2].reset_index(drop=True)))
+    nm2 = len(wb.calculate_streamers(sm, -2, contours=both[both.level == -2].reset_index(drop=True)))
+    assert n2 > 0 and nm2 > 0
+    got = wb.calculate_streamers(sm, 2, contours=both.copy())  # a copy: the host upload path, not the device cache
+    assert len(got) == n2 + nm2
+    assert sorted(set(got.level)) == [-2, 2]
+
+
+def test_device_contours_are_not_stored_in_attrs_emu(emu):
+    import copy
+    import json
+
+    data, grid, raw = demo_like(1)
+    sm = wb.calculate_smoothed_field(data, 5)
+    c = wb.calculate_contours(sm, 2, original_coordinates=False)
+    json.dumps(c.attrs)  # serialisable (to_parquet writes attrs as JSON)
+    sub = copy.deepcopy(c[c.closed])  # derived frames deep-copy attrs: must stay cheap and valid
+    assert isinstance(sub.attrs.get("_wbk_device_token"), int)
+    a = wb.calculate_cutoffs(sm, 2, contours=c)
+    b = wb.calculate_cutoffs(sm, 2, contours=c.copy(deep=True).assign(dummy=1))  # host upload path
+    assert len(a) == len(b) and list(a.event_area) == list(b.event_area)

@@ -124,3 +124,43 @@ def test_stream_uses_the_global_exp_lon_maximum_emu(emu, caplog):
     with caplog.at_level(logging.WARNING, logger="wavebreaking_b200.pipeline"):
         list(det.stream([spatial.to_device(broken)], depth=1))
     assert "re-run with gmax_nx" in caplog.text
+
+
+def test_packed_flags_emu(emu):
+    import torch
+
+    nlat, nlon, nt = 46, 90, 3
+    lat, lon = synthetic.grid_coords(nlat, nlon)
+    raw = synthetic.pv_field(nlat, nlon, np.arange(nt) * 6.0)
+    det = pipeline.Detector(lat, lon, levels=[2.0])
+    packed = torch.zeros(pipeline.packed_nbytes(3 * nt * nlat * nlon), dtype=torch.uint8)
+    slot = det._slot(nt)
+    det.submit(slot, spatial.to_device(raw), packed_host=packed)
+    res = det.collect(slot)
+    assert res.flags_packed is packed
+    assert np.array_equal(pipeline.unpack_flags(packed, nt, nlat, nlon), res.flags.cpu().numpy())
+    assert res.flags.cpu().numpy().any()
+
+
+@pytest.mark.gpu
+def test_cuda_graph_replay_equals_eager_gpu(gpu):
+    """Detector(graphs=True): the third submission of the same buffers replays a captured graph; results, packed
+    flags and host tables equal the eager run, for different data in the same buffers"""
+    import torch
+
+    nlat, nlon, T = 181, 360, 8
+    lat, lon = synthetic.grid_coords(nlat, nlon)
+    eager = pipeline.Detector(lat, lon, levels=[2.0])
+    det = pipeline.Detector(lat, lon, levels=[2.0], graphs=True)
+    host = torch.empty((T, nlat, nlon), dtype=torch.float32).pin_memory()
+    packed = torch.zeros(pipeline.packed_nbytes(3 * T * nlat * nlon), dtype=torch.uint8).pin_memory()
+    for rep in range(4):
+        raw = synthetic.pv_field(nlat, nlon, (np.arange(T) + 10 * rep) * 6.0).astype(np.float32)
+        host.copy_(torch.from_numpy(raw))
+        got = list(det.stream([host], depth=1, packed_host=[packed]))[0]
+        want = eager.run_batch(spatial.to_device(raw))
+        assert pipeline.summarize(got) == pipeline.summarize(want), rep
+        assert np.array_equal(pipeline.unpack_flags(packed, T, nlat, nlon), want.flags.cpu().numpy())
+        for kind in detect.KINDS:
+            assert np.array_equal(got.tables[kind].sums, want.tables[kind].sums)
+    assert det.graph_replays >= 2 and det.graph_kernel_launches > 20

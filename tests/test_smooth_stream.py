@@ -132,6 +132,19 @@ def test_detector_descending_latitude_with_regrow_emu(emu):
         assert det._grow, "the tiny arenas were expected to overflow"
         assert pipeline.summarize(res) == pipeline.summarize(ref)
         assert np.array_equal(res.flags.cpu().numpy(), ref.flags.cpu().numpy())
+    # the streaming entry (explicit global exp_lon maximum) must notice overflowing arenas too: the status bits of the
+    # contour / packing stages survive the index stage
+    det = pipeline.Detector(lat, lon, levels=[2.0])
+    tiny = dict(seg_cap=32, contour_cap=4, pair_cap=16, event_cap=1, sel_cap=1)
+    orig = detect.default_caps
+    detect.default_caps = lambda *a, **k: {**orig(*a, **k), **tiny}
+    try:
+        res = list(det.stream([spatial.to_device(raw)], depth=1))[0]
+        res_flags = res.flags.cpu().numpy().copy()
+    finally:
+        detect.default_caps = orig
+    assert det._grow and pipeline.summarize(res) == pipeline.summarize(ref)
+    assert np.array_equal(res_flags, ref.flags.cpu().numpy())
 
 
 def test_detector_int16_input_emu(emu):

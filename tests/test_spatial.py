@@ -52,8 +52,17 @@ def test_mflux_emu(emu):
     want = P.momentum_flux(u, v)
     got = spatial.momentum_flux(u, v).cpu().numpy()
     assert got.dtype == np.float32
-    # zonal means are accumulated in a different order than numpy's pairwise float32 sum: tolerance
-    np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-5, equal_nan=True)
+    # the zonal means follow numpy's pairwise float32 summation: bit-exact
+    assert np.array_equal(got, want, equal_nan=True)
+    for nlon, dtype in ((7, np.float32), (128, np.float32), (129, np.float64), (1440, np.float32), (1447, np.float64)):
+        a, b = _field(5, nlon, 1, dtype, 3), _field(5, nlon, 1, dtype, 4)
+        a[0, 1, nlon // 2] = np.nan
+        assert np.array_equal(spatial.momentum_flux(a, b).cpu().numpy(), P.momentum_flux(a, b), equal_nan=True)
+    # longitude not the contiguous axis of the user's array (dims time, lon, lat): numpy sums sequentially
+    a, b = _field(9, 300, 2, np.float32, 5), _field(9, 300, 2, np.float32, 6)
+    at, bt = np.ascontiguousarray(a.transpose(0, 2, 1)), np.ascontiguousarray(b.transpose(0, 2, 1))
+    want = ((at - np.nanmean(at, axis=1, keepdims=True)) * (bt - np.nanmean(bt, axis=1, keepdims=True))).transpose(0, 2, 1)
+    assert np.array_equal(spatial.momentum_flux(a, b, lon_contiguous=False).cpu().numpy(), want)
 
 
 # ------------------------------------------------------------------ GPU
@@ -79,7 +88,9 @@ def test_mflux_gpu(gpu):
     v = _field(181, 360, 2, np.float32, 2)
     want = P.momentum_flux(u, v)
     got = spatial.momentum_flux(u, v).cpu().numpy()
-    np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-5, equal_nan=True)
+    assert np.array_equal(got, want, equal_nan=True)  # numpy's pairwise float32 order reproduced
+    u64, v64 = _field(721, 1440, 1, np.float64, 3), _field(721, 1440, 1, np.float64, 4)
+    assert np.array_equal(spatial.momentum_flux(u64, v64).cpu().numpy(), P.momentum_flux(u64, v64))
 
 
 @pytest.mark.gpu

@@ -164,6 +164,35 @@ def combine_shared(lst):
 
 
 # ------------------------------------------------------------------------------------------- helpers
+_CANON_CACHE = []  # [(key, _Canon)], most recent last; the device copy of `data` is reused by the three index calls
+
+
+def _canon(data, kwargs, need_values=True, orient=True):
+    """Cached :class:`_Canon`: ``calculate_streamers / overturnings / cutoffs / contours`` of one analysis are called
+    on the same DataArray, so its upload (and re-orientation) happens once.  The key holds the identity of the
+    value buffer, its shape / strides and the dimension names; the cache keeps the two most recent fields."""
+    values = data.values
+    iface = getattr(values, "__array_interface__", None)
+    key = None
+    if iface is not None and need_values:
+        key = (iface["data"][0], values.shape, values.strides, str(values.dtype), tuple(data.dims), bool(orient),
+               tuple(sorted((k, str(v)) for k, v in kwargs.items() if k.endswith("_name"))))
+        for k, c in _CANON_CACHE:
+            if k == key and c.tensor is not None and c.owner() is values:
+                return c
+    c = _Canon(data, kwargs, need_values, orient)
+    if key is not None:
+        import weakref
+
+        try:
+            c.owner = weakref.ref(values)
+        except TypeError:
+            c.owner = lambda: None
+        _CANON_CACHE.append((key, c))
+        del _CANON_CACHE[:-2]
+    return c
+
+
 class _Canon:
     """``data`` as a device tensor [time, lat, lon] with ascending lat / lon (data_utils.py:196-213)."""
 
@@ -213,10 +242,12 @@ def _as_levels(contour_levels):
 def calculate_momentum_flux(u, v, *args, **kwargs):
     """Momentum flux u'v' from the deviations of both wind components from the zonal mean
     (processing/spatial.py:27-57)."""
-    cu = _Canon(u, kwargs)
+    cu = _canon(u, kwargs)
     vk = dict(kwargs)
-    cv = _Canon(v, vk)
-    out = spatial.momentum_flux(cu.tensor, cv.tensor).cpu().numpy()
+    cv = _canon(v, vk)
+    # numpy sums pairwise along a contiguous axis and sequentially along a strided one: follow the user's layout
+    lon_last = tuple(u.dims)[-1] == kwargs["lon_name"] and tuple(v.dims)[-1] == kwargs["lon_name"]
+    out = spatial.momentum_flux(cu.tensor, cv.tensor, lon_contiguous=lon_last).cpu().numpy()
     return compat.like(u, cu.to_input_layout(out), u.dims, name="mflux")
 
 
@@ -226,7 +257,7 @@ def calculate_smoothed_field(data, passes, weights=np.array([[0, 1, 0], [1, 2, 1
                              **kwargs):
     """``passes`` x 5-point smoothing (scipy.ndimage.convolve semantics), latitude border rows NaN
     (processing/spatial.py:60-128).  The result has dims (time, lat, lon) like the reference's."""
-    c = _Canon(data, kwargs, orient=False)  # the reference convolves the (lat, lon) slices as they are stored
+    c = _canon(data, kwargs, orient=False)  # the reference convolves the (lat, lon) slices as they are stored
     out = spatial.smooth(c.tensor, passes, np.asarray(weights), mode).cpu().numpy()
     dims = (c.time_name, c.lat_name, c.lon_name)
     attrs = dict(getattr(data, "attrs", {}) or {})
@@ -236,11 +267,26 @@ def calculate_smoothed_field(data, passes, weights=np.array([[0, 1, 0], [1, 2, 1
 
 # ------------------------------------------------------------------------------------------- contours
 class _DeviceContours:
-    """Device-resident contours attached to the frame returned by ``calculate_contours(original_coordinates=False)``."""
+    """Device-resident contours of a frame returned by ``calculate_contours(original_coordinates=False)``."""
 
     def __init__(self, batches, canon, levels, periodic_add):
         self.batches = batches  # list of (t0, ContourSet)
         self.key = (tuple(canon.time.tolist()), canon.nlat, canon.nlon, tuple(levels), periodic_add)
+
+
+# frame.attrs only carries a small integer token: pandas deep-copies attrs into every derived frame and serialises
+# them (to_parquet), which must not duplicate or choke on device buffers.  The buffers live here, most recent last.
+_DEVICE_CONTOURS = {}
+_DEVICE_TOKEN = [0]
+
+
+def _remember_device_contours(frame, dev):
+    _DEVICE_TOKEN[0] += 1
+    token = _DEVICE_TOKEN[0]
+    _DEVICE_CONTOURS[token] = dev
+    for old in sorted(_DEVICE_CONTOURS)[:-4]:
+        del _DEVICE_CONTOURS[old]
+    frame.attrs["_wbk_device_token"] = token
 
 
 def _batch_size(nlat, nlon, nlevels):
@@ -260,30 +306,49 @@ def _contour_batches(c, levels, periodic_add):
 
 
 def _contour_frame(c, batches, levels, original_coordinates):
-    rows = dict(date=[], level=[], closed=[], exp_lon=[], mean_lat=[])
-    geoms = []
+    """Frame of all contours (contour_index.py:149-194), built from the ragged host arrays of the batches: no
+    per-contour numpy work except the float mean of the original-coordinate latitudes (numpy's own summation order)."""
     nlev = len(levels)
+    xs, ys, lens, tsteps, lidx, closed, nx, sumy = [], [], [], [], [], [], [], []
     for t0, cs in batches:
         h = cs.host()
-        for k in range(cs.ncontours):
-            a, b = h["pt_off"][k], h["pt_off"][k + 1]
-            x, y = h["x"][a:b], h["y"][a:b]
-            t, l = divmod(int(h["job"][k]), nlev)
-            rows["date"].append(c.time[t0 + t])
-            rows["level"].append(levels[l])
-            rows["closed"].append(bool(h["closed"][k]))
-            if original_coordinates:
-                # contour_index.py:179-191: map to coordinates, drop repeated points (keep first)
-                xy = np.c_[c.lon[x % c.nlon], c.lat[y]]
-                _, first = np.unique(xy, axis=0, return_index=True)
-                xy = xy[np.sort(first)]
-                rows["exp_lon"].append(len(set(xy[:, 0].tolist())) * c.dlon)
-                rows["mean_lat"].append(np.round(xy[:, 1].mean(), 2))
-                geoms.append(compat.LineString(xy))
-            else:
-                rows["exp_lon"].append(int(h["nx"][k]) * c.dlon)
-                rows["mean_lat"].append(np.round(y.mean(), 2))
-                geoms.append(compat.LineString(np.c_[x, y]))
+        xs.append(h["x"])
+        ys.append(h["y"])
+        lens.append(np.diff(h["pt_off"]))
+        tsteps.append(t0 + h["job"] // nlev)
+        lidx.append(h["job"] % nlev)
+        closed.append(h["closed"])
+        nx.append(h["nx"])
+        sumy.append(h["sum_y"])
+    cat = lambda parts, dt: np.concatenate(parts).astype(dt) if parts else np.zeros(0, dtype=dt)
+    x, y, lens = cat(xs, np.int64), cat(ys, np.int64), cat(lens, np.int64)
+    tsteps, lidx = cat(tsteps, np.int64), cat(lidx, np.int64)
+    n = len(lens)
+    off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    rows = dict(date=np.asarray(c.time)[tsteps], level=np.asarray(levels, dtype=object)[lidx] if n else [],
+                closed=cat(closed, bool))
+    if not original_coordinates:
+        rows["exp_lon"] = cat(nx, np.int64) * c.dlon
+        # mean of the integer rows: the float64 sum of ints < 2^53 is exact in any order
+        rows["mean_lat"] = np.round(cat(sumy, np.int64) / np.maximum(lens, 1), 2)
+        geoms = compat.linestrings_from_ragged(np.c_[x, y], off)
+    else:
+        # contour_index.py:179-191: map to coordinates, drop repeated points (keep first) within every contour
+        cid = np.repeat(np.arange(n, dtype=np.int64), lens)
+        xm = x % c.nlon
+        key = (cid * c.nlon + xm) * c.nlat + y
+        _, first = np.unique(key, return_index=True)
+        keep = np.zeros(len(key), dtype=bool)
+        keep[first] = True
+        lon_v, lat_v = np.asarray(c.lon, dtype=np.float64)[xm[keep]], np.asarray(c.lat, dtype=np.float64)[y[keep]]
+        klens = np.bincount(cid[keep], minlength=n).astype(np.int64)
+        koff = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(klens, out=koff[1:])
+        ncol = np.bincount(np.unique(cid * c.nlon + xm) // c.nlon, minlength=n)
+        rows["exp_lon"] = ncol * c.dlon
+        rows["mean_lat"] = np.array([np.round(lat_v[a:b].mean(), 2) for a, b in zip(koff[:-1], koff[1:])]) if n else []
+        geoms = compat.linestrings_from_ragged(np.c_[lon_v, lat_v], koff)
     return compat.make_frame(rows, geoms)
 
 
@@ -292,59 +357,67 @@ def _contour_frame(c, batches, levels, original_coordinates):
 def calculate_contours(data, contour_levels, periodic_add=120, original_coordinates=True, *args, **kwargs):
     """Contour lines for a set of levels on the periodically extended grid
     (indices/contour_index.py:45-194; time / level loops of utils/index_utils.py:217-258 batched)."""
-    c = _Canon(data, kwargs)
+    c = _canon(data, kwargs)
     levels = _as_levels(contour_levels)
     batches = _contour_batches(c, levels, periodic_add)
     frame = _contour_frame(c, batches, levels, original_coordinates)
     if not original_coordinates:
-        frame.attrs["_wbk_device"] = _DeviceContours(batches, c, levels, periodic_add)
+        _remember_device_contours(frame, _DeviceContours(batches, c, levels, periodic_add))
     return frame
 
 
 def _contours_from_frame(contours, c, levels, periodic_add):
-    """Upload user-supplied contours (index coordinates) as packed contour sets, one per batch."""
-    dev = contours.attrs.get("_wbk_device") if hasattr(contours, "attrs") else None
+    """Contour sets for the index stage: the device-resident ones of ``calculate_contours`` when the frame is the
+    one it returned, else the user's frame uploaded as ONE packed contour set.  Like the reference
+    (streamer_index.py:104-108, contour_index.py:221-231) every contour of the frame takes part, whatever its level;
+    levels missing from ``contour_levels`` are appended to the level list."""
+    token = contours.attrs.get("_wbk_device_token") if hasattr(contours, "attrs") else None
+    dev = _DEVICE_CONTOURS.get(token)
     key = (tuple(c.time.tolist()), c.nlat, c.nlon, tuple(levels), periodic_add)
     if dev is not None and dev.key == key and sum(cs.ncontours for _, cs in dev.batches) == len(contours):
-        return dev.batches
+        return dev.batches, levels
     lib = _lib.get()
-    time_index = {t: i for i, t in enumerate(c.time.tolist())}
+    levels = list(levels)
+    for lv in pd.unique(contours.level):
+        if float(lv) not in [float(v) for v in levels]:
+            levels.append(lv)
     level_index = {float(l): i for i, l in enumerate(levels)}
     nlev = len(levels)
-    jobs, closed, nx, sumy, offs, xs, ys = [], [], [], [], [0], [], []
-    for row in contours.itertuples():
-        lv = float(row.level)
-        if lv not in level_index:
-            continue
-        date = pd.Timestamp(row.date).to_datetime64().astype(c.time.dtype).item() \
-            if np.issubdtype(c.time.dtype, np.datetime64) else row.date
-        if date not in time_index:
-            continue
-        xy = compat.line_coords(row.geometry).astype(np.int64)
-        jobs.append(time_index[date] * nlev + level_index[lv])
-        closed.append(int(bool(row.closed)))
-        nx.append(len(set(xy[:, 0].tolist())))
-        sumy.append(int(xy[:, 1].sum()))
-        xs.append(xy[:, 0])
-        ys.append(xy[:, 1])
-        offs.append(offs[-1] + len(xy))
-    order = np.argsort(np.asarray(jobs, dtype=np.int64), kind="stable")
+    dates = contours.date.values
+    if np.issubdtype(c.time.dtype, np.datetime64):
+        dates = dates.astype(c.time.dtype)
+    tpos = pd.Index(c.time).get_indexer(pd.Index(dates))
+    if (tpos < 0).any():
+        raise KeyError(contours.date.values[np.argmax(tpos < 0)])
+    lpos = np.array([level_index[float(v)] for v in contours.level.values], dtype=np.int64)
+    coords = [compat.line_coords(g) for g in contours.geometry]
+    lens = np.array([len(a) for a in coords], dtype=np.int64)
+    allxy = np.concatenate(coords).astype(np.int64) if coords else np.zeros((0, 2), dtype=np.int64)
+    jobs = tpos.astype(np.int64) * nlev + lpos
+    order = np.argsort(jobs, kind="stable")
     njobs = c.ntime * nlev
-    job_arr = np.asarray(jobs, dtype=np.int64)[order]
+    job_arr = jobs[order]
     job_off = np.searchsorted(job_arr, np.arange(njobs + 1)).astype(np.int32)
-    pts = [(xs[i] | (ys[i] << 16)).astype(np.uint32) for i in order]
-    lens = np.array([len(p) for p in pts], dtype=np.int64)
-    pt_off = np.zeros(len(pts) + 1, dtype=np.int32)
-    pt_off[1:] = np.cumsum(lens)
-    meta = np.c_[np.asarray(closed)[order], np.asarray(nx)[order], np.asarray(sumy)[order], job_arr].astype(np.int32)
-    allp = np.concatenate(pts).astype(np.uint32) if pts else np.zeros(0, dtype=np.uint32)
+    off = np.zeros(len(lens) + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    from .tracking import _ranges
+
+    sel = _ranges(off[:-1][order], lens[order])
+    px, py = allxy[sel, 0], allxy[sel, 1]
+    cid = np.repeat(np.arange(len(lens), dtype=np.int64), lens[order])
+    pt_off = np.zeros(len(lens) + 1, dtype=np.int32)
+    pt_off[1:] = np.cumsum(lens[order])
+    nxc = np.bincount(np.unique(cid * 65536 + px) // 65536, minlength=len(lens)) if len(lens) else np.zeros(0, dtype=np.int64)
+    sumy = np.bincount(cid, weights=py, minlength=len(lens)).astype(np.int64) if len(lens) else np.zeros(0, dtype=np.int64)
+    meta = np.c_[contours.closed.values.astype(np.int64)[order], nxc, sumy, job_arr].astype(np.int32)
+    allp = (px | (py << 16)).astype(np.uint32)
     dev_t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(lib.device)
     cs = detect.ContourSet(
         njobs=njobs, nlevels=nlev, nlat=c.nlat, nlon=c.nlon, add=int(periodic_add / c.dlon),
         levels=np.asarray(levels, dtype=np.float64), job_off=dev_t(job_off), pt_off=dev_t(pt_off),
         meta=dev_t(meta.reshape(-1, 4)), pts=dev_t(allp.view(np.int32)), status=np.zeros(njobs, dtype=np.int32),
-        max_nx=int(max(nx)) if nx else 0, h_ncontours=np.diff(job_off), h_npoints=None)
-    return [(0, cs)]
+        max_nx=int(nxc.max()) if len(nxc) else 0, h_ncontours=np.diff(job_off), h_npoints=None)
+    return [(0, cs)], levels
 
 
 def decorator_contour_calculation(func):
@@ -378,23 +451,74 @@ def decorator_contour_calculation(func):
 _EVENT_COLUMNS = ["date", "level", "com", "mean_var", "intensity", "event_area"]
 
 
+def _event_rings(cs, tab):
+    """Ragged index-space rings of the events of one table (vectorised): (xy int64 [N, 2], off [n + 1])."""
+    from .tracking import _ranges
+
+    n = len(tab)
+    if tab.kind == "overturnings":
+        x0, y0, x1, y1 = (tab.box[:, k].astype(np.int64) for k in range(4))
+        xy = np.stack([np.c_[x1, y0], np.c_[x1, y1], np.c_[x0, y1], np.c_[x0, y0]], axis=1).reshape(-1, 2)
+        return xy, np.arange(n + 1, dtype=np.int64) * 4
+    h = cs.host()
+    start = h["pt_off"][tab.contour].astype(np.int64) + tab.ind1.astype(np.int64)
+    lens = (tab.ind2.astype(np.int64) - tab.ind1.astype(np.int64) + 1) if n else np.zeros(0, dtype=np.int64)
+    idx = _ranges(start, lens)
+    off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    return np.c_[h["x"][idx], h["y"][idx]], off
+
+
+def _fold_and_split(xy, off, split, nlon):
+    """``transform_polygons`` (utils/index_utils.py:129-184) on ragged rings: fold with ``x % nlon``; the few events
+    that straddle the last meridian (split == 1) are cut into their pieces.  Returns (xy, ring_off, poly_off)."""
+    n = len(off) - 1
+    straddle = np.nonzero(np.asarray(split) == 1)[0]
+    if len(straddle) == 0:
+        out = xy.copy()
+        out[:, 0] %= nlon
+        return out, off, np.arange(n + 1, dtype=np.int64)
+    parts, ring_len, poly_nr = [], [], np.ones(n, dtype=np.int64)
+    prev = 0
+    for e in straddle:
+        if off[e] > off[prev]:
+            seg = xy[off[prev]:off[e]].copy()
+            seg[:, 0] %= nlon
+            parts.append(seg)
+            ring_len.extend(np.diff(off[prev:e + 1]).tolist())
+        pieces = geometry.transform_ring(xy[off[e]:off[e + 1]], nlon)
+        poly_nr[e] = len(pieces)
+        for pc in pieces:
+            parts.append(np.asarray(pc, dtype=np.int64).reshape(-1, 2))
+            ring_len.append(len(pc))
+        prev = e + 1
+    if off[n] > off[prev]:
+        seg = xy[off[prev]:off[n]].copy()
+        seg[:, 0] %= nlon
+        parts.append(seg)
+        ring_len.extend(np.diff(off[prev:n + 1]).tolist())
+    allxy = np.concatenate(parts) if parts else np.zeros((0, 2), dtype=np.int64)
+    return allxy, np.r_[0, np.cumsum(ring_len)].astype(np.int64), np.r_[0, np.cumsum(poly_nr)].astype(np.int64)
+
+
 def _run_index(kind, data, contour_levels, contours, intensity, periodic_add, kwargs, **params):
-    c = _Canon(data, kwargs)
+    c = _canon(data, kwargs)
     levels = _as_levels(contour_levels)
     inten = None
     if intensity is not None:
         if not compat.is_field(intensity):
             raise TypeError("intensity has to be a " + compat.field_type_name() + "!")
-        inten = _Canon(intensity, dict(kwargs)).tensor
-    batches = _contours_from_frame(contours, c, levels, periodic_add)
+        inten = _canon(intensity, dict(kwargs)).tensor
+    batches, levels = _contours_from_frame(contours, c, levels, periodic_add)
     # exp_lon.max() is global over all dates and levels (streamer_index.py:106)
     gmax = max([cs.max_nx for _, cs in batches] + [0])
     if len(contours):
         gmax = max(gmax, int(round(float(np.max(contours.exp_lon)) / c.dlon)))
     coords = detect.coord_tables(c.lat, c.lon, c.dlon, c.dlat)
     cols = {k: [] for k in _EVENT_COLUMNS}
-    orient, geoms = [], []
+    orient, xy_parts, ring_offs, poly_offs = [], [], [], []
     nlev = len(levels)
+    lon_v, lat_v = np.asarray(c.lon, dtype=np.float64), np.asarray(c.lat, dtype=np.float64)
     for t0, cs in batches:
         nt = cs.njobs // nlev
         field = c.tensor[t0:t0 + nt]
@@ -402,23 +526,36 @@ def _run_index(kind, data, contour_levels, contours, intensity, periodic_add, kw
                                        intensity=None if inten is None else inten[t0:t0 + nt], which=(kind,),
                                        gmax_nx=gmax, want_flags=False, **params)
         tab = tables[kind]
+        if len(tab) == 0:
+            continue
         props = detect.finish_properties(tab, c.lon, c.lat, c.nlon)
-        rings = detect.event_rings(cs, tab)
-        for e in range(len(tab)):
-            t, l = divmod(int(tab.job[e]), nlev)
-            cols["date"].append(c.time[t0 + t])
-            cols["level"].append(levels[l])
-            pieces = geometry.transform_ring(rings[e], c.nlon)
-            polys = [compat.Polygon(np.c_[c.lon[p[:, 0]], c.lat[p[:, 1]]]) for p in pieces]
-            geoms.append(compat.Polygon() if not polys else polys[0] if len(polys) == 1 else compat.MultiPolygon(polys))
-            orient.append("anticyclonic" if tab.orientation[e] else "cyclonic")
-        for k in ("com", "mean_var", "intensity", "event_area"):
-            cols[k].extend(list(props[k]))
-    if len(geoms) == 0:
+        t, l = np.divmod(tab.job.astype(np.int64), nlev)
+        cols["date"].append(np.asarray(c.time)[t0 + t])
+        cols["level"].append(np.asarray(levels, dtype=object)[l])
+        for k in ("mean_var", "intensity", "event_area"):
+            cols[k].append(np.asarray(props[k]))
+        cols["com"].extend(props["com"])
+        orient.append(np.where(tab.orientation != 0, "anticyclonic", "cyclonic"))
+        xy, off = _event_rings(cs, tab)
+        pxy, roff, poff = _fold_and_split(xy, off, tab.split, c.nlon)
+        xy_parts.append(np.c_[lon_v[pxy[:, 0]], lat_v[pxy[:, 1]]])
+        ring_offs.append(roff)
+        poly_offs.append(poff)
+    if not xy_parts:
         return compat.empty_frame()
+    # one ragged geometry column for all batches
+    vo = ro = 0
+    r_all, p_all = [np.zeros(1, dtype=np.int64)], [np.zeros(1, dtype=np.int64)]
+    for xyp, roff, poff in zip(xy_parts, ring_offs, poly_offs):
+        r_all.append(roff[1:] + vo)
+        p_all.append(poff[1:] + ro)
+        vo += len(xyp)
+        ro += len(roff) - 1
+    geoms = compat.polygons_from_ragged(np.concatenate(xy_parts), np.concatenate(r_all), np.concatenate(p_all))
+    frame_cols = {k: (np.concatenate(v) if k != "com" else v) for k, v in cols.items()}
     if kind == "overturnings":
-        cols["orientation"] = orient
-    return compat.make_frame(cols, geoms)
+        frame_cols["orientation"] = np.concatenate(orient)
+    return compat.make_frame(frame_cols, geoms)
 
 
 @check_argument_types(["data"], [_FIELD])
@@ -470,22 +607,30 @@ def to_xarray(data, events, flag="ones", name="flag", *args, **kwargs):
             set_val = np.asarray(events[flag].values, dtype=np.float64)
         except KeyError:
             raise KeyError("{} is not a column of the events geopandas.GeoDataFrame.".format(flag))
-    time_index = {t: i for i, t in enumerate(c.time.tolist())}
+    # ragged extraction of all rings, then ONE vectorised snap to grid indices
+    dates = np.asarray(events["date"].values)
+    if np.issubdtype(c.time.dtype, np.datetime64):
+        dates = dates.astype(c.time.dtype)
+    tpos = pd.Index(c.time).get_indexer(pd.Index(dates))
+    if (tpos < 0).any():
+        raise KeyError(events["date"].values[int(np.argmax(tpos < 0))])
+    per_event = [compat.geometry_rings(g) for g in events["geometry"]]
+    nring = np.array([len(r) for r in per_event], dtype=np.int64)
+    flat = [np.asarray(r, dtype=np.float64).reshape(-1, 2) for rr in per_event for r in rr]
     rings, ring_t, ring_v = [], [], []
-    lon0, lat0 = c.lon[0], c.lat[0]
-    for k, (date, geom) in enumerate(zip(events["date"], events["geometry"])):
-        key = pd.Timestamp(date).to_datetime64().astype(c.time.dtype).item() \
-            if np.issubdtype(c.time.dtype, np.datetime64) else date
-        if key not in time_index:
-            raise KeyError(date)
-        for ring in compat.geometry_rings(geom):
-            idx = np.c_[(ring[:, 0] - lon0) / c.dlon, (ring[:, 1] - lat0) / c.dlat]
-            snapped = np.rint(idx)
-            if not np.allclose(idx, snapped, atol=1e-6):
-                raise ValueError("to_xarray: event vertices must lie on grid points of `data`")
-            rings.append(snapped.astype(np.int32))
-            ring_t.append(time_index[key])
-            ring_v.append(1.0 if flag == "ones" else set_val[k])
+    if flat:
+        lens = np.array([len(r) for r in flat], dtype=np.int64)
+        allxy = np.concatenate(flat)
+        idx = np.c_[(allxy[:, 0] - c.lon[0]) / c.dlon, (allxy[:, 1] - c.lat[0]) / c.dlat]
+        snapped = np.rint(idx)
+        if not np.allclose(idx, snapped, atol=1e-6):
+            raise ValueError("to_xarray: event vertices must lie on grid points of `data`")
+        snapped = snapped.astype(np.int32)
+        cuts = np.cumsum(lens)[:-1]
+        rings = np.split(snapped, cuts)
+        ev_of_ring = np.repeat(np.arange(len(per_event)), nring)
+        ring_t = tpos[ev_of_ring].tolist()
+        ring_v = (np.ones(len(flat)) if flag == "ones" else set_val[ev_of_ring]).tolist()
     lib = _lib.get()
     if flag == "ones":
         out = detect.rasterize_rings(rings, ring_t, c.nlat, c.nlon, c.ntime, 0.5).cpu().numpy()

@@ -122,6 +122,13 @@ class LineString:
     def __init__(self, coords):
         self._xy = np.asarray(coords, dtype=np.float64).reshape(-1, 2)
 
+    @classmethod
+    def from_view(cls, xy):
+        """No-copy construction from a float64 (n, 2) slice of a shared coordinate array."""
+        obj = cls.__new__(cls)
+        obj._xy = xy
+        return obj
+
     class _Coords:
         def __init__(self, xy):
             self._xy = xy
@@ -173,6 +180,13 @@ class Polygon:
             xy = np.concatenate([xy, xy[:1]])
         self._xy = xy
 
+    @classmethod
+    def from_closed_view(cls, xy):
+        """No-copy construction from a float64 (n + 1, 2) slice whose last vertex repeats the first."""
+        obj = cls.__new__(cls)
+        obj._xy = xy
+        return obj
+
     @property
     def exterior(self):
         return LineString(self._xy)
@@ -216,6 +230,12 @@ class MultiPolygon:
 
     def __init__(self, polygons):
         self.geoms = [p if isinstance(p, Polygon) else Polygon(p) for p in polygons]
+
+    @classmethod
+    def from_parts(cls, polygons):
+        obj = cls.__new__(cls)
+        obj.geoms = polygons
+        return obj
 
     @property
     def is_empty(self):
@@ -286,3 +306,44 @@ def is_frame(obj):
 
 def frame_type_name():
     return "geopandas.geodataframe.GeoDataFrame"
+
+
+# --------------------------------------------------------------------------------------------- ragged construction
+def linestrings_from_ragged(xy, off):
+    """Geometry column of LineStrings from one (N, 2) float64 coordinate array and offsets [n + 1]: shapely's
+    vectorised ``from_ragged_array`` when shapely is installed, no-copy views otherwise."""
+    xy = np.ascontiguousarray(xy, dtype=np.float64)
+    off = np.asarray(off, dtype=np.int64)
+    if _shapely is not None:  # pragma: no cover
+        return list(_shapely.from_ragged_array(_shapely.GeometryType.LINESTRING, xy, (off,)))
+    return [LineString.from_view(xy[a:b]) for a, b in zip(off[:-1], off[1:])]
+
+
+def polygons_from_ragged(xy, ring_off, poly_off):
+    """Geometry column of (Multi)Polygons: polygon p = rings [poly_off[p], poly_off[p+1]) (0 rings: the empty
+    ``Polygon()``, 1: Polygon, more: MultiPolygon), ring r = OPEN vertices [ring_off[r], ring_off[r+1]) of ``xy``.
+    The rings are closed once, vectorised (first vertex appended), and the geometries are views into that array."""
+    xy = np.ascontiguousarray(xy, dtype=np.float64)
+    ring_off = np.asarray(ring_off, dtype=np.int64)
+    poly_off = np.asarray(poly_off, dtype=np.int64)
+    nr = len(ring_off) - 1
+    lens = np.diff(ring_off)
+    # closed copy: ring r occupies [ring_off[r] + r, ring_off[r+1] + r + 1)
+    closed = np.empty((len(xy) + nr, 2), dtype=np.float64)
+    src = np.arange(len(xy), dtype=np.int64)
+    shift = np.repeat(np.arange(nr, dtype=np.int64), lens)
+    closed[src + shift] = xy
+    if nr:
+        closed[ring_off[1:] + np.arange(nr)] = xy[np.minimum(ring_off[:-1], max(len(xy) - 1, 0))]
+    coff = ring_off + np.arange(nr + 1)
+    if _shapely is not None:  # pragma: no cover
+        polys = _shapely.from_ragged_array(_shapely.GeometryType.POLYGON, closed, (coff, np.arange(nr + 1)))
+        out = []
+        for a, b in zip(poly_off[:-1], poly_off[1:]):
+            out.append(_shapely.Polygon() if b == a else polys[a] if b - a == 1 else _shapely.MultiPolygon(list(polys[a:b])))
+        return out
+    rings = [Polygon.from_closed_view(closed[a:b]) for a, b in zip(coff[:-1], coff[1:])]
+    out = []
+    for a, b in zip(poly_off[:-1], poly_off[1:]):
+        out.append(Polygon() if b == a else rings[a] if b - a == 1 else MultiPolygon.from_parts(rings[a:b]))
+    return out

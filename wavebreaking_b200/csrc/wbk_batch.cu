@@ -14,12 +14,24 @@ __global__ void __launch_bounds__(1024) pack_scan_kernel(WbkDev d, WbkIdx x, int
   __syncthreads();
   const int C = wbk_block_excl_scan(job_off, njobs, sscan);
   const int P = wbk_block_excl_scan(pt_job_off, njobs, sscan);
+  const bool over = C > cap_c || P > cap_p;  // block-uniform (the scans return the totals to every thread)
+  if (over) {
+    // the caller's buffers are too small: nothing is packed (WBK_ST_PACK_OVERFLOW, the batch is re-run with larger
+    // buffers); the job offsets are zeroed so that the index kernels of this batch see an EMPTY contour set instead of
+    // offsets into buffers that were never written
+    for (int j = threadIdx.x; j <= njobs; j += blockDim.x) {
+      job_off[j] = 0;
+      pt_job_off[j] = 0;
+    }
+  }
   if (threadIdx.x == 0) {
-    job_off[njobs] = C;
-    pt_job_off[njobs] = P;
+    if (!over) {
+      job_off[njobs] = C;
+      pt_job_off[njobs] = P;
+    }
     x.total[2] = C;
     x.total[3] = P;
-    if (C > cap_c || P > cap_p) atomicOr(&d.status[0], (int)WBK_ST_PACK_OVERFLOW);
+    if (over) atomicOr(&d.status[0], (int)WBK_ST_PACK_OVERFLOW);
   }
 }
 
@@ -91,7 +103,16 @@ __global__ void __launch_bounds__(1024) ring_scan_kernel(WbkDev d, WbkIdx x, int
                                                          int* __restrict__ ring_off, int cap, int cap_ring) {
   __shared__ int sscan[40];
   const int total = x.ev_off[3 * njobs];
-  const int n = total < cap ? total : cap;
+  if (total > cap) {
+    // more events than the caller's buffers hold: the gather left records unwritten, nothing below may be trusted.
+    // The batch is re-run with larger buffers (WBK_ST_FETCH_OVERFLOW).
+    if (threadIdx.x == 0) {
+      ring_off[0] = 0;
+      atomicOr(&d.status[0], (int)WBK_ST_FETCH_OVERFLOW);
+    }
+    return;
+  }
+  const int n = total;
   const int n_box = x.ev_off[2 * njobs] - x.ev_off[njobs];  // overturnings carry a box, no ring
   const int b0 = x.ev_off[njobs];
   for (int e = threadIdx.x; e < n; e += blockDim.x) {
@@ -110,7 +131,8 @@ __global__ void ring_copy_kernel(WbkIdx x, int njobs, const int* __restrict__ o_
                                  const int* __restrict__ pt_off, const u32* __restrict__ pts, u32* __restrict__ ring_pts,
                                  int cap, int cap_ring) {
   const int total = x.ev_off[3 * njobs];
-  const int n = total < cap ? total : cap;
+  if (total > cap) return;  // see ring_scan_kernel
+  const int n = total;
   for (int e = blockIdx.x; e < n; e += gridDim.x) {
     const int a = ring_off[e], len = ring_off[e + 1] - a;
     if (len <= 0 || a + len > cap_ring) continue;
@@ -119,12 +141,16 @@ __global__ void ring_copy_kernel(WbkIdx x, int njobs, const int* __restrict__ o_
   }
 }
 
-// summary record: contours, points, events[3], OR of the status bits, max_nx, split events
+// summary record: contours, points, events[3], OR of the status bits, max_nx, split events; then the work counters
+// marching-squares segments, streamer candidate pairs, near-threshold decisions, active pair-scan tiles
 __global__ void __launch_bounds__(1024) summary_kernel(WbkDev d, WbkIdx x, int J, int njobs, int* __restrict__ out) {
   __shared__ int acc[8];
+  __shared__ unsigned long long acc64[2];
   if (threadIdx.x < 8) acc[threadIdx.x] = 0;
+  if (threadIdx.x < 2) acc64[threadIdx.x] = 0;
   __syncthreads();
   int c = 0, p = 0, e0 = 0, e1 = 0, e2 = 0, st = 0;
+  unsigned long long sg = 0, pr = 0;
   for (int j = threadIdx.x; j < njobs; j += blockDim.x) {
     c += d.out_nc[j];
     p += d.out_np[j];
@@ -132,14 +158,24 @@ __global__ void __launch_bounds__(1024) summary_kernel(WbkDev d, WbkIdx x, int J
     e1 += x.ev_count[1 * J + j];
     e2 += x.ev_count[2 * J + j];
     st |= d.status[j];
+    sg += (unsigned long long)d.seg_count[j];
+    for (int s = 0; s < x.SC; ++s)
+      if (s < x.nsel[j]) pr += (unsigned long long)x.cnt1[j * x.SC + s];
   }
   atomicAdd(&acc[0], c); atomicAdd(&acc[1], p); atomicAdd(&acc[2], e0); atomicAdd(&acc[3], e1); atomicAdd(&acc[4], e2);
   atomicOr(&acc[5], st);
+  atomicAdd(&acc64[0], sg);
+  atomicAdd(&acc64[1], pr);
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int k = 0; k < 6; ++k) out[k] = acc[k];
     out[6] = *d.max_nx;
     out[7] = x.split_count[1];
+    out[8] = (int)(acc64[0] > 0x7fffffffULL ? 0x7fffffffULL : acc64[0]);
+    out[9] = (int)(acc64[1] > 0x7fffffffULL ? 0x7fffffffULL : acc64[1]);
+    out[10] = *x.near_cnt;
+    out[11] = x.total[0];
+    out[12] = out[13] = out[14] = out[15] = 0;
   }
 }
 
@@ -153,7 +189,7 @@ extern "C" int wbk_batch_fetch(wbk_ctx* ctx, const int* d_pt_off, const uint32_t
   cudaStream_t st = (cudaStream_t)stream;
   const int nj = ctx->njobs, J = ctx->caps.max_jobs;
   if (nj == 0) {
-    WBK_CUDA_CHECK(cudaMemsetAsync(d_summary, 0, 8 * sizeof(int), st));
+    WBK_CUDA_CHECK(cudaMemsetAsync(d_summary, 0, 16 * sizeof(int), st));
     return WBK_OK;
   }
   WBK_LAUNCH(KID_EVENTS_GATHER, events_gather_all_kernel, dim3(3 * nj), dim3(128), 0, st, ctx->d, ctx->x, J, nj, d_out_int,
@@ -168,6 +204,45 @@ extern "C" int wbk_batch_fetch(wbk_ctx* ctx, const int* d_pt_off, const uint32_t
     WBK_LAUNCH_CHECK();
   }
   WBK_LAUNCH(KID_MISC, summary_kernel, dim3(1), dim3(1024), 0, st, ctx->d, ctx->x, J, nj, d_summary);
+  WBK_LAUNCH_CHECK();
+  return WBK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Bit-packing of the int8 flag grids for the device -> host link (processing/events.py:105-106 makes them int8; on
+// the wire one bit per cell is enough: 3.1 -> 0.39 MB per 721 x 1440 time step).  Cell c goes to bit (c & 7) of byte
+// c >> 3 (numpy.unpackbits(..., bitorder="little") restores the grid).  Every thread packs 32 cells (two 16-byte
+// loads) into one 32-bit store.
+__global__ void __launch_bounds__(256) pack_bits_kernel(const int8_t* __restrict__ in, u32* __restrict__ out, long long ncells) {
+  const long long nwords = (ncells + 31) >> 5;
+  for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += (long long)gridDim.x * blockDim.x) {
+    const long long c0 = w << 5;
+    u32 bits = 0;
+    if (c0 + 32 <= ncells) {
+      const uint4 a = *reinterpret_cast<const uint4*>(in + c0), b = *reinterpret_cast<const uint4*>(in + c0 + 16);
+      const u32 v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const u32 x = v[k];
+        const u32 nz = ((x & 0xffu) ? 1u : 0u) | ((x & 0xff00u) ? 2u : 0u) | ((x & 0xff0000u) ? 4u : 0u) | ((x & 0xff000000u) ? 8u : 0u);
+        bits |= nz << (4 * k);
+      }
+    } else {
+      for (int k = 0; k < 32 && c0 + k < ncells; ++k) bits |= (in[c0 + k] != 0 ? 1u : 0u) << k;
+    }
+    out[w] = bits;
+  }
+}
+
+extern "C" int wbk_pack_flags(const int8_t* d_flags, uint8_t* d_packed, long long ncells, void* stream) {
+  if (ncells < 0 || (ncells > 0 && (!d_flags || !d_packed)) || ((uintptr_t)d_flags & 15) || ((uintptr_t)d_packed & 3)) {
+    wbk_set_error("wbk_pack_flags: invalid argument (flags 16-byte, packed 4-byte aligned; packed holds 4 * ceil(ncells / 32) bytes)");
+    return WBK_ERR_INVALID;
+  }
+  if (ncells == 0) return WBK_OK;
+  const long long nwords = (ncells + 31) >> 5;
+  const int grid = (int)((nwords + 255) / 256 < 148 * 16 ? (nwords + 255) / 256 : 148 * 16);
+  WBK_LAUNCH(KID_MISC, pack_bits_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, d_flags, (u32*)d_packed, ncells);
   WBK_LAUNCH_CHECK();
   return WBK_OK;
 }

@@ -738,7 +738,7 @@ extern "C" int wbk_contours(wbk_ctx* ctx, const void* d_field, int dtype, int nt
 // column, the last strip wraps to column 0 = the periodic extension) and classifies all squares of the row with
 // the same bit expression as ms_segments_kernel.  Hits are compacted per warp and emitted by ms_emit_squares.
 #define MSP_THREADS 128
-#define MSP_ROWS 8
+#define MSP_ROWS 4
 
 __device__ __forceinline__ u64 msp_spread(u32 v) {
   u64 x = v;
@@ -755,25 +755,63 @@ struct MspGeom {
   int ntime, nchunks;
 };
 
-// 64-column bit row of plane word pair `w` (even, odd) of (t, row, strip s), bit j = strip column j; the bit right
-// of the last valid column is taken from the next strip
-__device__ __forceinline__ u64 msp_row(const u32* __restrict__ planes, const MspGeom& g, size_t row_base, int s, int w,
-                                       int vcols) {
-  const u32* p = planes + (row_base + s) * g.PW + w;
-  u64 m = msp_spread(p[0]) | (msp_spread(p[1]) << 1);
-  const int sn = s + 1 == g.nstrips ? 0 : s + 1;
-  const u32* q = planes + (row_base + sn) * g.PW + w;
-  const u32 nb = (q[g.P & 1] >> (g.P >> 1)) & 1u;  // strip column P of the next strip
-  const int j = g.P + vcols;                        // < 64
-  m = (m & ~(1ULL << j)) | ((u64)nb << j);
-  return m;
+// 64-column bit row from the even / odd column words (e, o) of a strip row; the bit right of the last valid column
+// (strip column P + vcols) is taken from the next strip's words (ne, no): its strip column P
+__device__ __forceinline__ u64 msp_bits(u32 e, u32 o, u32 ne, u32 no, int P, int vcols) {
+  const u64 m = msp_spread(e) | (msp_spread(o) << 1);
+  const u32 nb = (((P & 1) ? no : ne) >> (P >> 1)) & 1u;
+  const int j = P + vcols;  // < 64
+  return (m & ~(1ULL << j)) | ((u64)nb << j);
+}
+
+// Emission of the hits a warp found in its MSP_ROWS x 32 (row, strip) items: hit h goes to lane h % 32, so every
+// ms_emit_squares call works on (up to) 32 squares whatever their distribution over rows and strips.
+// masks: [MSP_ROWS][64] words of this warp (lane l: words 2l, 2l+1 of row i), prefix: [33] hits before lane l.
+template <typename T>
+__device__ __noinline__ void msp_emit(const WbkDev& d, const T* __restrict__ src, const u32* masks, const int* prefix,
+                                      int job, int item0, int nstrips, int V, int P, double level) {
+  const int lane = wbk_lane(), nlon = d.nlon;
+  const int total = prefix[32];
+  for (int h0 = 0; h0 < total; h0 += 32) {
+    const int h = h0 + lane;
+    const bool active = h < total;
+    int r0 = 0, c0 = 0;
+    double ul = 0, ur = 0, ll = 0, lr = 0;
+    if (active) {
+      int sl = 0;  // the lane whose item holds hit h: largest sl with prefix[sl] <= h
+#pragma unroll
+      for (int step = 16; step > 0; step >>= 1)
+        if (prefix[sl + step] <= h) sl += step;
+      int k = h - prefix[sl], i = 0;
+      u64 m = 0;
+      for (; i < MSP_ROWS; ++i) {
+        m = (u64)masks[i * 64 + 2 * sl] | ((u64)masks[i * 64 + 2 * sl + 1] << 32);
+        const int c = __popcll(m);
+        if (k < c) break;
+        k -= c;
+      }
+      for (; k > 0; --k) m &= m - 1;
+      const int bit = __ffsll((long long)m) - 1;
+      const int hit_item = item0 + sl;
+      const int hs = hit_item % nstrips, hchunk = hit_item / nstrips;
+      r0 = hchunk * MSP_ROWS + i;
+      c0 = hs * V + bit - P;
+      const int cr = c0 + 1 == nlon ? 0 : c0 + 1;
+      ul = (double)src[(size_t)r0 * nlon + c0];
+      ur = (double)src[(size_t)r0 * nlon + cr];
+      ll = (double)src[(size_t)(r0 + 1) * nlon + c0];
+      lr = (double)src[(size_t)(r0 + 1) * nlon + cr];
+    }
+    ms_emit_squares(d, job, active, r0, c0, ul, ur, ll, lr, level);
+  }
 }
 
 template <typename T>
-__global__ void __launch_bounds__(MSP_THREADS)
+__global__ void __launch_bounds__(MSP_THREADS, 5)
 ms_planes_kernel(const T* __restrict__ field, const u32* __restrict__ planes, const __grid_constant__ WbkDev d,
                  const __grid_constant__ LevelPack levels, int nlevels, const __grid_constant__ MspGeom g) {
-  __shared__ u32 smask[MSP_THREADS / 32][64];
+  __shared__ u32 smask[MSP_THREADS / 32][MSP_ROWS][64];
+  __shared__ int sprefix[MSP_THREADS / 32][33];
   const int lane = wbk_lane(), warp = wbk_warp();
   const int nlat = d.nlat, nlon = d.nlon, W = d.W;
   // items of one time step are padded to whole warps, so that a warp emits into ONE job per level
@@ -785,57 +823,63 @@ ms_planes_kernel(const T* __restrict__ field, const u32* __restrict__ planes, co
   const bool live = item0 + lane < per_t;
   const int it = live ? item0 + lane : 0;  // dead lanes shadow item 0 with an empty square mask
   const int s = it % g.nstrips, chunk = it / g.nstrips;
+  const int sn = s + 1 == g.nstrips ? 0 : s + 1;  // the strip to the right (the last one wraps: periodic extension)
   const int r_begin = chunk * MSP_ROWS;
   const int r_end = min(r_begin + MSP_ROWS, nlat - 1);  // squares r0 in [r_begin, r_end)
   const int vcols = min(g.V, nlon - s * g.V);
   // squares owned by this strip: strip columns [P, P + vcols) whose base square exists (c0 <= W - 2)
-  const int c_first = s * g.V;
-  int nsq = min(vcols, W - 1 - c_first);
+  int nsq = min(vcols, W - 1 - s * g.V);
   if (nsq < 0 || !live) nsq = 0;
   const u64 sqmask = nsq >= 64 ? ~0ULL : (((1ULL << nsq) - 1ULL) << g.P);
   const size_t trow = (size_t)t * nlat;
   const T* src = field + trow * nlon;
+  // plane words of (row, strip): planes[((t * nlat + row) * nstrips + strip) * PW + w]
+  const u32* own = planes + ((trow + r_begin) * g.nstrips + s) * (size_t)g.PW;
+  const u32* nxt = planes + ((trow + r_begin) * g.nstrips + sn) * (size_t)g.PW;
+  const size_t row_words = (size_t)g.nstrips * g.PW;
 
   for (int l = 0; l < nlevels; ++l) {
-    u64 g0 = msp_row(planes, g, (trow + r_begin) * g.nstrips, s, 2 + 2 * l, vcols);
-    u64 n0 = msp_row(planes, g, (trow + r_begin) * g.nstrips, s, 0, vcols);
-    for (int r = r_begin; r < r_begin + MSP_ROWS; ++r) {  // warp-uniform trip count
-      u64 hits = 0, g1 = 0, n1 = 0;
-      if (r < r_end) {
-        g1 = msp_row(planes, g, (trow + r + 1) * g.nstrips, s, 2 + 2 * l, vcols);
-        n1 = msp_row(planes, g, (trow + r + 1) * g.nstrips, s, 0, vcols);
+    // all MSP_ROWS + 1 rows are requested before any is used (independent loads in flight)
+    u32 w[MSP_ROWS + 1][8];  // n_e, n_o, g_e, g_o of the own strip, then of the next strip
+#pragma unroll
+    for (int i = 0; i <= MSP_ROWS; ++i) {
+      const bool ok = r_begin + i <= r_end;  // rows up to r_end are read (r_end <= nlat - 1)
+      const u32* po = own + (size_t)i * row_words;
+      const u32* pn = nxt + (size_t)i * row_words;
+      w[i][0] = ok ? po[0] : 0u;
+      w[i][1] = ok ? po[1] : 0u;
+      w[i][2] = ok ? po[2 + 2 * l] : 0u;
+      w[i][3] = ok ? po[3 + 2 * l] : 0u;
+      w[i][4] = ok ? pn[0] : 0u;
+      w[i][5] = ok ? pn[1] : 0u;
+      w[i][6] = ok ? pn[2 + 2 * l] : 0u;
+      w[i][7] = ok ? pn[3 + 2 * l] : 0u;
+    }
+    int cnt = 0;
+    u64 g0 = msp_bits(w[0][2], w[0][3], w[0][6], w[0][7], g.P, vcols);
+    u64 n0 = msp_bits(w[0][0], w[0][1], w[0][4], w[0][5], g.P, vcols);
+#pragma unroll
+    for (int i = 0; i < MSP_ROWS; ++i) {
+      const u64 g1 = msp_bits(w[i + 1][2], w[i + 1][3], w[i + 1][6], w[i + 1][7], g.P, vcols);
+      const u64 n1 = msp_bits(w[i + 1][0], w[i + 1][1], w[i + 1][4], w[i + 1][5], g.P, vcols);
+      u64 hits = 0;
+      if (r_begin + i < r_end) {
         const u64 both = g0 & g1, either = g0 | g1, nn = n0 | n1;
         hits = ((either | (either >> 1)) & ~(both & (both >> 1))) & ~(nn | (nn >> 1)) & sqmask;
       }
+      smask[warp][i][2 * lane] = (u32)hits;
+      smask[warp][i][2 * lane + 1] = (u32)(hits >> 32);
+      cnt += __popcll(hits);
       g0 = g1;
       n0 = n1;
-      if (!__any_sync(WBK_FULL, hits != 0)) continue;
-      __syncwarp();
-      smask[warp][2 * lane] = (u32)hits;
-      smask[warp][2 * lane + 1] = (u32)(hits >> 32);
-      __syncwarp();
-      int total = 0;
-      for (int i = 0; i < 64; ++i) total += __popc(smask[warp][i]);
-      for (int h0 = 0; h0 < total; h0 += 32) {
-        const int h = h0 + lane;
-        int mi = 0, sl = 0, r0 = 0, c0 = 0;
-        double ul = 0, ur = 0, ll = 0, lr = 0;
-        const bool active = h < total && ms_locate_hit(smask[warp], 64, h, mi, sl);
-        if (active) {  // the hit belongs to the item of lane mi >> 1 (same time step, maybe another row chunk)
-          const int hit_item = item0 + (mi >> 1);
-          const int hs = hit_item % g.nstrips, hchunk = hit_item / g.nstrips;
-          r0 = hchunk * MSP_ROWS + (r - r_begin);
-          c0 = hs * g.V + ((mi & 1) * 32 + sl) - g.P;
-          const int cr = c0 + 1 == nlon ? 0 : c0 + 1;
-          ul = (double)src[(size_t)r0 * nlon + c0];
-          ur = (double)src[(size_t)r0 * nlon + cr];
-          ll = (double)src[(size_t)(r0 + 1) * nlon + c0];
-          lr = (double)src[(size_t)(r0 + 1) * nlon + cr];
-        }
-        ms_emit_squares(d, t * nlevels + l, active, r0, c0, ul, ur, ll, lr, levels.v[l]);
-      }
-      __syncwarp();
     }
+    const int incl = wbk_warp_incl_scan(cnt);
+    if (__shfl_sync(WBK_FULL, incl, 31) == 0) continue;  // warp-uniform: no contour crosses these items
+    sprefix[warp][lane + 1] = incl;
+    if (lane == 0) sprefix[warp][0] = 0;
+    __syncwarp();
+    msp_emit<T>(d, src, &smask[warp][0][0], sprefix[warp], t * nlevels + l, item0, g.nstrips, g.V, g.P, levels.v[l]);
+    __syncwarp();
   }
 }
 

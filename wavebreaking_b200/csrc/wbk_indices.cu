@@ -958,6 +958,7 @@ __global__ void __launch_bounds__(ST_THREADS) streamer_finish_kernel(WbkDev d, W
     const int base = ps.pt_off[c];
     const u32* pts = ps.pts + base;
     int P = x.cnt1[slot];
+    if (P > x.PC) P = 0;  // the pair arena overflowed (WBK_ST_PAIR_OVERFLOW is set): the batch is re-run with larger arenas
     u64* A = x.pairs2 + (size_t)slot * x.PC;
     int* flag = x.flag + (size_t)slot * x.PC;
     u64* cur = A;
@@ -1138,6 +1139,11 @@ __global__ void __launch_bounds__(ST_THREADS) streamer_finish_kernel(WbkDev d, W
   }
 }
 
+__global__ void status_clear_kernel(int* status, int n, int keep_mask) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) status[i] &= keep_mask;
+}
+
 // ------------------------------------------------------------------------------------------ host API
 extern "C" int wbk_index_run(wbk_ctx* ctx, int njobs, int nlevels, const int* d_job_off, const int* d_pt_off,
                              const int* d_meta, const uint32_t* d_pts, int ncontours, int npoints,
@@ -1159,7 +1165,12 @@ extern "C" int wbk_index_run(wbk_ctx* ctx, int njobs, int nlevels, const int* d_
   const int J = ctx->caps.max_jobs;
   PackedSet ps{d_job_off, d_pt_off, d_meta, (const u32*)d_pts, njobs, nlevels, ncontours, npoints};
   CoordTabs ct = make_coords(d_coords, d.nlat);
-  if (prm->gmax_nx >= 0) WBK_CUDA_CHECK(cudaMemsetAsync(d.status, 0, sizeof(int) * njobs, st));
+  // status bits of an earlier index run on this context are cleared; the bits of the contour / packing stages
+  // (segment, contour, pack overflow, lattice vertex) belong to the batch and stay
+  WBK_LAUNCH(KID_MISC, status_clear_kernel, dim3((njobs + 255) / 256), dim3(256), 0, st, d.status, njobs,
+             ~(int)(WBK_ST_PAIR_OVERFLOW | WBK_ST_EVENT_OVERFLOW | WBK_ST_SEL_OVERFLOW | WBK_ST_WIDTH_OVERFLOW |
+                    WBK_ST_FETCH_OVERFLOW));
+  WBK_LAUNCH_CHECK();
   WBK_LAUNCH(KID_SELECT, select_kernel, dim3((njobs + 7) / 8), dim3(256), 0, st, d, x, ps, *prm, J);
   WBK_LAUNCH_CHECK();
   if (prm->do_overturnings) {

@@ -136,52 +136,171 @@ extern "C" int wbk_nan_border(void* d_field, int dtype, int ntime, int nlat, int
 }
 
 // ------------------------------------------------------------------------------------------
-// K2: momentum flux.  One CTA per (time, lat) row: NaN-skipping zonal means of u and v in double,
-// then (u - ubar) * (v - vbar) in the data dtype (xarray arithmetic keeps float32).
+// K2: momentum flux.  One CTA per (time, lat) row: NaN-skipping zonal means of u and v, then
+// (u - ubar) * (v - vbar) in the data dtype (xarray arithmetic keeps float32).
+// The means are xarray's `.mean(lon)` = numpy.nanmean along the contiguous longitude axis: NaNs replaced by 0,
+// numpy's PAIRWISE summation in the data dtype (blocks of <= 128 values with 8 interleaved accumulators, halves
+// split at multiples of 8; numpy/_core/src/umath/loops_utils.h.src), count of the non-NaN values, and the
+// quotient evaluated in float64 and rounded to the data dtype.  Reproducing that order makes the result
+// bit-identical to the reference on a (time, lat, lon) array.  `sequential` selects the plain left-to-right order
+// numpy uses when longitude is NOT the contiguous axis of the user's array (e.g. dims (time, lon, lat)).
 // ------------------------------------------------------------------------------------------
+#define MF_MAXLEAF 1024
+
+// leaves [off, off + len) of numpy's recursion for n values, in order; returns their number
+__device__ inline int mf_leaves(int n, int* off, int* len) {
+  int stack_o[40], stack_n[40], sp = 0, nl = 0;
+  stack_o[0] = 0;
+  stack_n[0] = n;
+  sp = 1;
+  while (sp > 0) {
+    --sp;
+    const int o = stack_o[sp], m = stack_n[sp];
+    if (m <= 128) {
+      if (nl < MF_MAXLEAF) {
+        off[nl] = o;
+        len[nl] = m;
+      }
+      ++nl;
+    } else {
+      int n2 = m / 2;
+      n2 -= n2 % 8;
+      // right half is pushed first so that the left one is expanded first (leaves come out in order)
+      stack_o[sp] = o + n2;
+      stack_n[sp] = m - n2;
+      ++sp;
+      stack_o[sp] = o;
+      stack_n[sp] = n2;
+      ++sp;
+    }
+  }
+  return nl;
+}
+
+// numpy's block sum of one leaf (n <= 128) over values with NaN -> 0
+template <typename T>
+__device__ inline T mf_leaf_sum(const T* __restrict__ a, int n) {
+  auto val = [&](int i) {
+    const T v = a[i];
+    return v != v ? (T)0 : v;
+  };
+  if (n < 8) {
+    T res = (T)-0.0;
+    for (int i = 0; i < n; ++i) res = res + val(i);
+    return res;
+  }
+  T r[8];
+  for (int j = 0; j < 8; ++j) r[j] = val(j);
+  int i = 8;
+  for (; i < n - (n % 8); i += 8)
+    for (int j = 0; j < 8; ++j) r[j] = r[j] + val(i + j);
+  T res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+  for (; i < n; ++i) res = res + val(i);
+  return res;
+}
+
+// combine the leaf sums in numpy's recursion order: sum(node) = sum(left) + sum(right)
+template <typename T>
+__device__ inline T mf_combine(const T* leaf, int n) {
+  // the recursion over (offset, length) is replayed with an explicit stack of partial results
+  struct Frame { int n; int state; T left; };
+  Frame st[40];
+  int sp = 0, next_leaf = 0;
+  T ret = (T)0;
+  st[0].n = n; st[0].state = 0; st[0].left = (T)0;
+  sp = 1;
+  while (sp > 0) {
+    Frame& f = st[sp - 1];
+    if (f.n <= 128) {
+      ret = leaf[next_leaf++];
+      --sp;
+      continue;
+    }
+    int n2 = f.n / 2;
+    n2 -= n2 % 8;
+    if (f.state == 0) {
+      f.state = 1;
+      st[sp].n = n2; st[sp].state = 0; st[sp].left = (T)0;
+      ++sp;
+    } else if (f.state == 1) {
+      f.left = ret;
+      f.state = 2;
+      st[sp].n = f.n - n2; st[sp].state = 0; st[sp].left = (T)0;
+      ++sp;
+    } else {
+      ret = f.left + ret;
+      --sp;
+    }
+  }
+  return ret;
+}
+
 template <typename T>
 __global__ void mflux_kernel(const T* __restrict__ u, const T* __restrict__ v, T* __restrict__ out, int nlon,
-                             long long nrows) {
-  __shared__ double red[34];
+                             long long nrows, int sequential) {
+  __shared__ int s_off[MF_MAXLEAF], s_len[MF_MAXLEAF];
+  __shared__ T s_leaf[2][MF_MAXLEAF];
+  __shared__ int s_nl, s_cnt[2];
   __shared__ double means[2];
+  if (threadIdx.x == 0) s_nl = sequential ? 0 : mf_leaves(nlon, s_off, s_len);
+  __syncthreads();
+  const int nl = s_nl;
   for (long long r = blockIdx.x; r < nrows; r += gridDim.x) {
-  const size_t row = (size_t)r * nlon;
-  double su = 0, sv = 0, cu = 0, cv = 0;
-  for (int x = threadIdx.x; x < nlon; x += blockDim.x) {
-    double a = (double)u[row + x], b = (double)v[row + x];
-    if (!isnan(a)) { su += a; cu += 1; }
-    if (!isnan(b)) { sv += b; cv += 1; }
-  }
-  su = wbk_block_sum_f64(su, red);
-  cu = wbk_block_sum_f64(cu, red);
-  sv = wbk_block_sum_f64(sv, red);
-  cv = wbk_block_sum_f64(cv, red);
-  if (threadIdx.x == 0) {
-    means[0] = (double)(T)(su / cu);  // nanmean returns the data dtype
-    means[1] = (double)(T)(sv / cv);
-  }
-  __syncthreads();
-  const T mu = (T)means[0], mv = (T)means[1];
-  for (int x = threadIdx.x; x < nlon; x += blockDim.x) {
-    T up = u[row + x] - mu;
-    T vp = v[row + x] - mv;
-    out[row + x] = up * vp;
-  }
-  __syncthreads();
+    const size_t row = (size_t)r * nlon;
+    if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    int cu = 0, cv = 0;
+    for (int x = threadIdx.x; x < nlon; x += blockDim.x) {
+      const T a = u[row + x], b = v[row + x];
+      cu += a == a;
+      cv += b == b;
+    }
+    atomicAdd(&s_cnt[0], cu);
+    atomicAdd(&s_cnt[1], cv);
+    if (!sequential) {
+      for (int k = threadIdx.x; k < 2 * nl; k += blockDim.x) {
+        const int w = k >= nl, l = w ? k - nl : k;
+        s_leaf[w][l] = mf_leaf_sum<T>((w ? v : u) + row + s_off[l], s_len[l]);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+      const T* src = (threadIdx.x ? v : u) + row;
+      T tot;
+      if (sequential) {
+        tot = (T)0;  // strided reduce: out = a[0], then out += a[i] one row of the other axis at a time
+        for (int x = 0; x < nlon; ++x) {
+          const T val = src[x];
+          tot = x == 0 ? (val != val ? (T)0 : val) : tot + (val != val ? (T)0 : val);
+        }
+      } else {
+        tot = mf_combine<T>(s_leaf[threadIdx.x], nlon);
+      }
+      // numpy's _divide_by_count: true_divide(float, intp) runs in float64 and is cast back to the data dtype
+      means[threadIdx.x] = (double)(T)((double)tot / (double)s_cnt[threadIdx.x]);
+    }
+    __syncthreads();
+    const T mu = (T)means[0], mv = (T)means[1];
+    for (int x = threadIdx.x; x < nlon; x += blockDim.x) {
+      T up = u[row + x] - mu;
+      T vp = v[row + x] - mv;
+      out[row + x] = up * vp;
+    }
+    __syncthreads();
   }
 }
 
 extern "C" int wbk_mflux(const void* d_u, const void* d_v, void* d_out, int dtype, int ntime, int nlat, int nlon,
-                         void* stream) {
-  if (!d_u || !d_v || !d_out || nlat < 1 || nlon < 1) {
+                         int sequential, void* stream) {
+  if (!d_u || !d_v || !d_out || nlat < 1 || nlon < 1 || (!sequential && nlon > 64 * MF_MAXLEAF)) {
     wbk_set_error("wbk_mflux: invalid argument");
     return WBK_ERR_INVALID;
   }
   if (ntime == 0) return WBK_OK;
   const long long nrows = (long long)nlat * ntime;
   dim3 grid((unsigned)(nrows < (1 << 20) ? nrows : (1 << 20)));
-  if (dtype == WBK_F32) WBK_LAUNCH(KID_MFLUX, mflux_kernel<float>, grid, dim3(256), 0, (cudaStream_t)stream, (const float*)d_u, (const float*)d_v, (float*)d_out, nlon, nrows);
-  else WBK_LAUNCH(KID_MFLUX, mflux_kernel<double>, grid, dim3(256), 0, (cudaStream_t)stream, (const double*)d_u, (const double*)d_v, (double*)d_out, nlon, nrows);
+  if (dtype == WBK_F32) WBK_LAUNCH(KID_MFLUX, mflux_kernel<float>, grid, dim3(256), 0, (cudaStream_t)stream, (const float*)d_u, (const float*)d_v, (float*)d_out, nlon, nrows, sequential);
+  else WBK_LAUNCH(KID_MFLUX, mflux_kernel<double>, grid, dim3(256), 0, (cudaStream_t)stream, (const double*)d_u, (const double*)d_v, (double*)d_out, nlon, nrows, sequential);
   WBK_LAUNCH_CHECK();
   return WBK_OK;
 }

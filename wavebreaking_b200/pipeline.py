@@ -37,6 +37,21 @@ class BatchResult:
     # int32 [m, 6] = time step, level index, contour, i, j, flags (1 kept, 2 geo in band, 4 cont in band)
     near: np.ndarray = None
     near_total: int = 0
+    work: dict = None  # device work counters of the batch: marching-squares segments, candidate pairs, scan tiles
+    flags_packed: torch.Tensor = None  # pinned uint8: the three grids, one bit per cell (unpack_flags restores them)
+
+
+def packed_nbytes(ncells):
+    """bytes of the bit-packed form of ``ncells`` flag cells (whole 32-bit words)."""
+    return 4 * ((int(ncells) + 31) // 32)
+
+
+def unpack_flags(packed, nt, nlat, nlon):
+    """int8 [3, nt, nlat, nlon] flag grids from the bit-packed download (host numpy)."""
+    ncells = 3 * nt * nlat * nlon
+    buf = packed.numpy() if isinstance(packed, torch.Tensor) else np.asarray(packed)
+    bits = np.unpackbits(buf[:packed_nbytes(ncells)], bitorder="little")[:ncells]
+    return bits.view(np.int8).reshape(3, nt, nlat, nlon)
 
 
 def _pinned(shape, dtype, lib):
@@ -56,7 +71,8 @@ class _Slot:
         want = detect.default_caps(det.nlat, det.nlon, det.add, J)
         if caps:
             for k, v in caps.items():
-                want[k] = max(want[k], int(v))
+                if k in want:  # (cap_c / cap_p / cap_e / cap_r size the slot's own buffers, below)
+                    want[k] = max(want[k], int(v))
         self.ctx = detect.Context(det.nlat, det.nlon, det.add, want)
         self.cap_c = int(max(64 * J, 1024))
         self.cap_p = int(max(min(want["seg_cap"], 16384) * J, 1 << 16))
@@ -85,8 +101,8 @@ class _Slot:
         self.ev_job = torch.empty(self.cap_e, dtype=i32, device=dev)
         self.ring_off = torch.empty(self.cap_e + 1, dtype=i32, device=dev)
         self.ring_pts = torch.empty(self.cap_r, dtype=i32, device=dev)
-        self.summary = torch.zeros(8, dtype=i32, device=dev)
-        self.h_summary = _pinned(8, i32, lib)
+        self.summary = torch.zeros(16, dtype=i32, device=dev)
+        self.h_summary = _pinned(16, i32, lib)
         self.near = torch.zeros((_lib.NEAR_CAP, 4), dtype=i32, device=dev)
         self.near_cnt = torch.zeros(1, dtype=i32, device=dev)
         self.h_near = _pinned((_lib.NEAR_CAP, 4), i32, lib)
@@ -100,8 +116,12 @@ class _Slot:
         self.done = torch.cuda.Event() if lib.is_cuda else None
         self.pending = None   # (raw, ntime, flags_dev, flags_host, gmax)
         self.grow_seen = 0
+        self.packed = None    # bit-packed flag grids (device), allocated on first use
+        self.graphs = {}      # buffers key -> (torch.cuda.CUDAGraph, pending record)
+        self.graph_seen = set()
 
     def close(self):
+        self.graphs.clear()
         self.ctx.close()
 
 
@@ -110,7 +130,7 @@ class Detector:
 
     def __init__(self, lat, lon, levels=(2.0,), periodic_add=120, passes=5, which=detect.KINDS, geo_dis=800.0,
                  cont_dis=1500.0, range_group=5.0, ot_min_exp=5.0, co_min_exp=5.0, want_flags=True, fuse=True,
-                 packing=None):
+                 packing=None, graphs=False, nvtx=True):
         self.lib = _lib.get()
         self.lat = np.asarray(lat, dtype=np.float64)
         self.lon = np.asarray(lon, dtype=np.float64)
@@ -137,6 +157,10 @@ class Detector:
         self.fuse = bool(fuse)
         # CF packing of int16 input (scale_factor, add_offset, _FillValue or None), decoded in the smoothing loads
         self.packing = tuple(packing) if packing is not None else (1.0, 0.0, None)
+        self.graphs = bool(graphs)  # replay one captured CUDA graph per batch (see submit)
+        self.graph_replays = 0
+        self.graph_kernel_launches = 0
+        self.nvtx = bool(nvtx)      # NVTX ranges per stage (upload / smooth+contours / indices / properties / download)
         self.coords = detect.coord_tables(self.lat, self.lon, self.dlon, self.dlat, self.lib)
         self._slots = {}
         self._grow = {}
@@ -172,105 +196,172 @@ class Detector:
             ot_min_exp=float(p["ot_min_exp"]), co_min_exp=float(p["co_min_exp"]))
 
     # ------------------------------------------------------------------ enqueue / collect
+    def _enqueue(self, slot, raw, flags_out, flags_host, gmax_nx, smoothed, intensity, packed_host):
+        """All device work of one batch on the CURRENT stream; returns what ``collect`` needs.  Allocation-free in
+        the steady state (so it can be captured into a CUDA graph)."""
+        lib = self.lib
+        nvtx = torch.cuda.nvtx if (lib.is_cuda and self.nvtx) else None
+        nt = int(raw.shape[0])
+        st = lib.stream()
+        if nvtx:
+            nvtx.range_push("wbk.upload")
+        if raw.device != lib.device:  # host input: H2D on this slot's stream
+            if slot.raw_dev is None or slot.raw_dev.dtype != raw.dtype:
+                slot.raw_dev = torch.empty((slot.T, self.nlat, self.nlon), dtype=raw.dtype, device=lib.device)
+            slot.raw_dev[:nt].copy_(raw, non_blocking=True)
+            raw = slot.raw_dev[:nt]
+        raw = raw.contiguous()
+        raw_in = raw  # what the caller handed over (the regrow path re-submits exactly this)
+        if intensity is not None:
+            intensity = intensity.to(lib.device).contiguous()
+        if nvtx:
+            nvtx.range_pop()
+            nvtx.range_push("wbk.smooth+contours")
+        h = slot.ctx.handle
+        L = len(self.levels)
+        lv = self.levels.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+        # the stored orientation (descending ERA5 latitudes, utils/data_utils.py:196-213) and the CF packing of
+        # int16 input are resolved inside the smoothing loads: no re-oriented / decoded copy of the batch
+        opts = _lib.smooth_opts(self.flip_lat, self.flip_lon, *self.packing) if (
+            self.flip_lat or self.flip_lon or raw.dtype == torch.int16) else None
+        fused = False
+        if smoothed is not None:
+            sm = smoothed
+        elif self.passes > 0:
+            f32 = raw.dtype == torch.float32
+            if f32 and not spatial._numpy2():
+                if slot.sm_f32 is None:
+                    slot.sm_f32 = torch.empty((slot.T, self.nlat, self.nlon), dtype=torch.float32, device=lib.device)
+                sm, rmode = slot.sm_f32[:nt], _lib.ROUND_ALL
+            else:
+                sm, rmode = slot.sm[:nt], (_lib.ROUND_FIRST if f32 else _lib.ROUND_NONE)
+            if self.fuse and sm.dtype == torch.float64 and self.passes <= _lib.SMOOTH_MAX_FUSED and self.nlat >= 4:
+                lib.call("wbk_smooth_contours", h, _lib.ptr(raw), _lib.dtype_code(raw.dtype), _lib.ptr(sm), nt,
+                         self.passes, lv, L, opts, st)
+                fused = True
+            else:
+                lib.call("wbk_smooth", _lib.ptr(raw), _lib.dtype_code(raw.dtype), _lib.ptr(sm),
+                         _lib.dtype_code(sm.dtype), _lib.ptr(slot.sm_tmp), nt, self.nlat, self.nlon, self.passes,
+                         rmode, opts, st)
+        else:
+            if opts is not None:  # no smoothing: orientation / decode only
+                want = torch.float64 if raw.dtype == torch.int16 else raw.dtype
+                if slot.flipped is None or slot.flipped.dtype != want:
+                    slot.flipped = torch.empty((slot.T, self.nlat, self.nlon), dtype=want, device=lib.device)
+                lib.call("wbk_orient", _lib.ptr(raw), _lib.dtype_code(raw.dtype), _lib.ptr(slot.flipped), nt,
+                         self.nlat, self.nlon, opts, st)
+                raw = slot.flipped[:nt]
+            sm = raw
+        if not fused:
+            lib.call("wbk_contours", h, _lib.ptr(sm), _lib.dtype_code(sm.dtype), nt, lv, L, st)
+        lib.call("wbk_contours_pack_auto", h, _lib.ptr(slot.job_off), _lib.ptr(slot.pt_off), _lib.ptr(slot.meta),
+                 _lib.ptr(slot.pts), slot.cap_c, slot.cap_p, st)
+        if nvtx:
+            nvtx.range_pop()
+            nvtx.range_push("wbk.indices")
+        if intensity is not None and intensity.dtype != sm.dtype:
+            intensity = intensity.to(sm.dtype)
+        prm = self._prm(-1 if gmax_nx is None else gmax_nx)
+        lib.call("wbk_index_run", h, nt * L, L, _lib.ptr(slot.job_off), _lib.ptr(slot.pt_off), _lib.ptr(slot.meta),
+                 _lib.ptr(slot.pts), slot.cap_c, slot.cap_p, _lib.ptr(self.coords), _lib.ptr(slot.work),
+                 ctypes.byref(prm), st)
+        lib.call("wbk_near_list", h, _lib.ptr(slot.near), _lib.NEAR_CAP, _lib.ptr(slot.near_cnt), st)
+        if nvtx:
+            nvtx.range_pop()
+            nvtx.range_push("wbk.properties+to_xarray")
+        flags = None
+        if self.want_flags:
+            if flags_out is not None:
+                flags = flags_out
+            else:
+                if slot.flags is None:
+                    slot.flags = torch.empty((3, slot.T, self.nlat, self.nlon), dtype=torch.int8, device=lib.device)
+                flags = slot.flags if nt == slot.T else torch.empty((3, nt, self.nlat, self.nlon), dtype=torch.int8,
+                                                                    device=lib.device)
+        lib.call("wbk_events_raster", h, _lib.ptr(slot.job_off), _lib.ptr(slot.pt_off), _lib.ptr(slot.pts),
+                 _lib.ptr(self.coords), _lib.ptr(sm), _lib.dtype_code(sm.dtype),
+                 None if intensity is None else _lib.ptr(intensity), nt, _lib.ptr(flags), ctypes.byref(prm), st)
+        lib.call("wbk_batch_fetch", h, _lib.ptr(slot.pt_off), _lib.ptr(slot.pts), _lib.ptr(slot.ev_int),
+                 _lib.ptr(slot.ev_f64), _lib.ptr(slot.ev_job), _lib.ptr(slot.ring_off), _lib.ptr(slot.ring_pts),
+                 slot.cap_e, slot.cap_r, _lib.ptr(slot.summary), st)
+        if nvtx:
+            nvtx.range_pop()
+            nvtx.range_push("wbk.download")
+        # asynchronous read-back of everything the host needs (tables are small; flags only on request)
+        slot.h_summary.copy_(slot.summary, non_blocking=True)
+        slot.h_near_cnt.copy_(slot.near_cnt, non_blocking=True)
+        slot.h_near.copy_(slot.near, non_blocking=True)
+        slot.h_ev_int.copy_(slot.ev_int, non_blocking=True)
+        slot.h_ev_f64.copy_(slot.ev_f64, non_blocking=True)
+        slot.h_ev_job.copy_(slot.ev_job, non_blocking=True)
+        slot.h_ring_off.copy_(slot.ring_off, non_blocking=True)
+        slot.h_ring_pts.copy_(slot.ring_pts, non_blocking=True)
+        if flags_host is not None and flags is not None:
+            flags_host[:, :nt].copy_(flags[:, :nt] if flags.shape[1] != nt else flags, non_blocking=True)
+        if packed_host is not None and flags is not None:
+            # one bit per cell on the wire (wbk_pack_flags); unpack_flags() restores the int8 grids on the host
+            ncells = 3 * nt * self.nlat * self.nlon
+            if slot.packed is None:
+                slot.packed = torch.empty(packed_nbytes(3 * slot.T * self.nlat * self.nlon), dtype=torch.uint8,
+                                          device=lib.device)
+            fl = flags if flags.shape[1] == nt and flags.is_contiguous() else flags[:, :nt].contiguous()
+            lib.call("wbk_pack_flags", _lib.ptr(fl), _lib.ptr(slot.packed), ncells, st)
+            nb = packed_nbytes(ncells)
+            packed_host[:nb].copy_(slot.packed[:nb], non_blocking=True)
+        if nvtx:
+            nvtx.range_pop()
+        return dict(raw=raw_in, nt=nt, flags=flags, flags_host=flags_host, gmax=gmax_nx, smoothed=smoothed, sm=sm,
+                    intensity=intensity, packed_host=packed_host)
+
     def submit(self, slot, raw, flags_out=None, flags_host=None, gmax_nx=None, smoothed=None, stream=None,
-               intensity=None):
+               intensity=None, packed_host=None):
         """Enqueue one batch on the slot's stream (or ``stream``).  ``raw``: device tensor or (pinned) host
-        tensor [T' <= T, nlat, nlon].  No host synchronisation happens here."""
+        tensor [T' <= T, nlat, nlon].  No host synchronisation happens here.
+
+        With ``Detector(graphs=True)`` the whole batch (uploads, ~25 kernels and memsets, downloads) is captured into
+        ONE CUDA graph per (slot, buffers) the second time the same buffers are submitted and replayed afterwards: one
+        launch per batch instead of ~40 driver calls, which is what limits several ranks sharing one host."""
         lib = self.lib
         nt = int(raw.shape[0])
         if nt > slot.T:
             raise ValueError("batch of {} time steps exceeds the slot size {}".format(nt, slot.T))
         use_stream = stream if stream is not None else slot.stream
-        ctx_mgr = torch.cuda.stream(use_stream) if use_stream is not None else _null()
-        with ctx_mgr:
-            if use_stream is not None:
-                use_stream.wait_stream(torch.cuda.default_stream(lib.device))
-            st = lib.stream()
-            if raw.device != lib.device:  # host input: H2D on this slot's stream
-                if slot.raw_dev is None or slot.raw_dev.dtype != raw.dtype:
-                    slot.raw_dev = torch.empty((slot.T, self.nlat, self.nlon), dtype=raw.dtype, device=lib.device)
-                slot.raw_dev[:nt].copy_(raw, non_blocking=True)
-                raw = slot.raw_dev[:nt]
-            raw = raw.contiguous()
-            raw_in = raw  # what the caller handed over (the regrow path re-submits exactly this)
-            if intensity is not None:
-                intensity = intensity.to(lib.device).contiguous()
-            h = slot.ctx.handle
-            L = len(self.levels)
-            lv = self.levels.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
-            # the stored orientation (descending ERA5 latitudes, utils/data_utils.py:196-213) and the CF packing of
-            # int16 input are resolved inside the smoothing loads: no re-oriented / decoded copy of the batch
-            opts = _lib.smooth_opts(self.flip_lat, self.flip_lon, *self.packing) if (
-                self.flip_lat or self.flip_lon or raw.dtype == torch.int16) else None
-            fused = False
-            if smoothed is not None:
-                sm = smoothed
-            elif self.passes > 0:
-                f32 = raw.dtype == torch.float32
-                if f32 and not spatial._numpy2():
-                    if slot.sm_f32 is None:
-                        slot.sm_f32 = torch.empty((slot.T, self.nlat, self.nlon), dtype=torch.float32, device=lib.device)
-                    sm, rmode = slot.sm_f32[:nt], _lib.ROUND_ALL
-                else:
-                    sm, rmode = slot.sm[:nt], (_lib.ROUND_FIRST if f32 else _lib.ROUND_NONE)
-                if self.fuse and sm.dtype == torch.float64 and self.passes <= _lib.SMOOTH_MAX_FUSED and self.nlat >= 4:
-                    lib.call("wbk_smooth_contours", h, _lib.ptr(raw), _lib.dtype_code(raw.dtype), _lib.ptr(sm), nt,
-                             self.passes, lv, L, opts, st)
-                    fused = True
-                else:
-                    lib.call("wbk_smooth", _lib.ptr(raw), _lib.dtype_code(raw.dtype), _lib.ptr(sm),
-                             _lib.dtype_code(sm.dtype), _lib.ptr(slot.sm_tmp), nt, self.nlat, self.nlon, self.passes,
-                             rmode, opts, st)
+        args = (slot, raw, flags_out, flags_host, gmax_nx, smoothed, intensity, packed_host)
+        if use_stream is None:  # emulator
+            slot.pending = self._enqueue(*args)
+            return slot
+        graphable = self.graphs and smoothed is None and intensity is None
+        key = None
+        if graphable:
+            key = (raw.data_ptr(), raw.dtype, nt, None if flags_out is None else flags_out.data_ptr(),
+                   None if flags_host is None else flags_host.data_ptr(),
+                   None if packed_host is None else packed_host.data_ptr(), gmax_nx, use_stream.cuda_stream)
+        with torch.cuda.stream(use_stream):
+            use_stream.wait_stream(torch.cuda.default_stream(lib.device))
+            if key is not None and key in slot.graphs:
+                g, pend, nk = slot.graphs[key]
+                g.replay()
+                self.graph_replays += 1
+                self.graph_kernel_launches += nk  # kernels inside the graph (the library only counts direct launches)
+                slot.pending = pend
+            elif key is not None and key in slot.graph_seen:
+                # second submission of these buffers: everything is allocated, capture the batch
+                use_stream.synchronize()
+                g = torch.cuda.CUDAGraph()
+                n0 = lib.cdll.wbk_launch_count()
+                with torch.cuda.graph(g, stream=use_stream, capture_error_mode="relaxed"):
+                    pend = self._enqueue(*args)
+                nk = int(lib.cdll.wbk_launch_count() - n0)
+                slot.graphs[key] = (g, pend, nk)
+                g.replay()
+                self.graph_replays += 1
+                self.graph_kernel_launches += nk
+                slot.pending = pend
             else:
-                if opts is not None:  # no smoothing: orientation / decode only
-                    want = torch.float64 if raw.dtype == torch.int16 else raw.dtype
-                    if slot.flipped is None or slot.flipped.dtype != want:
-                        slot.flipped = torch.empty((slot.T, self.nlat, self.nlon), dtype=want, device=lib.device)
-                    lib.call("wbk_orient", _lib.ptr(raw), _lib.dtype_code(raw.dtype), _lib.ptr(slot.flipped), nt,
-                             self.nlat, self.nlon, opts, st)
-                    raw = slot.flipped[:nt]
-                sm = raw
-            if not fused:
-                lib.call("wbk_contours", h, _lib.ptr(sm), _lib.dtype_code(sm.dtype), nt, lv, L, st)
-            lib.call("wbk_contours_pack_auto", h, _lib.ptr(slot.job_off), _lib.ptr(slot.pt_off), _lib.ptr(slot.meta),
-                     _lib.ptr(slot.pts), slot.cap_c, slot.cap_p, st)
-            if intensity is not None and intensity.dtype != sm.dtype:
-                intensity = intensity.to(sm.dtype)
-            prm = self._prm(-1 if gmax_nx is None else gmax_nx)
-            lib.call("wbk_index_run", h, nt * L, L, _lib.ptr(slot.job_off), _lib.ptr(slot.pt_off), _lib.ptr(slot.meta),
-                     _lib.ptr(slot.pts), slot.cap_c, slot.cap_p, _lib.ptr(self.coords), _lib.ptr(slot.work),
-                     ctypes.byref(prm), st)
-            lib.call("wbk_near_list", h, _lib.ptr(slot.near), _lib.NEAR_CAP, _lib.ptr(slot.near_cnt), st)
-            flags = None
-            if self.want_flags:
-                if flags_out is not None:
-                    flags = flags_out
-                else:
-                    if slot.flags is None:
-                        slot.flags = torch.empty((3, slot.T, self.nlat, self.nlon), dtype=torch.int8, device=lib.device)
-                    flags = slot.flags if nt == slot.T else torch.empty((3, nt, self.nlat, self.nlon), dtype=torch.int8,
-                                                                        device=lib.device)
-            lib.call("wbk_events_raster", h, _lib.ptr(slot.job_off), _lib.ptr(slot.pt_off), _lib.ptr(slot.pts),
-                     _lib.ptr(self.coords), _lib.ptr(sm), _lib.dtype_code(sm.dtype),
-                     None if intensity is None else _lib.ptr(intensity), nt, _lib.ptr(flags), ctypes.byref(prm), st)
-            lib.call("wbk_batch_fetch", h, _lib.ptr(slot.pt_off), _lib.ptr(slot.pts), _lib.ptr(slot.ev_int),
-                     _lib.ptr(slot.ev_f64), _lib.ptr(slot.ev_job), _lib.ptr(slot.ring_off), _lib.ptr(slot.ring_pts),
-                     slot.cap_e, slot.cap_r, _lib.ptr(slot.summary), st)
-            # asynchronous read-back of everything the host needs (tables are small; flags only on request)
-            slot.h_summary.copy_(slot.summary, non_blocking=True)
-            slot.h_near_cnt.copy_(slot.near_cnt, non_blocking=True)
-            slot.h_near.copy_(slot.near, non_blocking=True)
-            slot.h_ev_int.copy_(slot.ev_int, non_blocking=True)
-            slot.h_ev_f64.copy_(slot.ev_f64, non_blocking=True)
-            slot.h_ev_job.copy_(slot.ev_job, non_blocking=True)
-            slot.h_ring_off.copy_(slot.ring_off, non_blocking=True)
-            slot.h_ring_pts.copy_(slot.ring_pts, non_blocking=True)
-            if flags_host is not None and flags is not None:
-                flags_host[:, :nt].copy_(flags[:, :nt] if flags.shape[1] != nt else flags, non_blocking=True)
-            if slot.done is not None:
-                slot.done.record()
-        slot.pending = dict(raw=raw_in, nt=nt, flags=flags, flags_host=flags_host, gmax=gmax_nx, smoothed=smoothed, sm=sm,
-                            intensity=intensity)
+                slot.pending = self._enqueue(*args)
+                if key is not None:
+                    slot.graph_seen.add(key)
+            slot.done.record()
         return slot
 
     def collect(self, slot):
@@ -281,7 +372,8 @@ class Detector:
         if slot.done is not None:
             slot.done.synchronize()
         s = slot.h_summary.numpy()
-        C, P, ns, no, nc, status, max_nx, n_split = (int(v) for v in s)
+        C, P, ns, no, nc, status, max_nx, n_split = (int(v) for v in s[:8])
+        work = dict(segments=int(s[8]), pairs=int(s[9]), tiles=int(s[11]))
         bad = status & (_lib.ST_SEG_OVERFLOW | _lib.ST_CONTOUR_OVERFLOW | _lib.ST_PAIR_OVERFLOW | _lib.ST_EVENT_OVERFLOW
                         | _lib.ST_SEL_OVERFLOW | _lib.ST_PACK_OVERFLOW | _lib.ST_FETCH_OVERFLOW)
         if bad:
@@ -312,13 +404,14 @@ class Detector:
             job_off=slot.job_off[:nt * L + 1], pt_off=slot.pt_off[:C + 1], meta=slot.meta[:C], pts=slot.pts[:P],
             status=np.full(nt * L, status, dtype=np.int32), max_nx=max_nx, h_ncontours=None, h_npoints=None)
         flags = pend["flags_host"] if pend["flags_host"] is not None else pend["flags"]
+        packed = pend.get("packed_host")
         n_sp = int(sum(int((t.split == 1).sum()) for t in tables.values()))
         n_near = int(slot.h_near_cnt[0]) if "streamers" in self.which else 0
         rec = slot.h_near.numpy()[:min(n_near, _lib.NEAR_CAP)]
         near = np.c_[rec[:, 0] // L, rec[:, 0] % L, rec[:, 1], rec[:, 2], rec[:, 3] & 0x0FFFFFFF, (rec[:, 3] >> 28) & 7]
         return BatchResult(ntime=nt, contours=cs, tables=tables, flags=flags,
                            gmax_nx=max_nx if pend["gmax"] is None else int(pend["gmax"]), n_split=n_sp,
-                           near=near.astype(np.int32), near_total=n_near)
+                           near=near.astype(np.int32), near_total=n_near, flags_packed=packed, work=work)
 
     def _regrow_and_rerun(self, slot, status):
         pend = slot.pending
@@ -334,10 +427,14 @@ class Detector:
             grow["event_cap"] = caps["event_cap"] * 4
         if status & _lib.ST_SEL_OVERFLOW:
             grow["sel_cap"] = caps["sel_cap"] * 4
+        # the summary record holds the true totals of the batch: size the buffers for them (with headroom) in one go
+        C, P, ns, no, nc = (int(v) for v in slot.h_summary.numpy()[:5])
         if status & _lib.ST_PACK_OVERFLOW:
-            grow["cap_c"], grow["cap_p"] = slot.cap_c * 2, slot.cap_p * 2
+            grow["cap_c"] = max(slot.cap_c * 2, int(1.3 * C))
+            grow["cap_p"] = max(slot.cap_p * 2, int(1.3 * P))
         if status & _lib.ST_FETCH_OVERFLOW:
-            grow["cap_e"], grow["cap_r"] = slot.cap_e * 2, slot.cap_r * 2
+            grow["cap_e"] = max(slot.cap_e * 2, int(1.3 * (ns + no + nc)))
+            grow["cap_r"] = slot.cap_r * 2
         self._grow = grow
         self._grow_version += 1
         if len(grow) and max(grow.values()) > (1 << 28):
@@ -350,7 +447,7 @@ class Detector:
         new.grow_seen = self._grow_version
         self._slots[key] = new
         self.submit(new, pend["raw"], flags_out=pend["flags"], flags_host=pend["flags_host"], gmax_nx=pend["gmax"],
-                    smoothed=pend["smoothed"], intensity=pend["intensity"])
+                    smoothed=pend["smoothed"], intensity=pend["intensity"], packed_host=pend.get("packed_host"))
         return self.collect(new)
 
     # ------------------------------------------------------------------ convenience
@@ -377,7 +474,7 @@ class Detector:
         self.submit(slot, raw_host, flags_host=flags_host)
         return self.collect(slot)
 
-    def stream(self, batches, depth=3, flags_host=None, shared_stream=False, gmax_nx="full"):
+    def stream(self, batches, depth=3, flags_host=None, shared_stream=False, gmax_nx="full", packed_host=None):
         """Pipelined execution: yields one BatchResult per input batch, in order.
 
         ``batches``: iterable of device or pinned-host tensors of (at most) equal length.  ``depth`` batches are
@@ -385,6 +482,8 @@ class Detector:
         handling overlap.  With ``shared_stream`` all slots enqueue on ONE side stream: kernels of different
         batches do not overlap each other, the host merely runs ahead (device-resident inputs).
         ``flags_host``: optional list of pinned int8 buffers, one per slot.
+        ``packed_host``: optional list of pinned uint8 buffers (``packed_nbytes(3 * T * nlat * nlon)`` bytes), one per
+        slot: the flag grids come back bit-packed (8x less device -> host traffic; ``unpack_flags`` restores them).
         ``gmax_nx``: the global ``exp_lon.max()`` in columns.  The reference takes it over ALL dates of a call
         (streamer_index.py:106, overturning_index.py:105, cutoff_index.py:90), a stream only sees one batch at a
         time, so the default ``"full"`` uses the width of the extended grid, ``nlon + periodic_add / dlon``: the value
@@ -414,7 +513,8 @@ class Detector:
                 yield res
             slot = self._slot(int(raw.shape[0]), idx)
             fh = flags_host[idx] if flags_host is not None else None
-            inflight.append(self.submit(slot, raw, flags_host=fh, stream=common, gmax_nx=gmax_nx))
+            ph = packed_host[idx] if packed_host is not None else None
+            inflight.append(self.submit(slot, raw, flags_host=fh, stream=common, gmax_nx=gmax_nx, packed_host=ph))
             i += 1
         while inflight:
             res = self.collect(inflight.pop(0))
@@ -440,6 +540,7 @@ def summarize(res):
         ntime=res.ntime, contours=res.contours.ncontours, points=res.contours.npoints,
         streamers=len(res.tables["streamers"]), overturnings=len(res.tables["overturnings"]),
         cutoffs=len(res.tables["cutoffs"]), split=res.n_split, near=res.near_total,
+        segments=(res.work or {}).get("segments", 0), pairs=(res.work or {}).get("pairs", 0),
     )
 
 

@@ -98,8 +98,10 @@ def smooth(data, passes, weights=DEFAULT_WEIGHTS, mode="wrap", numpy2_promotion=
     return cur
 
 
-def momentum_flux(u, v):
-    """(u - zonal mean) * (v - zonal mean), NaN-skipping means (spatial.py:50-54)."""
+def momentum_flux(u, v, lon_contiguous=True):
+    """(u - zonal mean) * (v - zonal mean), NaN-skipping means (spatial.py:50-54), bit-identical to the reference's
+    numpy arithmetic: ``lon_contiguous`` tells whether longitude is the fastest axis of the user's array (numpy then
+    sums pairwise) or not (plain sequential sums)."""
     lib = _lib.get()
     a, b = to_device(u, lib), to_device(v, lib)
     if a.shape != b.shape or a.dim() != 3:
@@ -109,7 +111,7 @@ def momentum_flux(u, v):
     out = torch.empty_like(a)
     ntime, nlat, nlon = a.shape
     lib.call("wbk_mflux", _lib.ptr(a), _lib.ptr(b), _lib.ptr(out), _lib.dtype_code(a.dtype), ntime, nlat, nlon,
-             lib.stream())
+             0 if lon_contiguous else 1, lib.stream())
     return out
 
 
