@@ -267,6 +267,14 @@ int wbk_batch_fetch(wbk_ctx* ctx, const int* d_pt_off, const uint32_t* d_pts, in
                     int* d_out_job, int* d_ring_off, uint32_t* d_ring_pts, int cap_events, int cap_ring, int* d_summary,
                     void* stream);
 
+/* Pieces of the events that straddle the last meridian (utils/index_utils.py:148-173 transform_polygons), as the
+ * device clipper of the last wbk_events_raster left them (flags must have been requested): ring r = vertices
+ * [d_ring_off[r], d_ring_off[r+1]) of d_xy (int32 x, y: folded index coordinates of the real grid), d_ring_ev[r] = row of
+ * the event in the wbk_batch_fetch tables.  d_count[3] = pieces, vertices, clipper overflow flag (pieces > cap_rings
+ * or vertices > cap_vertices: the caller's buffers were too small).  Asynchronous. */
+int wbk_split_fetch(wbk_ctx* ctx, int* d_ring_ev, int* d_ring_off, int* d_xy, int cap_rings, int cap_vertices,
+                    int* d_count, void* stream);
+
 /* Bit-packed copy of flag grids for the device -> host link: cell c of d_flags (int8, != 0 means set) becomes bit
  * (c & 7) of byte c >> 3 of d_packed (numpy.unpackbits(..., bitorder="little") restores the grid).  d_packed holds
  * 4 * ceil(ncells / 32) bytes; d_flags 16-byte aligned, d_packed 4-byte aligned. */

@@ -145,28 +145,40 @@ def buffered_contains(rings, r, px, py, edge_chunk=128):
 
 
 def ring_is_simple(ring):
-    """True if the closed lattice ring neither touches nor crosses itself."""
-    ring = np.asarray(ring, dtype=np.int64)
+    """True if the closed lattice ring neither touches nor crosses itself (vectorised over all edge pairs)."""
+    ring = np.asarray(ring, dtype=np.int64).reshape(-1, 2)
     n = len(ring)
     if n < 3:
         return False
-    nxt = np.roll(ring, -1, axis=0)
-    for i in range(n):
-        for j in range(i + 1, n):
-            adjacent = (j == i + 1) or (i == 0 and j == n - 1)
-            if adjacent:
-                # adjacent edges share one vertex; they must not fold back onto each other
-                if j == i + 1:
-                    a, b, c = ring[i], ring[j], nxt[j]
-                else:
-                    a, b, c = ring[j], ring[i], nxt[i]
-                if _orient(a[0], a[1], b[0], b[1], c[0], c[1]) == 0:
-                    if (a[0] - b[0]) * (c[0] - b[0]) + (a[1] - b[1]) * (c[1] - b[1]) > 0:
-                        return False
-                continue
-            if segments_intersect(ring[i], nxt[i], ring[j], nxt[j]):
-                return False
-    return True
+    a, b = ring, np.roll(ring, -1, axis=0)
+    if np.any(np.all(a == b, axis=1)):
+        return False  # repeated consecutive vertex
+    # adjacent edges share one vertex; they must not fold back onto each other
+    c = np.roll(ring, -2, axis=0)
+    cr = (b[:, 0] - a[:, 0]) * (c[:, 1] - b[:, 1]) - (b[:, 1] - a[:, 1]) * (c[:, 0] - b[:, 0])
+    dot = (a[:, 0] - b[:, 0]) * (c[:, 0] - b[:, 0]) + (a[:, 1] - b[:, 1]) * (c[:, 1] - b[:, 1])
+    if np.any((cr == 0) & (dot > 0)):
+        return False
+    if n == 3:
+        return True
+    # non-adjacent edges must not share any point (closed segments)
+    ax, ay, bx, by = a[:, 0][:, None], a[:, 1][:, None], b[:, 0][:, None], b[:, 1][:, None]
+    cx, cy, dx, dy = a[:, 0][None, :], a[:, 1][None, :], b[:, 0][None, :], b[:, 1][None, :]
+    d1 = (bx - ax) * (cy - ay) - (by - ay) * (cx - ax)
+    d2 = (bx - ax) * (dy - ay) - (by - ay) * (dx - ax)
+    d3 = (dx - cx) * (ay - cy) - (dy - cy) * (ax - cx)
+    d4 = (dx - cx) * (by - cy) - (dy - cy) * (bx - cx)
+    proper = (np.sign(d1) * np.sign(d2) < 0) & (np.sign(d3) * np.sign(d4) < 0)
+
+    def on(px, py, qx, qy, rx, ry):  # r on the closed segment pq, given collinear
+        return (np.minimum(px, qx) <= rx) & (rx <= np.maximum(px, qx)) & (np.minimum(py, qy) <= ry) & (ry <= np.maximum(py, qy))
+
+    touch = ((d1 == 0) & on(ax, ay, bx, by, cx, cy)) | ((d2 == 0) & on(ax, ay, bx, by, dx, dy)) | \
+            ((d3 == 0) & on(cx, cy, dx, dy, ax, ay)) | ((d4 == 0) & on(cx, cy, dx, dy, bx, by))
+    hit = proper | touch
+    i, j = np.indices((n, n))
+    adjacent = (i == j) | ((i + 1) % n == j) | ((j + 1) % n == i)
+    return not bool(np.any(hit & ~adjacent))
 
 
 # --------------------------------------------------------------------------- meridian split
@@ -320,9 +332,9 @@ def split_ring_at_meridian(ring, nlon):
             keep[1:] = np.any(xy[1:] != xy[:-1], axis=1)
             if len(xy) > 1 and np.all(xy[0] == xy[-1]):
                 keep[-1] = False
-            xy = xy[keep]
-            if len(xy) >= 3:
-                pieces.append(xy)
+            # a sliver face may collapse to two points (or one) under the truncation: it is kept -- GEOS buffers a
+            # degenerate ring like the segment / point it collapses to, so to_xarray still flags the cells next to it
+            pieces.append(xy[keep])
     return pieces
 
 

@@ -257,3 +257,22 @@ def test_device_contours_are_not_stored_in_attrs_emu(emu):
     a = wb.calculate_cutoffs(sm, 2, contours=c)
     b = wb.calculate_cutoffs(sm, 2, contours=c.copy(deep=True).assign(dummy=1))  # host upload path
     assert len(a) == len(b) and list(a.event_area) == list(b.event_area)
+
+
+def test_results_stay_on_the_device_until_read_emu(emu):
+    """calculate_smoothed_field / to_xarray return Fields whose values are downloaded on first access; the index
+    functions take the device tensor of the smoothed Field directly -- results equal the eager path"""
+    data, grid, raw = demo_like(2)
+    sm = wb.calculate_smoothed_field(data, 5)
+    assert sm._values is None and sm.shape == raw.shape and sm.dtype == np.float64  # nothing downloaded yet
+    c = wb.calculate_contours(sm, 2, original_coordinates=False)
+    st = wb.calculate_streamers(sm, 2, contours=c)
+    fl = wb.to_xarray(sm, st)
+    assert sm._values is None and fl._values is None
+    want_sm = P.smooth_field(raw, 5)
+    # an eagerly materialised copy of the same field gives identical results
+    sm2 = compat.Field(want_sm, ("time", "lat", "lon"), {"time": grid.time, "lat": grid.lat, "lon": grid.lon}, name="smooth_PV")
+    st2 = wb.calculate_streamers(sm2, 2, contours=wb.calculate_contours(sm2, 2, original_coordinates=False))
+    assert len(st) == len(st2) and list(st.event_area) == list(st2.event_area)
+    assert np.array_equal(np.asarray(fl.values), np.asarray(wb.to_xarray(sm2, st2).values)) and fl.values.dtype == np.int8
+    assert np.array_equal(np.nan_to_num(sm.values), np.nan_to_num(want_sm))

@@ -189,3 +189,43 @@ def test_near_threshold_pairs_are_listed_kept_and_rejected_emu(emu):
             else:
                 assert bool(flags & 1) == (cont[i, j] > kw[which])  # the reference's row cumsum decides inside the band
             assert res.near_total == len(res.near) >= 1
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_split_ring_fuzz_regions_and_flag_cells(seed):
+    """Simple lattice polygons on a SMALL lattice around the seam, so that vertices on the two cut lines, edges that
+    run along them, pinch points and slivers that collapse under the integer truncation are frequent.  The product's
+    pieces must cover exactly the region of the oracle's polygonize faces AND flag exactly the same cells under the
+    buffer rule of to_xarray (a zero-area antenna or a zero-width bridge along the cut line would add cells)."""
+    rng = np.random.default_rng(seed)
+    nlon, nlat = 20, 24
+    yy, xx = np.mgrid[0:nlat, 0:nlon]
+    px, py = xx.ravel().astype(float), yy.ravel().astype(float)
+
+    def cells(pieces):
+        return G.buffered_contains([np.asarray(p) for p in pieces], 0.5, px, py) if pieces else np.zeros(len(px), bool)
+
+    tested = 0
+    for _ in range(900):
+        cx, cy = nlon + rng.integers(-2, 3), 10
+        k = rng.integers(4, 14)
+        ang = np.sort(rng.uniform(0, 2 * np.pi, k))
+        rad = rng.uniform(1.5, 7, k)
+        ring = np.c_[np.rint(cx + rad * np.cos(ang)), np.rint(cy + rad * np.sin(ang))].astype(int)
+        keep = [0]
+        for i in range(1, len(ring)):
+            if (ring[i] != ring[keep[-1]]).any():
+                keep.append(i)
+        ring = ring[keep]
+        if len(ring) > 1 and (ring[0] == ring[-1]).all():
+            ring = ring[:-1]
+        if len(ring) < 3 or not G.ring_is_simple(ring):
+            continue
+        x = ring[:, 0]
+        if not ((x >= nlon).any() and not (x >= nlon).all()):
+            continue
+        got, want = geometry.transform_ring(ring, nlon), G.split_ring_at_meridian(ring, nlon)
+        assert G.regions_equal(got, want), ring.tolist()
+        assert np.array_equal(cells(got), cells(want)), ring.tolist()
+        tested += 1
+    assert tested > 500

@@ -9,6 +9,7 @@ import time
 sys.path.insert(0, ".")
 import numpy as np
 
+from oracle import geom as G
 from oracle import pipeline as P
 from wavebreaking_b200 import detect, pipeline, spatial, synthetic
 
@@ -20,7 +21,9 @@ raw = spatial.synth_pv(n, nlat, nlon, hour0=hour0, hour_step=37.0)  # spread ove
 det = pipeline.Detector(lat, lon, levels=[2.0])
 res = det.run_batch(raw)
 raw_h = raw.cpu().numpy()
-tot = dict(events=0, mismatched_events=0, flag_cells_diff=0, near=0, contours=0, points=0)
+tot = dict(events=0, mismatched_events=0, flag_cells_diff=0, near_listed=int(res.near_total), contours=0, points=0,
+           non_simple_rings=0)
+non_simple = []  # (step, kind, event) whose ring touches / crosses itself: invalid for GEOS ("GEOS-invalid class")
 for t in range(n):
     t0 = time.time()
     grid = P.Grid(lon, lat, synthetic.time_axis(1, 1))
@@ -54,8 +57,16 @@ for t in range(n):
         tot["events"] += len(w)
         tot["mismatched_events"] += bad
         tot["flag_cells_diff"] += fd
-        tot["near"] += int(tab.near[idx].sum())
-        line.append("{} {} bad {} flagdiff {}".format(kind, len(w), bad, fd))
+        ns = 0
+        if kind != "overturnings":
+            for j, e in enumerate(idx):
+                if not G.ring_is_simple(np.asarray(tab.rings[e])):
+                    ns += 1
+                    non_simple.append((t, kind, j))
+        tot["non_simple_rings"] += ns
+        line.append("{} {} bad {} flagdiff {} non-simple {}".format(kind, len(w), bad, fd, ns))
     line.append("({:.1f} s)".format(time.time() - t0))
     print(" | ".join(line), flush=True)
+print("NEAR-THRESHOLD PAIRS (step, level, contour, i, j, flags 1 kept 2 geo 4 cont):", res.near.tolist())
+print("NON-SIMPLE EVENT RINGS (step, kind, event):", non_simple)
 print("SUMMARY", tot)

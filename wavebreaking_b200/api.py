@@ -171,6 +171,12 @@ def _canon(data, kwargs, need_values=True, orient=True):
     """Cached :class:`_Canon`: ``calculate_streamers / overturnings / cutoffs / contours`` of one analysis are called
     on the same DataArray, so its upload (and re-orientation) happens once.  The key holds the identity of the
     value buffer, its shape / strides and the dimension names; the cache keeps the two most recent fields."""
+    lazy = getattr(data, "_lazy", None)
+    if (lazy is not None and lazy.device is not None and need_values and getattr(data, "_values", None) is None
+            and lazy.device_meta == (tuple(data.dims), bool(orient))):
+        c = _Canon(data, kwargs, need_values=False, orient=orient)
+        c.tensor = lazy.device  # result of an earlier API call that is still on the device: no upload
+        return c
     values = data.values
     iface = getattr(values, "__array_interface__", None)
     key = None
@@ -228,6 +234,19 @@ class _Canon:
         return np.transpose(arr, inv)
 
 
+def _to_host(dev):
+    """Device tensor -> numpy array backed by page-locked memory (one asynchronous copy at link speed; a plain
+    ``.cpu()`` lands in freshly allocated pageable memory at a fraction of it).  torch recycles the pinned block
+    when the array is released."""
+    lib = _lib.get()
+    if not lib.is_cuda:
+        return dev.cpu().numpy()
+    host = torch.empty(dev.shape, dtype=dev.dtype, pin_memory=True)
+    host.copy_(dev, non_blocking=True)
+    torch.cuda.current_stream(lib.device).synchronize()
+    return host.numpy()
+
+
 def _as_levels(contour_levels):
     try:
         iter(contour_levels)
@@ -258,11 +277,20 @@ def calculate_smoothed_field(data, passes, weights=np.array([[0, 1, 0], [1, 2, 1
     """``passes`` x 5-point smoothing (scipy.ndimage.convolve semantics), latitude border rows NaN
     (processing/spatial.py:60-128).  The result has dims (time, lat, lon) like the reference's."""
     c = _canon(data, kwargs, orient=False)  # the reference convolves the (lat, lon) slices as they are stored
-    out = spatial.smooth(c.tensor, passes, np.asarray(weights), mode).cpu().numpy()
+    out = spatial.smooth(c.tensor, passes, np.asarray(weights), mode)
     dims = (c.time_name, c.lat_name, c.lon_name)
     attrs = dict(getattr(data, "attrs", {}) or {})
     attrs["smooth_passes"] = passes
-    return compat.like(data, out, dims, name="smooth_" + str(data.name), attrs=attrs)
+    # the smoothed field stays on the device until its values are read; the index functions take the device tensor
+    # (re-oriented to ascending coordinates if the input is stored descending) without another upload
+    lat = compat.coord_info(data, c.lat_name)[0]
+    lon = compat.coord_info(data, c.lon_name)[0]
+    fl = bool(len(lat) > 1 and np.average(np.diff(lat)) < 0)
+    fo = bool(len(lon) > 1 and np.average(np.diff(lon)) < 0)
+    canonical = out if not (fl or fo) else None  # (descending input: the next call re-orients its own copy)
+    lazy = compat.LazyValues(tuple(out.shape), np.float64 if out.dtype == torch.float64 else np.float32,
+                             lambda: _to_host(out), device=canonical, device_meta=(dims, True))
+    return compat.like(data, lazy, dims, name="smooth_" + str(data.name), attrs=attrs)
 
 
 # ------------------------------------------------------------------------------------------- contours
@@ -633,12 +661,17 @@ def to_xarray(data, events, flag="ones", name="flag", *args, **kwargs):
         ring_v = (np.ones(len(flat)) if flag == "ones" else set_val[ev_of_ring]).tolist()
     lib = _lib.get()
     if flag == "ones":
-        out = detect.rasterize_rings(rings, ring_t, c.nlat, c.nlon, c.ntime, 0.5).cpu().numpy()
+        dev = detect.rasterize_rings(rings, ring_t, c.nlat, c.nlon, c.ntime, 0.5)
+        out_dtype = np.dtype(np.int8)
     else:
         grid = torch.zeros((c.ntime, c.nlat, c.nlon), dtype=torch.float64, device=lib.device)
-        out = detect.rasterize_rings(rings, ring_t, c.nlat, c.nlon, c.ntime, 0.5, values=(grid, ring_v)).cpu().numpy()
-        out = out.astype(np.asarray(data.values).dtype, copy=False)
-    res = compat.like(data, c.to_input_layout(out), data.dims, name=name, attrs=dict(getattr(data, "attrs", {}) or {}))
+        dev = detect.rasterize_rings(rings, ring_t, c.nlat, c.nlon, c.ntime, 0.5, values=(grid, ring_v))
+        out_dtype = np.dtype(data.dtype)
+    shape = tuple(len(data[d]) for d in data.dims)
+    # the grid stays on the device until its values are read (a DataArray result is downloaded at once)
+    lazy = compat.LazyValues(shape, out_dtype,
+                             lambda: np.ascontiguousarray(c.to_input_layout(_to_host(dev)).astype(out_dtype, copy=False)))
+    res = compat.like(data, lazy, data.dims, name=name, attrs=dict(getattr(data, "attrs", {}) or {}))
     res.attrs["long_name"] = "flag wave breaking"
     return res
 

@@ -52,19 +52,35 @@ class _Coord:
         return self.values[i]
 
 
+class LazyValues:
+    """Values that still live on the device: ``load()`` brings them to the host (once) as a numpy array in the
+    Field's dimension order.  ``device`` is the canonical device tensor [time, lat, lon] (ascending lat / lon) that
+    the next API call can use without any upload."""
+
+    def __init__(self, shape, dtype, load, device=None, device_meta=None):
+        self.shape, self.dtype, self._load = tuple(shape), np.dtype(dtype), load
+        self.device, self.device_meta = device, device_meta
+
+
 class Field:
-    """Minimal labelled array: ``values`` with named ``dims`` and 1-D ``coords`` (DataArray stand-in)."""
+    """Minimal labelled array: ``values`` with named ``dims`` and 1-D ``coords`` (DataArray stand-in).
+
+    ``values`` may be a :class:`LazyValues`: results of ``calculate_smoothed_field`` / ``to_xarray`` stay on the
+    device until ``.values`` is read, and the index functions take the device tensor directly (a DataArray result
+    cannot be lazy; with xarray installed the values are downloaded at once)."""
 
     def __init__(self, values, dims, coords, name=None, attrs=None):
-        self.values = np.asarray(values)
+        self._lazy = values if isinstance(values, LazyValues) else None
+        self._values = None if self._lazy is not None else np.asarray(values)
         self.dims = tuple(dims)
-        if len(self.dims) != self.values.ndim:
+        shape = self._lazy.shape if self._lazy is not None else self._values.shape
+        if len(self.dims) != len(shape):
             raise ValueError("dims do not match the array rank")
         self.coords = {}
         for d in self.dims:
             c = coords[d]
             self.coords[d] = c if isinstance(c, _Coord) else _Coord(c)
-            if len(self.coords[d]) != self.values.shape[self.dims.index(d)]:
+            if len(self.coords[d]) != shape[self.dims.index(d)]:
                 raise ValueError("coordinate {} does not match the array shape".format(d))
         for k, v in coords.items():  # scalar / extra coordinates (e.g. a level) are carried along
             if k not in self.coords:
@@ -72,16 +88,22 @@ class Field:
         self.name = name
         self.attrs = dict(attrs or {})
 
+    @property
+    def values(self):
+        if self._values is None:
+            self._values = np.asarray(self._lazy._load())
+        return self._values
+
     def __getitem__(self, dim):
         return self.coords[dim]
 
     @property
     def shape(self):
-        return self.values.shape
+        return self._lazy.shape if self._values is None else self._values.shape
 
     @property
     def dtype(self):
-        return self.values.dtype
+        return self._lazy.dtype if self._values is None else self._values.dtype
 
     def to_xarray(self):  # pragma: no cover
         if _xr is None:
@@ -106,9 +128,12 @@ def coord_info(data, dim):
 
 
 def like(data, values, dims, name=None, attrs=None):
-    """A new labelled array of the same flavour as ``data`` (DataArray in, DataArray out)."""
+    """A new labelled array of the same flavour as ``data`` (DataArray in, DataArray out).  ``values`` may be a
+    :class:`LazyValues` (kept lazy in a Field, downloaded at once for a DataArray)."""
     coords = {d: np.asarray(data[d].values) for d in dims}
     if _xr is not None and isinstance(data, _xr.DataArray):  # pragma: no cover
+        if isinstance(values, LazyValues):
+            values = values._load()
         return _xr.DataArray(values, dims=dims, coords=coords, name=name, attrs=attrs or {})
     return Field(values, dims, coords, name=name, attrs=attrs)
 

@@ -246,3 +246,52 @@ extern "C" int wbk_pack_flags(const int8_t* d_flags, uint8_t* d_packed, long lon
   WBK_LAUNCH_CHECK();
   return WBK_OK;
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// Pieces of the events that straddle the last meridian (utils/index_utils.py:148-173), as the device clipper of
+// wbk_events_raster left them: compacted into ring r = vertices [ring_off[r], ring_off[r+1]) of d_xy (folded index
+// coordinates of the real grid), ring_ev[r] = the event (row of the wbk_batch_fetch tables) the piece belongs to.
+__global__ void __launch_bounds__(1024) split_scan_kernel(WbkIdx x, int* __restrict__ ring_ev, int* __restrict__ ring_off,
+                                                          int cap_rings, int cap_vertices, int* __restrict__ count) {
+  __shared__ int sscan[40];
+  const int n = min(min(x.split_count[1], x.SPR), cap_rings);
+  for (int r = threadIdx.x; r < n; r += blockDim.x) {
+    ring_off[r] = x.split_ring[4 * (size_t)r + 1];
+    ring_ev[r] = x.split_ring[4 * (size_t)r + 3] >> 2;
+  }
+  __syncthreads();
+  const int tot = wbk_block_excl_scan(ring_off, n, sscan);
+  if (threadIdx.x == 0) {
+    ring_off[n] = tot;
+    count[0] = x.split_count[1];  // pieces found (> cap_rings: the caller's buffers were too small)
+    count[1] = tot;               // their vertices (> cap_vertices: too small)
+    count[2] = x.split_count[2];  // the clipper's own arenas overflowed
+  }
+}
+
+__global__ void split_copy_kernel(WbkIdx x, const int* __restrict__ ring_off, int* __restrict__ xy, int cap_rings,
+                                  int cap_vertices) {
+  const int n = min(min(x.split_count[1], x.SPR), cap_rings);
+  for (int r = blockIdx.x; r < n; r += gridDim.x) {
+    const int a = ring_off[r], len = ring_off[r + 1] - a;
+    if (a + len > cap_vertices) continue;
+    const int* src = x.split_xy + 2 * (size_t)x.split_ring[4 * (size_t)r];
+    for (int k = threadIdx.x; k < 2 * len; k += blockDim.x) xy[2 * (size_t)a + k] = src[k];
+  }
+}
+
+extern "C" int wbk_split_fetch(wbk_ctx* ctx, int* d_ring_ev, int* d_ring_off, int* d_xy, int cap_rings, int cap_vertices,
+                               int* d_count, void* stream) {
+  if (!ctx || !d_ring_ev || !d_ring_off || !d_xy || !d_count || cap_rings < 1 || cap_vertices < 1) {
+    wbk_set_error("wbk_split_fetch: invalid argument");
+    return WBK_ERR_INVALID;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  WBK_LAUNCH(KID_EVENTS_GATHER, split_scan_kernel, dim3(1), dim3(1024), 0, st, ctx->x, d_ring_ev, d_ring_off, cap_rings,
+             cap_vertices, d_count);
+  WBK_LAUNCH_CHECK();
+  WBK_LAUNCH(KID_EVENTS_GATHER, split_copy_kernel, dim3(148), dim3(128), 0, st, ctx->x, (const int*)d_ring_off, d_xy,
+             cap_rings, cap_vertices);
+  WBK_LAUNCH_CHECK();
+  return WBK_OK;
+}

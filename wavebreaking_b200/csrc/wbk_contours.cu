@@ -40,7 +40,7 @@ size_t layout(WbkDev& d, const wbk_caps& c, int nlat, int nlon, int add, unsigne
   d.out_pts = b.take<u32>(J * R); d.out_tab = b.take<int>(J * CC * 4); d.out_sumy = b.take<int>(J * CC);
   d.out_nc = b.take<int>(J); d.out_np = b.take<int>(J); d.max_nx = b.take<int>(64);
   // comparison bit planes of the fused smoothing: <= 4 words per (job, row, strip), strips of >= 48 valid columns
-  d.planes = b.take<u32>(J * 4 * (size_t)nlat * (size_t)((nlon + 47) / 48));
+  d.planes = b.take<u32>(J * 4 * (size_t)nlat * (size_t)((nlon + 47) / 48) + 8);
   return (b.off + 255) & ~(size_t)255;
 }
 
@@ -806,22 +806,65 @@ __device__ __noinline__ void msp_emit(const WbkDev& d, const T* __restrict__ src
   }
 }
 
+// The plane rows a CTA needs are ONE contiguous block of global memory ([t][row][strip][PW] words, rows of
+// nstrips * PW * 4 bytes, a multiple of 16): they are staged in shared memory with a single TMA bulk copy
+// (cp.async.bulk.shared.global + mbarrier transaction count) instead of ~40 scattered loads per thread.
+__device__ __forceinline__ void msp_stage_rows(u32* smem_dst, const u32* gsrc, unsigned bytes, u64* bar) {
+#ifndef WBK_EMU
+  const unsigned bar_s = (unsigned)__cvta_generic_to_shared(bar);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned dst_s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_s),
+                 "l"(gsrc), "r"(bytes), "r"(bar_s)
+                 : "memory");
+  }
+  // every thread waits for phase 0 of the barrier (the copy's bytes have landed)
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tMSP_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t@p bra MSP_DONE;\n\tbra MSP_WAIT;\n\t"
+      "MSP_DONE:\n\t}" ::"r"(bar_s)
+      : "memory");
+#else
+  if (threadIdx.x == 0)
+    for (unsigned i = 0; i < bytes / 4; ++i) smem_dst[i] = gsrc[i];
+  __syncthreads();
+#endif
+}
+
+// grid: (bands of MSP_THREADS items, time steps); item = (row chunk, strip) of the time step, strip fastest
 template <typename T>
 __global__ void __launch_bounds__(MSP_THREADS, 5)
 ms_planes_kernel(const T* __restrict__ field, const u32* __restrict__ planes, const __grid_constant__ WbkDev d,
-                 const __grid_constant__ LevelPack levels, int nlevels, const __grid_constant__ MspGeom g) {
+                 const __grid_constant__ LevelPack levels, int nlevels, const __grid_constant__ MspGeom g, int t_base) {
   __shared__ u32 smask[MSP_THREADS / 32][MSP_ROWS][64];
   __shared__ int sprefix[MSP_THREADS / 32][33];
+  __shared__ __align__(8) u64 s_bar;
+  WBK_DYN_SMEM(u32, srows);  // plane words of rows [row0, row0 + nrows) of this time step
   const int lane = wbk_lane(), warp = wbk_warp();
   const int nlat = d.nlat, nlon = d.nlon, W = d.W;
-  // items of one time step are padded to whole warps, so that a warp emits into ONE job per level
-  const int per_t = g.nchunks * g.nstrips, wpt = (per_t + 31) / 32;
-  const long long wglobal = (long long)blockIdx.x * (MSP_THREADS / 32) + warp;
-  if (wglobal >= (long long)g.ntime * wpt) return;  // whole warp
-  const int t = (int)(wglobal / wpt);
-  const int item0 = (int)(wglobal % wpt) * 32;  // first item of this warp within the time step
+  const int per_t = g.nchunks * g.nstrips;
+  const int t = t_base + (int)blockIdx.y;
+  const int item_first = (int)blockIdx.x * MSP_THREADS;
+  const int item_last = min(item_first + MSP_THREADS, per_t) - 1;  // the grid covers exactly ceil(per_t / MSP_THREADS) bands
+  const size_t trow = (size_t)t * nlat;
+  const size_t row_words = (size_t)g.nstrips * g.PW;
+  const int row0 = (item_first / g.nstrips) * MSP_ROWS;
+  const int row1 = min((item_last / g.nstrips + 1) * MSP_ROWS, nlat - 1);  // last row read
+  // the bulk copy wants 16-byte aligned addresses and sizes: rows are only 8-byte multiples for an even number of
+  // levels, so the block is widened to the enclosing 16-byte range (`delta` words precede the first row)
+  const size_t gstart = (trow + row0) * row_words;
+  const int delta = (int)(gstart & 3);
+  const unsigned bytes = (unsigned)((((size_t)delta + (size_t)(row1 - row0 + 1) * row_words) * 4 + 15) & ~(size_t)15);
+  msp_stage_rows(srows, planes + (gstart - delta), bytes, &s_bar);
+
+  const int item0 = item_first + warp * 32;  // first item of this warp
   const bool live = item0 + lane < per_t;
-  const int it = live ? item0 + lane : 0;  // dead lanes shadow item 0 with an empty square mask
+  const int it = live ? item0 + lane : item_first;  // dead lanes shadow a staged item with an empty square mask
   const int s = it % g.nstrips, chunk = it / g.nstrips;
   const int sn = s + 1 == g.nstrips ? 0 : s + 1;  // the strip to the right (the last one wraps: periodic extension)
   const int r_begin = chunk * MSP_ROWS;
@@ -831,39 +874,23 @@ ms_planes_kernel(const T* __restrict__ field, const u32* __restrict__ planes, co
   int nsq = min(vcols, W - 1 - s * g.V);
   if (nsq < 0 || !live) nsq = 0;
   const u64 sqmask = nsq >= 64 ? ~0ULL : (((1ULL << nsq) - 1ULL) << g.P);
-  const size_t trow = (size_t)t * nlat;
   const T* src = field + trow * nlon;
-  // plane words of (row, strip): planes[((t * nlat + row) * nstrips + strip) * PW + w]
-  const u32* own = planes + ((trow + r_begin) * g.nstrips + s) * (size_t)g.PW;
-  const u32* nxt = planes + ((trow + r_begin) * g.nstrips + sn) * (size_t)g.PW;
-  const size_t row_words = (size_t)g.nstrips * g.PW;
+  const u32* own = srows + delta + (size_t)(r_begin - row0) * row_words + (size_t)s * g.PW;
+  const u32* nxt = srows + delta + (size_t)(r_begin - row0) * row_words + (size_t)sn * g.PW;
 
   for (int l = 0; l < nlevels; ++l) {
-    // all MSP_ROWS + 1 rows are requested before any is used (independent loads in flight)
-    u32 w[MSP_ROWS + 1][8];  // n_e, n_o, g_e, g_o of the own strip, then of the next strip
-#pragma unroll
-    for (int i = 0; i <= MSP_ROWS; ++i) {
-      const bool ok = r_begin + i <= r_end;  // rows up to r_end are read (r_end <= nlat - 1)
-      const u32* po = own + (size_t)i * row_words;
-      const u32* pn = nxt + (size_t)i * row_words;
-      w[i][0] = ok ? po[0] : 0u;
-      w[i][1] = ok ? po[1] : 0u;
-      w[i][2] = ok ? po[2 + 2 * l] : 0u;
-      w[i][3] = ok ? po[3 + 2 * l] : 0u;
-      w[i][4] = ok ? pn[0] : 0u;
-      w[i][5] = ok ? pn[1] : 0u;
-      w[i][6] = ok ? pn[2 + 2 * l] : 0u;
-      w[i][7] = ok ? pn[3 + 2 * l] : 0u;
-    }
     int cnt = 0;
-    u64 g0 = msp_bits(w[0][2], w[0][3], w[0][6], w[0][7], g.P, vcols);
-    u64 n0 = msp_bits(w[0][0], w[0][1], w[0][4], w[0][5], g.P, vcols);
+    const bool ok0 = r_begin <= r_end;
+    u64 g0 = ok0 ? msp_bits(own[2 + 2 * l], own[3 + 2 * l], nxt[2 + 2 * l], nxt[3 + 2 * l], g.P, vcols) : 0;
+    u64 n0 = ok0 ? msp_bits(own[0], own[1], nxt[0], nxt[1], g.P, vcols) : 0;
 #pragma unroll
     for (int i = 0; i < MSP_ROWS; ++i) {
-      const u64 g1 = msp_bits(w[i + 1][2], w[i + 1][3], w[i + 1][6], w[i + 1][7], g.P, vcols);
-      const u64 n1 = msp_bits(w[i + 1][0], w[i + 1][1], w[i + 1][4], w[i + 1][5], g.P, vcols);
-      u64 hits = 0;
+      u64 hits = 0, g1 = 0, n1 = 0;
       if (r_begin + i < r_end) {
+        const u32* po = own + (size_t)(i + 1) * row_words;
+        const u32* pn = nxt + (size_t)(i + 1) * row_words;
+        g1 = msp_bits(po[2 + 2 * l], po[3 + 2 * l], pn[2 + 2 * l], pn[3 + 2 * l], g.P, vcols);
+        n1 = msp_bits(po[0], po[1], pn[0], pn[1], g.P, vcols);
         const u64 both = g0 & g1, either = g0 | g1, nn = n0 | n1;
         hits = ((either | (either >> 1)) & ~(both & (both >> 1))) & ~(nn | (nn >> 1)) & sqmask;
       }
@@ -921,15 +948,22 @@ extern "C" int wbk_smooth_contours(wbk_ctx* ctx, const void* d_in, int in_dtype,
   g.PW = 2 + 2 * nlevels;
   g.ntime = ntime;
   g.nchunks = (d.nlat - 1 + MSP_ROWS - 1) / MSP_ROWS;
-  const long long nwarps = (long long)ntime * ((g.nchunks * g.nstrips + 31) / 32);
-  const long long nblocks = (nwarps + MSP_THREADS / 32 - 1) / (MSP_THREADS / 32);
-  if (nblocks > 0x7fffffffLL) {
-    wbk_set_error("wbk_smooth_contours: batch too long, split the time axis");
-    return WBK_ERR_INVALID;
+  const int per_t = g.nchunks * g.nstrips;
+  const int bands = (per_t + MSP_THREADS - 1) / MSP_THREADS;
+  // rows staged per CTA: the row chunks its MSP_THREADS items span, plus the row below the last one
+  const int max_chunks = (MSP_THREADS + g.nstrips - 2) / g.nstrips + 1;
+  const size_t smem = (size_t)(max_chunks * MSP_ROWS + 1) * g.nstrips * g.PW * sizeof(u32) + 32;
+  if (smem > 160 * 1024) {
+    wbk_set_error("wbk_smooth_contours: %d strips x %d levels do not fit the plane staging buffer", g.nstrips, nlevels);
+    return WBK_ERR_CAPACITY;
   }
-  WBK_LAUNCH(KID_MS_SEGMENTS, ms_planes_kernel<double>, dim3((unsigned)nblocks), dim3(MSP_THREADS), 0, st,
-             (const double*)d_smoothed, (const u32*)d.planes, d, lv, nlevels, g);
-  WBK_LAUNCH_CHECK();
+  WBK_CUDA_CHECK(cudaFuncSetAttribute(ms_planes_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  for (int t0 = 0; t0 < ntime; t0 += 65535) {  // gridDim.y <= 65535
+    const int nt = ntime - t0 < 65535 ? ntime - t0 : 65535;
+    WBK_LAUNCH(KID_MS_SEGMENTS, ms_planes_kernel<double>, dim3(bands, nt), dim3(MSP_THREADS), smem, st,
+               (const double*)d_smoothed, (const u32*)d.planes, d, lv, nlevels, g, t0);
+    WBK_LAUNCH_CHECK();
+  }
   WBK_LAUNCH(KID_CONTOUR_LINK, contour_link_kernel, dim3(njobs), dim3(WBK_CONTOUR_THREADS), 0, st, d, njobs);
   WBK_LAUNCH_CHECK();
   return WBK_OK;

@@ -436,13 +436,13 @@ __device__ __forceinline__ bool frac_eq(long long an, long long ad, long long bn
 }
 
 // clip one ring against x = c keeping x <= c (keep_le) or x >= c; appends pieces to the ring list
-__device__ void split_clip_side(const RingView& rv, int c, bool keep_le, int nlon, int t, int kind, WbkIdx& x) {
+__device__ void split_clip_side(const RingView& rv, int c, bool keep_le, int nlon, int t, int kind, int ev, WbkIdx& x) {
   const int n = rv.n;
   int nin = 0;
   for (int k = 0; k < n; ++k) {
     int vx, vy;
     rv.get(k, vx, vy);
-    nin += (keep_le ? vx <= c : vx >= c) ? 1 : 0;
+    nin += (keep_le ? vx < c : vx > c) ? 1 : 0;
   }
   if (nin == 0) return;
   SplitChain ch[SPLIT_MAX_CHAINS];
@@ -456,10 +456,15 @@ __device__ void split_clip_side(const RingView& rv, int c, bool keep_le, int nlo
   }
   int* sxy = x.split_xy + 2 * (size_t)sbase;
   int sp = 0;
+  // A chain is a maximal run of vertices STRICTLY beyond the line; it is entered and left through a crossing point on
+  // the line: the neighbouring ring vertex if that one lies on the line, else the exact intersection of the edge.
+  // Ring edges that run along the line belong to no chain -- whether they bound a face is decided by the pairing of
+  // the crossings below, as in the overlay + polygonize of the reference (index_utils.py:158-163): no vertex on the
+  // line sticks out of a face as a zero-area antenna, parts that only meet along the line stay separate faces.
   auto inside = [&](int k) {
     int vx, vy;
     rv.get(k, vx, vy);
-    return keep_le ? vx <= c : vx >= c;
+    return keep_le ? vx < c : vx > c;
   };
   if (nin == n) {
     ch[0].off = 0;
@@ -491,15 +496,18 @@ __device__ void split_clip_side(const RingView& rv, int c, bool keep_le, int nlo
         int kx, ky, px, py;
         rv.get(k, kx, ky);
         rv.get(prev, px, py);
-        if (kx != c) {  // entry crossing strictly inside the edge prev -> k
+        if (px != c) {  // entry crossing strictly inside the edge prev -> k
           long long den = (long long)kx - px, num = (long long)py * den + (long long)(c - px) * (ky - py);
           if (den < 0) { den = -den; num = -num; }
           cc.yin_n = num; cc.yin_d = den;
           sxy[2 * sp] = c;
           sxy[2 * sp + 1] = (int)(num >= 0 ? num / den : -((-num) / den));  // astype(int): truncation
           ++sp;
-        } else {
-          cc.yin_n = ky; cc.yin_d = 1;
+        } else {  // the ring vertex before the chain lies on the line: it is the crossing point
+          cc.yin_n = py; cc.yin_d = 1;
+          sxy[2 * sp] = c;
+          sxy[2 * sp + 1] = py;
+          ++sp;
         }
         int j = k;
         while (inside(j)) {
@@ -515,15 +523,18 @@ __device__ void split_clip_side(const RingView& rv, int c, bool keep_le, int nlo
         int lx, ly, jx, jy;
         rv.get(last, lx, ly);
         rv.get(j, jx, jy);
-        if (lx != c) {
+        if (jx != c) {
           long long den = (long long)jx - lx, num = (long long)ly * den + (long long)(c - lx) * (jy - ly);
           if (den < 0) { den = -den; num = -num; }
           cc.yout_n = num; cc.yout_d = den;
           sxy[2 * sp] = c;
           sxy[2 * sp + 1] = (int)(num >= 0 ? num / den : -((-num) / den));
           ++sp;
-        } else {
-          cc.yout_n = ly; cc.yout_d = 1;
+        } else {  // the ring vertex after the chain lies on the line
+          cc.yout_n = jy; cc.yout_d = 1;
+          sxy[2 * sp] = c;
+          sxy[2 * sp + 1] = jy;
+          ++sp;
         }
         cc.cnt = sp - cc.off;
         ++nch;
@@ -629,7 +640,7 @@ __device__ void split_clip_side(const RingView& rv, int c, bool keep_le, int nlo
     }
     if (m > 1 && oxy[0] == oxy[2 * (m - 1)] && oxy[1] == oxy[2 * (m - 1) + 1]) --m;
     int* rr = x.split_ring + 4 * (size_t)ridx;
-    rr[0] = obase; rr[1] = m; rr[2] = t; rr[3] = kind;
+    rr[0] = obase; rr[1] = m; rr[2] = t; rr[3] = kind | (ev << 2);  // ev: index of the event in gather order
   }
 }
 
@@ -671,8 +682,8 @@ split_events_kernel(WbkDev d, WbkIdx x, const int* __restrict__ pt_off, const u3
     }
     if (lane == 0) {
       const int t = job / nlevels;
-      split_clip_side(rv, d.nlon - 1, true, d.nlon, t, kind, x);
-      split_clip_side(rv, d.nlon, false, d.nlon, t, kind, x);
+      split_clip_side(rv, d.nlon - 1, true, d.nlon, t, kind, w, x);
+      split_clip_side(rv, d.nlon, false, d.nlon, t, kind, w, x);
     }
   }
 }
@@ -693,7 +704,7 @@ split_raster_kernel(WbkIdx x, int nlat, int nlon, int ntime, int8_t* __restrict_
     rv.xy = x.split_xy + 2 * (size_t)rr[0];
     rv.n = rr[1];
     rv.bx0 = rv.by0 = rv.bx1 = rv.by1 = 0;
-    const int t = rr[2], kind = rr[3];
+    const int t = rr[2], kind = rr[3] & 3;
     if (tid == 0) {
       s_box[0] = 0x7fffffff; s_box[1] = 0x7fffffff; s_box[2] = -1; s_box[3] = -1;
     }

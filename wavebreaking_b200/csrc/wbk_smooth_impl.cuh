@@ -18,6 +18,7 @@
 // (halo recompute 64 / (64 - 2P) in x only; in y a warp marches over the whole chunk plus 3P warm-up rows).
 // The field is read once and written once whatever `passes` is.
 #pragma once
+#include <cstdlib>
 #include "wbk_common.cuh"
 #include "wbk_ms.cuh"
 
@@ -341,6 +342,7 @@ static void ss_geometry(SsParams& p, int passes) {
   const int rows = p.nlat - 2 * p.nan_border;
   // two latitude chunks per strip on tall grids: better balance over the SMs for 3P extra rows per chunk
   p.nchunks = rows >= 256 ? 2 : 1;
+  if (const char* e = getenv("WBK_SS_NCHUNKS")) p.nchunks = atoi(e) > 0 ? atoi(e) : p.nchunks;  // experiment knob
   p.chunk_rows = rows > 0 ? (rows + p.nchunks - 1) / p.nchunks : 1;
 }
 

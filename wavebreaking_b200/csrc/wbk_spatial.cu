@@ -95,19 +95,31 @@ extern "C" int wbk_convolve2d(const void* d_in, int in_dtype, void* d_out, int o
       }
     }
   cudaStream_t st = (cudaStream_t)stream;
-  dim3 block(128);
-  dim3 grid((nlon + 127) / 128, nlat, ntime);
-  if (in_dtype == WBK_F32 && out_dtype == WBK_F32) {
-    WBK_LAUNCH(KID_CONVOLVE, (convolve2d_cast_kernel<float, float, float>), grid, block, 0, st, (const float*)d_in, (float*)d_out, nlat, nlon, taps, mode, divide, divisor);
-  } else if (in_dtype == WBK_F32 && out_dtype == WBK_F64) {
-    WBK_LAUNCH(KID_CONVOLVE, (convolve2d_cast_kernel<float, float, double>), grid, block, 0, st, (const float*)d_in, (double*)d_out, nlat, nlon, taps, mode, divide, divisor);
-  } else if (in_dtype == WBK_F64 && out_dtype == WBK_F64) {
-    WBK_LAUNCH(KID_CONVOLVE, (convolve2d_cast_kernel<double, double, double>), grid, block, 0, st, (const double*)d_in, (double*)d_out, nlat, nlon, taps, mode, divide, divisor);
-  } else {
-    wbk_set_error("wbk_convolve2d: unsupported dtype combination");
+  if (nlat > 65535) {
+    wbk_set_error("wbk_convolve2d: more than 65535 latitudes");
     return WBK_ERR_INVALID;
   }
-  WBK_LAUNCH_CHECK();
+  dim3 block(128);
+  const size_t isz = in_dtype == WBK_F32 ? 4 : 8, osz = out_dtype == WBK_F32 ? 4 : 8;
+  const size_t plane = (size_t)nlat * nlon;
+  // gridDim.z is limited to 65535: long records go in chunks of time steps
+  for (int t0 = 0; t0 < ntime; t0 += 65535) {
+    const int nt = ntime - t0 < 65535 ? ntime - t0 : 65535;
+    dim3 grid((nlon + 127) / 128, nlat, nt);
+    const char* pin = (const char*)d_in + plane * t0 * isz;
+    char* pout = (char*)d_out + plane * t0 * osz;
+    if (in_dtype == WBK_F32 && out_dtype == WBK_F32) {
+      WBK_LAUNCH(KID_CONVOLVE, (convolve2d_cast_kernel<float, float, float>), grid, block, 0, st, (const float*)pin, (float*)pout, nlat, nlon, taps, mode, divide, divisor);
+    } else if (in_dtype == WBK_F32 && out_dtype == WBK_F64) {
+      WBK_LAUNCH(KID_CONVOLVE, (convolve2d_cast_kernel<float, float, double>), grid, block, 0, st, (const float*)pin, (double*)pout, nlat, nlon, taps, mode, divide, divisor);
+    } else if (in_dtype == WBK_F64 && out_dtype == WBK_F64) {
+      WBK_LAUNCH(KID_CONVOLVE, (convolve2d_cast_kernel<double, double, double>), grid, block, 0, st, (const double*)pin, (double*)pout, nlat, nlon, taps, mode, divide, divisor);
+    } else {
+      wbk_set_error("wbk_convolve2d: unsupported dtype combination");
+      return WBK_ERR_INVALID;
+    }
+    WBK_LAUNCH_CHECK();
+  }
   return WBK_OK;
 }
 
@@ -128,10 +140,14 @@ extern "C" int wbk_nan_border(void* d_field, int dtype, int ntime, int nlat, int
     return WBK_ERR_INVALID;
   }
   if (ntime == 0 || border == 0) return WBK_OK;
-  dim3 grid((nlon + 255) / 256, 2 * border, ntime);
-  if (dtype == WBK_F32) WBK_LAUNCH(KID_NAN_BORDER, nan_border_kernel<float>, grid, dim3(256), 0, (cudaStream_t)stream, (float*)d_field, nlat, nlon, border);
-  else WBK_LAUNCH(KID_NAN_BORDER, nan_border_kernel<double>, grid, dim3(256), 0, (cudaStream_t)stream, (double*)d_field, nlat, nlon, border);
-  WBK_LAUNCH_CHECK();
+  const size_t plane = (size_t)nlat * nlon;
+  for (int t0 = 0; t0 < ntime; t0 += 65535) {  // gridDim.z <= 65535: long records go in chunks of time steps
+    const int nt = ntime - t0 < 65535 ? ntime - t0 : 65535;
+    dim3 grid((nlon + 255) / 256, 2 * border, nt);
+    if (dtype == WBK_F32) WBK_LAUNCH(KID_NAN_BORDER, nan_border_kernel<float>, grid, dim3(256), 0, (cudaStream_t)stream, (float*)d_field + plane * t0, nlat, nlon, border);
+    else WBK_LAUNCH(KID_NAN_BORDER, nan_border_kernel<double>, grid, dim3(256), 0, (cudaStream_t)stream, (double*)d_field + plane * t0, nlat, nlon, border);
+    WBK_LAUNCH_CHECK();
+  }
   return WBK_OK;
 }
 
@@ -421,8 +437,9 @@ __global__ void synth_pv_kernel(T* out, int nlat, int nlon, double hour0, double
 
 extern "C" int wbk_synth_pv(void* d_out, int dtype, int ntime, int nlat, int nlon, double hour0, double hour_step,
                             const double* h_blobs, int n_blob, void* stream) {
-  if (!d_out || nlat < 2 || nlon < 1 || n_blob < 0 || n_blob > SYN_MAX_BLOB || (n_blob > 0 && !h_blobs)) {
-    wbk_set_error("wbk_synth_pv: invalid argument");
+  if (!d_out || nlat < 2 || nlon < 1 || n_blob < 0 || n_blob > SYN_MAX_BLOB || (n_blob > 0 && !h_blobs) || ntime > 65535 ||
+      nlat > 65535) {
+    wbk_set_error("wbk_synth_pv: invalid argument (at most 65535 time steps per call)");
     return WBK_ERR_INVALID;
   }
   if (ntime == 0) return WBK_OK;

@@ -12,16 +12,27 @@ import numpy as np
 
 
 def _clip_vertical(xs, ys, c, keep_le):
-    """Faces of the closed ring (xs, ys) on one side of x = c; list of (x, y_num, y_den) vertex lists."""
+    """Faces of the closed ring (xs, ys) strictly on one side of x = c; list of (x, y_num, y_den) vertex lists.
+
+    A chain is a maximal run of vertices STRICTLY beyond the line; it is entered and left through a crossing point
+    on the line: the neighbouring ring vertex if that one lies on the line, else the exact intersection of the edge.
+    Ring edges that run along the line belong to no chain -- whether they bound a face is decided by the pairing of
+    the crossings (even-odd along the line), exactly as in the overlay + polygonize of the reference
+    (index_utils.py:158-163): a vertex on the line never sticks out of a face as a zero-area antenna, and two parts
+    of the polygon that only meet along the line stay separate faces."""
     n = len(xs)
-    inside = (xs <= c) if keep_le else (xs >= c)
-    if inside.all():
-        return [[(int(x), int(y), 1) for x, y in zip(xs, ys)]]
+    inside = (xs < c) if keep_le else (xs > c)
     if not inside.any():
         return []
+    if inside.all():
+        return [[(int(x), int(y), 1) for x, y in zip(xs, ys)]]
 
     def cross(i, j):
-        # y of edge i->j at x = c as an exact fraction (num, den), den > 0
+        # y of edge i->j at x = c as an exact fraction (num, den), den > 0 (the end point itself if it is on the line)
+        if xs[i] == c:
+            return int(ys[i]), 1
+        if xs[j] == c:
+            return int(ys[j]), 1
         den = int(xs[j] - xs[i])
         num = int(ys[i]) * den + (c - int(xs[i])) * int(ys[j] - ys[i])
         if den < 0:
@@ -33,24 +44,17 @@ def _clip_vertical(xs, ys, c, keep_le):
     k, visited = start, 0
     while visited < n:
         if inside[k] and not inside[k - 1]:
-            pts = []
             prev = (k - 1) % n
-            if xs[k] != c:
-                y_in = cross(prev, k)
-                pts.append((c, y_in[0], y_in[1]))
-            else:
-                y_in = (int(ys[k]), 1)
+            y_in = cross(prev, k)
+            pts = [(c, y_in[0], y_in[1])]
             j = k
             while inside[j]:
                 pts.append((int(xs[j]), int(ys[j]), 1))
                 j = (j + 1) % n
                 visited += 1
             last = (j - 1) % n
-            if xs[last] != c:
-                y_out = cross(last, j)
-                pts.append((c, y_out[0], y_out[1]))
-            else:
-                y_out = (int(ys[last]), 1)
+            y_out = cross(last, j)
+            pts.append((c, y_out[0], y_out[1]))
             chains.append((pts, y_in, y_out))
             k = j
         else:

@@ -37,6 +37,8 @@ class BatchResult:
     # int32 [m, 6] = time step, level index, contour, i, j, flags (1 kept, 2 geo in band, 4 cont in band)
     near: np.ndarray = None
     near_total: int = 0
+    pieces: dict = None  # device-clipped pieces of the straddling events: ev (row in kind-major order), off, xy
+    counts: tuple = None  # events per kind (streamers, overturnings, cutoffs)
     work: dict = None  # device work counters of the batch: marching-squares segments, candidate pairs, scan tiles
     flags_packed: torch.Tensor = None  # pinned uint8: the three grids, one bit per cell (unpack_flags restores them)
 
@@ -103,6 +105,20 @@ class _Slot:
         self.ring_pts = torch.empty(self.cap_r, dtype=i32, device=dev)
         self.summary = torch.zeros(16, dtype=i32, device=dev)
         self.h_summary = _pinned(16, i32, lib)
+        # pieces of the events that straddle the last meridian (device clipper output, wbk_split_fetch)
+        self.cap_sr = int(max(16 * J, 1024))
+        self.cap_sv = int(max(4096 * J, 1 << 16))
+        if caps:
+            self.cap_sr = max(self.cap_sr, int(caps.get("cap_sr", 0)))
+            self.cap_sv = max(self.cap_sv, int(caps.get("cap_sv", 0)))
+        self.sp_ev = torch.zeros(self.cap_sr, dtype=i32, device=dev)
+        self.sp_off = torch.zeros(self.cap_sr + 1, dtype=i32, device=dev)
+        self.sp_xy = torch.zeros((self.cap_sv, 2), dtype=i32, device=dev)
+        self.sp_cnt = torch.zeros(4, dtype=i32, device=dev)
+        self.h_sp_ev = _pinned(self.cap_sr, i32, lib)
+        self.h_sp_off = _pinned(self.cap_sr + 1, i32, lib)
+        self.h_sp_xy = _pinned((self.cap_sv, 2), i32, lib)
+        self.h_sp_cnt = _pinned(4, i32, lib)
         self.near = torch.zeros((_lib.NEAR_CAP, 4), dtype=i32, device=dev)
         self.near_cnt = torch.zeros(1, dtype=i32, device=dev)
         self.h_near = _pinned((_lib.NEAR_CAP, 4), i32, lib)
@@ -130,7 +146,7 @@ class Detector:
 
     def __init__(self, lat, lon, levels=(2.0,), periodic_add=120, passes=5, which=detect.KINDS, geo_dis=800.0,
                  cont_dis=1500.0, range_group=5.0, ot_min_exp=5.0, co_min_exp=5.0, want_flags=True, fuse=True,
-                 packing=None, graphs=False, nvtx=True):
+                 packing=None, graphs=False, nvtx=True, want_pieces=False):
         self.lib = _lib.get()
         self.lat = np.asarray(lat, dtype=np.float64)
         self.lon = np.asarray(lon, dtype=np.float64)
@@ -157,6 +173,9 @@ class Detector:
         self.fuse = bool(fuse)
         # CF packing of int16 input (scale_factor, add_offset, _FillValue or None), decoded in the smoothing loads
         self.packing = tuple(packing) if packing is not None else (1.0, 0.0, None)
+        # also download the device clipper's pieces of the events that straddle the last meridian (events_soup then
+        # needs no host-side polygon clipping; used by the tracking leg)
+        self.want_pieces = bool(want_pieces)
         self.graphs = bool(graphs)  # replay one captured CUDA graph per batch (see submit)
         self.graph_replays = 0
         self.graph_kernel_launches = 0
@@ -284,6 +303,13 @@ class Detector:
         lib.call("wbk_batch_fetch", h, _lib.ptr(slot.pt_off), _lib.ptr(slot.pts), _lib.ptr(slot.ev_int),
                  _lib.ptr(slot.ev_f64), _lib.ptr(slot.ev_job), _lib.ptr(slot.ring_off), _lib.ptr(slot.ring_pts),
                  slot.cap_e, slot.cap_r, _lib.ptr(slot.summary), st)
+        if flags is not None and self.want_pieces:
+            lib.call("wbk_split_fetch", h, _lib.ptr(slot.sp_ev), _lib.ptr(slot.sp_off), _lib.ptr(slot.sp_xy), slot.cap_sr,
+                     slot.cap_sv, _lib.ptr(slot.sp_cnt), st)
+            slot.h_sp_cnt.copy_(slot.sp_cnt, non_blocking=True)
+            slot.h_sp_ev.copy_(slot.sp_ev, non_blocking=True)
+            slot.h_sp_off.copy_(slot.sp_off, non_blocking=True)
+            slot.h_sp_xy.copy_(slot.sp_xy, non_blocking=True)
         if nvtx:
             nvtx.range_pop()
             nvtx.range_push("wbk.download")
@@ -406,12 +432,24 @@ class Detector:
         flags = pend["flags_host"] if pend["flags_host"] is not None else pend["flags"]
         packed = pend.get("packed_host")
         n_sp = int(sum(int((t.split == 1).sum()) for t in tables.values()))
+        pieces = None
+        if self.want_pieces and pend["flags"] is not None:
+            npc, nvx, clip_over = (int(v) for v in slot.h_sp_cnt.numpy()[:3])
+            if npc > slot.cap_sr or nvx > slot.cap_sv:
+                grow = dict(self._grow)
+                grow["cap_sr"], grow["cap_sv"] = max(2 * slot.cap_sr, 2 * npc), max(2 * slot.cap_sv, 2 * nvx)
+                self._grow = grow
+                return self._regrow_and_rerun(slot, 0)
+            off = slot.h_sp_off.numpy()[:npc + 1].astype(np.int64)
+            pieces = dict(ev=slot.h_sp_ev.numpy()[:npc].copy(), off=off, xy=slot.h_sp_xy.numpy()[:nvx].copy(),
+                          overflow=bool(clip_over))
         n_near = int(slot.h_near_cnt[0]) if "streamers" in self.which else 0
         rec = slot.h_near.numpy()[:min(n_near, _lib.NEAR_CAP)]
         near = np.c_[rec[:, 0] // L, rec[:, 0] % L, rec[:, 1], rec[:, 2], rec[:, 3] & 0x0FFFFFFF, (rec[:, 3] >> 28) & 7]
         return BatchResult(ntime=nt, contours=cs, tables=tables, flags=flags,
                            gmax_nx=max_nx if pend["gmax"] is None else int(pend["gmax"]), n_split=n_sp,
-                           near=near.astype(np.int32), near_total=n_near, flags_packed=packed, work=work)
+                           near=near.astype(np.int32), near_total=n_near, flags_packed=packed, work=work, pieces=pieces,
+                           counts=(ns, no, nc))
 
     def _regrow_and_rerun(self, slot, status):
         pend = slot.pending
@@ -566,6 +604,34 @@ def events_soup(res, kind, det):
     if len(straddle) == 0:
         xy[:, 0] %= nlon
         soup = tracking.PolygonSoup(xy.astype(np.int32), off, np.arange(n + 1), True)
+    elif res.pieces is not None and not res.pieces["overflow"]:
+        # pieces from the device clipper (wbk_split_fetch): everything stays vectorised.  Rows of this kind start at
+        # `first` in the kind-major gather order of the batch
+        first = int(sum(res.counts[:detect.KINDS.index(kind)]))
+        pev = res.pieces["ev"].astype(np.int64) - first
+        mine = np.nonzero((pev >= 0) & (pev < n))[0]
+        order = mine[np.argsort(pev[mine], kind="stable")]
+        plen = np.diff(res.pieces["off"])[order]
+        pxy = res.pieces["xy"][tracking._ranges(res.pieces["off"][:-1][order], plen)].astype(np.int64)
+        npieces = np.bincount(pev[order], minlength=n).astype(np.int64)
+        keep_ev = tab.split != 1
+        lens = np.diff(off)
+        # interleave: ordinary events keep their single folded ring, straddling ones get their pieces
+        nrings = np.where(keep_ev, 1, npieces)
+        poly_off = np.r_[0, np.cumsum(nrings)]
+        ring_len = np.zeros(int(poly_off[-1]), dtype=np.int64)
+        ring_len[poly_off[:-1][keep_ev]] = lens[keep_ev]
+        piece_slots = tracking._ranges(poly_off[:-1][~keep_ev], npieces[~keep_ev])
+        ring_len[piece_slots] = plen
+        ring_off = np.r_[0, np.cumsum(ring_len)]
+        allxy = np.zeros((int(ring_off[-1]), 2), dtype=np.int64)
+        src = tracking._ranges(off[:-1][keep_ev], lens[keep_ev])
+        dst = tracking._ranges(ring_off[:-1][poly_off[:-1][keep_ev]], lens[keep_ev])
+        folded = xy[src]
+        folded[:, 0] %= nlon
+        allxy[dst] = folded
+        allxy[tracking._ranges(ring_off[:-1][piece_slots], plen)] = pxy
+        soup = tracking.PolygonSoup(allxy.astype(np.int32), ring_off, poly_off, True)
     else:
         # only the few events that straddle the meridian are rebuilt one by one
         ring_xy, ring_len, poly_nr = [], [], np.ones(n, dtype=np.int64)

@@ -339,7 +339,18 @@ def link_events(keys_sorted, win, method="by_overlap", soup=None, com=None, over
     Returns ``(links, npairs_in_range, near)``: links (m, 2) positions i < j in the sorted order with i in
     [first, last); near lists the pairs decided within NEAR_REL of a threshold (float64 decisions only; the exact
     overlap test has no such pairs)."""
+    import time as _time
+
+    tick = [_time.perf_counter()]
+
+    def lap(name):
+        if stats is not None:
+            now = _time.perf_counter()
+            stats["t_" + name] = stats.get("t_" + name, 0.0) + now - tick[0]
+            tick[0] = now
+
     lo, hi = windows(keys_sorted, win)
+    lap("windows")
     n = len(lo)
     last = n if last is None else last
     n_in_range = int((hi[first:last] - lo[first:last]).sum())
@@ -364,8 +375,10 @@ def link_events(keys_sorted, win, method="by_overlap", soup=None, com=None, over
                 box = np.c_[np.floor(box[:, :2]), np.ceil(box[:, 2:])]
                 box = np.clip(box, -2**30, 2**30)
             pairs = candidate_pairs(lo, hi, box.astype(np.int32), first, last)
+        lap("candidates")
         if soup.lattice:
             flag = overlap_exact(soup, pairs)
+            lap("overlap_exact")
             pos = (flag & 1) == 1
             if overlap == 0:
                 check = pos
