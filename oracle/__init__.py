@@ -23,10 +23,17 @@ shapely, scikit-image are absent and there is no network) and its only fixture
 ``tests/data/demo_data.nc`` is missing from the checkout.  The oracle is pinned
 against (i) the reference's own fixture-free known-answer tests
 (``tests/test_wavebreaking.py:101-104,116-128,130-144``), (ii) live outputs of
-the real scipy / sklearn routines, and (iii) hand-derived vectors for the
-skimage / GEOS restatements (``tests/golden``).  Everything that depends on
-skimage / GEOS semantics beyond those vectors is therefore **parity unpinned**
-and says so in DESIGN.md.
+the real scipy / sklearn routines, (iii) scikit-image's published vectors and the
+Shapely manual's predicate examples, and (iv) an evaluator written from the DE-9IM
+definitions (``tests/test_predicates.py``).  Everything that depends on skimage /
+GEOS semantics beyond those vectors is therefore **parity unpinned** and says so
+in DESIGN.md; ``tools/make_reference_fixtures.py`` produces the fixture that pins
+it wherever the real package can be installed (``tests/test_reference_fixtures.py``).
+
+The meridian split (:func:`oracle.geom.split_ring_at_meridian`, a planar-graph face
+walk) and the overlap decision of ``track_events``
+(:func:`oracle.geom.overlap_positive_exact`, a rational slab sweep) are formulated
+independently of the product's algorithms (chain clipper; crossing / touching rules).
 """
 
 from . import skimage_contours, geom, pipeline  # noqa: F401

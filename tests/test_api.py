@@ -155,9 +155,14 @@ def _check_contours(data, grid, raw):
 
 def _rings_equal(geom, want_rings):
     got = compat.geometry_rings(geom)
-    assert len(got) == len(want_rings)
-    for a, b in zip(got, want_rings):
-        assert np.array_equal(a, np.asarray(b, dtype=float))
+    if len(got) == 1 and len(want_rings) == 1 and len(got[0]) == len(want_rings[0]):
+        if np.array_equal(got[0], np.asarray(want_rings[0], dtype=float)):
+            return
+    # events split at the last meridian: the oracle's face walk and the product's clipper list the vertices of a piece
+    # in different orders -- compared as regions, exactly (demo_like coordinates are integer degrees)
+    from oracle import geom as G
+
+    assert G.regions_equal(got, want_rings)
 
 
 def _check_indices(sm, want_sm, grid, index):

@@ -4,7 +4,9 @@
 
 #define WBK_MAX_LEVELS 16
 #define WBK_VERTEX_ID 0x80000000u  // point id of a contour vertex that coincides with a grid vertex
-#define WBK_CONTOUR_THREADS 1024
+#ifndef WBK_CONTOUR_THREADS
+#define WBK_CONTOUR_THREADS 512  // 2 CTAs per SM: all 296 jobs of a batch are resident at once (1024: 1.38 us, 512: 1.32, 256: 1.84 per step)
+#endif
 
 // Device-side view of the arenas (passed to kernels by value).  Per-job arrays have a fixed
 // stride; `S` = seg_cap, `CC` = contour_cap, `R` = S + CC (raw contour points per job),

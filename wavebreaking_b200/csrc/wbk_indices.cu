@@ -289,7 +289,9 @@ __global__ void __launch_bounds__(OT_THREADS) overturning_kernel(WbkDev d, WbkId
 }
 
 // ------------------------------------------------------------------------------------------ streamers
+#ifndef ST_THREADS
 #define ST_THREADS 1024
+#endif
 #define PT 32            // pair-scan tile edge (one point per lane)
 #define CS_SORT 16384    // surviving pairs sorted in shared memory
 #define CS_SMEM ((size_t)CS_SORT * 8)
@@ -775,7 +777,9 @@ __device__ inline int compact_pairs(const u64* src, u64* dst, const int* flag, i
 // The geometric test: the contour's segments are binned into TB x TB lattice cells (CSR in shared memory), a chord
 // is tested against the segments of the bins its line passes through.  Exact integer predicates.
 #define TB_SHIFT 4                 // 16 x 16 cells per bin
+#ifndef TOUCH_THREADS
 #define TOUCH_THREADS 1024
+#endif
 #define TOUCH_MAXPTS 12288        // contour points staged in shared memory
 #define TOUCH_MAXSEG 20480         // CSR capacity (segment incidences) in shared memory
 

@@ -18,13 +18,15 @@
 // (halo recompute 64 / (64 - 2P) in x only; in y a warp marches over the whole chunk plus 3P warm-up rows).
 // The field is read once and written once whatever `passes` is.
 #pragma once
-#include <cstdlib>
 #include "wbk_common.cuh"
 #include "wbk_ms.cuh"
 
 #define SS_THREADS 128
+#ifndef SS_MINCTA_SMALL
+#define SS_MINCTA_SMALL 4  // resident CTAs per SM the register budget is sized for (P <= 5)
+#endif
 #ifndef SS_RING
-#define SS_RING 8  // rows of the shared-memory input ring (power of two)
+#define SS_RING 4  // rows of the shared-memory input ring (power of two); 4 / 8 / 16 measured within 2 % on B200
 #endif
 
 __device__ __forceinline__ int ss_wrap(int i, int n) {
@@ -138,7 +140,7 @@ __device__ __forceinline__ void ss_step(double (&w)[P][3][2], double in0, double
 
 // PL: 0 no bit planes, 1 planes for exactly one level (one 16-byte store per row), 2 planes for any level count
 template <int P, typename TIn, typename TOut, int RMODE, int PL>
-__global__ void __launch_bounds__(SS_THREADS, (P <= 5 ? 4 : 3))
+__global__ void __launch_bounds__(SS_THREADS, (P <= 5 ? SS_MINCTA_SMALL : 3))
 smooth_stream_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, const __grid_constant__ SsParams prm) {
   constexpr int RFIRST = RMODE == WBK_ROUND_ALL ? 2 : (RMODE == WBK_ROUND_FIRST ? 1 : 0);
   constexpr int RREST = RMODE == WBK_ROUND_ALL ? 2 : 0;
@@ -342,7 +344,6 @@ static void ss_geometry(SsParams& p, int passes) {
   const int rows = p.nlat - 2 * p.nan_border;
   // two latitude chunks per strip on tall grids: better balance over the SMs for 3P extra rows per chunk
   p.nchunks = rows >= 256 ? 2 : 1;
-  if (const char* e = getenv("WBK_SS_NCHUNKS")) p.nchunks = atoi(e) > 0 ? atoi(e) : p.nchunks;  // experiment knob
   p.chunk_rows = rows > 0 ? (rows + p.nchunks - 1) / p.nchunks : 1;
 }
 

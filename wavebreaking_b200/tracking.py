@@ -283,11 +283,26 @@ def overlap_exact(soup, pairs):
         return np.zeros(0, dtype=np.int32)
     if not soup.lattice:
         raise ValueError("overlap_exact needs lattice polygons")
-    edges, vsign = _edge_table(soup)
-    if len(edges) == 0:
+    if len(soup.xy) == 0:
         return np.zeros(len(pairs), dtype=np.int32)
-    out = torch.empty(len(pairs), dtype=torch.int32, device=lib.device)
-    bufs = [_dev(a, lib) for a in (edges, vsign, soup.ring_off, soup.poly_off, pairs)]  # alive until the result is read
+    # edge table (x0, y0, x1, y1 per vertex) and ring orientation signs, built ON the device from the uploaded vertices
+    # (tens of millions of vertices for a decade of events: numpy would dominate the whole tracking step)
+    dev = lib.device
+    xy = torch.from_numpy(np.ascontiguousarray(soup.xy, dtype=np.int32)).to(dev)
+    ring_off = torch.from_numpy(soup.ring_off.astype(np.int64)).to(dev)
+    V = xy.shape[0]
+    nv = ring_off[1:] - ring_off[:-1]
+    nxt = torch.arange(1, V + 1, device=dev, dtype=torch.int64)
+    live = nv > 0
+    nxt[ring_off[1:][live] - 1] = ring_off[:-1][live]
+    edges = torch.cat([xy, xy[nxt]], dim=1).contiguous()  # int32 [V, 4]
+    e64 = edges.to(torch.int64)
+    cross = e64[:, 0] * e64[:, 3] - e64[:, 2] * e64[:, 1]
+    csum = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(cross, 0)])
+    area2 = csum[ring_off[1:]] - csum[ring_off[:-1]]
+    vsign = torch.repeat_interleave(torch.sign(area2).to(torch.int32), nv).contiguous()
+    out = torch.empty(len(pairs), dtype=torch.int32, device=dev)
+    bufs = [edges, vsign, _dev(soup.ring_off, lib), _dev(soup.poly_off, lib), _dev(pairs, lib)]  # alive until the read
     lib.call("wbk_track_overlap_exact", *[_lib.ptr(b) for b in bufs], len(pairs), _lib.ptr(out), lib.stream())
     return out.cpu().numpy()
 
