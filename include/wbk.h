@@ -86,6 +86,10 @@ typedef struct wbk_smooth_opts {
 int wbk_smooth(const void* d_in, int in_dtype, void* d_out, int out_dtype, void* d_tmp, int ntime, int nlat,
                int nlon, int passes, int round_mode, const wbk_smooth_opts* opts, void* stream);
 
+/* tuning knob (process-wide): 64-column halves a warp of the smoothing kernel marches side by side; 0 / 1 = one
+ * (default, the faster one on B200: 16 instead of 8 warps per SM), 2 = two (<= 5 passes).  Results do not depend on it. */
+void wbk_tune_smooth_halves(int halves);
+
 /* orientation fix (and int16 decode) alone: d_out[t, y, x] = decode(d_in[t, flip_lat ? nlat-1-y : y,
  * flip_lon ? nlon-1-x : x]); output dtype = in_dtype, float64 for WBK_I16 */
 int wbk_orient(const void* d_in, int in_dtype, void* d_out, int ntime, int nlat, int nlon, const wbk_smooth_opts* opts,

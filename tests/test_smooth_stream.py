@@ -163,6 +163,49 @@ def test_detector_int16_input_emu(emu):
         assert np.array_equal(a.tables[kind].sums, b.tables[kind].sums)
 
 
+@pytest.fixture
+def two_halves():
+    """force the 128-column strips (two 64-column halves per warp) that wide grids use, whatever the grid width"""
+    lib = _lib.get()
+    lib.cdll.wbk_tune_smooth_halves(2)
+    yield
+    lib.cdll.wbk_tune_smooth_halves(0)
+
+
+@pytest.mark.parametrize("shape", [(9, 20), (33, 118), (30, 119), (26, 131), (21, 260)])
+@pytest.mark.parametrize("passes", [1, 4, 5])
+def test_two_halves_per_warp_emu(emu, two_halves, shape, passes):
+    """strips of 128 columns: the seam between the halves, strips narrower / wider than the grid, flips, all dtypes"""
+    nlat, nlon = shape
+    f = _field(nlat, nlon, 2, np.float32, 13)
+    f[1, nlat // 2, nlon // 3] = np.inf  # one slow-path stretch
+    with np.errstate(all="ignore"):
+        want = P.smooth_field(f, passes)
+        stored = np.ascontiguousarray(f[:, ::-1, ::-1])
+        _eq(_smooth_raw(torch.from_numpy(stored), passes, _lib.ROUND_FIRST, torch.float64, _lib.smooth_opts(True, True)), want)
+        f64 = f.astype(np.float64) * 1.0000001
+        _eq(_smooth_raw(torch.from_numpy(f64), passes, _lib.ROUND_NONE, torch.float64), P.smooth_field(f64, passes))
+    packed = np.round(_field(nlat, nlon, 1, np.float64, 14) * 3000).astype(np.int16)
+    got = _smooth_raw(torch.from_numpy(packed), passes, _lib.ROUND_NONE, torch.float64, _lib.smooth_opts(False, False, 1 / 3000.0, 0.25, None))
+    _eq(got, P.smooth_field(packed.astype(np.float64) * (1 / 3000.0) + 0.25, passes))
+
+
+@pytest.mark.parametrize("nlon", [90, 118, 120, 128, 236, 238])
+@pytest.mark.parametrize("levels", [[2.0], [2.0, -2.0, 1.5]])
+def test_two_halves_bit_planes_detector_emu(emu, two_halves, nlon, levels):
+    """the marching-squares stage reads the planes of both halves: same contours / events as the unfused path"""
+    nlat = nlon // 2 + 1  # dlon == dlat
+    lat, lon = synthetic.grid_coords(nlat, nlon)
+    raw = synthetic.pv_field(nlat, nlon, np.arange(2) * 6.0)
+    a = pipeline.Detector(lat, lon, levels=levels).run_batch(spatial.to_device(raw))
+    b = pipeline.Detector(lat, lon, levels=levels, fuse=False).run_batch(spatial.to_device(raw))
+    assert pipeline.summarize(a) == pipeline.summarize(b)
+    ha, hb = a.contours.host(), b.contours.host()
+    for k in ("job", "pt_off", "closed", "x", "y"):
+        assert np.array_equal(ha[k], hb[k]), k
+    assert np.array_equal(a.flags.cpu().numpy(), b.flags.cpu().numpy())
+
+
 @pytest.mark.gpu
 def test_smooth_stream_gpu_full_size_special_cases(gpu):
     f = _field(721, 1440, 1, np.float32, 3)

@@ -88,6 +88,7 @@ _SIGNATURES = {
     "wbk_contours": (c_int, [c_void_p, c_void_p, c_int, c_int, POINTER(c_double), c_int, c_void_p]),
     "wbk_smooth_contours": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, POINTER(c_double), c_int,
                                     POINTER(SmoothOpts), c_void_p]),
+    "wbk_tune_smooth_halves": (None, [c_int]),
     "wbk_orient": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, POINTER(SmoothOpts), c_void_p]),
     "wbk_contours_counts": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int), c_void_p]),
     "wbk_contours_pack": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), c_void_p, c_void_p, c_void_p, c_void_p,

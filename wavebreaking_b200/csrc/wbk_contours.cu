@@ -5,6 +5,8 @@
 #include "wbk_ms.cuh"
 
 // ------------------------------------------------------------------------------------------ context
+int wbk_smooth_plane_strips_max(int nlon);  // wbk_smooth.cu
+
 namespace {
 struct Bump {
   unsigned char* base;
@@ -39,8 +41,8 @@ size_t layout(WbkDev& d, const wbk_caps& c, int nlat, int nlon, int add, unsigne
   d.cymax = b.take<int>(J * CC); d.cout = b.take<int>(J * CC); d.cand = b.take<int>(J * CC * 2);
   d.out_pts = b.take<u32>(J * R); d.out_tab = b.take<int>(J * CC * 4); d.out_sumy = b.take<int>(J * CC);
   d.out_nc = b.take<int>(J); d.out_np = b.take<int>(J); d.max_nx = b.take<int>(64);
-  // comparison bit planes of the fused smoothing: <= 4 words per (job, row, strip), strips of >= 48 valid columns
-  d.planes = b.take<u32>(J * 4 * (size_t)nlat * (size_t)((nlon + 47) / 48) + 8);
+  // comparison bit planes of the fused smoothing: <= 4 words per (job, row, plane strip)
+  d.planes = b.take<u32>(J * 4 * (size_t)nlat * (size_t)wbk_smooth_plane_strips_max(nlon) + 8);
   return (b.off + 255) & ~(size_t)255;
 }
 
@@ -733,9 +735,10 @@ extern "C" int wbk_contours(wbk_ctx* ctx, const void* d_field, int dtype, int nt
 // ------------------------------------------------------------------------------------------ K3b
 // Marching squares on the comparison bit planes the smoothing kernel leaves behind (wbk_smooth.cu): the smoothed
 // field is not re-read; only the four corner values of the squares a contour actually crosses are fetched.
-// One thread per (time step, chunk of MSP_ROWS rows, strip): it turns the even / odd column words of two
-// consecutive rows into 64-column bit rows (the column right of the strip comes from the next strip's first valid
-// column, the last strip wraps to column 0 = the periodic extension) and classifies all squares of the row with
+// One thread per (time step, chunk of MSP_ROWS rows, plane strip = 64-column half of a smoothing strip): it turns the
+// even / odd column words of two consecutive rows into bit rows that start at the half's first valid column (the
+// column right of its last valid one comes from the next half, or from the next strip's first valid column; the
+// last strip wraps to column 0 = the periodic extension) and classifies all squares of the row with
 // the same bit expression as ms_segments_kernel.  Hits are compacted per warp and emitted by ms_emit_squares.
 #define MSP_THREADS 128
 #define MSP_ROWS 4
@@ -751,17 +754,25 @@ __device__ __forceinline__ u64 msp_spread(u32 v) {
 }
 
 struct MspGeom {
-  int nstrips, V, P, PW;  // strips per row, valid columns per strip, left halo (= passes), words per (t, row, strip)
+  int nstrips, V, P, PW;  // smoothing strips per row, valid columns per strip, left halo (= passes), words per (t, row, plane strip)
+  int H, nps;             // 64-column halves per smoothing strip, plane strips per row (= nstrips * H)
   int ntime, nchunks;
 };
 
-// 64-column bit row from the even / odd column words (e, o) of a strip row; the bit right of the last valid column
-// (strip column P + vcols) is taken from the next strip's words (ne, no): its strip column P
-__device__ __forceinline__ u64 msp_bits(u32 e, u32 o, u32 ne, u32 no, int P, int vcols) {
-  const u64 m = msp_spread(e) | (msp_spread(o) << 1);
-  const u32 nb = (((P & 1) ? no : ne) >> (P >> 1)) & 1u;
-  const int j = P + vcols;  // < 64
-  return (m & ~(1ULL << j)) | ((u64)nb << j);
+// valid bits [lo, lo + n) of half h of smoothing strip s, and the grid column of bit lo (n <= 63 since P >= 1)
+__device__ __forceinline__ void msp_half_range(const MspGeom& g, int nlon, int s, int h, int& lo, int& n, int& col0) {
+  const int vcols = min(g.V, nlon - s * g.V);  // valid strip columns [P, P + vcols)
+  lo = max(g.P - 64 * h, 0);
+  n = max(min(g.P + vcols - 64 * h, 64) - lo, 0);
+  col0 = s * g.V + 64 * h + lo - g.P;
+}
+
+// Bit row of a plane strip from its even / odd column words (e, o): bit i = strip bit lo + i; the bit right of the
+// last valid column (i = n) is bit `nbit` of the words (ne, no) of the plane strip that follows
+__device__ __forceinline__ u64 msp_bits(u32 e, u32 o, u32 ne, u32 no, int lo, int n, int nbit) {
+  const u64 m = (msp_spread(e) | (msp_spread(o) << 1)) >> lo;
+  const u32 nb = (((nbit & 1) ? no : ne) >> (nbit >> 1)) & 1u;
+  return (m & ~(1ULL << n)) | ((u64)nb << n);
 }
 
 // Emission of the hits a warp found in its MSP_ROWS x 32 (row, strip) items: hit h goes to lane h % 32, so every
@@ -769,7 +780,7 @@ __device__ __forceinline__ u64 msp_bits(u32 e, u32 o, u32 ne, u32 no, int P, int
 // masks: [MSP_ROWS][64] words of this warp (lane l: words 2l, 2l+1 of row i), prefix: [33] hits before lane l.
 template <typename T>
 __device__ __noinline__ void msp_emit(const WbkDev& d, const T* __restrict__ src, const u32* masks, const int* prefix,
-                                      int job, int item0, int nstrips, int V, int P, double level) {
+                                      int job, int item0, const MspGeom& g, double level) {
   const int lane = wbk_lane(), nlon = d.nlon;
   const int total = prefix[32];
   for (int h0 = 0; h0 < total; h0 += 32) {
@@ -793,9 +804,11 @@ __device__ __noinline__ void msp_emit(const WbkDev& d, const T* __restrict__ src
       for (; k > 0; --k) m &= m - 1;
       const int bit = __ffsll((long long)m) - 1;
       const int hit_item = item0 + sl;
-      const int hs = hit_item % nstrips, hchunk = hit_item / nstrips;
+      const int hps = hit_item % g.nps, hchunk = hit_item / g.nps;
+      int lo, n, col0;
+      msp_half_range(g, nlon, hps / g.H, hps % g.H, lo, n, col0);
       r0 = hchunk * MSP_ROWS + i;
-      c0 = hs * V + bit - P;
+      c0 = col0 + bit;
       const int cr = c0 + 1 == nlon ? 0 : c0 + 1;
       ul = (double)src[(size_t)r0 * nlon + c0];
       ur = (double)src[(size_t)r0 * nlon + cr];
@@ -806,8 +819,8 @@ __device__ __noinline__ void msp_emit(const WbkDev& d, const T* __restrict__ src
   }
 }
 
-// The plane rows a CTA needs are ONE contiguous block of global memory ([t][row][strip][PW] words, rows of
-// nstrips * PW * 4 bytes, a multiple of 16): they are staged in shared memory with a single TMA bulk copy
+// The plane rows a CTA needs are ONE contiguous block of global memory ([t][row][plane strip][PW] words, rows of
+// nps * PW * 4 bytes): they are staged in shared memory with a single TMA bulk copy
 // (cp.async.bulk.shared.global + mbarrier transaction count) instead of ~40 scattered loads per thread.
 __device__ __forceinline__ void msp_stage_rows(u32* smem_dst, const u32* gsrc, unsigned bytes, u64* bar) {
 #ifndef WBK_EMU
@@ -847,14 +860,14 @@ ms_planes_kernel(const T* __restrict__ field, const u32* __restrict__ planes, co
   WBK_DYN_SMEM(u32, srows);  // plane words of rows [row0, row0 + nrows) of this time step
   const int lane = wbk_lane(), warp = wbk_warp();
   const int nlat = d.nlat, nlon = d.nlon, W = d.W;
-  const int per_t = g.nchunks * g.nstrips;
+  const int per_t = g.nchunks * g.nps;
   const int t = t_base + (int)blockIdx.y;
   const int item_first = (int)blockIdx.x * MSP_THREADS;
   const int item_last = min(item_first + MSP_THREADS, per_t) - 1;  // the grid covers exactly ceil(per_t / MSP_THREADS) bands
   const size_t trow = (size_t)t * nlat;
-  const size_t row_words = (size_t)g.nstrips * g.PW;
-  const int row0 = (item_first / g.nstrips) * MSP_ROWS;
-  const int row1 = min((item_last / g.nstrips + 1) * MSP_ROWS, nlat - 1);  // last row read
+  const size_t row_words = (size_t)g.nps * g.PW;
+  const int row0 = (item_first / g.nps) * MSP_ROWS;
+  const int row1 = min((item_last / g.nps + 1) * MSP_ROWS, nlat - 1);  // last row read
   // the bulk copy wants 16-byte aligned addresses and sizes: rows are only 8-byte multiples for an even number of
   // levels, so the block is widened to the enclosing 16-byte range (`delta` words precede the first row)
   const size_t gstart = (trow + row0) * row_words;
@@ -865,32 +878,38 @@ ms_planes_kernel(const T* __restrict__ field, const u32* __restrict__ planes, co
   const int item0 = item_first + warp * 32;  // first item of this warp
   const bool live = item0 + lane < per_t;
   const int it = live ? item0 + lane : item_first;  // dead lanes shadow a staged item with an empty square mask
-  const int s = it % g.nstrips, chunk = it / g.nstrips;
-  const int sn = s + 1 == g.nstrips ? 0 : s + 1;  // the strip to the right (the last one wraps: periodic extension)
+  const int ps = it % g.nps, chunk = it / g.nps;
+  const int s = ps / g.H, h = ps - s * g.H;
   const int r_begin = chunk * MSP_ROWS;
   const int r_end = min(r_begin + MSP_ROWS, nlat - 1);  // squares r0 in [r_begin, r_end)
-  const int vcols = min(g.V, nlon - s * g.V);
-  // squares owned by this strip: strip columns [P, P + vcols) whose base square exists (c0 <= W - 2)
-  int nsq = min(vcols, W - 1 - s * g.V);
+  int lo, n, col0;
+  msp_half_range(g, nlon, s, h, lo, n, col0);
+  // the column right of the last valid one: bit 0 of the next half when this half is valid up to its last bit,
+  // else the first valid column of the strip to the right (the last strip wraps: periodic extension)
+  const bool next_half = lo + n == 64;  // implies h + 1 < H (the last half ends at bit 64 - P)
+  const int pn = next_half ? ps + 1 : (s + 1 == g.nstrips ? 0 : s + 1) * g.H;
+  const int nbit = next_half ? 0 : g.P;
+  // squares owned by this plane strip: its valid columns whose base square exists (c0 <= W - 2)
+  int nsq = min(n, W - 1 - col0);
   if (nsq < 0 || !live) nsq = 0;
-  const u64 sqmask = nsq >= 64 ? ~0ULL : (((1ULL << nsq) - 1ULL) << g.P);
+  const u64 sqmask = (1ULL << nsq) - 1ULL;  // nsq <= 63
   const T* src = field + trow * nlon;
-  const u32* own = srows + delta + (size_t)(r_begin - row0) * row_words + (size_t)s * g.PW;
-  const u32* nxt = srows + delta + (size_t)(r_begin - row0) * row_words + (size_t)sn * g.PW;
+  const u32* own = srows + delta + (size_t)(r_begin - row0) * row_words + (size_t)ps * g.PW;
+  const u32* nxt = srows + delta + (size_t)(r_begin - row0) * row_words + (size_t)pn * g.PW;
 
   for (int l = 0; l < nlevels; ++l) {
     int cnt = 0;
     const bool ok0 = r_begin <= r_end;
-    u64 g0 = ok0 ? msp_bits(own[2 + 2 * l], own[3 + 2 * l], nxt[2 + 2 * l], nxt[3 + 2 * l], g.P, vcols) : 0;
-    u64 n0 = ok0 ? msp_bits(own[0], own[1], nxt[0], nxt[1], g.P, vcols) : 0;
+    u64 g0 = ok0 ? msp_bits(own[2 + 2 * l], own[3 + 2 * l], nxt[2 + 2 * l], nxt[3 + 2 * l], lo, n, nbit) : 0;
+    u64 n0 = ok0 ? msp_bits(own[0], own[1], nxt[0], nxt[1], lo, n, nbit) : 0;
 #pragma unroll
     for (int i = 0; i < MSP_ROWS; ++i) {
       u64 hits = 0, g1 = 0, n1 = 0;
       if (r_begin + i < r_end) {
         const u32* po = own + (size_t)(i + 1) * row_words;
-        const u32* pn = nxt + (size_t)(i + 1) * row_words;
-        g1 = msp_bits(po[2 + 2 * l], po[3 + 2 * l], pn[2 + 2 * l], pn[3 + 2 * l], g.P, vcols);
-        n1 = msp_bits(po[0], po[1], pn[0], pn[1], g.P, vcols);
+        const u32* px = nxt + (size_t)(i + 1) * row_words;
+        g1 = msp_bits(po[2 + 2 * l], po[3 + 2 * l], px[2 + 2 * l], px[3 + 2 * l], lo, n, nbit);
+        n1 = msp_bits(po[0], po[1], px[0], px[1], lo, n, nbit);
         const u64 both = g0 & g1, either = g0 | g1, nn = n0 | n1;
         hits = ((either | (either >> 1)) & ~(both & (both >> 1))) & ~(nn | (nn >> 1)) & sqmask;
       }
@@ -905,7 +924,7 @@ ms_planes_kernel(const T* __restrict__ field, const u32* __restrict__ planes, co
     sprefix[warp][lane + 1] = incl;
     if (lane == 0) sprefix[warp][0] = 0;
     __syncwarp();
-    msp_emit<T>(d, src, &smask[warp][0][0], sprefix[warp], t * nlevels + l, item0, g.nstrips, g.V, g.P, levels.v[l]);
+    msp_emit<T>(d, src, &smask[warp][0][0], sprefix[warp], t * nlevels + l, item0, g, levels.v[l]);
     __syncwarp();
   }
 }
@@ -913,7 +932,7 @@ ms_planes_kernel(const T* __restrict__ field, const u32* __restrict__ planes, co
 int wbk_launch_smooth(const void* d_in, int in_dtype, void* d_out, int out_dtype, int ntime, int nlat, int nlon, int passes,
                       int round_mode, int nan_border, const wbk_smooth_opts* opts, u32* d_planes, const double* h_levels,
                       int nlevels, cudaStream_t st);  // wbk_smooth.cu
-void wbk_smooth_plane_geometry(int nlon, int passes, int* nstrips, int* V);
+void wbk_smooth_plane_geometry(int nlon, int passes, int* nstrips, int* V, int* halves);
 
 extern "C" int wbk_smooth_contours(wbk_ctx* ctx, const void* d_in, int in_dtype, double* d_smoothed, int ntime,
                                    int passes, const double* h_levels, int nlevels, const wbk_smooth_opts* opts,
@@ -943,16 +962,17 @@ extern "C" int wbk_smooth_contours(wbk_ctx* ctx, const void* d_in, int in_dtype,
                              h_levels, nlevels, st);
   if (rc != WBK_OK) return rc;
   MspGeom g;
-  wbk_smooth_plane_geometry(d.nlon, passes, &g.nstrips, &g.V);
+  wbk_smooth_plane_geometry(d.nlon, passes, &g.nstrips, &g.V, &g.H);
+  g.nps = g.nstrips * g.H;
   g.P = passes;
   g.PW = 2 + 2 * nlevels;
   g.ntime = ntime;
   g.nchunks = (d.nlat - 1 + MSP_ROWS - 1) / MSP_ROWS;
-  const int per_t = g.nchunks * g.nstrips;
+  const int per_t = g.nchunks * g.nps;
   const int bands = (per_t + MSP_THREADS - 1) / MSP_THREADS;
   // rows staged per CTA: the row chunks its MSP_THREADS items span, plus the row below the last one
-  const int max_chunks = (MSP_THREADS + g.nstrips - 2) / g.nstrips + 1;
-  const size_t smem = (size_t)(max_chunks * MSP_ROWS + 1) * g.nstrips * g.PW * sizeof(u32) + 32;
+  const int max_chunks = (MSP_THREADS + g.nps - 2) / g.nps + 1;
+  const size_t smem = (size_t)(max_chunks * MSP_ROWS + 1) * g.nps * g.PW * sizeof(u32) + 32;
   if (smem > 160 * 1024) {
     wbk_set_error("wbk_smooth_contours: %d strips x %d levels do not fit the plane staging buffer", g.nstrips, nlevels);
     return WBK_ERR_CAPACITY;

@@ -10,8 +10,20 @@ int wbk_ss_launch_f64_f64(const void* in, void* out, int passes, SsParams& prm, 
 int wbk_ss_launch_i16_f64(const void* in, void* out, int passes, SsParams& prm, cudaStream_t st);  // ROUND_NONE
 
 // geometry of the bit planes a fused smoothing of `passes` (<= WBK_SMOOTH_MAX_FUSED) passes writes
-void wbk_smooth_plane_geometry(int nlon, int passes, int* nstrips, int* V) {
-  *V = 64 - 2 * passes;
+static int g_halves_override = 0;
+int wbk_smooth_halves_override() { return g_halves_override; }
+extern "C" void wbk_tune_smooth_halves(int halves) { g_halves_override = halves == 1 || halves == 2 ? halves : 0; }
+
+// upper bound of the plane strips per grid row over every pass count and strip width the smoothing kernel may use
+int wbk_smooth_plane_strips_max(int nlon) {
+  const int one = (nlon + (64 - 2 * WBK_SMOOTH_MAX_FUSED) - 1) / (64 - 2 * WBK_SMOOTH_MAX_FUSED);
+  const int two = 2 * ((nlon + (128 - 2 * SS_MAX_P_H2) - 1) / (128 - 2 * SS_MAX_P_H2));
+  return one > two ? one : two;
+}
+
+void wbk_smooth_plane_geometry(int nlon, int passes, int* nstrips, int* V, int* halves) {
+  *halves = ss_halves(nlon, passes);
+  *V = 64 * *halves - 2 * passes;
   *nstrips = (nlon + *V - 1) / *V;
 }
 

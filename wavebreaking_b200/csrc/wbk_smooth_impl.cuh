@@ -25,6 +25,9 @@
 #ifndef SS_MINCTA_SMALL
 #define SS_MINCTA_SMALL 4  // resident CTAs per SM the register budget is sized for (P <= 5)
 #endif
+#ifndef SS_MAX_P_H2
+#define SS_MAX_P_H2 5  // largest pass count that uses two 64-column halves per warp (register budget)
+#endif
 #ifndef SS_RING
 #define SS_RING 4  // rows of the shared-memory input ring (power of two); 4 / 8 / 16 measured within 2 % on B200
 #endif
@@ -97,53 +100,71 @@ __device__ __forceinline__ bool ss_unsafe_raw(short a, short b, const SsParams& 
   return (int)a == p.fill || (int)b == p.fill;  // finite scale / offset keep the decoded values in range
 }
 
-// One marching step.  PH = k mod 3 selects which register row of every level is the oldest one (it is consumed
-// for the last time in this step and then overwritten by the level's new row).
-template <int P, int RFIRST, int RREST, bool SAFE, int PH>
-__device__ __forceinline__ void ss_step(double (&w)[P][3][2], double in0, double in1, double& o0, double& o1) {
+// One marching step of a strip of H halves of 64 columns (lane l of half h: strip columns 64h + 2l, 64h + 2l + 1).
+// PH = k mod 3 selects which register row of every level is the oldest one (it is consumed for the last time in this
+// step and then overwritten by the level's new row).  West / east neighbours: one rotation shuffle per half and
+// direction; across the seam between two halves lane 0 / lane 31 take the value of the other half.
+template <int P, int H, int RFIRST, int RREST, bool SAFE, int PH>
+__device__ __forceinline__ void ss_step(double (&w)[P][3][2 * H], const double (&in)[2 * H], double (&o)[2 * H], int lane_up,
+                                        int lane_dn, bool first_lane, bool last_lane) {
   constexpr int OLD = PH % 3, MID = (PH + 1) % 3, NEW = (PH + 2) % 3;
 #pragma unroll
   for (int p = P; p >= 1; --p) {
-    const double nx = w[p - 1][OLD][0], ny = w[p - 1][OLD][1];
-    const double cx = w[p - 1][MID][0], cy = w[p - 1][MID][1];
-    const double sx = w[p - 1][NEW][0], sy = w[p - 1][NEW][1];
-    const double wv = __shfl_up_sync(WBK_FULL, cy, 1);    // column 2l-1 (lane 0: halo garbage, never valid)
-    const double ev = __shfl_down_sync(WBK_FULL, cx, 1);  // column 2l+2
-    // scipy's tap order ((((N + W) + 2C) + E) + S); (N+W) + 2C in one FMA is the same single rounding
-    double a0 = __dadd_rn(nx, wv);
-    a0 = __fma_rn(2.0, cx, a0);
-    a0 = __dadd_rn(a0, cy);
-    a0 = __dadd_rn(a0, sx);
-    double a1 = __dadd_rn(ny, cx);
-    a1 = __fma_rn(2.0, cy, a1);
-    a1 = __dadd_rn(a1, ev);
-    a1 = __dadd_rn(a1, sy);
-    double r0, r1;
-    if (p == 1) {
-      r0 = ss_finish<RFIRST, SAFE>(a0);
-      r1 = ss_finish<RFIRST, SAFE>(a1);
-    } else {
-      r0 = ss_finish<RREST, SAFE>(a0);
-      r1 = ss_finish<RREST, SAFE>(a1);
+    double wv[H], ev[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      wv[h] = __shfl_sync(WBK_FULL, w[p - 1][MID][2 * h + 1], lane_up);  // column 2l-1 of the half (lane 0: lane 31's)
+      ev[h] = __shfl_sync(WBK_FULL, w[p - 1][MID][2 * h], lane_dn);      // column 2l+2 of the half (lane 31: lane 0's)
     }
-    if (p == P) {
-      o0 = r0;
-      o1 = r1;
-    } else {
-      w[p][OLD][0] = r0;  // level p + 1 has already consumed this row (levels run from P downwards)
-      w[p][OLD][1] = r1;
+    if (H == 2) {
+      // seam: column 63 is lane 31 of half 0, column 64 lane 0 of half 1 (the outer ends of the strip keep the
+      // rotated garbage: halo columns, never valid)
+      const double w1 = first_lane ? wv[0] : wv[1], e0 = last_lane ? ev[1] : ev[0];
+      wv[H - 1] = w1;
+      ev[0] = e0;
+    }
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      const double nx = w[p - 1][OLD][2 * h], ny = w[p - 1][OLD][2 * h + 1];
+      const double cx = w[p - 1][MID][2 * h], cy = w[p - 1][MID][2 * h + 1];
+      const double sx = w[p - 1][NEW][2 * h], sy = w[p - 1][NEW][2 * h + 1];
+      // scipy's tap order ((((N + W) + 2C) + E) + S); (N+W) + 2C in one FMA is the same single rounding
+      double a0 = __dadd_rn(nx, wv[h]);
+      a0 = __fma_rn(2.0, cx, a0);
+      a0 = __dadd_rn(a0, cy);
+      a0 = __dadd_rn(a0, sx);
+      double a1 = __dadd_rn(ny, cx);
+      a1 = __fma_rn(2.0, cy, a1);
+      a1 = __dadd_rn(a1, ev[h]);
+      a1 = __dadd_rn(a1, sy);
+      double r0, r1;
+      if (p == 1) {
+        r0 = ss_finish<RFIRST, SAFE>(a0);
+        r1 = ss_finish<RFIRST, SAFE>(a1);
+      } else {
+        r0 = ss_finish<RREST, SAFE>(a0);
+        r1 = ss_finish<RREST, SAFE>(a1);
+      }
+      if (p == P) {
+        o[2 * h] = r0;
+        o[2 * h + 1] = r1;
+      } else {
+        w[p][OLD][2 * h] = r0;  // level p + 1 has already consumed this row (levels run from P downwards)
+        w[p][OLD][2 * h + 1] = r1;
+      }
     }
   }
-  w[0][OLD][0] = in0;
-  w[0][OLD][1] = in1;
+#pragma unroll
+  for (int c = 0; c < 2 * H; ++c) w[0][OLD][c] = in[c];
 }
 
-// PL: 0 no bit planes, 1 planes for exactly one level (one 16-byte store per row), 2 planes for any level count
-template <int P, typename TIn, typename TOut, int RMODE, int PL>
-__global__ void __launch_bounds__(SS_THREADS, (P <= 5 ? SS_MINCTA_SMALL : 3))
+// PL: 0 no bit planes, 1 planes for exactly one level (one 16-byte store per row and half), 2 planes for any level count
+template <int P, int H, typename TIn, typename TOut, int RMODE, int PL>
+__global__ void __launch_bounds__(SS_THREADS, (H == 2 ? 2 : (P <= 5 ? SS_MINCTA_SMALL : 3)))
 smooth_stream_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, const __grid_constant__ SsParams prm) {
   constexpr int RFIRST = RMODE == WBK_ROUND_ALL ? 2 : (RMODE == WBK_ROUND_FIRST ? 1 : 0);
   constexpr int RREST = RMODE == WBK_ROUND_ALL ? 2 : 0;
+  constexpr int WS = 64 * H;  // strip width
   const int lane = wbk_lane();
   const int nlat = prm.nlat, nlon = prm.nlon;
   // the warp index through a shuffle: the compiler then treats everything derived from it as warp-uniform and
@@ -162,44 +183,60 @@ smooth_stream_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, const _
   const int y0 = row_lo + chunk * prm.chunk_rows;
   const int y1 = min(y0 + prm.chunk_rows, row_hi);
 
-  // columns of this lane: strip columns 2l, 2l+1 = logical grid columns x0 + 2l (+1), periodic
+  // columns of this lane: strip columns 64h + 2l, 64h + 2l + 1 = logical grid columns x0 + ..., periodic
   const int x0 = s * prm.V - P;
-  const int lx0 = ss_wrap(x0 + 2 * lane, nlon), lx1 = ss_wrap(x0 + 2 * lane + 1, nlon);
-  const int px0 = prm.flip_lon ? nlon - 1 - lx0 : lx0, px1 = prm.flip_lon ? nlon - 1 - lx1 : lx1;
   const size_t plane = (size_t)nlat * nlon;
   const TIn* src = in + plane * t;
   TOut* dst = out + plane * t;
   // valid outputs of this lane: strip columns [P, P + V) that exist in the grid
   const int vcols = min(prm.V, nlon - s * prm.V);
-  const bool ok0 = 2 * lane >= P && 2 * lane < P + vcols;
-  const bool ok1 = 2 * lane + 1 >= P && 2 * lane + 1 < P + vcols;
-  const int ox = s * prm.V + 2 * lane - P;  // output column of strip column 2l (valid lanes only)
+  int pxa[H], d1[H], ox[H];
+  bool ok0[H], ok1[H];
+#pragma unroll
+  for (int h = 0; h < H; ++h) {
+    const int sc = 64 * h + 2 * lane;
+    const int lx0 = ss_wrap(x0 + sc, nlon), lx1 = ss_wrap(x0 + sc + 1, nlon);
+    const int p0 = prm.flip_lon ? nlon - 1 - lx0 : lx0, p1 = prm.flip_lon ? nlon - 1 - lx1 : lx1;
+    pxa[h] = p0;
+    d1[h] = p1 - p0;
+    ok0[h] = sc >= P && sc < P + vcols;
+    ok1[h] = sc + 1 >= P && sc + 1 < P + vcols;
+    ox[h] = s * prm.V + sc - P;  // output column of strip column sc (valid lanes only)
+  }
   const int PW = 2 + 2 * prm.nlevels;
-  const size_t pl_row = (size_t)prm.nstrips * (size_t)PW;  // plane words per grid row
-  u32* pl_base = PL ? prm.planes + ((size_t)t * nlat * prm.nstrips + s) * (size_t)PW : nullptr;
+  // bit planes: one record of PW words per (row, 64-column half); half h of strip s is plane strip s * H + h
+  const size_t pl_row = (size_t)prm.nstrips * H * (size_t)PW;  // plane words per grid row
+  u32* pl_base = PL ? prm.planes + ((size_t)t * nlat * prm.nstrips * H + (size_t)s * H) * (size_t)PW : nullptr;
   const double level0 = prm.levels.v[0];
+  const int lane_up = (lane + 31) & 31, lane_dn = (lane + 1) & 31;
+  const bool first_lane = lane == 0, last_lane = lane == 31;
 
   // bit planes of one finished row: ballots of the values the lanes hold (NaN can only occur on the slow path)
-  auto emit_planes = [&](u32* pl, double v0, double v1, bool may_nan) {
-    u32 n0 = 0, n1 = 0;
-    if (may_nan) {
-      n0 = __ballot_sync(WBK_FULL, v0 != v0);
-      n1 = __ballot_sync(WBK_FULL, v1 != v1);
-    }
-    if (PL == 1) {
-      const u32 g0 = __ballot_sync(WBK_FULL, v0 > level0), g1 = __ballot_sync(WBK_FULL, v1 > level0);
-      if (lane == 0) *reinterpret_cast<uint4*>(pl) = make_uint4(n0, n1, g0, g1);
-    } else {
-      if (lane == 0) {
-        pl[0] = n0;
-        pl[1] = n1;
+  auto emit_planes = [&](u32* pl, const double (&v)[2 * H], bool may_nan) {
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      u32* ph = pl + h * PW;
+      const double v0 = v[2 * h], v1 = v[2 * h + 1];
+      u32 n0 = 0, n1 = 0;
+      if (may_nan) {
+        n0 = __ballot_sync(WBK_FULL, v0 != v0);
+        n1 = __ballot_sync(WBK_FULL, v1 != v1);
       }
-      for (int l = 0; l < prm.nlevels; ++l) {
-        const double level = prm.levels.v[l];
-        const u32 g0 = __ballot_sync(WBK_FULL, v0 > level), g1 = __ballot_sync(WBK_FULL, v1 > level);
+      if (PL == 1) {
+        const u32 g0 = __ballot_sync(WBK_FULL, v0 > level0), g1 = __ballot_sync(WBK_FULL, v1 > level0);
+        if (lane == 0) *reinterpret_cast<uint4*>(ph) = make_uint4(n0, n1, g0, g1);
+      } else {
         if (lane == 0) {
-          pl[2 + 2 * l] = g0;
-          pl[3 + 2 * l] = g1;
+          ph[0] = n0;
+          ph[1] = n1;
+        }
+        for (int l = 0; l < prm.nlevels; ++l) {
+          const double level = prm.levels.v[l];
+          const u32 g0 = __ballot_sync(WBK_FULL, v0 > level), g1 = __ballot_sync(WBK_FULL, v1 > level);
+          if (lane == 0) {
+            ph[2 + 2 * l] = g0;
+            ph[3 + 2 * l] = g1;
+          }
         }
       }
     }
@@ -208,32 +245,39 @@ smooth_stream_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, const _
   // ---- NaN border rows (spatial.py:106-107): written by the first / last chunk of the strip
   if (nb > 0) {
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    double vq[2 * H];
+#pragma unroll
+    for (int c = 0; c < 2 * H; ++c) vq[c] = qnan;
     for (int i = 0; i < 2 * nb; ++i) {
       const bool top = i < nb;
       const int row = top ? i : nlat - 2 * nb + i;
       if (top ? chunk != 0 : (chunk != prm.nchunks - 1 || row < nb)) continue;  // warp-uniform
-      if (ok0) dst[(size_t)row * nlon + ox] = (TOut)qnan;
-      if (ok1) dst[(size_t)row * nlon + ox + 1] = (TOut)qnan;
-      if (PL) emit_planes(pl_base + (size_t)row * pl_row, qnan, qnan, true);
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        if (ok0[h]) dst[(size_t)row * nlon + ox[h]] = (TOut)qnan;
+        if (ok1[h]) dst[(size_t)row * nlon + ox[h] + 1] = (TOut)qnan;
+      }
+      if (PL) emit_planes(pl_base + (size_t)row * pl_row, vq, true);
     }
   }
   if (y0 >= y1) return;
 
   // ---- march: input rows k = y0 - P .. (rows past y1 + P - 1 are loaded too but never reach a valid output),
   //      level p emits row k - 2p, the output row of step k is k - 2P
-  double w[P][3][2];
+  double w[P][3][2 * H];
 #pragma unroll
   for (int p = 0; p < P; ++p)
 #pragma unroll
-    for (int r = 0; r < 3; ++r) w[p][r][0] = w[p][r][1] = 0.0;
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 2 * H; ++c) w[p][r][c] = 0.0;
 
   const int k_begin = y0 - P, k_end = y1 + 2 * P;  // steps k in [k_begin, k_end)
-  // prefetch cursor: logical row gy_pf, physical row pointer of this lane's first column
+  // prefetch cursor: logical row gy_pf, physical row pointer of the time step
   int gy_pf = ss_wrap(k_begin, nlat);
   const long long rstride = prm.flip_lat ? -(long long)nlon : (long long)nlon;
-  const TIn* pfp = src + (long long)(prm.flip_lat ? nlat - 1 - gy_pf : gy_pf) * nlon + px0;
+  const TIn* pfp = src + (long long)(prm.flip_lat ? nlat - 1 - gy_pf : gy_pf) * nlon;
   const long long pf_wrap = rstride * nlat;  // back to logical row 0
-  const int d1 = px1 - px0;
   auto advance = [&]() {
     pfp += rstride;
     if (++gy_pf == nlat) {
@@ -246,36 +290,48 @@ smooth_stream_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, const _
   // them, and every lane reads back only what it copied itself (no barrier).  Packed shorts (2 bytes, below the
   // cp.async granularity) use plain loads two steps ahead instead.
   constexpr bool ASYNC = sizeof(TIn) >= 4;
-  __shared__ __align__(16) TIn s_ring[ASYNC ? SS_THREADS / 32 : 1][ASYNC ? SS_RING : 1][64];
+  __shared__ __align__(16) TIn s_ring[ASYNC ? SS_THREADS / 32 : 1][ASYNC ? SS_RING : 1][WS];
   TIn* const my_ring = &s_ring[ASYNC ? warp_u : 0][0][ASYNC ? 2 * lane : 0];
   int slot_in = 0, slot_out = 0;  // ring slots of the next row to request / to consume
-  TIn pf[3][2];
+  TIn pf[3][2 * H];
   auto request_row = [&]() {
     if (ASYNC) {
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        const TIn* g0 = pfp + pxa[h];
 #ifndef WBK_EMU
-      const unsigned dst_s = (unsigned)__cvta_generic_to_shared(my_ring + slot_in * 64);
-      asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst_s), "l"(pfp), "n"(sizeof(TIn)) : "memory");
-      asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst_s + (unsigned)sizeof(TIn)), "l"(pfp + d1), "n"(sizeof(TIn)) : "memory");
-      asm volatile("cp.async.commit_group;" ::: "memory");
+        const unsigned dst_s = (unsigned)__cvta_generic_to_shared(my_ring + slot_in * WS + 64 * h);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst_s), "l"(g0), "n"(sizeof(TIn)) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst_s + (unsigned)sizeof(TIn)), "l"(g0 + d1[h]), "n"(sizeof(TIn)) : "memory");
 #else
-      my_ring[slot_in * 64] = pfp[0];
-      my_ring[slot_in * 64 + 1] = pfp[d1];
+        my_ring[slot_in * WS + 64 * h] = g0[0];
+        my_ring[slot_in * WS + 64 * h + 1] = g0[d1[h]];
+#endif
+      }
+#ifndef WBK_EMU
+      asm volatile("cp.async.commit_group;" ::: "memory");
 #endif
       slot_in = (slot_in + 1) & (SS_RING - 1);
       advance();
     }
   };
-  auto take_row = [&](TIn& r0, TIn& r1) {
+  auto take_row = [&](TIn (&r)[2 * H]) {
 #ifndef WBK_EMU
     asm volatile("cp.async.wait_group %0;" ::"n"(SS_RING - 1) : "memory");
 #endif
-    r0 = my_ring[slot_out * 64];
-    r1 = my_ring[slot_out * 64 + 1];
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      r[2 * h] = my_ring[slot_out * WS + 64 * h];
+      r[2 * h + 1] = my_ring[slot_out * WS + 64 * h + 1];
+    }
     slot_out = (slot_out + 1) & (SS_RING - 1);
   };
-  auto prefetch = [&](TIn (&slot)[2]) {
-    slot[0] = pfp[0];
-    slot[1] = pfp[d1];
+  auto prefetch = [&](TIn (&slot)[2 * H]) {
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      slot[2 * h] = pfp[pxa[h]];
+      slot[2 * h + 1] = pfp[pxa[h] + d1[h]];
+    }
     advance();
   };
   if (ASYNC) {
@@ -286,37 +342,47 @@ smooth_stream_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, const _
     // (refilling the slot that is being consumed makes the compiler copy the fresh value, i.e. wait for the load)
     prefetch(pf[0]);
     prefetch(pf[1]);
-    pf[2][0] = pf[2][1] = (TIn)0;
+#pragma unroll
+    for (int c = 0; c < 2 * H; ++c) pf[2][c] = (TIn)0;
   }
 
   int slow_until = k_begin;  // steps before this one use the plain division
   int k = k_begin;
-  TOut* dp = dst + (long long)(k_begin - 2 * P) * nlon + ox;  // output row of step k (valid once k - 2P >= y0)
+  long long drow = (long long)(k_begin - 2 * P) * nlon;  // output row offset of step k (valid once k - 2P >= y0)
   u32* plp = PL ? pl_base + (long long)(k_begin - 2 * P) * (long long)pl_row : nullptr;
-
 #define SS_ONE_STEP(PH)                                                                              \
   {                                                                                                  \
-    TIn raw0, raw1;                                                                                  \
+    TIn raw[2 * H];                                                                                  \
     if (ASYNC) {                                                                                     \
       request_row();                                                                                 \
-      take_row(raw0, raw1);                                                                          \
+      take_row(raw);                                                                                 \
     } else {                                                                                         \
       prefetch(pf[(PH + 2) % 3]);                                                                    \
-      raw0 = pf[PH][0];                                                                              \
-      raw1 = pf[PH][1];                                                                              \
+      _Pragma("unroll") for (int c = 0; c < 2 * H; ++c) raw[c] = pf[PH][c];                          \
     }                                                                                                \
-    const double in0 = ss_decode<TIn>(raw0, prm), in1 = ss_decode<TIn>(raw1, prm);                   \
-    if (__any_sync(WBK_FULL, ss_unsafe_raw(raw0, raw1, prm))) slow_until = k + 3 * P + 1;            \
-    double o0, o1;                                                                                   \
+    double inv[2 * H], o[2 * H];                                                                     \
+    bool bad = false;                                                                                \
+    _Pragma("unroll") for (int h = 0; h < H; ++h) {                                                  \
+      inv[2 * h] = ss_decode<TIn>(raw[2 * h], prm);                                                  \
+      inv[2 * h + 1] = ss_decode<TIn>(raw[2 * h + 1], prm);                                          \
+      bad = bad || ss_unsafe_raw(raw[2 * h], raw[2 * h + 1], prm);                                   \
+    }                                                                                                \
+    if (__any_sync(WBK_FULL, bad)) slow_until = k + 3 * P + 1;                                       \
     const bool slow = k < slow_until;                                                                \
-    if (slow) ss_step<P, RFIRST, RREST, false, PH>(w, in0, in1, o0, o1);                              \
-    else ss_step<P, RFIRST, RREST, true, PH>(w, in0, in1, o0, o1);                                    \
+    if (slow) ss_step<P, H, RFIRST, RREST, false, PH>(w, inv, o, lane_up, lane_dn, first_lane, last_lane); \
+    else ss_step<P, H, RFIRST, RREST, true, PH>(w, inv, o, lane_up, lane_dn, first_lane, last_lane); \
     if (k - 2 * P >= y0) {                                                                           \
-      if (ok0) dp[0] = (TOut)o0;                                                                     \
-      if (ok1) dp[1] = (TOut)o1;                                                                     \
-      if (PL) emit_planes(plp, (double)(TOut)o0, (double)(TOut)o1, slow);                            \
+      _Pragma("unroll") for (int h = 0; h < H; ++h) {                                                \
+        if (ok0[h]) dst[drow + ox[h]] = (TOut)o[2 * h];                                              \
+        if (ok1[h]) dst[drow + ox[h] + 1] = (TOut)o[2 * h + 1];                                      \
+      }                                                                                              \
+      if (PL) {                                                                                      \
+        double ov[2 * H];                                                                            \
+        _Pragma("unroll") for (int c = 0; c < 2 * H; ++c) ov[c] = (double)(TOut)o[c];                \
+        emit_planes(plp, ov, slow);                                                                  \
+      }                                                                                              \
     }                                                                                                \
-    dp += nlon;                                                                                      \
+    drow += nlon;                                                                                    \
     if (PL) plp += pl_row;                                                                           \
     ++k;                                                                                             \
   }
@@ -338,8 +404,18 @@ smooth_stream_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, const _
 }
 
 // ------------------------------------------------------------------------------------------ launch
+// Halves of 64 columns per warp strip.  Two halves cut the halo recompute from 64 / (64 - 2P) to 128 / (128 - 2P)
+// and amortise the per-step overhead over twice the cells, but the 244 registers they need leave 8 warps per SM
+// instead of 16: measured 1.43 ms against 1.31 ms per 296 steps of 721x1440 (tools/ab_halves.py), so
+// one half is the default and two are opt-in through wbk_tune_smooth_halves().
+int wbk_smooth_halves_override();  // wbk_smooth.cu: 0 = default
+static int ss_halves(int nlon, int passes) {
+  (void)nlon;
+  return (passes <= SS_MAX_P_H2 && wbk_smooth_halves_override() == 2) ? 2 : 1;
+}
+
 static void ss_geometry(SsParams& p, int passes) {
-  p.V = 64 - 2 * passes;
+  p.V = 64 * ss_halves(p.nlon, passes) - 2 * passes;
   p.nstrips = (p.nlon + p.V - 1) / p.V;
   const int rows = p.nlat - 2 * p.nan_border;
   // two latitude chunks per strip on tall grids: better balance over the SMs for 3P extra rows per chunk
@@ -347,8 +423,8 @@ static void ss_geometry(SsParams& p, int passes) {
   p.chunk_rows = rows > 0 ? (rows + p.nchunks - 1) / p.nchunks : 1;
 }
 
-template <int P, typename TIn, typename TOut, int RMODE>
-static int ss_launch_p(const void* in, void* out, SsParams& prm, cudaStream_t st) {
+template <int P, int H, typename TIn, typename TOut, int RMODE>
+static int ss_launch_ph(const void* in, void* out, SsParams& prm, cudaStream_t st) {
   ss_geometry(prm, P);
   // the kernel indexes items with 64 bits, the grid with 31: very long series go in chunks of time steps
   const long long per_step = (long long)prm.nchunks * prm.nstrips;
@@ -359,17 +435,17 @@ static int ss_launch_p(const void* in, void* out, SsParams& prm, cudaStream_t st
   for (int t0 = 0; t0 < ntime; t0 += max_t) {
     SsParams q = prm;
     q.ntime = ntime - t0 < max_t ? ntime - t0 : max_t;
-    if (q.planes) q.planes += (size_t)t0 * prm.nlat * prm.nstrips * (size_t)(2 + 2 * prm.nlevels);
+    if (q.planes) q.planes += (size_t)t0 * prm.nlat * prm.nstrips * H * (size_t)(2 + 2 * prm.nlevels);
     const long long nitems = per_step * q.ntime;
     const int grid = (int)((nitems + wpb - 1) / wpb);
     bool launched = false;
     if constexpr (sizeof(TOut) == 8) {  // bit planes go with float64 output only
       if (prm.planes && prm.nlevels == 1) {
-        WBK_LAUNCH(KID_SMOOTH, (smooth_stream_kernel<P, TIn, TOut, RMODE, 1>), dim3(grid), dim3(SS_THREADS), 0, st,
+        WBK_LAUNCH(KID_SMOOTH, (smooth_stream_kernel<P, H, TIn, TOut, RMODE, 1>), dim3(grid), dim3(SS_THREADS), 0, st,
                    (const TIn*)in + plane * t0, (TOut*)out + plane * t0, q);
         launched = true;
       } else if (prm.planes) {
-        WBK_LAUNCH(KID_SMOOTH, (smooth_stream_kernel<P, TIn, TOut, RMODE, 2>), dim3(grid), dim3(SS_THREADS), 0, st,
+        WBK_LAUNCH(KID_SMOOTH, (smooth_stream_kernel<P, H, TIn, TOut, RMODE, 2>), dim3(grid), dim3(SS_THREADS), 0, st,
                    (const TIn*)in + plane * t0, (TOut*)out + plane * t0, q);
         launched = true;
       }
@@ -378,12 +454,20 @@ static int ss_launch_p(const void* in, void* out, SsParams& prm, cudaStream_t st
       return WBK_ERR_INVALID;
     }
     if (!launched) {
-      WBK_LAUNCH(KID_SMOOTH, (smooth_stream_kernel<P, TIn, TOut, RMODE, 0>), dim3(grid), dim3(SS_THREADS), 0, st,
+      WBK_LAUNCH(KID_SMOOTH, (smooth_stream_kernel<P, H, TIn, TOut, RMODE, 0>), dim3(grid), dim3(SS_THREADS), 0, st,
                  (const TIn*)in + plane * t0, (TOut*)out + plane * t0, q);
     }
     WBK_LAUNCH_CHECK();
   }
   return WBK_OK;
+}
+
+template <int P, typename TIn, typename TOut, int RMODE>
+static int ss_launch_p(const void* in, void* out, SsParams& prm, cudaStream_t st) {
+  if constexpr (P <= SS_MAX_P_H2) {
+    if (ss_halves(prm.nlon, P) == 2) return ss_launch_ph<P, 2, TIn, TOut, RMODE>(in, out, prm, st);
+  }
+  return ss_launch_ph<P, 1, TIn, TOut, RMODE>(in, out, prm, st);
 }
 
 template <typename TIn, typename TOut, int RMODE>
