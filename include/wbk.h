@@ -272,10 +272,13 @@ int wbk_batch_fetch(wbk_ctx* ctx, const int* d_pt_off, const uint32_t* d_pts, in
                     void* stream);
 
 /* Pieces of the events that straddle the last meridian (utils/index_utils.py:148-173 transform_polygons), as the
- * device clipper of the last wbk_events_raster left them (flags must have been requested): ring r = vertices
+ * device clipper of the last wbk_events_raster / wbk_split_clip left them: ring r = vertices
  * [d_ring_off[r], d_ring_off[r+1]) of d_xy (int32 x, y: folded index coordinates of the real grid), d_ring_ev[r] = row of
  * the event in the wbk_batch_fetch tables.  d_count[3] = pieces, vertices, clipper overflow flag (pieces > cap_rings
  * or vertices > cap_vertices: the caller's buffers were too small).  Asynchronous. */
+/* Run the device clipper on the straddling events of the last wbk_events_raster when that call had no flag grids
+ * (d_flags == NULL; with flag grids the clipper has already run and this is a no-op).  Asynchronous. */
+int wbk_split_clip(wbk_ctx* ctx, const int* d_pt_off, const uint32_t* d_pts, void* stream);
 int wbk_split_fetch(wbk_ctx* ctx, int* d_ring_ev, int* d_ring_off, int* d_xy, int cap_rings, int cap_vertices,
                     int* d_count, void* stream);
 

@@ -94,6 +94,43 @@ def test_indices_emu_one_degree(emu):
     assert np.array_equal(props["intensity"], want["streamers"].intensity.values)
 
 
+def test_device_pieces_without_flag_grids_emu(emu):
+    """wbk_split_clip + wbk_split_fetch (no flag grids requested): the pieces of every event that straddles the last
+    meridian cover the same region as the oracle's independent face-walk split"""
+    grid, pv, sm = make_case(91, 180, 3)
+    add = int(120 / grid.dlon)
+    field = spatial.to_device(sm)
+    cs = detect.contours(field, [2], add)
+    coords = detect.coord_tables(grid.lat, grid.lon, grid.dlon, grid.dlat)
+    nsplit = 0
+    for kind in ("streamers", "cutoffs"):
+        tables, _, pieces = detect.run_indices(cs, field, coords, grid.dlon, grid.dlat, which=(kind,), want_pieces=True)
+        tab = tables[kind]
+        straddle = np.nonzero(tab.split == 1)[0]
+        if len(straddle) == 0:
+            assert pieces is None
+            continue
+        assert pieces is not None and not pieces["overflow"]
+        h = cs.host()
+        start = h["pt_off"][tab.contour].astype(np.int64) + tab.ind1
+        lens = tab.ind2.astype(np.int64) - tab.ind1 + 1
+        off = np.r_[0, np.cumsum(lens)]
+        idx = np.concatenate([np.arange(a, a + n) for a, n in zip(start, lens)])
+        xy = np.c_[h["x"][idx], h["y"][idx]]
+        allxy, roff, poff = geometry.interleave_pieces(xy, off, tab.split, pieces, 0, grid.nlon)
+        assert len(poff) == len(tab) + 1 and poff[-1] == len(roff) - 1
+        for e in range(len(tab)):
+            got = [allxy[roff[r]:roff[r + 1]] for r in range(poff[e], poff[e + 1])]
+            ring = xy[off[e]:off[e + 1]]
+            if tab.split[e] == 1:
+                want = [np.asarray(pc) for pc in G.split_ring_at_meridian(ring, grid.nlon)]
+                assert G.regions_equal(got, want), (kind, e)
+                nsplit += 1
+            else:
+                assert len(got) == 1 and np.array_equal(got[0], np.c_[ring[:, 0] % grid.nlon, ring[:, 1]])
+    assert nsplit > 0
+
+
 def test_rasterize_rings_kat_emu(emu):
     """tests/test_wavebreaking.py:116-128: square (0,0)-(10,10) flags lon 5 / lat 5."""
     lat = np.arange(-89.0, 90.0)

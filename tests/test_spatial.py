@@ -2,6 +2,7 @@
 
 import numpy as np
 import pytest
+import torch
 
 from oracle import pipeline as P
 from wavebreaking_b200 import spatial, synthetic
@@ -100,3 +101,19 @@ def test_synth_gpu_matches_host_recipe(gpu):
     got = spatial.synth_pv(2, 91, 180, hour0=0.0, hour_step=6.0, dtype=torch.float64).cpu().numpy()
     want = synthetic.pv_field(91, 180, np.array([0.0, 6.0]), dtype=np.float64)
     np.testing.assert_allclose(got, want, rtol=0, atol=1e-9)
+
+
+@pytest.mark.gpu
+def test_staged_upload_of_pageable_arrays_gpu(gpu):
+    """arrays of >= 128 MiB in ordinary host memory go up through the pinned staging ring: every byte arrives, for
+    sizes that are not a multiple of the chunk, twice in a row (buffer reuse) and from a read-only source"""
+    rng = np.random.default_rng(5)
+    for dtype, n in ((np.float32, (40 << 20) + 12345), (np.float64, (17 << 20) + 7)):
+        a = rng.standard_normal(n).astype(dtype)
+        a.setflags(write=False)
+        for _ in range(2):
+            t = spatial.to_device(a)
+            assert t.dtype == torch.from_numpy(a[:1].copy()).dtype and tuple(t.shape) == a.shape
+            assert np.array_equal(t.cpu().numpy(), a)
+    b = rng.standard_normal((37, 721, 1440)).astype(np.float32)
+    assert np.array_equal(spatial.to_device(b).cpu().numpy(), b)

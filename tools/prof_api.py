@@ -13,12 +13,13 @@ from wavebreaking_b200 import compat, spatial, synthetic
 
 T = int(sys.argv[1]) if len(sys.argv) > 1 else 148
 lat, lon = synthetic.grid_coords(721, 1440)
-host_np = spatial.synth_pv(T, 721, 1440, hour0=0.0).cpu().numpy()
+host_nps = [spatial.synth_pv(T, 721, 1440, hour0=float(k * T)).cpu().numpy() for k in range(3)]  # no reuse across passes
 tt = np.datetime64("2000-01-01T00", "ns") + np.arange(T) * np.timedelta64(3600 * 10**9, "ns")
 
 
-def api_pass():
-    pv = compat.Field(host_np, ("time", "lat", "lon"), {"time": tt, "lat": lat, "lon": lon}, name="PV")
+def api_pass(k=0):
+    t00 = time.perf_counter()
+    pv = compat.Field(host_nps[k], ("time", "lat", "lon"), {"time": tt, "lat": lat, "lon": lon}, name="PV")
     t = [time.perf_counter()]
 
     def lap(name):
@@ -38,13 +39,16 @@ def api_pass():
     for ev in evs:
         g = np.asarray(wb.to_xarray(sm, ev).values)
         lap("to_xarray + values")
+    print("  pass total {:8.1f} ms".format(1000 * (time.perf_counter() - t00)))
     return evs
 
 
-api_pass()
-print("second pass")
+api_pass(0)
+print("second pass (fresh host array)")
+api_pass(1)
+print("third pass (fresh host array, under cProfile)")
 pr = cProfile.Profile()
 pr.enable()
-api_pass()
+api_pass(2)
 pr.disable()
 pstats.Stats(pr).sort_stats("cumulative").print_stats(28)

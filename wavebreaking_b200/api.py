@@ -497,15 +497,18 @@ def _event_rings(cs, tab):
     return np.c_[h["x"][idx], h["y"][idx]], off
 
 
-def _fold_and_split(xy, off, split, nlon):
+def _fold_and_split(xy, off, split, nlon, pieces=None, first=0):
     """``transform_polygons`` (utils/index_utils.py:129-184) on ragged rings: fold with ``x % nlon``; the few events
-    that straddle the last meridian (split == 1) are cut into their pieces.  Returns (xy, ring_off, poly_off)."""
+    that straddle the last meridian (split == 1) are cut into their pieces (taken from the device clipper when
+    ``pieces`` is given, else clipped on the host).  Returns (xy, ring_off, poly_off)."""
     n = len(off) - 1
     straddle = np.nonzero(np.asarray(split) == 1)[0]
     if len(straddle) == 0:
         out = xy.copy()
         out[:, 0] %= nlon
         return out, off, np.arange(n + 1, dtype=np.int64)
+    if pieces is not None:
+        return geometry.interleave_pieces(xy, off, split, pieces, first, nlon)
     parts, ring_len, poly_nr = [], [], np.ones(n, dtype=np.int64)
     prev = 0
     for e in straddle:
@@ -550,9 +553,9 @@ def _run_index(kind, data, contour_levels, contours, intensity, periodic_add, kw
     for t0, cs in batches:
         nt = cs.njobs // nlev
         field = c.tensor[t0:t0 + nt]
-        tables, _ = detect.run_indices(cs, field, coords, c.dlon, c.dlat,
-                                       intensity=None if inten is None else inten[t0:t0 + nt], which=(kind,),
-                                       gmax_nx=gmax, want_flags=False, **params)
+        tables, _, pieces = detect.run_indices(cs, field, coords, c.dlon, c.dlat,
+                                               intensity=None if inten is None else inten[t0:t0 + nt], which=(kind,),
+                                               gmax_nx=gmax, want_flags=False, want_pieces=True, **params)
         tab = tables[kind]
         if len(tab) == 0:
             continue
@@ -565,7 +568,7 @@ def _run_index(kind, data, contour_levels, contours, intensity, periodic_add, kw
         cols["com"].extend(props["com"])
         orient.append(np.where(tab.orientation != 0, "anticyclonic", "cyclonic"))
         xy, off = _event_rings(cs, tab)
-        pxy, roff, poff = _fold_and_split(xy, off, tab.split, c.nlon)
+        pxy, roff, poff = _fold_and_split(xy, off, tab.split, c.nlon, pieces)
         xy_parts.append(np.c_[lon_v[pxy[:, 0]], lat_v[pxy[:, 1]]])
         ring_offs.append(roff)
         poly_offs.append(poff)

@@ -87,4 +87,5 @@ struct wbk_ctx {
   int njobs;      // jobs of the last wbk_contours call
   int nlevels;
   void* owned;    // workspace allocated by the library (NULL if caller-owned)
+  int split_clipped;  // the meridian-split work list of the last wbk_events_raster has been clipped into pieces
 };

@@ -403,7 +403,7 @@ events_raster_kernel(WbkDev d, WbkIdx x, const int* __restrict__ job_off, const 
         ev[3] = vx0; ev[4] = vy0; ev[5] = vx1; ev[6] = vy1;
       }
       ev[8] = split;
-      if (split == 1 && flags) {  // work list of the meridian split
+      if (split == 1) {  // work list of the meridian split
         const int pos = atomicAdd(&x.split_count[3], 1);
         if (pos < x.SPR) x.split_list[pos] = w;
         else atomicExch(&x.split_count[2], 1);
@@ -783,6 +783,7 @@ extern "C" int wbk_events_raster(wbk_ctx* ctx, const int* d_job_off, const int* 
     return WBK_ERR_INVALID;
   }
   WBK_LAUNCH_CHECK();
+  ctx->split_clipped = d_flags != nullptr;
   if (d_flags) {
     // events straddling the last meridian: clip on the device, rasterise the pieces
     WBK_LAUNCH(KID_SPLIT, split_events_kernel, dim3(148 * 2), dim3(32 * SPLIT_WARPS), 0, st, d, ctx->x, d_pt_off,
@@ -795,6 +796,21 @@ extern "C" int wbk_events_raster(wbk_ctx* ctx, const int* d_job_off, const int* 
                ntime, d_flags, rc2);
     WBK_LAUNCH_CHECK();
   }
+  return WBK_OK;
+}
+
+// The clipper alone, for callers that want the pieces of the straddling events (wbk_split_fetch) but no flag grids
+extern "C" int wbk_split_clip(wbk_ctx* ctx, const int* d_pt_off, const uint32_t* d_pts, void* stream) {
+  if (!ctx || !d_pt_off) {
+    wbk_set_error("wbk_split_clip: invalid argument");
+    return WBK_ERR_INVALID;
+  }
+  if (ctx->split_clipped || ctx->njobs == 0) return WBK_OK;  // wbk_events_raster already did it for its flag grids
+  cudaStream_t st = (cudaStream_t)stream;
+  WBK_LAUNCH(KID_SPLIT, split_events_kernel, dim3(148 * 2), dim3(32 * SPLIT_WARPS), 0, st, ctx->d, ctx->x, d_pt_off,
+             (const u32*)d_pts, ctx->nlevels, ctx->caps.max_jobs, ctx->njobs);
+  WBK_LAUNCH_CHECK();
+  ctx->split_clipped = 1;
   return WBK_OK;
 }
 

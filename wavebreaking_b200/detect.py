@@ -256,12 +256,15 @@ class EventTable:
 
 
 def run_indices(cs, data, coords, dlon, dlat, intensity=None, which=KINDS, gmax_nx=None, geo_dis=800.0,
-                cont_dis=1500.0, range_group=5.0, ot_min_exp=5.0, co_min_exp=5.0, want_flags=False, min_caps=None):
+                cont_dis=1500.0, range_group=5.0, ot_min_exp=5.0, co_min_exp=5.0, want_flags=False, min_caps=None,
+                want_pieces=False):
     """Streamers / overturnings / cutoffs + properties (+ to_xarray flags) for a contour set.
 
     ``data`` / ``intensity``: device tensors [ntime, nlat, nlon].  Returns ``(tables, flags)`` where
     tables maps kind -> EventTable and flags is an int8 tensor [3, ntime, nlat, nlon] or None.
     Events that straddle the last meridian (split == 1) are clipped and rasterised on the device too.
+    ``want_pieces``: returns ``(tables, flags, pieces)`` with the device clipper's pieces of those events
+    (``geometry.interleave_pieces``), or None for pieces when the clipper's arenas overflowed.
     """
     lib = _lib.get()
     ntime = int(data.shape[0])
@@ -314,7 +317,33 @@ def run_indices(cs, data, coords, dlon, dlat, intensity=None, which=KINDS, gmax_
         tables[kind] = EventTable(kind=kind, job=job, contour=ints[:, 0].copy(), ind1=ints[:, 1].copy(),
                                   ind2=ints[:, 2].copy(), box=ints[:, 3:7].copy(), orientation=ints[:, 7].copy(),
                                   split=ints[:, 8].copy(), near=ints[:, 9].copy(), sums=f64)
-    return tables, flags
+    if not want_pieces:
+        return tables, flags
+    pieces = None
+    if any(int((t.split == 1).sum()) for t in tables.values()):
+        pieces = _fetch_pieces(lib, ctx, cs)
+    return tables, flags, pieces
+
+
+def _fetch_pieces(lib, ctx, cs):
+    """Pieces of the straddling events from the device clipper (wbk_split_clip + wbk_split_fetch)."""
+    lib.call("wbk_split_clip", ctx.handle, _lib.ptr(cs.pt_off), _lib.ptr(cs.pts), lib.stream())
+    cap_r, cap_v = 4096, 1 << 18
+    for _attempt in range(6):
+        ev = torch.empty(cap_r, dtype=torch.int32, device=lib.device)
+        off = torch.empty(cap_r + 1, dtype=torch.int32, device=lib.device)
+        xy = torch.empty((cap_v, 2), dtype=torch.int32, device=lib.device)
+        cnt = torch.zeros(4, dtype=torch.int32, device=lib.device)
+        lib.call("wbk_split_fetch", ctx.handle, _lib.ptr(ev), _lib.ptr(off), _lib.ptr(xy), cap_r, cap_v, _lib.ptr(cnt),
+                 lib.stream())
+        npc, nvx, over = (int(v) for v in cnt.cpu().numpy()[:3])
+        if over:
+            return None  # the clipper's own arenas were too small: the caller clips these events on the host
+        if npc <= cap_r and nvx <= cap_v:
+            return dict(ev=ev[:npc].cpu().numpy(), off=off[:npc + 1].cpu().numpy().astype(np.int64),
+                        xy=xy[:nvx].cpu().numpy(), overflow=False)
+        cap_r, cap_v = max(cap_r, 2 * npc), max(cap_v, 2 * nvx)
+    return None
 
 
 def event_rings(cs, table):

@@ -145,3 +145,39 @@ def transform_ring(ring, nlon):
         out[:, 0] %= nlon
         return [out]
     return split_ring(ring, nlon)
+
+
+def interleave_pieces(xy, off, split, pieces, first, nlon):
+    """Ragged rings of a table of events after ``transform_polygons`` (utils/index_utils.py:129-184), vectorised:
+    ordinary events keep their single ring folded with ``x % nlon``; events that straddle the last meridian
+    (``split == 1``) are replaced by the pieces the device clipper produced (``wbk_split_fetch``: dict with ``ev`` =
+    event row in the batch's kind-major order, ``off``, ``xy``).  ``first`` = row of the table's first event in that
+    order.  Returns ``(xy int64 [N, 2], ring_off, poly_off)``: polygon e = rings [poly_off[e], poly_off[e + 1])."""
+    from .tracking import _ranges
+
+    n = len(off) - 1
+    split = np.asarray(split)
+    pev = np.asarray(pieces["ev"]).astype(np.int64) - first
+    mine = np.nonzero((pev >= 0) & (pev < n))[0]
+    order = mine[np.argsort(pev[mine], kind="stable")]
+    poff = np.asarray(pieces["off"], dtype=np.int64)
+    plen = np.diff(poff)[order]
+    pxy = np.asarray(pieces["xy"])[_ranges(poff[:-1][order], plen)].astype(np.int64)
+    npieces = np.bincount(pev[order], minlength=n).astype(np.int64)
+    keep_ev = split != 1
+    lens = np.diff(off)
+    nrings = np.where(keep_ev, 1, npieces)
+    poly_off = np.r_[0, np.cumsum(nrings)].astype(np.int64)
+    ring_len = np.zeros(int(poly_off[-1]), dtype=np.int64)
+    ring_len[poly_off[:-1][keep_ev]] = lens[keep_ev]
+    piece_slots = _ranges(poly_off[:-1][~keep_ev], npieces[~keep_ev])
+    ring_len[piece_slots] = plen
+    ring_off = np.r_[0, np.cumsum(ring_len)].astype(np.int64)
+    allxy = np.zeros((int(ring_off[-1]), 2), dtype=np.int64)
+    src = _ranges(np.asarray(off[:-1])[keep_ev], lens[keep_ev])
+    dst = _ranges(ring_off[:-1][poly_off[:-1][keep_ev]], lens[keep_ev])
+    folded = np.asarray(xy)[src].astype(np.int64)
+    folded[:, 0] %= nlon
+    allxy[dst] = folded
+    allxy[_ranges(ring_off[:-1][piece_slots], plen)] = pxy
+    return allxy, ring_off, poly_off

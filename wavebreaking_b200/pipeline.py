@@ -608,29 +608,7 @@ def events_soup(res, kind, det):
         # pieces from the device clipper (wbk_split_fetch): everything stays vectorised.  Rows of this kind start at
         # `first` in the kind-major gather order of the batch
         first = int(sum(res.counts[:detect.KINDS.index(kind)]))
-        pev = res.pieces["ev"].astype(np.int64) - first
-        mine = np.nonzero((pev >= 0) & (pev < n))[0]
-        order = mine[np.argsort(pev[mine], kind="stable")]
-        plen = np.diff(res.pieces["off"])[order]
-        pxy = res.pieces["xy"][tracking._ranges(res.pieces["off"][:-1][order], plen)].astype(np.int64)
-        npieces = np.bincount(pev[order], minlength=n).astype(np.int64)
-        keep_ev = tab.split != 1
-        lens = np.diff(off)
-        # interleave: ordinary events keep their single folded ring, straddling ones get their pieces
-        nrings = np.where(keep_ev, 1, npieces)
-        poly_off = np.r_[0, np.cumsum(nrings)]
-        ring_len = np.zeros(int(poly_off[-1]), dtype=np.int64)
-        ring_len[poly_off[:-1][keep_ev]] = lens[keep_ev]
-        piece_slots = tracking._ranges(poly_off[:-1][~keep_ev], npieces[~keep_ev])
-        ring_len[piece_slots] = plen
-        ring_off = np.r_[0, np.cumsum(ring_len)]
-        allxy = np.zeros((int(ring_off[-1]), 2), dtype=np.int64)
-        src = tracking._ranges(off[:-1][keep_ev], lens[keep_ev])
-        dst = tracking._ranges(ring_off[:-1][poly_off[:-1][keep_ev]], lens[keep_ev])
-        folded = xy[src]
-        folded[:, 0] %= nlon
-        allxy[dst] = folded
-        allxy[tracking._ranges(ring_off[:-1][piece_slots], plen)] = pxy
+        allxy, ring_off, poly_off = geometry.interleave_pieces(xy, off, tab.split, res.pieces, first, nlon)
         soup = tracking.PolygonSoup(allxy.astype(np.int32), ring_off, poly_off, True)
     else:
         # only the few events that straddle the meridian are rebuilt one by one
