@@ -794,9 +794,13 @@ __global__ void __launch_bounds__(TOUCH_THREADS) streamer_touch_kernel(WbkDev d,
   __shared__ int s_total, s_cnt;
   const int tid = threadIdx.x, nt = blockDim.x;
   const int lane = wbk_lane(), warp = wbk_warp(), nwarps = nt >> 5;
-  for (int slot = blockIdx.x; slot < nslots; slot += gridDim.x) {
-    const int job = slot / x.SC, si = slot - job * x.SC;
-    if (job >= ps.njobs || si >= x.nsel[job]) continue;
+  // Slots are walked selection-major (all first selected contours of the jobs, then the second ones, ...): the heavy
+  // slot of a job is its first one (the circumpolar contour), and a CTA-strided walk over job-major slots would hand
+  // those to every SC-th CTA only while the others idle.
+  for (int q = blockIdx.x; q < nslots; q += gridDim.x) {
+    const int si = q / ps.njobs, job = q - si * ps.njobs;
+    const int slot = job * x.SC + si;
+    if (si >= x.nsel[job]) continue;
     const int P = x.cnt1[slot];
     if (P <= 1 || P > x.PC) continue;  // nothing to filter (streamer_index.py:261) / overflow already reported
     const int c = x.sel[slot];

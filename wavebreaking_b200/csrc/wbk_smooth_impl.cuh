@@ -113,8 +113,14 @@ __device__ __forceinline__ void ss_step(double (&w)[P][3][2 * H], const double (
     double wv[H], ev[H];
 #pragma unroll
     for (int h = 0; h < H; ++h) {
-      wv[h] = __shfl_sync(WBK_FULL, w[p - 1][MID][2 * h + 1], lane_up);  // column 2l-1 of the half (lane 0: lane 31's)
-      ev[h] = __shfl_sync(WBK_FULL, w[p - 1][MID][2 * h], lane_dn);      // column 2l+2 of the half (lane 31: lane 0's)
+      if (H == 1) {
+        // one half: shifts with an immediate distance (the strip's outer columns are halo, never valid)
+        wv[h] = __shfl_up_sync(WBK_FULL, w[p - 1][MID][1], 1);
+        ev[h] = __shfl_down_sync(WBK_FULL, w[p - 1][MID][0], 1);
+      } else {
+        wv[h] = __shfl_sync(WBK_FULL, w[p - 1][MID][2 * h + 1], lane_up);  // column 2l-1 of the half (lane 0: lane 31's)
+        ev[h] = __shfl_sync(WBK_FULL, w[p - 1][MID][2 * h], lane_dn);      // column 2l+2 of the half (lane 31: lane 0's)
+      }
     }
     if (H == 2) {
       // seam: column 63 is lane 31 of half 0, column 64 lane 0 of half 1 (the outer ends of the strip keep the
@@ -190,7 +196,7 @@ smooth_stream_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, const _
   TOut* dst = out + plane * t;
   // valid outputs of this lane: strip columns [P, P + V) that exist in the grid
   const int vcols = min(prm.V, nlon - s * prm.V);
-  int pxa[H], d1[H], ox[H];
+  int pxa[H], d1[H];  // physical column of the lane's first column of half h, offset of its second column
   bool ok0[H], ok1[H];
 #pragma unroll
   for (int h = 0; h < H; ++h) {
@@ -201,8 +207,8 @@ smooth_stream_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, const _
     d1[h] = p1 - p0;
     ok0[h] = sc >= P && sc < P + vcols;
     ok1[h] = sc + 1 >= P && sc + 1 < P + vcols;
-    ox[h] = s * prm.V + sc - P;  // output column of strip column sc (valid lanes only)
   }
+  const int ox = s * prm.V + 2 * lane - P;  // output column of strip column 2l (valid lanes only); half h: + 64h
   const int PW = 2 + 2 * prm.nlevels;
   // bit planes: one record of PW words per (row, 64-column half); half h of strip s is plane strip s * H + h
   const size_t pl_row = (size_t)prm.nstrips * H * (size_t)PW;  // plane words per grid row
@@ -254,8 +260,8 @@ smooth_stream_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, const _
       if (top ? chunk != 0 : (chunk != prm.nchunks - 1 || row < nb)) continue;  // warp-uniform
 #pragma unroll
       for (int h = 0; h < H; ++h) {
-        if (ok0[h]) dst[(size_t)row * nlon + ox[h]] = (TOut)qnan;
-        if (ok1[h]) dst[(size_t)row * nlon + ox[h] + 1] = (TOut)qnan;
+        if (ok0[h]) dst[(size_t)row * nlon + ox + 64 * h] = (TOut)qnan;
+        if (ok1[h]) dst[(size_t)row * nlon + ox + 64 * h + 1] = (TOut)qnan;
       }
       if (PL) emit_planes(pl_base + (size_t)row * pl_row, vq, true);
     }
@@ -273,10 +279,13 @@ smooth_stream_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, const _
       for (int c = 0; c < 2 * H; ++c) w[p][r][c] = 0.0;
 
   const int k_begin = y0 - P, k_end = y1 + 2 * P;  // steps k in [k_begin, k_end)
-  // prefetch cursor: logical row gy_pf, physical row pointer of the time step
+  // prefetch cursor: logical row gy_pf, physical row pointer of this lane's first column (half h: + dh[h])
   int gy_pf = ss_wrap(k_begin, nlat);
   const long long rstride = prm.flip_lat ? -(long long)nlon : (long long)nlon;
-  const TIn* pfp = src + (long long)(prm.flip_lat ? nlat - 1 - gy_pf : gy_pf) * nlon;
+  const TIn* pfp = src + (long long)(prm.flip_lat ? nlat - 1 - gy_pf : gy_pf) * nlon + pxa[0];
+  int dh[H];
+#pragma unroll
+  for (int h = 0; h < H; ++h) dh[h] = pxa[h] - pxa[0];
   const long long pf_wrap = rstride * nlat;  // back to logical row 0
   auto advance = [&]() {
     pfp += rstride;
@@ -298,7 +307,7 @@ smooth_stream_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, const _
     if (ASYNC) {
 #pragma unroll
       for (int h = 0; h < H; ++h) {
-        const TIn* g0 = pfp + pxa[h];
+        const TIn* g0 = pfp + dh[h];
 #ifndef WBK_EMU
         const unsigned dst_s = (unsigned)__cvta_generic_to_shared(my_ring + slot_in * WS + 64 * h);
         asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst_s), "l"(g0), "n"(sizeof(TIn)) : "memory");
@@ -329,8 +338,8 @@ smooth_stream_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, const _
   auto prefetch = [&](TIn (&slot)[2 * H]) {
 #pragma unroll
     for (int h = 0; h < H; ++h) {
-      slot[2 * h] = pfp[pxa[h]];
-      slot[2 * h + 1] = pfp[pxa[h] + d1[h]];
+      slot[2 * h] = pfp[dh[h]];
+      slot[2 * h + 1] = pfp[dh[h] + d1[h]];
     }
     advance();
   };
@@ -348,7 +357,7 @@ smooth_stream_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, const _
 
   int slow_until = k_begin;  // steps before this one use the plain division
   int k = k_begin;
-  long long drow = (long long)(k_begin - 2 * P) * nlon;  // output row offset of step k (valid once k - 2P >= y0)
+  TOut* dp = dst + (long long)(k_begin - 2 * P) * nlon + ox;  // output row of step k (valid once k - 2P >= y0)
   u32* plp = PL ? pl_base + (long long)(k_begin - 2 * P) * (long long)pl_row : nullptr;
 #define SS_ONE_STEP(PH)                                                                              \
   {                                                                                                  \
@@ -373,8 +382,8 @@ smooth_stream_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, const _
     else ss_step<P, H, RFIRST, RREST, true, PH>(w, inv, o, lane_up, lane_dn, first_lane, last_lane); \
     if (k - 2 * P >= y0) {                                                                           \
       _Pragma("unroll") for (int h = 0; h < H; ++h) {                                                \
-        if (ok0[h]) dst[drow + ox[h]] = (TOut)o[2 * h];                                              \
-        if (ok1[h]) dst[drow + ox[h] + 1] = (TOut)o[2 * h + 1];                                      \
+        if (ok0[h]) dp[64 * h] = (TOut)o[2 * h];                                                     \
+        if (ok1[h]) dp[64 * h + 1] = (TOut)o[2 * h + 1];                                             \
       }                                                                                              \
       if (PL) {                                                                                      \
         double ov[2 * H];                                                                            \
@@ -382,7 +391,7 @@ smooth_stream_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, const _
         emit_planes(plp, ov, slow);                                                                  \
       }                                                                                              \
     }                                                                                                \
-    drow += nlon;                                                                                    \
+    dp += nlon;                                                                                      \
     if (PL) plp += pl_row;                                                                           \
     ++k;                                                                                             \
   }
