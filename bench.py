@@ -56,7 +56,7 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=3, help="time steps of the CPU baseline sample (~4-8 s each)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--depth", type=int, default=3, help="batches in flight (slots / streams)")
+    ap.add_argument("--depth", type=int, default=6, help="batches in flight in the device-resident leg (slots / streams)")
     ap.add_argument("--serial", action="store_true", help="device-resident leg on ONE stream (no kernel overlap)")
     ap.add_argument("--no-graphs", action="store_true", help="eager launches instead of one CUDA graph per batch")
     ap.add_argument("--no-extras", action="store_true", help="skip the stress line, the e2e variants and the link test")
@@ -338,13 +338,14 @@ def run_b200(a):
     torch.cuda.synchronize()
     sampler = ClockSampler(local)
     sampler.start()
-    depth = a.depth
+    depth = n_resident = a.depth
 
-    def timed_region(detector, inputs, k_steps, shared_stream, profile):
+    def timed_region(detector, inputs, k_steps, shared_stream, profile, depth=depth):
         """k_steps batches, `depth` in flight; returns (ms, per-kernel profile, kernel launches, per-batch counts)."""
         n_in = len(inputs)
-        # warm-up: also lets every (slot, buffer) combination be captured into its CUDA graph
-        warm = max(W, 3 * depth * (n_in // math.gcd(n_in, depth)) if detector.graphs else W)
+        # warm-up: every slot allocates its arenas on first use, and every (slot, buffer) combination is captured
+        # into its CUDA graph on its second submission
+        warm = max(W, 3 * depth * (n_in // math.gcd(n_in, depth)) if detector.graphs else 2 * depth)
         for res in detector.stream((inputs[s % n_in] for s in range(warm)), depth=depth, shared_stream=shared_stream):
             pass
         barrier()
@@ -382,7 +383,7 @@ def run_b200(a):
     det_prof = pipeline.Detector(lat, lon, levels=[2.0], passes=a.passes, graphs=False)
     k_prof = min(K, 20)
     sampler = ClockSampler(local)
-    ms_ser, prof, _, counts_ser = timed_region(det_prof, slabs, k_prof, shared_stream=True, profile=True)
+    ms_ser, prof, _, counts_ser = timed_region(det_prof, slabs, k_prof, shared_stream=True, profile=True, depth=min(depth, 3))
     value_serial = world * k_prof * T / (_max_over_ranks(ms_ser, world) / 1000.0)
 
     # per-time-step work statistics (device counters of the batches) for the algorithmic byte counts
@@ -406,16 +407,23 @@ def run_b200(a):
                 "device_busy_frac": tot / ms_ser,
                 "measured_in": "second timed region: {} of the same batches on ONE CUDA stream with eager launches "
                                "(value_single_stream); the headline region replays one CUDA graph per batch on {} "
-                               "streams".format(k_prof, depth),
+                               "streams".format(k_prof, n_resident),
                 "note": "smooth_fused (wbk_smooth_impl.cuh) is bounded by the FP64 pipe before HBM: 5 passes x 7 DP ops "
                         "per cell on 64-column strips with a 5-column halo = 2.5 us per 721x1440 step at 64 DP "
                         "lanes/clk/SM, HBM floor 1.9 us (DESIGN.md 4)"}
     det_prof.close()
-    log("single-stream profile leg done")
+    # the later legs keep three batches in flight: release the slots of the device-resident leg (arenas, smoothed
+    # fields and flag grids of `depth` batches) so that they run without memory pressure
+    det.close()
+    det = pipeline.Detector(lat, lon, levels=[2.0], passes=a.passes, graphs=graphs)
+    torch.cuda.empty_cache()
+    log("single-stream profile leg done (peak device memory {:.1f} GB)".format(torch.cuda.max_memory_allocated() / 1e9))
 
     # ---- end-to-end leg (host buffers): float32 field in pinned host memory -> bit-packed flag grids + tables
+    #      (three batches in flight: the leg is bound by the host link, more slots only pin more host memory)
     e2e = None
     extras = {}
+    depth = min(depth, 3)
     if not a.no_e2e:
         ncells = 3 * T * a.nlat * a.nlon
         host_in = [torch.empty((T, a.nlat, a.nlon), dtype=torch.float32, pin_memory=True) for _ in range(depth)]
@@ -487,6 +495,8 @@ def run_b200(a):
         import wavebreaking_b200 as wb
         from wavebreaking_b200 import compat
 
+        det.close()
+        torch.cuda.empty_cache()
         log("e2e through the drop-in API")
         tt = np.datetime64("2000-01-01T00", "ns") + np.arange(T) * np.timedelta64(3600 * 10**9, "ns")
         host_nps = [slabs[i % nslab].cpu().numpy() for i in range(3)]  # a different host array per pass: no reuse
@@ -501,9 +511,11 @@ def run_b200(a):
 
         api_pass(0)
         torch.cuda.synchronize()
-        n_api = 2
+        n_api = 3
         t_api = time.perf_counter()
+        grids = None
         for k in range(n_api):
+            del grids  # a user loop drops the previous result: its page-locked host blocks are recycled
             nev, grids = api_pass(k + 1)
         torch.cuda.synchronize()
         dt_api = _max_over_ranks((time.perf_counter() - t_api) * 1000.0, world) / 1000.0
@@ -526,7 +538,11 @@ def run_b200(a):
         del noise
         k_st = max(3, min(K, 12))
         log("stress line")
-        ms_st, _, _, cnt_st = timed_region(det, noisy, k_st, shared_stream=a.serial, profile=False)
+        # (arenas grow to ~25 GB per slot on this field: three batches in flight)
+        det.close()
+        det = pipeline.Detector(lat, lon, levels=[2.0], passes=a.passes, graphs=graphs)
+        ms_st, _, _, cnt_st = timed_region(det, noisy, k_st, shared_stream=a.serial, profile=False, depth=min(n_resident, 3))
+        det.close()
         log("stress line done")
         extras["stress"] = {"value": world * k_st * T / (_max_over_ranks(ms_st, world) / 1000.0), "unit": UNIT,
                             "recipe": "benchmark field + 1.5 PVU white noise per cell (before the 5 smoothing passes)",
@@ -600,7 +616,7 @@ def run_decade_track(a):
                     for b0 in starts[c0:c0 + chunk_batches]]
         torch.cuda.synchronize()
         tc = time.perf_counter()
-        for res in det.stream(resident, depth=a.depth):
+        for res in det.stream(resident, depth=min(a.depth, 3)):
             soup, _ = pipeline.events_soup(res, "streamers", det)
             soups.append(soup)
             dates.append(step0 + res.tables["streamers"].job.astype(np.int64))

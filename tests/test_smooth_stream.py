@@ -218,3 +218,19 @@ def test_smooth_stream_gpu_full_size_special_cases(gpu):
     f64[0, 500, 1439] = np.nan
     with np.errstate(all="ignore"):
         _eq(_smooth_raw(torch.from_numpy(f64), 5, _lib.ROUND_NONE, torch.float64), P.smooth_field(f64, 5))
+
+
+@pytest.mark.gpu
+def test_two_halves_full_size_gpu(gpu, two_halves):
+    """the opt-in 128-column strips at the benchmark shape: smoothed field bit-exact, detection results unchanged"""
+    f = _field(721, 1440, 2, np.float32, 4)
+    _eq(_smooth_raw(torch.from_numpy(f), 5, _lib.ROUND_FIRST, torch.float64), P.smooth_field(f, 5))
+    lat, lon = synthetic.grid_coords(721, 1440)
+    raw = spatial.synth_pv(3, 721, 1440, hour0=500.0)
+    a = pipeline.Detector(lat, lon, levels=[2.0]).run_batch(raw)
+    _lib.get().cdll.wbk_tune_smooth_halves(1)
+    b = pipeline.Detector(lat, lon, levels=[2.0]).run_batch(raw)
+    assert pipeline.summarize(a) == pipeline.summarize(b)
+    assert torch.equal(a.flags, b.flags)
+    for kind in detect.KINDS:
+        assert np.array_equal(a.tables[kind].sums, b.tables[kind].sums)
