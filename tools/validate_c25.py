@@ -1,13 +1,16 @@
 """Parity sweep at the benchmark shape: N hourly 721x1440 time steps, CUDA pipeline vs the oracle, event by event.
 
-  python tools/validate_c25.py [nsteps] [hour0]      (needs a GPU; the oracle takes ~8 s per step on the box)
-Writes a one-line-per-step report and a summary (used for profiles/r1_parity_c25.txt).
+  python tools/validate_c25.py [nsteps] [hour0] [noise]   (needs a GPU; the oracle takes ~8 s per step on the box)
+`noise` (PVU, default 0): white noise per cell added before the smoothing, the recipe of bench.py's stress line
+(1.5 gives ~3x the contour points and hundreds of contours per step; the oracle then needs ~1 min per step).
+Writes a one-line-per-step report and a summary (profiles/r*_parity_c25*.txt).
 """
 import sys
 import time
 
 sys.path.insert(0, ".")
 import numpy as np
+import torch
 
 from oracle import geom as G
 from oracle import pipeline as P
@@ -15,9 +18,13 @@ from wavebreaking_b200 import detect, pipeline, spatial, synthetic
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 6
 hour0 = float(sys.argv[2]) if len(sys.argv) > 2 else 1000.0
+noise = float(sys.argv[3]) if len(sys.argv) > 3 else 0.0
 nlat, nlon = 721, 1440
 lat, lon = synthetic.grid_coords(nlat, nlon)
 raw = spatial.synth_pv(n, nlat, nlon, hour0=hour0, hour_step=37.0)  # spread over the year
+if noise:
+    g = torch.Generator(device="cuda").manual_seed(20260101)
+    raw = raw + noise * torch.randn(raw.shape, generator=g, device="cuda", dtype=torch.float32)
 det = pipeline.Detector(lat, lon, levels=[2.0])
 res = det.run_batch(raw)
 raw_h = raw.cpu().numpy()
