@@ -490,7 +490,10 @@ __global__ void __launch_bounds__(ST_THREADS) streamer_prep_kernel(WbkDev d, Wbk
 // inside the margin evaluate the reference's fp64 expression (and carry the near-threshold flag).
 #define PS_WARPS (PS_THREADS / 32)
 #define PS_BUF 256
-__global__ void __launch_bounds__(PS_THREADS) pair_scan_kernel(WbkDev d, WbkIdx x, PackedSet ps, CoordTabs ct,
+#ifndef PS_MINCTA
+#define PS_MINCTA 3  // resident CTAs per SM the register budget is sized for (2 -> 3: 1.03 -> 0.83 us per step)
+#endif
+__global__ void __launch_bounds__(PS_THREADS, PS_MINCTA) pair_scan_kernel(WbkDev d, WbkIdx x, PackedSet ps, CoordTabs ct,
                                                                const double* __restrict__ on,
                                                                const double* __restrict__ pfx, wbk_index_params prm,
                                                                int nslots) {
@@ -547,30 +550,34 @@ __global__ void __launch_bounds__(PS_THREADS) pair_scan_kernel(WbkDev d, WbkIdx 
       cnt = 0;
       __syncwarp();
     };
+    const double cont_tol = 1e-9 * prm.cont_dis;
     for (int jj = 0; jj < nj; ++jj) {
       const int j = bj * PT + jj;
       bool cand = false;
       u64 key = 0;
-      if (act && j > i) {
-        const float4 q4 = sj4[warp][jj];
-        const u32 pj = __float_as_uint(q4.x);
-        int dxi = xi - wbk_px(pj);
-        if (dxi < 0) dxi = -dxi;
-        double cont = __dsub_rn(sjpf[warp][jj], pfi);
-        // hard-coded 120 index units (streamer_index.py:157), cont > cont_dis (:138).  Inside the tolerance band of
-        // the threshold the reference's own summation decides: cont[i, j] = on[i+1] + ... + on[j], left to right
-        // (streamer_index.py:133-135; a prefix difference differs from it by rounding)
-        const bool cont_near = fabs(cont - prm.cont_dis) <= 1e-9 * prm.cont_dis;
-        if (cont_near && dxi <= 120) {
+      // The common case (pair too far along x, too close along the contour, or geographically too far) is decided
+      // without a branch: every lane evaluates the cheap tests, only the few surviving lanes enter the block below.
+      const float4 q4 = sj4[warp][jj];
+      const u32 pj = __float_as_uint(q4.x);
+      int dxi = xi - wbk_px(pj);
+      if (dxi < 0) dxi = -dxi;
+      double cont = __dsub_rn(sjpf[warp][jj], pfi);
+      // hard-coded 120 index units (streamer_index.py:157), cont > cont_dis (:138).  Inside the tolerance band of
+      // the threshold the reference's own summation decides: cont[i, j] = on[i+1] + ... + on[j], left to right
+      // (streamer_index.py:133-135; a prefix difference differs from it by rounding)
+      const bool cont_near = fabs(cont - prm.cont_dis) <= cont_tol;
+      const float s0 = __sinf(0.5f * (lai - q4.y)), s1 = __sinf(0.5f * (loi - q4.z));
+      const float h = s0 * s0 + ci * q4.w * s1 * s1;
+      const bool pass = act && j > i && dxi <= 120 && (cont > prm.cont_dis || cont_near) && !(h > h_hi);
+      if (pass) {
+        if (cont_near) {
           double acc = 0.0;
           for (int k = i + 1; k <= j; ++k) acc = __dadd_rn(acc, on[base + k]);
           cont = acc;
         }
         const bool cont_ok = cont > prm.cont_dis;
-        if (dxi <= 120 && (cont_ok || cont_near)) {
-          const float s0 = __sinf(0.5f * (lai - q4.y)), s1 = __sinf(0.5f * (loi - q4.z));
-          const float h = s0 * s0 + ci * q4.w * s1 * s1;
-          if (!(h > h_hi)) {
+        {
+          {
             int near = cont_near;
             bool ok = cont_ok;
             if (h >= h_lo) {  // inside the margin: the reference's fp64 expression decides
