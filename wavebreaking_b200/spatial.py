@@ -37,7 +37,7 @@ def _upload_pageable(a, device):
         _stage["pool"] = ThreadPoolExecutor(max_workers=_STAGE_BUFS, thread_name_prefix="wbk-upload")
     bufs, views, pool = _stage["bufs"], _stage["views"], _stage["pool"]
     src = a.reshape(-1).view(np.uint8)
-    out = torch.empty(a.shape, dtype=torch.from_numpy(a[:0]).dtype, device=device)
+    out = torch.empty(a.shape, dtype=torch.float32 if a.dtype == np.float32 else torch.float64, device=device)
     dst = out.view(-1).view(torch.uint8)
     n = src.size
     events = [None] * _STAGE_BUFS
