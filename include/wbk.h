@@ -54,6 +54,9 @@ extern "C" {
 #define WBK_ST_WIDTH_OVERFLOW 64    /* extended grid wider than the shared-memory column tables */
 #define WBK_ST_PACK_OVERFLOW 128    /* (job 0 only) packed contour set larger than the caller's buffers */
 #define WBK_ST_FETCH_OVERFLOW 256   /* (job 0 only) more events / ring vertices than the caller's fetch buffers */
+#define WBK_ST_SPLIT_CHAINS 512     /* (job 0 only) an event leaves and re-enters one side of the last meridian more than
+                                       24 times: the device clipper cannot split it, its cells are missing from the
+                                       flag grids (an error, not a capacity) */
 
 const char* wbk_last_error(void);
 int wbk_version(void);

@@ -266,3 +266,82 @@ def test_split_ring_fuzz_regions_and_flag_cells(seed):
         assert np.array_equal(cells(got), cells(want)), ring.tolist()
         tested += 1
     assert tested > 500
+
+
+def _random_seam_rings(rng, nlon, count):
+    """simple lattice polygons around x = nlon (vertices on the cut lines, edges along them, pinch points, slivers)"""
+    out = []
+    while len(out) < count:
+        cx, cy = nlon + rng.integers(-2, 3), 10
+        k = rng.integers(4, 14)
+        ang = np.sort(rng.uniform(0, 2 * np.pi, k))
+        rad = rng.uniform(1.5, 7, k)
+        ring = np.c_[np.rint(cx + rad * np.cos(ang)), np.rint(cy + rad * np.sin(ang))].astype(int)
+        keep = [0]
+        for i in range(1, len(ring)):
+            if (ring[i] != ring[keep[-1]]).any():
+                keep.append(i)
+        ring = ring[keep]
+        if len(ring) > 1 and (ring[0] == ring[-1]).all():
+            ring = ring[:-1]
+        if len(ring) < 3 or not G.ring_is_simple(ring):
+            continue
+        x = ring[:, 0]
+        if (x >= nlon).any() and not (x >= nlon).all():
+            out.append(ring)
+    return out
+
+
+@pytest.mark.parametrize("seed,per_job,njobs", [(0, 120, 2), (1, 120, 2), (2, 200, 1)])
+def test_device_clipper_fuzz_pieces_and_flag_cells_emu(emu, seed, per_job, njobs):
+    """The DEVICE clipper (split_events_kernel) and the rasteriser of its pieces on the same hostile rings as the host
+    clipper's fuzz: the rings enter as closed contours of a hand-made contour set, the cutoff index turns each into an
+    event, and the pieces / flag cells must equal the oracle's independent face-walk split under the to_xarray rule.
+    Third case: 200 straddling events of ONE job against a clipper work list sized for 128 (event_cap 256): the
+    overflow must be reported (WBK_ST_EVENT_OVERFLOW) and the batch re-run with larger arenas, not answered with
+    incomplete grids."""
+    detect.clear_contexts()
+    rng = np.random.default_rng(100 + seed)
+    nlon, nlat, add = 40, 21, 10  # dlon == dlat == 9 degrees, extended width 50
+    lat, lon = synthetic.grid_coords(nlat, nlon)
+    dlon = dlat = 9.0
+    rings = _random_seam_rings(rng, nlon, per_job * njobs)
+    closed = [np.vstack([r, r[:1]]) for r in rings]  # contours repeat their first point (skimage)
+    lens = np.array([len(c) for c in closed], dtype=np.int64)
+    allxy = np.concatenate(closed).astype(np.int64)
+    pt_off = np.r_[0, np.cumsum(lens)].astype(np.int32)
+    job = np.repeat(np.arange(njobs), per_job)
+    job_off = (np.arange(njobs + 1) * per_job).astype(np.int32)
+    cid = np.repeat(np.arange(len(lens)), lens)
+    nx = np.array([len(np.unique(c[:, 0])) for c in closed])
+    sumy = np.bincount(cid, weights=allxy[:, 1]).astype(np.int64)
+    meta = np.c_[np.ones(len(lens), dtype=np.int64), nx, sumy, job].astype(np.int32)
+    pts = (allxy[:, 0] | (allxy[:, 1] << 16)).astype(np.uint32)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(spatial.to_device(np.zeros(1)).device)
+    cs = detect.ContourSet(njobs=njobs, nlevels=1, nlat=nlat, nlon=nlon, add=add, levels=np.array([2.0]),
+                           job_off=dev(job_off), pt_off=dev(pt_off), meta=dev(meta), pts=dev(pts.view(np.int32)),
+                           status=np.zeros(njobs, dtype=np.int32), max_nx=int(nx.max()), h_ncontours=np.diff(job_off),
+                           h_npoints=None)
+    field = spatial.to_device(np.zeros((njobs, nlat, nlon)))
+    coords = detect.coord_tables(lat, lon, dlon, dlat)
+    tables, flags, pieces = detect.run_indices(cs, field, coords, dlon, dlat, which=("cutoffs",), gmax_nx=10 ** 6,
+                                               co_min_exp=0.0, want_flags=True, want_pieces=True,
+                                               min_caps=dict(sel_cap=256, seg_cap=8192))
+    tab = tables["cutoffs"]
+    assert len(tab) == len(rings) and (tab.split == 1).all() and pieces is not None and not pieces["overflow"]
+    assert np.array_equal(tab.contour, np.arange(len(rings)))  # one event per contour, in contour order
+    off = np.r_[0, np.cumsum(lens)]
+    allp, roff, poff = geometry.interleave_pieces(allxy, off, tab.split, pieces, 0, nlon)
+    yy, xx = np.mgrid[0:nlat, 0:nlon]
+    px, py = xx.ravel().astype(float), yy.ravel().astype(float)
+    want_flags = np.zeros((njobs, nlat * nlon), dtype=bool)
+    for e, ring in enumerate(rings):
+        got = [allp[roff[r]:roff[r + 1]] for r in range(poff[e], poff[e + 1])]
+        want = [np.asarray(p) for p in G.split_ring_at_meridian(ring, nlon)]
+        assert G.regions_equal(got, want), ring.tolist()
+        if want:
+            want_flags[job[e]] |= G.buffered_contains(want, 0.5, px, py)
+    got_flags = flags[detect.KINDS.index("cutoffs")].cpu().numpy().reshape(njobs, -1) != 0
+    assert np.array_equal(got_flags, want_flags)
+    grown = max(c.caps["event_cap"] for c in detect._CTX_CACHE.values())
+    assert grown > 256, grown  # the clipper's vertex pool / work list overflowed and the arenas were regrown

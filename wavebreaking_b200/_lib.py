@@ -27,6 +27,7 @@ ST_SEL_OVERFLOW = 32
 ST_WIDTH_OVERFLOW = 64
 ST_PACK_OVERFLOW = 128
 ST_FETCH_OVERFLOW = 256
+ST_SPLIT_CHAINS = 512
 
 
 class WbkError(RuntimeError):

@@ -47,8 +47,10 @@ size_t wbk_index_layout(struct wbk_ctx* ctx, unsigned char* base, size_t off) {
   x.NB = (c.seg_cap + c.contour_cap + PT_HOST - 1) / PT_HOST;
   x.blk_x = (int*)take(J * SC * (size_t)x.NB * 4 * 4);
   x.blk_pf = (double*)take(J * SC * (size_t)x.NB * 2 * 8);
-  x.SPV = (int)(J * 4096 < (size_t)1 << 26 ? J * 4096 : (size_t)1 << 26);
-  x.SPR = (int)(J * 32);
+  // meridian-split arenas grow with event_cap: their overflow is reported as WBK_ST_EVENT_OVERFLOW (wbk_raster.cu)
+  const size_t spv_job = EC * 32 > 4096 ? EC * 32 : 4096, spr_job = EC / 2 > 32 ? EC / 2 : 32;
+  x.SPV = (int)(J * spv_job < (size_t)1 << 26 ? J * spv_job : (size_t)1 << 26);
+  x.SPR = (int)(J * spr_job < (size_t)1 << 24 ? J * spr_job : (size_t)1 << 24);
   x.split_xy = (int*)take((size_t)x.SPV * 2 * 4);
   x.split_ring = (int*)take((size_t)x.SPR * 4 * 4);
   x.split_count = (int*)take(64);
@@ -1184,7 +1186,7 @@ extern "C" int wbk_index_run(wbk_ctx* ctx, int njobs, int nlevels, const int* d_
   // (segment, contour, pack overflow, lattice vertex) belong to the batch and stay
   WBK_LAUNCH(KID_MISC, status_clear_kernel, dim3((njobs + 255) / 256), dim3(256), 0, st, d.status, njobs,
              ~(int)(WBK_ST_PAIR_OVERFLOW | WBK_ST_EVENT_OVERFLOW | WBK_ST_SEL_OVERFLOW | WBK_ST_WIDTH_OVERFLOW |
-                    WBK_ST_FETCH_OVERFLOW));
+                    WBK_ST_FETCH_OVERFLOW | WBK_ST_SPLIT_CHAINS));
   WBK_LAUNCH_CHECK();
   WBK_LAUNCH(KID_SELECT, select_kernel, dim3((njobs + 7) / 8), dim3(256), 0, st, d, x, ps, *prm, J);
   WBK_LAUNCH_CHECK();
@@ -1257,6 +1259,10 @@ extern "C" int wbk_events_counts(wbk_ctx* ctx, int* h_counts, int* h_status, voi
     WBK_CUDA_CHECK(cudaMemcpyAsync(h_counts + (size_t)k * n, ctx->x.ev_count + (size_t)k * J, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
   WBK_CUDA_CHECK(cudaMemcpyAsync(h_status, ctx->d.status, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
   WBK_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (h_status[0] & WBK_ST_SPLIT_CHAINS) {
+    wbk_set_error("wbk_events_raster: an event crosses the last meridian too often for the device clipper (status %d)", h_status[0]);
+    return WBK_ERR_INVALID;
+  }
   for (int j = 0; j < n; ++j) {
     if (h_status[j] & (WBK_ST_PAIR_OVERFLOW | WBK_ST_EVENT_OVERFLOW | WBK_ST_SEL_OVERFLOW)) {
       wbk_set_error("wbk_index_run: job %d overflowed an arena (status %d); raise pair_cap / event_cap / sel_cap", j, h_status[j]);

@@ -406,7 +406,7 @@ events_raster_kernel(WbkDev d, WbkIdx x, const int* __restrict__ job_off, const 
       if (split == 1) {  // work list of the meridian split
         const int pos = atomicAdd(&x.split_count[3], 1);
         if (pos < x.SPR) x.split_list[pos] = w;
-        else atomicExch(&x.split_count[2], 1);
+        else atomicOr(&x.split_count[2], 1);
       }
     }
     __syncthreads();
@@ -451,7 +451,7 @@ __device__ void split_clip_side(const RingView& rv, int c, bool keep_le, int nlo
   const int scratch_cap = n + 2 * SPLIT_MAX_CHAINS;
   const int sbase = atomicAdd(&x.split_count[0], scratch_cap);
   if (sbase + scratch_cap > x.SPV) {
-    atomicExch(&x.split_count[2], 1);
+    atomicOr(&x.split_count[2], 1);
     return;
   }
   int* sxy = x.split_xy + 2 * (size_t)sbase;
@@ -488,7 +488,7 @@ __device__ void split_clip_side(const RingView& rv, int c, bool keep_le, int nlo
       const int prev = k == 0 ? n - 1 : k - 1;
       if (inside(k) && !inside(prev)) {
         if (nch >= SPLIT_MAX_CHAINS) {
-          atomicExch(&x.split_count[2], 1);
+          atomicOr(&x.split_count[2], 2);  // not a capacity the host can raise: reported as WBK_ST_SPLIT_CHAINS
           return;
         }
         SplitChain& cc = ch[nch];
@@ -620,7 +620,7 @@ __device__ void split_clip_side(const RingView& rv, int c, bool keep_le, int nlo
     const int obase = atomicAdd(&x.split_count[0], cnt);
     const int ridx = atomicAdd(&x.split_count[1], 1);
     if (obase + cnt > x.SPV || ridx >= x.SPR) {
-      atomicExch(&x.split_count[2], 1);
+      atomicOr(&x.split_count[2], 1);
       return;
     }
     int* oxy = x.split_xy + 2 * (size_t)obase;
@@ -690,10 +690,16 @@ split_events_kernel(WbkDev d, WbkIdx x, const int* __restrict__ pt_off, const u3
 
 // rasterise the split pieces (real grid, r = 1/2 cell: processing/events.py:75-79) into the flag grids
 __global__ void __launch_bounds__(RS_THREADS)
-split_raster_kernel(WbkIdx x, int nlat, int nlon, int ntime, int8_t* __restrict__ flags, int rowcap) {
+split_raster_kernel(WbkIdx x, int nlat, int nlon, int ntime, int8_t* __restrict__ flags, int rowcap, int* status) {
   WBK_DYN_SMEM(int, sm);
   __shared__ int s_box[4];
   const int tid = threadIdx.x, lane = wbk_lane(), warp = wbk_warp(), nwarps = blockDim.x >> 5;
+  // the work list, the vertex pool or the ring list of the clipper overflowed: some straddling event is missing from
+  // the flag grids -> the host regrows event_cap (which sizes these arenas) and re-runs the batch
+  if (blockIdx.x == 0 && tid == 0) {
+    if (x.split_count[2] & 1) atomicOr(&status[0], (int)WBK_ST_EVENT_OVERFLOW);
+    if (x.split_count[2] & 2) atomicOr(&status[0], (int)WBK_ST_SPLIT_CHAINS);
+  }
   int* acc = sm + (size_t)warp * 2 * rowcap;
   u32* flg = reinterpret_cast<u32*>(acc + rowcap);
   const int nrings = min(x.split_count[1], x.SPR);
@@ -793,7 +799,7 @@ extern "C" int wbk_events_raster(wbk_ctx* ctx, const int* d_job_off, const int* 
     const size_t smem2 = (size_t)(RS_THREADS / 32) * 2 * rc2 * sizeof(int);
     WBK_CUDA_CHECK(cudaFuncSetAttribute(split_raster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     WBK_LAUNCH(KID_SPLIT_RASTER, split_raster_kernel, dim3(148 * 2), dim3(RS_THREADS), smem2, st, ctx->x, d.nlat, d.nlon,
-               ntime, d_flags, rc2);
+               ntime, d_flags, rc2, d.status);
     WBK_LAUNCH_CHECK();
   }
   return WBK_OK;

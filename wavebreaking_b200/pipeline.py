@@ -402,6 +402,9 @@ class Detector:
         work = dict(segments=int(s[8]), pairs=int(s[9]), tiles=int(s[11]))
         bad = status & (_lib.ST_SEG_OVERFLOW | _lib.ST_CONTOUR_OVERFLOW | _lib.ST_PAIR_OVERFLOW | _lib.ST_EVENT_OVERFLOW
                         | _lib.ST_SEL_OVERFLOW | _lib.ST_PACK_OVERFLOW | _lib.ST_FETCH_OVERFLOW)
+        if status & _lib.ST_SPLIT_CHAINS:
+            raise _lib.WbkError(_lib.ERR_INVALID, "an event crosses the last meridian too often for the device clipper; "
+                                                  "its cells would be missing from the flag grids")
         if bad:
             return self._regrow_and_rerun(slot, status)
         slot.pending = None
