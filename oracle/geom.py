@@ -136,8 +136,9 @@ def buffered_contains(rings, r, px, py, edge_chunk=128):
             len2 = dx * dx + dy * dy
             dot = (cx - x0) * dx + (cy - y0) * dy
             within = (dot >= 0) & (dot <= len2) & (cross * cross < r2 * len2)
-            # on the edge itself (also covers r == 0)
-            on = (cross == 0) & (dot >= 0) & (dot <= len2)
+            # on the edge itself (also covers r == 0); a zero-length edge (repeated vertex) is only its end point,
+            # which the last term below covers -- without the len2 test it would claim every candidate point
+            on = (cross == 0) & (dot >= 0) & (dot <= len2) & (len2 > 0)
             disc = (cx - x0) ** 2 + (cy - y0) ** 2 < r2
             near |= (within | on | disc | ((cx == x0) & (cy == y0))).any(axis=1)
         out[cand] |= (wn != 0) | near

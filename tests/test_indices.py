@@ -345,3 +345,72 @@ def test_device_clipper_fuzz_pieces_and_flag_cells_emu(emu, seed, per_job, njobs
     assert np.array_equal(got_flags, want_flags)
     grown = max(c.caps["event_cap"] for c in detect._CTX_CACHE.values())
     assert grown > 256, grown  # the clipper's vertex pool / work list overflowed and the arenas were regrown
+
+
+def _contour_set_from_rings(rings, jobs, njobs, nlat, nlon, add):
+    """hand-made packed contour set: every ring a closed contour of job jobs[i] (no repeated first point: the
+    reference's keep-first dedupe, contour_index.py:118-121, removes it from real contours too)"""
+    closed = [np.asarray(r) for r in rings]
+    lens = np.array([len(c) for c in closed], dtype=np.int64)
+    allxy = np.concatenate(closed).astype(np.int64)
+    pt_off = np.r_[0, np.cumsum(lens)].astype(np.int32)
+    job_off = np.searchsorted(jobs, np.arange(njobs + 1)).astype(np.int32)
+    cid = np.repeat(np.arange(len(lens)), lens)
+    nx = np.array([len(np.unique(c[:, 0])) for c in closed])
+    sumy = np.bincount(cid, weights=allxy[:, 1]).astype(np.int64)
+    meta = np.c_[np.ones(len(lens), dtype=np.int64), nx, sumy, jobs].astype(np.int32)
+    pts = (allxy[:, 0] | (allxy[:, 1] << 16)).astype(np.uint32)
+    device = spatial.to_device(np.zeros(1)).device
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+    cs = detect.ContourSet(njobs=njobs, nlevels=1, nlat=nlat, nlon=nlon, add=add, levels=np.array([2.0]),
+                           job_off=dev(job_off), pt_off=dev(pt_off), meta=dev(meta), pts=dev(pts.view(np.int32)),
+                           status=np.zeros(njobs, dtype=np.int32), max_nx=int(nx.max()), h_ncontours=np.diff(job_off),
+                           h_npoints=None)
+    return cs, closed, nx
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_properties_and_flags_of_random_polygons_emu(emu, seed):
+    """calculate_properties + to_xarray (index_utils.py:35-126, events.py:66-106) on random simple lattice polygons
+    with long oblique edges, slivers and vertices anywhere on the extended grid (inside, across and beyond the last
+    meridian), entered as closed contours: member counts, area-weighted sums, com / mean_var / intensity / event_area
+    and the flag grids equal the oracle's buffer + contains rule."""
+    import pandas as pd
+
+    detect.clear_contexts()
+    rng = np.random.default_rng(300 + seed)
+    nlon, nlat, add, njobs, per_job = 40, 21, 10, 2, 70
+    lat, lon = synthetic.grid_coords(nlat, nlon)
+    grid = P.Grid(lon, lat, synthetic.time_axis(njobs, 6.0))
+    rings = []
+    while len(rings) < njobs * per_job:
+        cx, cy = rng.integers(7, nlon + add - 7), rng.integers(7, nlat - 7)
+        k = rng.integers(3, 12)
+        ang = np.sort(rng.uniform(0, 2 * np.pi, k))
+        rad = rng.uniform(0.8, 6.4, k)
+        ring = np.c_[np.rint(cx + rad * np.cos(ang)), np.rint(cy + rad * np.sin(ang))].astype(int)
+        keep = [0]
+        for i in range(1, len(ring)):
+            if (ring[i] != ring[keep[-1]]).any():
+                keep.append(i)
+        ring = ring[keep]
+        if len(ring) > 1 and (ring[0] == ring[-1]).all():
+            ring = ring[:-1]
+        if len(ring) >= 3 and G.ring_is_simple(ring) and abs(G._ring_area2(ring)) > 0:
+            rings.append(ring)
+    jobs = np.repeat(np.arange(njobs), per_job)
+    cs, closed, nx = _contour_set_from_rings(rings, jobs, njobs, nlat, nlon, add)
+    data = rng.standard_normal((njobs, nlat, nlon))
+    inten = rng.standard_normal((njobs, nlat, nlon))
+    coords = detect.coord_tables(lat, lon, grid.dlon, grid.dlat)
+    tables, flags = detect.run_indices(cs, spatial.to_device(data), coords, grid.dlon, grid.dlat,
+                                       intensity=spatial.to_device(inten), which=("cutoffs",), gmax_nx=int(nx.max()),
+                                       want_flags=True, min_caps=dict(seg_cap=8192))
+    frame = pd.DataFrame({"date": grid.time[jobs], "level": 2.0, "closed": True, "exp_lon": nx * grid.dlon,
+                          "mean_lat": 0.0, "geometry": closed})
+    want = dict(streamers=pd.DataFrame(), overturnings=pd.DataFrame(),
+                cutoffs=P.calculate_cutoffs(data, grid, frame, intensity=inten, periodic_add=add * grid.dlon))
+    assert len(want["cutoffs"]) >= njobs * per_job - 8  # all but the widest rings (exp_lon == max) are events
+    compare_events(cs, tables, flags, want, grid, [2.0], data)
+    props = detect.finish_properties(tables["cutoffs"], grid.lon, grid.lat, grid.nlon)
+    assert np.array_equal(props["intensity"], want["cutoffs"].intensity.values)
