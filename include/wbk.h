@@ -202,8 +202,10 @@ typedef struct wbk_index_params {
 /* ints per event record: contour (index into the packed set), i1, i2 (streamer base points; cutoff:
  * 0, npts-1), x0, y0, x1, y1 (overturning box min_lon, min_lat, max_lon, max_lat; else bounding box),
  * orientation (overturning: 0 cyclonic, 1 anticyclonic), split (1 if a vertex has x >= nlon and one has
- * x <= nlon-1: needs the meridian split of utils/index_utils.py:148-173), near (streamers: the decision
- * that kept this pair had a distance within 1e-9 relative of geo_dis / cont_dis) */
+ * x <= nlon-1: needs the meridian split of utils/index_utils.py:148-173), near (streamers; bit 0: the decision
+ * that kept this pair had a distance within 1e-9 relative of geo_dis / cont_dis; bit 1: the pair won its group
+ * (streamer_index.py:240-247, longest member) against a member whose length is within 1e-12 relative -- a tie that
+ * the last bits of the libm decide, the reference may have kept the other member) */
 #define WBK_EV_INTS 10
 /* doubles per event record: sum(area), sum(area*data), sum(area*intensity), sum(area*x), sum(area*y),
  * number of member cells  (utils/index_utils.py:66-102) */

@@ -310,6 +310,16 @@ def _random_seam_rings(rng, nlon, count):
 
 @pytest.mark.parametrize("seed,per_job,njobs", [(0, 120, 2), (1, 120, 2), (2, 200, 1)])
 def test_device_clipper_fuzz_pieces_and_flag_cells_emu(emu, seed, per_job, njobs):
+    _device_clipper_fuzz(seed, per_job, njobs)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,per_job,njobs", [(3, 120, 2), (4, 200, 1)])
+def test_device_clipper_fuzz_pieces_and_flag_cells_gpu(gpu, seed, per_job, njobs):
+    _device_clipper_fuzz(seed, per_job, njobs)
+
+
+def _device_clipper_fuzz(seed, per_job, njobs):
     """The DEVICE clipper (split_events_kernel) and the rasteriser of its pieces on the same hostile rings as the host
     clipper's fuzz: the rings enter as closed contours of a hand-made contour set, the cutoff index turns each into an
     event, and the pieces / flag cells must equal the oracle's independent face-walk split under the to_xarray rule.
@@ -387,6 +397,16 @@ def _contour_set_from_rings(rings, jobs, njobs, nlat, nlon, add):
 
 @pytest.mark.parametrize("seed", [0, 1])
 def test_properties_and_flags_of_random_polygons_emu(emu, seed):
+    _random_polygons_fuzz(seed)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", [2, 3])
+def test_properties_and_flags_of_random_polygons_gpu(gpu, seed):
+    _random_polygons_fuzz(seed)
+
+
+def _random_polygons_fuzz(seed):
     """calculate_properties + to_xarray (index_utils.py:35-126, events.py:66-106) on random simple lattice polygons
     with long oblique edges, slivers and vertices anywhere on the extended grid (inside, across and beyond the last
     meridian), entered as closed contours: member counts, area-weighted sums, com / mean_var / intensity / event_area
@@ -459,6 +479,30 @@ def _random_walk_contour(rng, W, nlat):
 
 @pytest.mark.parametrize("seed", [0, 1, 2])
 def test_streamers_and_overturnings_on_random_walk_contours_emu(emu, seed):
+    _random_walk_fuzz(seed)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", [3, 4, 5, 6])
+def test_streamers_and_overturnings_on_random_walk_contours_gpu(gpu, seed):
+    """as above on the GPU.  CUDA's sin / cos / asin differ from glibc's in the last bit, which decides the longest
+    member of a group (streamer_index.py:240-247) when two members are equally long up to rounding -- frequent on this
+    coarse lattice (mirrored steps).  Such events may differ from the oracle, and only such: they carry bit 1 of the
+    `near` column."""
+    _random_walk_fuzz(seed, allow_marked_ties=True)
+
+
+def test_near_tie_group_winner_is_marked_emu(emu):
+    """seed 3, job 2: the members (216, 224) and (217, 225) of one group are equally long to 1.6e-15 (relative);
+    whichever is kept must be marked as decided by a near-tie"""
+    tables = _random_walk_fuzz(3)
+    tab = tables["streamers"]
+    e = np.nonzero((tab.job == 2) & np.isin(tab.ind1, (216, 217)))[0]
+    assert len(e) == 1 and tab.near[e[0]] & 2
+    assert (tab.near & 2).sum() < len(tab) // 2  # a mark, not a default
+
+
+def _random_walk_fuzz(seed, allow_marked_ties=False):
     """The pair scan, the duplicate / intersection / overlap / group cascade, the overturning index and the event
     properties on hostile contours: random walks across the extended grid with overhangs, spikes, self-touching
     stretches and jumps where revisited points were dropped.  Entered as a hand-made contour set; every event (base
@@ -488,4 +532,28 @@ def test_streamers_and_overturnings_on_random_walk_contours_emu(emu, seed):
     want = dict(streamers=P.calculate_streamers(data, grid, frame), overturnings=P.calculate_overturnings(data, grid, frame),
                 cutoffs=P.calculate_cutoffs(data, grid, frame))
     assert len(want["streamers"]) + len(want["overturnings"]) > 0 and len(want["cutoffs"]) == 0
+    tab, w = tables["streamers"], want["streamers"]
+    tpos = {t: i for i, t in enumerate(grid.time.tolist())}
+    got_keys = list(zip(tab.job.tolist(), tab.ind1.tolist(), tab.ind2.tolist()))
+    want_rings = w.attrs["_index_rings"]
+    want_keys = []
+    for j, date in enumerate(w.date.values):
+        job = tpos[pd.Timestamp(date).to_datetime64().astype(grid.time.dtype).item()]
+        first = np.asarray(want_rings[j])[0]
+        i1 = int(np.nonzero((walks[job] == first).all(axis=1))[0][0])
+        want_keys.append((job, i1, i1 + len(want_rings[j]) - 1))
+    if allow_marked_ties and set(got_keys) != set(want_keys):
+        only_dev = [k for k in got_keys if k not in set(want_keys)]
+        assert len(got_keys) == len(want_keys) and len(only_dev) <= 4, (len(got_keys), len(want_keys), only_dev)
+        for k in only_dev:
+            assert tab.near[got_keys.index(k)] & 2, k  # only near-tie winners may differ
+        props = detect.finish_properties(tab, grid.lon, grid.lat, grid.nlon)
+        for j, k in enumerate(want_keys):  # every other event: same properties
+            if k in set(got_keys):
+                e = got_keys.index(k)
+                row = w.iloc[j]
+                assert props["com"][e] == row.com and props["mean_var"][e] == row.mean_var
+                assert props["event_area"][e] == row.event_area
+        return tables
     compare_events(cs, tables, flags, want, grid, [2.0], data, simple_pieces_only=True)
+    return tables

@@ -29,7 +29,7 @@ det = pipeline.Detector(lat, lon, levels=[2.0])
 res = det.run_batch(raw)
 raw_h = raw.cpu().numpy()
 tot = dict(events=0, mismatched_events=0, flag_cells_diff=0, near_listed=int(res.near_total), contours=0, points=0,
-           non_simple_rings=0)
+           non_simple_rings=0, near_tie_group_winners=int(((res.tables["streamers"].near & 2) != 0).sum()))
 non_simple = []  # (step, kind, event) whose ring touches / crosses itself: invalid for GEOS ("GEOS-invalid class")
 for t in range(n):
     t0 = time.time()

@@ -1097,10 +1097,14 @@ __global__ void __launch_bounds__(ST_THREADS) streamer_finish_kernel(WbkDev d, W
         for (int a = tid; a < P; a += nt) label[a] = slab[a];
         __syncthreads();
       }
-      // winner of every component: max of on[ind1 : ind2 + 1].sum(), first index on ties
+      // winner of every component: max of on[ind1 : ind2 + 1].sum(), first index on ties.  A component whose two
+      // longest members lie within 1e-12 (relative) of each other is marked (bit 1 of the event's `near` column): such
+      // a tie is broken by the last bits of sin / cos / asin, which are not the same in CUDA's and the host's libm,
+      // so the reference may have kept the other member
       for (int a = tid; a < P; a += nt) {
         hk[a] = 0ull;
         hv1[a] = WBK_NONE;
+        flag[a] = 0;  // members within the tie band, per component root
       }
       __syncthreads();
       for (int a = tid; a < P; a += nt) {
@@ -1117,17 +1121,19 @@ __global__ void __launch_bounds__(ST_THREADS) streamer_finish_kernel(WbkDev d, W
         const int i1 = (int)(k >> 32), i2 = (int)(((u32)k) >> 1);
         const double len = reinterpret_cast<const double*>(oth)[a];
         (void)i1; (void)i2;
+        const double top = __longlong_as_double((long long)hk[label[a]]);
         if ((u64)__double_as_longlong(len) == hk[label[a]]) atomicMin(&hv1[label[a]], (u32)a);
+        if (top - len <= 1e-12 * top) atomicAdd(&flag[label[a]], 1);
       }
       __syncthreads();
       // components in order of their smallest member (combine_shared output order)
-      for (int a = tid; a < P; a += nt) flag[a] = label[a] == a ? 1 : 0;
+      for (int a = tid; a < P; a += nt) flag[a] = (label[a] == a ? 1 : 0) | (flag[a] >= 2 ? 2 : 0);
       __syncthreads();
-      for (int a = tid; a < P; a += nt) scanb[a] = flag[a];
+      for (int a = tid; a < P; a += nt) scanb[a] = flag[a] & 1;
       __syncthreads();
       nout = wbk_block_excl_scan(scanb, P, sscan);
       for (int a = tid; a < P; a += nt)
-        if (flag[a]) oth[scanb[a]] = cur[hv1[a]];
+        if (flag[a] & 1) oth[scanb[a]] = cur[hv1[a]] | ((flag[a] & 2) ? (1ull << 31) : 0ull);  // bit 31: tie mark
       __syncthreads();
       u64* t = cur; cur = oth; oth = t;
     }
@@ -1139,9 +1145,9 @@ __global__ void __launch_bounds__(ST_THREADS) streamer_finish_kernel(WbkDev d, W
       if (e >= x.EC) continue;
       const u64 k = cur[a];
       int* ev = ev_int_ptr(x, J, WBK_EV_STREAMER, job, e);
-      ev[0] = c; ev[1] = (int)(k >> 32); ev[2] = (int)(((u32)k) >> 1);
+      ev[0] = c; ev[1] = (int)(k >> 32); ev[2] = (int)((((u32)k) & 0x7fffffffu) >> 1);
       for (int q = 3; q < WBK_EV_INTS - 1; ++q) ev[q] = 0;
-      ev[9] = (int)(k & 1ull);
+      ev[9] = (int)(k & 1ull) | (int)((k >> 31) & 1ull) << 1;  // 1: near-threshold pair, 2: near-tie group winner
     }
     if (tid == 0) s_nev = ev_base + nout;
     __syncthreads();
