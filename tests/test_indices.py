@@ -557,3 +557,41 @@ def _random_walk_fuzz(seed, allow_marked_ties=False):
         return tables
     compare_events(cs, tables, flags, want, grid, [2.0], data, simple_pieces_only=True)
     return tables
+
+
+def _rings_raster_fuzz(seed):
+    """wbk_rasterize_rings (to_xarray for arbitrary event tables, events.py:66-106) on random simple polygons with
+    long oblique edges at three buffer radii (0: boundary only, 0.5: the to_xarray rule on a regular grid, 4.5: many
+    cells) against the oracle's buffer + contains rule"""
+    rng = np.random.default_rng(700 + seed)
+    nlat, nlon = 40, 64
+    yy, xx = np.mgrid[0:nlat, 0:nlon]
+    px, py = xx.ravel().astype(float), yy.ravel().astype(float)
+    rings = []
+    while len(rings) < 40:
+        cx, cy = rng.integers(9, nlon - 9), rng.integers(9, nlat - 9)
+        k = rng.integers(3, 12)
+        ang = np.sort(rng.uniform(0, 2 * np.pi, k))
+        rad = rng.uniform(0.8, 8.4, k)
+        ring = np.unique(np.c_[np.rint(cx + rad * np.cos(ang)), np.rint(cy + rad * np.sin(ang))].astype(int), axis=0)
+        ring = ring[np.argsort(np.arctan2(ring[:, 1] - ring[:, 1].mean(), ring[:, 0] - ring[:, 0].mean()))]
+        if len(ring) >= 3 and G.ring_is_simple(ring) and abs(G._ring_area2(ring)) > 0:
+            rings.append(ring)
+    ring_t = rng.integers(0, 3, len(rings))
+    for r in (0.0, 0.5, 4.5):
+        got = detect.rasterize_rings(rings, ring_t, nlat, nlon, 3, r).cpu().numpy() != 0
+        want = np.zeros((3, nlat * nlon), dtype=bool)
+        for ring, t in zip(rings, ring_t):
+            want[t] |= G.buffered_contains([ring], r, px, py)
+        assert np.array_equal(got.reshape(3, -1), want), r
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_rings_raster_fuzz_emu(emu, seed):
+    _rings_raster_fuzz(seed)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", [2, 3])
+def test_rings_raster_fuzz_gpu(gpu, seed):
+    _rings_raster_fuzz(seed)
