@@ -308,7 +308,7 @@ def _random_seam_rings(rng, nlon, count):
     return out
 
 
-@pytest.mark.parametrize("seed,per_job,njobs", [(0, 120, 2), (1, 120, 2), (2, 200, 1)])
+@pytest.mark.parametrize("seed,per_job,njobs", [(0, 120, 2), (2, 200, 1)])
 def test_device_clipper_fuzz_pieces_and_flag_cells_emu(emu, seed, per_job, njobs):
     _device_clipper_fuzz(seed, per_job, njobs)
 
@@ -568,7 +568,7 @@ def _rings_raster_fuzz(seed):
     yy, xx = np.mgrid[0:nlat, 0:nlon]
     px, py = xx.ravel().astype(float), yy.ravel().astype(float)
     rings = []
-    while len(rings) < 40:
+    while len(rings) < 30:
         cx, cy = rng.integers(9, nlon - 9), rng.integers(9, nlat - 9)
         k = rng.integers(3, 12)
         ang = np.sort(rng.uniform(0, 2 * np.pi, k))
@@ -586,7 +586,7 @@ def _rings_raster_fuzz(seed):
         assert np.array_equal(got.reshape(3, -1), want), r
 
 
-@pytest.mark.parametrize("seed", [0, 1])
+@pytest.mark.parametrize("seed", [0])
 def test_rings_raster_fuzz_emu(emu, seed):
     _rings_raster_fuzz(seed)
 
