@@ -164,3 +164,40 @@ def test_cuda_graph_replay_equals_eager_gpu(gpu):
         for kind in detect.KINDS:
             assert np.array_equal(got.tables[kind].sums, want.tables[kind].sums)
     assert det.graph_replays >= 2 and det.graph_kernel_launches > 20
+
+
+def _nan_patch_case(seed, fuse):
+    """missing values in the input: a NaN blob and a NaN at the seam column.  The smoothing spreads them by `passes`
+    cells (scipy semantics), the contour stage must skip every square that touches one (skimage), and the events
+    whose members would include a NaN cell carry NaN properties as in the reference.  (Infinite values are not a
+    parity target: skimage's interpolation fraction is NaN beside them and the reference casts that to int.)"""
+    from test_contours import compare_contours
+
+    rng = np.random.default_rng(900 + seed)
+    nlat, nlon, nt = 91, 180, 2
+    lat, lon = synthetic.grid_coords(nlat, nlon)
+    raw = synthetic.pv_field(nlat, nlon, np.arange(nt) * 6.0).astype(np.float32)
+    raw += 0.2 * rng.standard_normal(raw.shape).astype(np.float32)
+    for t in range(nt):
+        cy, cx = rng.integers(25, 65), rng.integers(20, 160)
+        raw[t, cy:cy + rng.integers(1, 4), cx:cx + rng.integers(1, 5)] = np.nan
+        raw[t, rng.integers(20, 70), nlon - 1] = np.nan  # its spread wraps around the seam
+    grid = P.Grid(lon, lat, synthetic.time_axis(nt, 6.0))
+    with np.errstate(all="ignore"):
+        want = P.detect_steps(raw, grid, levels=[2.0])
+    det = pipeline.Detector(lat, lon, levels=[2.0], fuse=fuse)
+    res = det.run_batch(spatial.to_device(raw))
+    compare_contours(res.contours, want["contours"], grid, [2.0])
+    _compare(res, want)
+    assert np.isnan(want["smoothed"]).sum() > 100
+
+
+@pytest.mark.parametrize("fuse", [True, False])
+def test_missing_values_in_the_input_emu(emu, fuse):
+    _nan_patch_case(0, fuse)
+
+
+@pytest.mark.gpu
+def test_missing_values_in_the_input_gpu(gpu):
+    _nan_patch_case(1, True)
+    _nan_patch_case(2, False)
