@@ -502,7 +502,13 @@ def test_near_tie_group_winner_is_marked_emu(emu):
     assert (tab.near & 2).sum() < len(tab) // 2  # a mark, not a default
 
 
-def _random_walk_fuzz(seed, allow_marked_ties=False):
+def test_several_full_width_contours_per_job_emu(emu):
+    """three full-width contours in every job: more than sel_cap (regrown), one touch-kernel slot per contour"""
+    tables = _random_walk_fuzz(7, per_job=3)
+    assert len(np.unique(tables["streamers"].contour)) >= 7
+
+
+def _random_walk_fuzz(seed, allow_marked_ties=False, per_job=1):
     """The pair scan, the duplicate / intersection / overlap / group cascade, the overturning index and the event
     properties on hostile contours: random walks across the extended grid with overhangs, spikes, self-touching
     stretches and jumps where revisited points were dropped.  Entered as a hand-made contour set; every event (base
@@ -516,8 +522,8 @@ def _random_walk_fuzz(seed, allow_marked_ties=False):
     lat, lon = synthetic.grid_coords(nlat, nlon)
     grid = P.Grid(lon, lat, synthetic.time_axis(njobs, 6.0))
     add = int(120 / grid.dlon)
-    walks = [_random_walk_contour(rng, nlon + add, nlat) for _ in range(njobs)]
-    jobs = np.arange(njobs)
+    walks = [_random_walk_contour(rng, nlon + add, nlat) for _ in range(njobs * per_job)]
+    jobs = np.repeat(np.arange(njobs), per_job)
     cs, contours, nx = _contour_set_from_rings(walks, jobs, njobs, nlat, nlon, add)
     meta = cs.meta.cpu().numpy().copy()
     meta[:, 0] = 0  # open contours
@@ -532,6 +538,10 @@ def _random_walk_fuzz(seed, allow_marked_ties=False):
     want = dict(streamers=P.calculate_streamers(data, grid, frame), overturnings=P.calculate_overturnings(data, grid, frame),
                 cutoffs=P.calculate_cutoffs(data, grid, frame))
     assert len(want["streamers"]) + len(want["overturnings"]) > 0 and len(want["cutoffs"]) == 0
+    if per_job > 1:
+        assert not allow_marked_ties
+        compare_events(cs, tables, flags, want, grid, [2.0], data, simple_pieces_only=True)
+        return tables
     tab, w = tables["streamers"], want["streamers"]
     tpos = {t: i for i, t in enumerate(grid.time.tolist())}
     got_keys = list(zip(tab.job.tolist(), tab.ind1.tolist(), tab.ind2.tolist()))
