@@ -201,3 +201,34 @@ def test_missing_values_in_the_input_emu(emu, fuse):
 def test_missing_values_in_the_input_gpu(gpu):
     _nan_patch_case(1, True)
     _nan_patch_case(2, False)
+
+
+def _noisy_detector_case(seed, amp, levels):
+    """the fused path (smoothing with bit planes -> marching squares on planes -> ... -> flags) on a rough field:
+    contours point by point, every event with its properties, and the flag grids against the oracle"""
+    from test_contours import compare_contours
+    from test_indices import compare_events
+
+    rng = np.random.default_rng(1100 + seed)
+    nlat, nlon, nt = 91, 180, 2
+    lat, lon = synthetic.grid_coords(nlat, nlon)
+    raw = synthetic.pv_field(nlat, nlon, np.arange(nt) * 6.0).astype(np.float32)
+    raw += amp * rng.standard_normal(raw.shape).astype(np.float32)
+    grid = P.Grid(lon, lat, synthetic.time_axis(nt, 6.0))
+    want = P.detect_steps(raw, grid, levels=levels)
+    res = pipeline.Detector(lat, lon, levels=levels).run_batch(spatial.to_device(raw))
+    compare_contours(res.contours, want["contours"], grid, levels)
+    compare_events(res.contours, res.tables, res.flags, want["events"], grid, levels, want["smoothed"], simple_pieces_only=True)
+    return res
+
+
+def test_detector_on_rough_fields_emu(emu):
+    res = _noisy_detector_case(0, 6.0, [2.0])
+    assert res.contours.ncontours > 60
+    _noisy_detector_case(1, 3.0, [2.0, -2.0])
+
+
+@pytest.mark.gpu
+def test_detector_on_rough_fields_gpu(gpu):
+    _noisy_detector_case(2, 6.0, [2.0])
+    _noisy_detector_case(3, 3.0, [2.0, -2.0])

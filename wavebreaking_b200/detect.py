@@ -392,12 +392,22 @@ def rasterize_rings(rings, ring_t, nlat, nlon, ntime, r_cells, out_i8=None, valu
 
 
 def finish_properties(table, lon, lat, nlon):
-    """com / mean_var / intensity / event_area columns from the device sums (index_utils.py:105-120)."""
+    """com / mean_var / intensity / event_area columns from the device sums (index_utils.py:105-120).
+
+    ``com_near_integer`` marks the events whose area-weighted mean index lies within 1e-12 (relative) of an integer:
+    the reference truncates the quotient of two pandas (Kahan) sums (``.astype("int")``, index_utils.py:105-106), and
+    for an event that is symmetric about a grid line -- a single column of cells, say -- the exact quotient IS an
+    integer, so the last bit of the summation decides between two neighbouring grid points.  The device sums are
+    exact (double-double); in that case the reference may name the neighbouring point."""
     s = table.sums
     with np.errstate(divide="ignore", invalid="ignore"):
-        xi = (s[:, 3] / s[:, 0]).astype("int") % nlon if len(s) else np.zeros(0, dtype=int)
-        yi = (s[:, 4] / s[:, 0]).astype("int") if len(s) else np.zeros(0, dtype=int)
+        qx = s[:, 3] / s[:, 0] if len(s) else np.zeros(0)
+        qy = s[:, 4] / s[:, 0] if len(s) else np.zeros(0)
+        xi = qx.astype("int") % nlon
+        yi = qy.astype("int")
         mean_var = np.round(s[:, 1] / s[:, 0], 2)
         intensity = np.round(s[:, 2] / s[:, 0], 2)
+        near = (np.abs(qx - np.rint(qx)) <= 1e-12 * np.maximum(np.abs(qx), 1.0)) | \
+               (np.abs(qy - np.rint(qy)) <= 1e-12 * np.maximum(np.abs(qy), 1.0))
     com = list(map(tuple, np.c_[np.asarray(lon)[xi], np.asarray(lat)[yi]]))
-    return dict(com=com, mean_var=mean_var, intensity=intensity, event_area=np.round(s[:, 0], 2))
+    return dict(com=com, mean_var=mean_var, intensity=intensity, event_area=np.round(s[:, 0], 2), com_near_integer=near)
