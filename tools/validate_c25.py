@@ -53,6 +53,7 @@ for t in range(n):
             bad = max(len(idx), len(w))
         else:
             props = detect.finish_properties(tab, lon, lat, nlon)
+            tot["com_near_integer"] = tot.get("com_near_integer", 0) + int(props["com_near_integer"][idx].sum())
             for j, e in enumerate(idx):
                 row = w.iloc[j]
                 same = (tuple(props["com"][e]) == tuple(row.com) and props["mean_var"][e] == row.mean_var
