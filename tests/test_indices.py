@@ -477,9 +477,12 @@ def _random_walk_contour(rng, W, nlat):
     return np.asarray(out, dtype=np.int64)
 
 
-@pytest.mark.parametrize("seed", [0, 1, 2])
+@pytest.mark.parametrize("seed", [0, 1, 17])
 def test_streamers_and_overturnings_on_random_walk_contours_emu(emu, seed):
-    _random_walk_fuzz(seed)
+    """seed 17 holds an EXACT tie (two members of a group with bit-identical lengths): the reference keeps the one
+    that comes first in the iteration order of a CPython set (combine_shared returns list(set), index_utils.py:211),
+    the device the first in row order; the event is marked and only marked events may differ"""
+    _random_walk_fuzz(seed, allow_marked_ties=True)
 
 
 @pytest.mark.gpu
